@@ -1,0 +1,142 @@
+"""ctypes front end of oracle/liborc.so (the C restatement in vl_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see vl_oracle.c's header.  Arrays are numpy float64, SoA
+[field][z][y][x] flattened exactly like the reference's `dev_conserved`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PCM, PLMC, PPMC = 0, 1, 2
+HLLC, ROE = 0, 1
+_lib = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborc.so")
+    src = os.path.join(_HERE, "vl_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liborc.so"])
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        d, i, p, l = C.c_double, C.c_int, C.c_void_p, C.c_long
+        _lib.orc_ppm_single_variable.argtypes = [d] * 5 + [p, p]
+        _lib.orc_reconstruct.argtypes = [i, p, p, p, i, i, i, d, i]
+        _lib.orc_riemann.argtypes = [i, p, p, p, i, i, i, d, i]
+        _lib.orc_riemann_single.argtypes = [i, p, p, d, p]
+        _lib.orc_vl_step.argtypes = [p, i, i, i, i, d, d, d, d, d, i, i, d]
+        _lib.orc_hydro_inverse_crossing_time.argtypes = [d] * 10
+        _lib.orc_hydro_inverse_crossing_time.restype = d
+        _lib.orc_calc_dti.argtypes = [p, i, i, i, i, d, d, d, d]
+        _lib.orc_calc_dti.restype = d
+        _lib.orc_temperature_floor.argtypes = [p, i, i, i, i, d]
+        _lib.orc_boundary_extents.argtypes = [i, i, i, i, i, p, p]
+        _lib.orc_set_ghost_cells.argtypes = [p, i, i, i, i, i, p, i]
+        _lib.orc_set_boundaries.argtypes = [p, i, i, i, i, i, p]
+        _lib.orc_pack.argtypes = [p, p, i, i, i, l, l, i, i, i]
+        _lib.orc_unpack.argtypes = [p, p, i, i, i, l, l, i, i, i]
+    return _lib
+
+
+def _ptr(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ppm_single_variable(cm2, cm1, c0, cp1, cp2):
+    L, R = C.c_double(), C.c_double()
+    lib().orc_ppm_single_variable(cm2, cm1, c0, cp1, cp2, C.byref(L), C.byref(R))
+    return L.value, R.value
+
+
+def reconstruct(recon, U, nx, ny, nz, gamma, direction):
+    """One launch of PLMC_cuda / PPMC_VL: returns (Q_L, Q_R), zero where the guard skips."""
+    QL, QR = np.zeros_like(U), np.zeros_like(U)
+    lib().orc_reconstruct(recon, _ptr(U), _ptr(QL), _ptr(QR), nx, ny, nz, gamma, direction)
+    return QL, QR
+
+
+def riemann(solver, QL, QR, nx, ny, nz, gamma, direction):
+    F = np.zeros_like(QL)
+    lib().orc_riemann(solver, _ptr(QL), _ptr(QR), _ptr(F), nx, ny, nz, gamma, direction)
+    return F
+
+
+def riemann_single(solver, left, right, gamma):
+    l = np.ascontiguousarray(left, dtype=np.float64)
+    r = np.ascontiguousarray(right, dtype=np.float64)
+    f = np.zeros(5)
+    lib().orc_riemann_single(solver, _ptr(l), _ptr(r), gamma, _ptr(f))
+    return f
+
+
+def vl_step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor=0.0):
+    """In-place VL_Algorithm_{1,2,3}D_CUDA on U (flat SoA incl. ghosts)."""
+    lib().orc_vl_step(_ptr(U), nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor)
+    return U
+
+
+def hydro_inverse_crossing_time(E, d, d_inv, vx, vy, vz, dx, dy, dz, gamma):
+    return lib().orc_hydro_inverse_crossing_time(E, d, d_inv, vx, vy, vz, dx, dy, dz, gamma)
+
+
+def calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma):
+    return lib().orc_calc_dti(_ptr(U), nx, ny, nz, n_ghost, dx, dy, dz, gamma)
+
+
+def temperature_floor(U, nx, ny, nz, n_ghost, U_floor):
+    lib().orc_temperature_floor(_ptr(U), nx, ny, nz, n_ghost, U_floor)
+    return U
+
+
+def boundary_extents(direction, nx, ny, nz, n_ghost):
+    lo, hi = (C.c_int * 3)(), (C.c_int * 3)()
+    lib().orc_boundary_extents(direction, nx, ny, nz, n_ghost, lo, hi)
+    return list(lo), list(hi)
+
+
+def set_ghost_cells(U, nx, ny, nz, n_fields, n_ghost, flags, direction):
+    fl = (C.c_int * 6)(*flags)
+    lib().orc_set_ghost_cells(_ptr(U), nx, ny, nz, n_fields, n_ghost, fl, direction)
+    return U
+
+
+def set_boundaries(U, nx, ny, nz, n_fields, n_ghost, flags):
+    fl = (C.c_int * 6)(*flags)
+    lib().orc_set_boundaries(_ptr(U), nx, ny, nz, n_fields, n_ghost, fl)
+    return U
+
+
+def pack(U, nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize):
+    buf = np.zeros(n_fields * isize * jsize * ksize)
+    lib().orc_pack(_ptr(buf), _ptr(U), nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize)
+    return buf
+
+
+def unpack(buf, U, nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize):
+    lib().orc_unpack(_ptr(buf), _ptr(U), nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize)
+    return U
+
+
+def advance(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_steps, cfl=0.3,
+            density_floor=0.0, U_floor=0.0):
+    """The reference's main loop body (main.cpp:247-379) without I/O: dt from the CFL reduction, VL step,
+    temperature floor, ghost fill.  Returns the list of dt used."""
+    dts = []
+    dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
+    for _ in range(n_steps):
+        dt = cfl / dti
+        vl_step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor)
+        temperature_floor(U, nx, ny, nz, n_ghost, U_floor)
+        dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
+        set_boundaries(U, nx, ny, nz, 5, n_ghost, flags)
+        dts.append(dt)
+    return dts

@@ -1,0 +1,711 @@
+/*
+ * vl_oracle.c -- CPU restatement of Cholla's Van Leer hydro hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the shipped product (cholla_b200/, the C-ABI
+ * library) links, imports or calls this file; only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may.  It exists to be the checker that
+ * the hand-written sm_100a kernels are compared against.
+ *
+ * It restates, stage by stage and in the reference's floating-point operation order, the
+ * algorithm of (all paths relative to the reference tree, commit 8478c9e):
+ *   src/integrators/VL_{1,2,3}D_cuda.cu      six-stage predictor/corrector driver
+ *   src/reconstruction/pcm_cuda.cu           piecewise-constant interfaces
+ *   src/reconstruction/plmc_cuda.cu          PLM, characteristic limiting
+ *   src/reconstruction/ppmc_cuda.cu:540-695  PPMC_VL
+ *   src/reconstruction/reconstruction.h      shared helpers (hydro branches)
+ *   src/riemann_solvers/hllc_cuda.cu, roe_cuda.cu
+ *   src/hydro/hydro_cuda.cu                  conserved update, Calc_dt, temperature floor
+ *   src/grid/cuda_boundaries.cu, src/grid/boundary_conditions.cpp:419-  ghost cells
+ * Build with -O2 -ffp-contract=off (the reference device code is built -fmad=false,
+ * Makefile:148), so every + and * rounds exactly as the reference's does.
+ *
+ * Parity pin: checked against the reference's own unit-test fiducials (the JSON fixtures under tests/golden,
+ * extracted from plmc_cuda_tests.cu, ppmc_cuda_tests.cu, reconstruction_tests.cu,
+ * hydro_cuda_tests.cu, hllc_cuda_tests.cu) by tests/test_oracle_golden.py, and against the
+ * reference's own kernels compiled for sm_100 (oracle/_ref) by tests/test_gpu_reference.py.
+ *
+ * Scope: hydro (5 fields; density, momentum xyz, Energy), fp64.  Layout is the reference's:
+ * SoA, field stride N = nx*ny*nz, cell id = x + nx*(y + ny*z), ghosts included.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_TINY 1.0e-20 /* global.h:25 */
+
+enum { ORC_PCM = 0, ORC_PLMC = 1, ORC_PPMC = 2 };
+enum { ORC_HLLC = 0, ORC_ROE = 1 };
+
+typedef struct {
+  double d, vx, vy, vz, p;
+} prim_t;
+
+/* global.h:144 -- note SIGN(0) = +1 */
+static inline double sign_macro(double a) { return (a < 0.) ? -1. : 1.; }
+
+/* math_utilities.h:78-98: a1*b1 + ((a2*b2) + (a3*b3)) */
+static inline double square_mag(double a, double b, double c) { return a * a + ((b * b) + (c * c)); }
+
+static inline void dir_perm(int dir, int *o1, int *o2, int *o3)
+{ /* plmc_cuda.cu:41-58 */
+  if (dir == 0) { *o1 = 1; *o2 = 2; *o3 = 3; }
+  else if (dir == 1) { *o1 = 2; *o2 = 3; *o3 = 1; }
+  else { *o1 = 3; *o2 = 1; *o3 = 2; }
+}
+
+/* reconstruction.h:139-212 (hydro, no DE) + hydro_utilities.h:34-45 */
+static prim_t load_prim(const double *U, size_t id, size_t N, int o1, int o2, int o3, double gamma)
+{
+  prim_t w;
+  w.d  = U[id];
+  w.vx = U[(size_t)o1 * N + id] / w.d;
+  w.vy = U[(size_t)o2 * N + id] / w.d;
+  w.vz = U[(size_t)o3 * N + id] / w.d;
+  double pr = U[4 * N + id] - 0.5 * w.d * square_mag(w.vx, w.vy, w.vz);
+  w.p = fmax((gamma - 1.) * pr, ORC_TINY);
+  return w;
+}
+
+/* reconstruction.h:918-968 + hydro_utilities.h:106-118 */
+static void store_interface(prim_t q, double *Q, size_t id, size_t N, int o1, int o2, int o3, double gamma)
+{
+  Q[id]                  = q.d;
+  Q[(size_t)o1 * N + id] = q.d * q.vx;
+  Q[(size_t)o2 * N + id] = q.d * q.vy;
+  Q[(size_t)o3 * N + id] = q.d * q.vz;
+  Q[4 * N + id]          = (fmax(q.p, ORC_TINY) / (gamma - 1.)) + 0.5 * q.d * square_mag(q.vx, q.vy, q.vz);
+}
+
+/* reconstruction.h:95-119 */
+static int outside_guard(int order, int nx, int ny, int nz, int x, int y, int z)
+{
+  int out = x < order - 1 || x >= nx - order;
+  if (ny > 1) out = y < order - 1 || y >= ny - order || out;
+  if (nz > 1) out = z < order - 1 || z >= nz - order || out;
+  else out = z >= nz || out;
+  return out;
+}
+
+/* ---- characteristic projections, hydro (reconstruction.h:423-431, 482-488) ---- */
+typedef struct { double a0, a1, a2, a3, a4; } char_t;
+
+static char_t to_char(prim_t c, prim_t s, double a, double a2)
+{
+  char_t o;
+  o.a0 = -c.d * s.vx / (2.0 * a) + s.p / (2.0 * a2);
+  o.a1 = s.d - s.p / (a2);
+  o.a2 = s.vy;
+  o.a3 = s.vz;
+  o.a4 = c.d * s.vx / (2.0 * a) + s.p / (2.0 * a2);
+  return o;
+}
+
+static prim_t from_char(prim_t c, char_t s, double a, double a2)
+{
+  prim_t o;
+  o.d  = s.a0 + s.a1 + s.a4;
+  o.vx = a / c.d * (s.a4 - s.a0);
+  o.vy = s.a2;
+  o.vz = s.a3;
+  o.p  = a2 * (s.a0 + s.a4);
+  return o;
+}
+
+/* ---- PLMC pieces (reconstruction.h:224-296, 512-559, 645-723) ---- */
+static inline double vl_slope(double l, double r) { return (l * r > 0.0) ? 2.0 * l * r / (l + r) : 0.0; }
+
+static inline double mono(double l, double r, double c, double g)
+{
+  if (l * r > 0.0) {
+    double la = 2.0 * fmin(fabs(l), fabs(r));
+    double lb = fmin(fabs(c), fabs(g));
+    return copysign(fmin(la, lb), c);
+  }
+  return 0.0;
+}
+
+static inline void clamp_pair(double *l_iph, double *r_imh, double vm, double vi, double vp)
+{
+  *r_imh = fmax(fmin(vi, vm), *r_imh);
+  *r_imh = fmin(fmax(vi, vm), *r_imh);
+  *l_iph = fmax(fmin(vi, vp), *l_iph);
+  *l_iph = fmin(fmax(vi, vp), *l_iph);
+}
+
+static prim_t prim_diff(prim_t l, prim_t r, double coef)
+{
+  prim_t s;
+  s.d = coef * (r.d - l.d); s.vx = coef * (r.vx - l.vx); s.vy = coef * (r.vy - l.vy);
+  s.vz = coef * (r.vz - l.vz); s.p = coef * (r.p - l.p);
+  return s;
+}
+
+/* one cell of PLMC_cuda (plmc_cuda.cu:60-128, 287-299; the #ifndef VL block is dead) */
+static void plmc_cell(prim_t wm, prim_t wi, prim_t wp, double gamma, prim_t *L, prim_t *R)
+{
+  double a  = sqrt(gamma * wi.p / wi.d);
+  double a2 = a * a;
+  prim_t dL = prim_diff(wm, wi, 1.0), dR = prim_diff(wi, wp, 1.0), dC = prim_diff(wm, wp, 0.5);
+  prim_t dG;
+  dG.d = vl_slope(dL.d, dR.d); dG.vx = vl_slope(dL.vx, dR.vx); dG.vy = vl_slope(dL.vy, dR.vy);
+  dG.vz = vl_slope(dL.vz, dR.vz); dG.p = vl_slope(dL.p, dR.p);
+  char_t aL = to_char(wi, dL, a, a2), aR = to_char(wi, dR, a, a2), aC = to_char(wi, dC, a, a2),
+         aG = to_char(wi, dG, a, a2);
+  char_t am;
+  am.a0 = mono(aL.a0, aR.a0, aC.a0, aG.a0);
+  am.a1 = mono(aL.a1, aR.a1, aC.a1, aG.a1);
+  am.a2 = mono(aL.a2, aR.a2, aC.a2, aG.a2);
+  am.a3 = mono(aL.a3, aR.a3, aC.a3, aG.a3);
+  am.a4 = mono(aL.a4, aR.a4, aC.a4, aG.a4);
+  prim_t dm = from_char(wi, am, a, a2);
+  prim_t l, r;
+  l.d = wi.d + 1.0 * 0.5 * dm.d;    r.d = wi.d + -1.0 * 0.5 * dm.d;
+  l.vx = wi.vx + 1.0 * 0.5 * dm.vx; r.vx = wi.vx + -1.0 * 0.5 * dm.vx;
+  l.vy = wi.vy + 1.0 * 0.5 * dm.vy; r.vy = wi.vy + -1.0 * 0.5 * dm.vy;
+  l.vz = wi.vz + 1.0 * 0.5 * dm.vz; r.vz = wi.vz + -1.0 * 0.5 * dm.vz;
+  l.p = wi.p + 1.0 * 0.5 * dm.p;    r.p = wi.p + -1.0 * 0.5 * dm.p;
+  clamp_pair(&l.d, &r.d, wm.d, wi.d, wp.d);
+  clamp_pair(&l.vx, &r.vx, wm.vx, wi.vx, wp.vx);
+  clamp_pair(&l.vy, &r.vy, wm.vy, wi.vy, wp.vy);
+  clamp_pair(&l.vz, &r.vz, wm.vz, wi.vz, wp.vz);
+  clamp_pair(&l.p, &r.p, wm.p, wi.p, wp.p);
+  r.d = fmax(r.d, ORC_TINY); l.d = fmax(l.d, ORC_TINY);
+  r.p = fmax(r.p, ORC_TINY); l.p = fmax(l.p, ORC_TINY);
+  *L = l; *R = r;
+}
+
+/* ---- PPM_Single_Variable (reconstruction.h:794-901) ---- */
+static double ppm_limit_face(double ci, double cim1, double face, double s2_i, double s2_im1)
+{
+  const double C2 = 1.25;
+  double s2_c = 3.0 * (cim1 + ci - 2.0 * face);
+  double lim = 0.0;
+  if (sign_macro(s2_c) == sign_macro(s2_im1) && sign_macro(s2_c) == sign_macro(s2_i)) {
+    lim = sign_macro(s2_c) * fmin(C2 * fabs(s2_im1), fmin(C2 * fabs(s2_i), fabs(s2_c)));
+  }
+  double dl = face - cim1, dr = ci - face;
+  if (dl * dr < 0.0) return 0.5 * (cim1 + ci) - lim / 6.0;
+  return face;
+}
+
+void orc_ppm_single_variable(double cm2, double cm1, double c0, double cp1, double cp2, double *L_iph, double *R_imh)
+{
+  const double C2 = 1.25;
+  double sl = (c0 - cm1), sr = (cp1 - c0);
+  double avg_m1 = 0.5 * sl + 0.5 * (cm1 - cm2);
+  double avg_0  = 0.5 * sr + 0.5 * sl;
+  double avg_p1 = 0.5 * (cp2 - cp1) + 0.5 * sr;
+  double R = 0.5 * (cm1 + c0) + (avg_m1 - avg_0) / 6.0;
+  double L = 0.5 * (c0 + cp1) + (avg_0 - avg_p1) / 6.0;
+  double s2_m1 = cm2 + c0 - 2.0 * cm1;
+  double s2_0  = cm1 + cp1 - 2.0 * c0;
+  double s2_p1 = c0 + cp2 - 2.0 * cp1;
+  R = ppm_limit_face(c0, cm1, R, s2_0, s2_m1);
+  L = ppm_limit_face(cp1, c0, L, s2_p1, s2_0);
+  double s2_f = 6.0 * (R + L - 2.0 * c0);
+  double s2_lim = 0.0;
+  if (sign_macro(s2_m1) == sign_macro(s2_0) && sign_macro(s2_m1) == sign_macro(s2_p1) &&
+      sign_macro(s2_m1) == sign_macro(s2_f)) {
+    s2_lim = sign_macro(s2_f) * fmin(fmin(C2 * fabs(s2_m1), C2 * fabs(s2_0)), fmin(C2 * fabs(s2_p1), fabs(s2_f)));
+  }
+  double cmax = fmax(fabs(cm2), fabs(cm1));
+  cmax = fmax(cmax, fabs(c0));
+  cmax = fmax(cmax, fabs(cp1));
+  cmax = fmax(cmax, fabs(cp2));
+  double rho = (fabs(s2_f) > (1.0e-12) * cmax) ? s2_lim / s2_f : 0.0;
+  double fl = c0 - R, fr = L - c0;
+  if ((fl * fr) <= 0.0 || ((cp1 - c0) * (c0 - cm1)) <= 0.0) {
+    if (rho <= (1.0 - (1.0e-12))) {
+      R = c0 - rho * fl;
+      L = c0 + rho * fr;
+    }
+  } else {
+    if (fabs(fl) >= 2.0 * fabs(fr)) R = c0 - 2.0 * fr;
+    if (fabs(fr) >= 2.0 * fabs(fl)) L = c0 + 2.0 * fl;
+  }
+  *L_iph = L; *R_imh = R;
+}
+
+/* one cell of PPMC_VL (ppmc_cuda.cu:576-684, hydro) */
+static void ppmc_cell(prim_t wm2, prim_t wm1, prim_t wi, prim_t wp1, prim_t wp2, double gamma, prim_t *L, prim_t *R)
+{
+  double a  = sqrt(gamma * wi.p / wi.d);
+  double a2 = a * a;
+  char_t c0 = to_char(wi, wi, a, a2), cm1 = to_char(wi, wm1, a, a2), cm2 = to_char(wi, wm2, a, a2),
+         cp1 = to_char(wi, wp1, a, a2), cp2 = to_char(wi, wp2, a, a2);
+  char_t cl, cr;
+  orc_ppm_single_variable(cm2.a0, cm1.a0, c0.a0, cp1.a0, cp2.a0, &cl.a0, &cr.a0);
+  orc_ppm_single_variable(cm2.a1, cm1.a1, c0.a1, cp1.a1, cp2.a1, &cl.a1, &cr.a1);
+  orc_ppm_single_variable(cm2.a2, cm1.a2, c0.a2, cp1.a2, cp2.a2, &cl.a2, &cr.a2);
+  orc_ppm_single_variable(cm2.a3, cm1.a3, c0.a3, cp1.a3, cp2.a3, &cl.a3, &cr.a3);
+  orc_ppm_single_variable(cm2.a4, cm1.a4, c0.a4, cp1.a4, cp2.a4, &cl.a4, &cr.a4);
+  prim_t l = from_char(wi, cl, a, a2), r = from_char(wi, cr, a, a2);
+  r.d = fmax(r.d, ORC_TINY); l.d = fmax(l.d, ORC_TINY);
+  r.p = fmax(r.p, ORC_TINY); l.p = fmax(l.p, ORC_TINY);
+  *L = l; *R = r;
+}
+
+/* Full-grid reconstruction pass in one direction: what one launch of PLMC_cuda / PPMC_VL does.
+ * Q_L[id] = left state at face id+1/2 (from cell id); Q_R[id - stride] = right state at
+ * face id-1/2 (from cell id).  Cells outside the guard are left untouched. */
+void orc_reconstruct(int recon, const double *U, double *QL, double *QR, int nx, int ny, int nz, double gamma, int dir)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int o1, o2, o3;
+  dir_perm(dir, &o1, &o2, &o3);
+  long stride = dir == 0 ? 1 : (dir == 1 ? nx : (long)nx * ny);
+  int order = recon == ORC_PPMC ? 3 : 2;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        if (outside_guard(order, nx, ny, nz, x, y, z)) continue;
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        prim_t wi = load_prim(U, id, N, o1, o2, o3, gamma);
+        prim_t wm = load_prim(U, id - stride, N, o1, o2, o3, gamma);
+        prim_t wp = load_prim(U, id + stride, N, o1, o2, o3, gamma);
+        prim_t L, R;
+        if (recon == ORC_PPMC) {
+          prim_t wm2 = load_prim(U, id - 2 * stride, N, o1, o2, o3, gamma);
+          prim_t wp2 = load_prim(U, id + 2 * stride, N, o1, o2, o3, gamma);
+          ppmc_cell(wm2, wm, wi, wp, wp2, gamma, &L, &R);
+        } else {
+          plmc_cell(wm, wi, wp, gamma, &L, &R);
+        }
+        store_interface(L, QL, id, N, o1, o2, o3, gamma);
+        store_interface(R, QR, id - stride, N, o1, o2, o3, gamma);
+      }
+}
+
+/* PCM (pcm_cuda.cu:13-424): L[id] = U[id], R[id - stride] = U[id] */
+static void pcm_dir(const double *U, double *QL, double *QR, int nx, int ny, int nz, int dir)
+{
+  size_t N = (size_t)nx * ny * nz;
+  long stride = dir == 0 ? 1 : (dir == 1 ? nx : (long)nx * ny);
+  for (int f = 0; f < 5; f++) {
+#pragma omp parallel for schedule(static)
+    for (long id = 0; id < (long)N; id++) {
+      QL[f * N + id] = U[f * N + id];
+      int x = id % nx, y = (id / nx) % ny, z = id / ((long)nx * ny);
+      int c = dir == 0 ? x : (dir == 1 ? y : z);
+      if (c > 0) QR[f * N + id - stride] = U[f * N + id];
+    }
+  }
+}
+
+/* ---- Riemann solvers: one interface ---- */
+typedef struct { double d, mx, my, mz, E; } cons_t;
+
+/* hllc_cuda.cu:103-305 */
+static cons_t hllc_flux(cons_t l, cons_t r, double gamma)
+{
+  cons_t f;
+  double g1 = gamma - 1.0;
+  double vxl = l.mx / l.d, vyl = l.my / l.d, vzl = l.mz / l.d;
+  double pl = (l.E - 0.5 * l.d * (vxl * vxl + vyl * vyl + vzl * vzl)) * (gamma - 1.0);
+  pl = fmax(pl, ORC_TINY);
+  double vxr = r.mx / r.d, vyr = r.my / r.d, vzr = r.mz / r.d;
+  double pr = (r.E - 0.5 * r.d * (vxr * vxr + vyr * vyr + vzr * vzr)) * (gamma - 1.0);
+  pr = fmax(pr, ORC_TINY);
+  double Hl = (l.E + pl) / l.d, Hr = (r.E + pr) / r.d;
+  double sl = sqrt(l.d), sr = sqrt(r.d);
+  double vx = (sl * vxl + sr * vxr) / (sl + sr);
+  double vy = (sl * vyl + sr * vyr) / (sl + sr);
+  double vz = (sl * vzl + sr * vzr) / (sl + sr);
+  double H  = (sl * Hl + sr * Hr) / (sl + sr);
+  double vsq = (vx * vx + vy * vy + vz * vz);
+  double asq = g1 * (H - 0.5 * vsq);
+  double a = sqrt(asq);
+  double lm = vx - a, lp = vx + a;
+  double cfl = sqrt(gamma * pl / l.d), cfr = sqrt(gamma * pr / r.d);
+  double Sl = fmin(lm, vxl - cfl), Sr = fmax(lp, vxr + cfr);
+  /* etah = 0: S = sgn(S)*fmax(|S|,0), sgn(0)=+1 (global_cuda.h:41-48) */
+  Sl = ((Sl < 0) ? -1 : 1) * fmax(fabs(Sl), 0.0);
+  Sr = ((Sr < 0) ? -1 : 1) * fmax(fabs(Sr), 0.0);
+  double fdl = l.mx, fmxl = l.mx * vxl + pl, fmyl = l.my * vxl, fmzl = l.mz * vxl, fEl = (l.E + pl) * vxl;
+  double fdr = r.mx, fmxr = r.mx * vxr + pr, fmyr = r.my * vxr, fmzr = r.mz * vxr, fEr = (r.E + pr) * vxr;
+  if (Sl > 0.0) { f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl; return f; }
+  if (Sr < 0.0) { f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr; return f; }
+  double Sm = (r.d * vxr * (Sr - vxr) - l.d * vxl * (Sl - vxl) + pl - pr) / (r.d * (Sr - vxr) - l.d * (Sl - vxl));
+  double ps = l.d * (vxl - Sl) * (vxl - Sm) + pl;
+  double dls = l.d * (Sl - vxl) / (Sl - Sm);
+  double mxls = (l.mx * (Sl - vxl) + ps - pl) / (Sl - Sm);
+  double myls = dls * vyl, mzls = dls * vzl;
+  double Els = (l.E * (Sl - vxl) - pl * vxl + ps * Sm) / (Sl - Sm);
+  double drs = r.d * (Sr - vxr) / (Sr - Sm);
+  double mxrs = (r.mx * (Sr - vxr) + ps - pr) / (Sr - Sm);
+  double myrs = drs * vyr, mzrs = drs * vzr;
+  double Ers = (r.E * (Sr - vxr) - pr * vxr + ps * Sm) / (Sr - Sm);
+  f.d  = 0.5 * (fdl + fdr + (Sr - fabs(Sm)) * drs + (Sl + fabs(Sm)) * dls - Sl * l.d - Sr * r.d);
+  f.mx = 0.5 * (fmxl + fmxr + (Sr - fabs(Sm)) * mxrs + (Sl + fabs(Sm)) * mxls - Sl * l.mx - Sr * r.mx);
+  f.my = 0.5 * (fmyl + fmyr + (Sr - fabs(Sm)) * myrs + (Sl + fabs(Sm)) * myls - Sl * l.my - Sr * r.my);
+  f.mz = 0.5 * (fmzl + fmzr + (Sr - fabs(Sm)) * mzrs + (Sl + fabs(Sm)) * mzls - Sl * l.mz - Sr * r.mz);
+  f.E  = 0.5 * (fEl + fEr + (Sr - fabs(Sm)) * Ers + (Sl + fabs(Sm)) * Els - Sl * l.E - Sr * r.E);
+  return f;
+}
+
+/* roe_cuda.cu:105-398 (etah = 0) */
+static cons_t roe_flux(cons_t l, cons_t r, double gamma)
+{
+  cons_t f;
+  double g1 = gamma - 1.0, etah = 0.0;
+  double vxl = l.mx / l.d, vyl = l.my / l.d, vzl = l.mz / l.d;
+  double pl = (l.E - 0.5 * l.d * (vxl * vxl + vyl * vyl + vzl * vzl)) * (gamma - 1.0);
+  pl = fmax(pl, ORC_TINY);
+  double vxr = r.mx / r.d, vyr = r.my / r.d, vzr = r.mz / r.d;
+  double pr = (r.E - 0.5 * r.d * (vxr * vxr + vyr * vyr + vzr * vzr)) * (gamma - 1.0);
+  pr = fmax(pr, ORC_TINY);
+  double Hl = (l.E + pl) / l.d, Hr = (r.E + pr) / r.d;
+  double sl = sqrt(l.d), sr = sqrt(r.d);
+  double vx = (sl * vxl + sr * vxr) / (sl + sr);
+  double vy = (sl * vyl + sr * vyr) / (sl + sr);
+  double vz = (sl * vzl + sr * vzr) / (sl + sr);
+  double H  = (sl * Hl + sr * Hr) / (sl + sr);
+  double vsq = (vx * vx + vy * vy + vz * vz);
+  double asq = g1 * fmax((H - 0.5 * vsq), ORC_TINY);
+  double a = sqrt(asq);
+  double lm = vx - a, l0 = vx, lp = vx + a;
+  double fdl = l.mx, fmxl = l.mx * vxl + pl, fmyl = l.mx * vyl, fmzl = l.mx * vzl, fEl = (l.E + pl) * vxl;
+  double fdr = r.mx, fmxr = r.mx * vxr + pr, fmyr = r.mx * vyr, fmzr = r.mx * vzr, fEr = (r.E + pr) * vxr;
+  if (lm >= 0.0) { f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl; return f; }
+  if (lp <= 0.0) { f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr; return f; }
+  double dd = r.d - l.d, dmx = r.mx - l.mx, dmy = r.my - l.my, dmz = r.mz - l.mz, dE = r.E - l.E;
+  double Na = 0.5 / asq, coeff;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+  double a0 = dd * Na * (0.5 * g1 * vsq + vx * a) - dmx * Na * (g1 * vx + a) - dmy * Na * g1 * vy -
+              dmz * Na * g1 * vz + dE * Na * g1;
+  coeff = a0 * fmax(fabs(lm), etah);
+  s0 += coeff; s1 += coeff * (vx - a); s2 += coeff * vy; s3 += coeff * vz; s4 += coeff * (H - vx * a);
+  double a1 = -dd * vy + dmy;
+  coeff = a1 * fmax(fabs(l0), etah);
+  s2 += coeff; s4 += coeff * vy;
+  double a2 = -dd * vz + dmz;
+  coeff = a2 * fmax(fabs(l0), etah);
+  s3 += coeff; s4 += coeff * vz;
+  double a3 = dd * (1.0 - Na * g1 * vsq) + dmx * g1 * vx / asq + dmy * g1 * vy / asq + dmz * g1 * vz / asq -
+              dE * g1 / asq;
+  coeff = a3 * fmax(fabs(l0), etah);
+  s0 += coeff; s1 += coeff * vx; s2 += coeff * vy; s3 += coeff * vz; s4 += coeff * 0.5 * vsq;
+  double a4 = dd * Na * (0.5 * g1 * vsq - vx * a) - dmx * Na * (g1 * vx - a) - dmy * Na * g1 * vy -
+              dmz * Na * g1 * vz + dE * Na * g1;
+  coeff = a4 * fmax(fabs(lp), etah);
+  s0 += coeff; s1 += coeff * (vx + a); s2 += coeff * vy; s3 += coeff * vz; s4 += coeff * (H + vx * a);
+  int hlle = 0;
+  double t0 = l.d + a0, t1 = l.mx + a0 * (vx - a), t2 = l.my + a0 * vy, t3 = l.mz + a0 * vz,
+         t4 = l.E + a0 * (H - vx * a);
+  if (l0 > lm) {
+    if (t0 <= 0.0) hlle = 1;
+    if (t4 - 0.5 * (t1 * t1 + t2 * t2 + t3 * t3) / t0 < 0.0) hlle = 2;
+  }
+  t0 += a3 + a4;
+  t1 += a3 * vx;
+  t2 += a1 + a3 * vy;
+  t3 += a2 + a3 * vz;
+  t4 += a1 * vy + a2 * vz + a3 * 0.5 * vsq;
+  if (lp > l0) {
+    if (t0 <= 0.0) hlle = 1;
+    if (t4 - 0.5 * (t1 * t1 + t2 * t2 + t3 * t3) / t0 < 0.0) hlle = 2;
+  }
+  if (hlle != 0) {
+    double cfl = sqrt(gamma * pl / l.d), cfr = sqrt(gamma * pr / r.d);
+    double bm = fmin(fmin(lm, vxl - cfl), 0.0), bp = fmax(fmax(lp, vxr + cfr), 0.0);
+    fdl = l.mx - bm * l.d;             fdr = r.mx - bp * r.d;
+    fmxl = l.mx * (vxl - bm) + pl;     fmxr = r.mx * (vxr - bp) + pr;
+    fmyl = l.my * (vxl - bm);          fmyr = r.my * (vxr - bp);
+    fmzl = l.mz * (vxl - bm);          fmzr = r.mz * (vxr - bp);
+    fEl = l.E * (vxl - bm) + pl * vxl; fEr = r.E * (vxr - bp) + pr * vxr;
+    double tmp = 0.5 * (bp + bm) / (bp - bm);
+    f.d  = 0.5 * (fdl + fdr) + (fdl - fdr) * tmp;
+    f.mx = 0.5 * (fmxl + fmxr) + (fmxl - fmxr) * tmp;
+    f.my = 0.5 * (fmyl + fmyr) + (fmyl - fmyr) * tmp;
+    f.mz = 0.5 * (fmzl + fmzr) + (fmzl - fmzr) * tmp;
+    f.E  = 0.5 * (fEl + fEr) + (fEl - fEr) * tmp;
+    return f;
+  }
+  f.d  = 0.5 * (fdl + fdr - s0);
+  f.mx = 0.5 * (fmxl + fmxr - s1);
+  f.my = 0.5 * (fmyl + fmyr - s2);
+  f.mz = 0.5 * (fmzl + fmzr - s3);
+  f.E  = 0.5 * (fEl + fEr - s4);
+  return f;
+}
+
+/* one launch of Calculate_{HLLC,Roe}_Fluxes_CUDA: every cell, F[id] = flux(Q_L[id], Q_R[id]) */
+void orc_riemann(int solver, const double *QL, const double *QR, double *F, int nx, int ny, int nz, double gamma,
+                 int dir)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int o1, o2, o3;
+  dir_perm(dir, &o1, &o2, &o3);
+#pragma omp parallel for schedule(static)
+  for (long id = 0; id < (long)N; id++) {
+    cons_t l = {QL[id], QL[o1 * N + id], QL[o2 * N + id], QL[o3 * N + id], QL[4 * N + id]};
+    cons_t r = {QR[id], QR[o1 * N + id], QR[o2 * N + id], QR[o3 * N + id], QR[4 * N + id]};
+    cons_t f = solver == ORC_ROE ? roe_flux(l, r, gamma) : hllc_flux(l, r, gamma);
+    F[id] = f.d; F[o1 * N + id] = f.mx; F[o2 * N + id] = f.my; F[o3 * N + id] = f.mz; F[4 * N + id] = f.E;
+  }
+}
+
+void orc_riemann_single(int solver, const double *l5, const double *r5, double gamma, double *f5)
+{
+  cons_t l = {l5[0], l5[1], l5[2], l5[3], l5[4]}, r = {r5[0], r5[1], r5[2], r5[3], r5[4]};
+  cons_t f = solver == ORC_ROE ? roe_flux(l, r, gamma) : hllc_flux(l, r, gamma);
+  f5[0] = f.d; f5[1] = f.mx; f5[2] = f.my; f5[3] = f.mz; f5[4] = f.E;
+}
+
+/* ---- one full VL step (VL_3D_cuda.cu:38-360; VL_2D_cuda.cu; VL_1D_cuda.cu) ---- */
+void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz, double dt,
+                 double gamma, int recon, int solver, double density_floor)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int ndim = 1 + (ny > 1) + (nz > 1);
+  double dd[3] = {dx, dy, dz};
+  long st[3] = {1, nx, (long)nx * ny};
+  double *Uh = calloc(5 * N, sizeof(double));
+  double *QL[3], *QR[3], *F[3];
+  for (int d = 0; d < ndim; d++) {
+    QL[d] = calloc(5 * N, sizeof(double));
+    QR[d] = calloc(5 * N, sizeof(double));
+    F[d]  = calloc(5 * N, sizeof(double));
+  }
+  /* stage 1-2: PCM + first-order fluxes */
+  for (int d = 0; d < ndim; d++) {
+    pcm_dir(U, QL[d], QR[d], nx, ny, nz, d);
+    orc_riemann(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d);
+  }
+  /* stage 3: half-step update on all but the outermost ring (VL_3D_cuda.cu:379-495) */
+  {
+    double h = 0.5 * dt;
+    double dto[3] = {h / dx, h / dy, h / dz};
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+          if (!(x > 0 && x < nx - 1)) continue;
+          if (ndim > 1 && !(y > 0 && y < ny - 1)) continue;
+          if (ndim > 2 && !(z > 0 && z < nz - 1)) continue;
+          size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+          for (int f = 0; f < 5; f++) {
+            double v = U[f * N + id];
+            for (int d = 0; d < ndim; d++) v = v + dto[d] * (F[d][f * N + id - st[d]] - F[d][f * N + id]);
+            Uh[f * N + id] = v;
+          }
+          if (ndim == 3 && Uh[id] < density_floor) { /* DENSITY_FLOOR, 3-D half step only */
+            double d0 = Uh[id];
+            Uh[id] = density_floor;
+            for (int f = 1; f < 5; f++) Uh[f * N + id] *= (density_floor / d0);
+          }
+        }
+  }
+  /* stage 4-5: second-order interfaces from the half-step state, then fluxes */
+  for (int d = 0; d < ndim; d++) {
+    if (recon == ORC_PCM) pcm_dir(Uh, QL[d], QR[d], nx, ny, nz, d);
+    else orc_reconstruct(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
+    orc_riemann(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d);
+  }
+  /* stage 6: full update of the real cells, in place (hydro_cuda.cu:20-300) */
+  {
+    double dto[3] = {dt / dx, dt / dy, dt / dz};
+    int g = n_ghost;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+          if (!(x > g - 1 && x < nx - g)) continue;
+          if (ndim > 1 && !(y > g - 1 && y < ny - g)) continue;
+          if (ndim > 2 && !(z > g - 1 && z < nz - g)) continue;
+          size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+          for (int f = 0; f < 5; f++) {
+            double s = dto[0] * (F[0][f * N + id - st[0]] - F[0][f * N + id]);
+            for (int d = 1; d < ndim; d++) s = s + dto[d] * (F[d][f * N + id - st[d]] - F[d][f * N + id]);
+            U[f * N + id] += s;
+          }
+          if (ndim == 3 && U[id] < density_floor && U[id] > 0) { /* hydro_cuda.cu:279-291 */
+            double d0 = U[id];
+            U[id] = density_floor;
+            for (int f = 1; f < 5; f++) U[f * N + id] *= (density_floor / d0);
+          }
+          /* the rho<=0 neighbour-averaging branch (hydro_cuda.cu:292-297) races in the
+           * reference and is not restated */
+        }
+  }
+  (void)dd;
+  free(Uh);
+  for (int d = 0; d < ndim; d++) { free(QL[d]); free(QR[d]); free(F[d]); }
+}
+
+/* hydro_cuda.cu:404-418 */
+double orc_hydro_inverse_crossing_time(double E, double d, double d_inv, double vx, double vy, double vz, double dx,
+                                       double dy, double dz, double gamma)
+{
+  double P  = (E - 0.5 * d * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
+  double cs = sqrt(d_inv * gamma * P);
+  double m = fmax((fabs(vx) + cs) / dx, (fabs(vy) + cs) / dy);
+  m = fmax(m, (fabs(vz) + cs) / dz);
+  m = fmax(m, 0.0);
+  return m;
+}
+
+/* Calc_dt_{1,2,3}D (hydro_cuda.cu:437-560): max inverse crossing time over real cells */
+double orc_calc_dti(const double *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz, double gamma)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int ndim = 1 + (ny > 1) + (nz > 1);
+  if (nx == 1 && ny == 1 && nz == 1) ndim = 3; /* the reference unit test drives Calc_dt_3D on one cell */
+  int g = n_ghost;
+  double best = -DBL_MAX;
+#pragma omp parallel for collapse(2) reduction(max : best) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        if (!(x > g - 1 && x < nx - g)) continue;
+        if (ndim > 1 && !(y > g - 1 && y < ny - g)) continue;
+        if (ndim > 2 && !(z > g - 1 && z < nz - g)) continue;
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        double d = U[id], d_inv = 1.0 / d;
+        double vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv;
+        double E = U[4 * N + id], v;
+        if (ndim == 3) {
+          v = orc_hydro_inverse_crossing_time(E, d, d_inv, vx, vy, vz, dx, dy, dz, gamma);
+        } else {
+          double P = (E - 0.5 * d * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
+          P = fmax(P, ORC_TINY);
+          double cs = sqrt(d_inv * gamma * P);
+          v = (fabs(vx) + cs) / dx;
+          if (ndim == 2) v = fmax(v, (fabs(vy) + cs) / dy);
+        }
+        best = fmax(best, v);
+      }
+  return best;
+}
+
+/* Temperature_Floor_Kernel (hydro_cuda.cu:1117-1153): the guard needs zid > n_ghost-1, so it is a
+ * no-op when nz == 1 */
+void orc_temperature_floor(double *U, int nx, int ny, int nz, int n_ghost, double U_floor)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int g = n_ghost;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        if (!(x > g - 1 && x < nx - g && y > g - 1 && y < ny - g && z > g - 1 && z < nz - g)) continue;
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        double d = U[id], d_inv = 1.0 / d;
+        double vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv;
+        double E = U[4 * N + id];
+        double Ekin = 0.5 * d * (vx * vx + vy * vy + vz * vz);
+        double Ue = (E - Ekin) / d;
+        if (Ue < U_floor) U[4 * N + id] = Ekin + d * U_floor;
+      }
+}
+
+/* ---- ghost cells (cuda_boundaries.cu:71-303, boundary_conditions.cpp:419-) ---- */
+static int map_index(int ig, int n, int flag, int face, int g, double *a)
+{ /* FindIndex */
+  if (face == 0) {
+    switch (flag) {
+      case 2: *a = -1.0; return 2 * g - ig - 1;
+      case 3: return g;
+      case 4: return -1;
+      case 5: return ig;
+      default: return ig + n - 2 * g; /* 1 and anything else: periodic */
+    }
+  }
+  switch (flag) {
+    case 2: *a = -1.0; return 2 * (n - g) - ig - 1;
+    case 3: return n - g - 1;
+    case 4: return -1;
+    case 5: return ig;
+    default: return ig - n + 2 * g;
+  }
+}
+
+static long map_cell(int ig, int jg, int kg, double *a, const int *flags, int nx, int ny, int nz, int g)
+{ /* SetBoundaryMapping */
+  long idx = 0;
+  int n[3] = {nx, ny, nz}, c[3] = {ig, jg, kg};
+  long st[3] = {1, nx, (long)nx * ny};
+  for (int d = 0; d < 3; d++) {
+    if (n[d] <= 1) continue;
+    int r;
+    if (c[d] < g) r = map_index(c[d], n[d], flags[2 * d], 0, g, &a[d]);
+    else if (c[d] >= n[d] - g) r = map_index(c[d], n[d], flags[2 * d + 1], 1, g, &a[d]);
+    else r = c[d];
+    if (r < 0) return -1;
+    idx += st[d] * r;
+  }
+  return idx;
+}
+
+void orc_boundary_extents(int dir, int nx, int ny, int nz, int g, int *imin, int *imax)
+{ /* Set_Boundary_Extents: x faces span real j,k; y faces all i, real k; z faces all i,j */
+  int lo[3] = {0, 0, 0}, hi[3] = {nx, ny, nz};
+  if (ny > 1) { lo[1] = g; hi[1] = ny - g; }
+  if (nz > 1) { lo[2] = g; hi[2] = nz - g; }
+  int n[3] = {nx, ny, nz};
+  int ax = dir / 2;
+  for (int d = 0; d < ax; d++) { lo[d] = 0; hi[d] = n[d]; }
+  if (dir % 2 == 0) { lo[ax] = 0; hi[ax] = g; }
+  else { lo[ax] = n[ax] - g; hi[ax] = n[ax]; }
+  for (int d = 0; d < 3; d++) { imin[d] = lo[d]; imax[d] = hi[d]; }
+}
+
+/* one call of Grid3D::Set_Boundaries(dir, flags) -> SetGhostCells (hydro build: diode on) */
+void orc_set_ghost_cells(double *U, int nx, int ny, int nz, int n_fields, int g, const int *flags, int dir)
+{
+  if (flags[dir] == 4 || flags[dir] == 5) return;
+  size_t N = (size_t)nx * ny * nz;
+  int lo[3], hi[3];
+  orc_boundary_extents(dir, nx, ny, nz, g, lo, hi);
+  for (int k = lo[2]; k < hi[2]; k++)
+    for (int j = lo[1]; j < hi[1]; j++)
+      for (int i = lo[0]; i < hi[0]; i++) {
+        double a[3] = {1., 1., 1.};
+        size_t gidx = (size_t)i + (size_t)nx * ((size_t)j + (size_t)ny * k);
+        long idx = map_cell(i, j, k, a, flags, nx, ny, nz, g);
+        if (idx < 0) continue;
+        for (int f = 0; f < n_fields; f++) U[gidx + f * N] = U[idx + f * N];
+        if (flags[0] == 2 || flags[1] == 2) U[gidx + N] *= a[0];
+        if (flags[2] == 2 || flags[3] == 2) U[gidx + 2 * N] *= a[1];
+        if (flags[4] == 2 || flags[5] == 2) U[gidx + 3 * N] *= a[2];
+        if (flags[dir] == 3) {
+          size_t m = gidx + (dir / 2 + 1) * N;
+          if ((dir % 2 == 0) ? (U[m] > 0.0) : (U[m] < 0.0)) {
+            U[gidx + 4 * N] -= 0.5 * (U[m] * U[m]) / U[gidx];
+            U[m] = 0.0;
+          }
+        }
+      }
+}
+
+/* Grid3D::Set_Boundary_Conditions, non-MPI branch: faces 0..5 in order */
+void orc_set_boundaries(double *U, int nx, int ny, int nz, int n_fields, int g, const int *flags)
+{
+  int ndim = 1 + (ny > 1) + (nz > 1);
+  for (int dir = 0; dir < 2 * ndim; dir++) orc_set_ghost_cells(U, nx, ny, nz, n_fields, g, flags, dir);
+}
+
+/* PackBuffers3D / UnpackBuffers3D (cuda_boundaries.cu:11-69): buffer[field][k][j][i] */
+void orc_pack(double *buf, const double *U, int nx, int ny, int n_fields, long n_cells, long idxoffset, int isize,
+              int jsize, int ksize)
+{
+  long nb = (long)isize * jsize * ksize;
+  for (long id = 0; id < nb; id++) {
+    long k = id / ((long)isize * jsize), j = (id - k * isize * jsize) / isize, i = id - k * isize * jsize - j * isize;
+    long idx = i + (j + k * ny) * nx + idxoffset;
+    for (int f = 0; f < n_fields; f++) buf[id + f * nb] = U[idx + f * n_cells];
+  }
+}
+
+void orc_unpack(const double *buf, double *U, int nx, int ny, int n_fields, long n_cells, long idxoffset, int isize,
+                int jsize, int ksize)
+{
+  long nb = (long)isize * jsize * ksize;
+  for (long id = 0; id < nb; id++) {
+    long k = id / ((long)isize * jsize), j = (id - k * isize * jsize) / isize, i = id - k * isize * jsize - j * isize;
+    long idx = i + (j + k * ny) * nx + idxoffset;
+    for (int f = 0; f < n_fields; f++) U[idx + f * n_cells] = buf[id + f * nb];
+  }
+}
