@@ -1,0 +1,43 @@
+// chl_internal.h -- glue between the mode-agnostic C-ABI TU (chl_api.cu) and the per-mode kernel TUs
+// (vl_sweep_inst.cu compiled once per arithmetic mode: f64 strict, f64 fast, f32 fast).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace chl
+{
+struct SweepArgs {  // everything in double; each mode TU narrows to its Real
+  const void *in;
+  void *out;
+  int nx, ny, nz;
+  int lo[3], hi[3];
+  int has_y, has_z;
+  int zchunk;
+  double dtodx, dtody, dtodz, gamma, density_floor;
+  int apply_tfloor;
+  double U_floor;
+  int do_dti;
+  double dx, dy, dz;
+  unsigned long long *dti_key;
+};
+
+struct ModeOps {
+  // stage 0 = predictor (U -> W half), stage 1 = corrector (W half, U -> U)
+  cudaError_t (*sweep)(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s);
+  cudaError_t (*calc_dti)(const void *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz,
+                          double gamma, unsigned long long *key, cudaStream_t s);
+  cudaError_t (*tfloor)(void *U, int nx, int ny, int nz, int n_ghost, double U_floor, cudaStream_t s);
+  size_t real_bytes;
+};
+
+ModeOps const *mode_ops_f64_strict();
+ModeOps const *mode_ops_f64_fast();
+ModeOps const *mode_ops_f32_fast();  // nullptr when the fp32 TU is not linked
+
+// element-type-templated copy kernels (ghost cells, pack/unpack), aux_kernels.cu
+cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields, long n_cells, int n_ghost,
+                                   const int flags[6], int isize, int jsize, int ksize, int imin, int jmin, int kmin,
+                                   int dir, size_t real_bytes, cudaStream_t s);
+cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset,
+                        int isize, int jsize, int ksize, int unpack, size_t real_bytes, cudaStream_t s);
+}  // namespace chl

@@ -1,0 +1,145 @@
+// vl_sweep_inst.cu -- instantiates the fused sweep kernels for ONE arithmetic mode.  The build compiles this
+// file three times:   -DCHL_STRICT=1 -DCHL_REAL=double -fmad=false   (mode f64_strict)
+//                     -DCHL_STRICT=0 -DCHL_REAL=double               (mode f64_fast)
+//                     -DCHL_STRICT=0 -DCHL_REAL=float                (mode f32_fast)
+// CHL_MODE names the exported factory.
+#include <float.h>
+#include <string.h>
+
+#include "chl_internal.h"
+#include "vl_sweep.cuh"
+
+#ifndef CHL_MODE
+#error "CHL_MODE must be defined (f64_strict | f64_fast | f32_fast)"
+#endif
+#define CHL_CAT2(a, b) a##b
+#define CHL_CAT(a, b) CHL_CAT2(a, b)
+
+namespace chl
+{
+namespace
+{
+template <int RECON, int SOLVER, int STAGE>
+cudaError_t launch(SweepParams const &p, cudaStream_t s)
+{
+  int const ox = p.hi[0] - p.lo[0], oy = p.hi[1] - p.lo[1], oz = p.hi[2] - p.lo[2];
+  if (ox <= 0 || oy <= 0 || oz <= 0) return cudaSuccess;
+  dim3 grid((ox + TX - 1) / TX, (oy + TY - 1) / TY, p.has_z ? (oz + p.zchunk - 1) / p.zchunk : 1);
+  dim3 block(TX, TY, 1);
+  vl_sweep_kernel<RECON, SOLVER, STAGE><<<grid, block, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t sweep(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s)
+{
+  SweepParams p;
+  p.in  = (const Real *)a.in;
+  p.out = (Real *)a.out;
+  p.nx = a.nx; p.ny = a.ny; p.nz = a.nz;
+  for (int d = 0; d < 3; d++) { p.lo[d] = a.lo[d]; p.hi[d] = a.hi[d]; }
+  p.has_y = a.has_y; p.has_z = a.has_z; p.zchunk = a.zchunk;
+  p.dtodx = (Real)a.dtodx; p.dtody = (Real)a.dtody; p.dtodz = (Real)a.dtodz;
+  p.gamma = (Real)a.gamma; p.density_floor = (Real)a.density_floor;
+  p.apply_tfloor = a.apply_tfloor; p.U_floor = (Real)a.U_floor; p.do_dti = a.do_dti;
+  p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
+  p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
+  p.dti_key = a.dti_key;
+  if (stage == 0) {
+    if (solver == kROE) return launch<kPCM, kROE, 0>(p, s);
+    return launch<kPCM, kHLLC, 0>(p, s);
+  }
+  switch (recon * 2 + (solver == kROE ? 1 : 0)) {
+    case kPCM * 2 + 0: return launch<kPCM, kHLLC, 1>(p, s);
+    case kPCM * 2 + 1: return launch<kPCM, kROE, 1>(p, s);
+    case kPLMC * 2 + 0: return launch<kPLMC, kHLLC, 1>(p, s);
+    case kPLMC * 2 + 1: return launch<kPLMC, kROE, 1>(p, s);
+    case kPPMC * 2 + 0: return launch<kPPMC, kHLLC, 1>(p, s);
+    case kPPMC * 2 + 1: return launch<kPPMC, kROE, 1>(p, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// Calc_dt_{1,2,3}D (hydro_cuda.cu:437-560): grid-stride max over real cells, warp shuffle, one atomic per CTA
+template <int NDIM>
+__global__ void __launch_bounds__(256) calc_dti_kernel(const Real *__restrict__ U, int nx, int ny, int nz, int g,
+                                                       Real dx, Real dy, Real dz, Real gamma,
+                                                       unsigned long long *key)
+{
+  __shared__ double sred[8];
+  size_t const N = (size_t)nx * ny * nz;
+  int const rx = nx - 2 * g, ry = NDIM > 1 ? ny - 2 * g : 1, rz = NDIM > 2 ? nz - 2 * g : 1;
+  size_t const nreal = (size_t)rx * ry * rz;
+  Real const idx = RC(1.0) / dx, idy = RC(1.0) / dy, idz = RC(1.0) / dz;
+  double m = -DBL_MAX;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < nreal; t += (size_t)gridDim.x * blockDim.x) {
+    int const x = (int)(t % rx) + g;
+    size_t const r = t / rx;
+    int const y = NDIM > 1 ? (int)(r % ry) + g : 0;
+    int const z = NDIM > 2 ? (int)(r / ry) + g : 0;
+    size_t const id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+    m = fmax(m, (double)inverse_crossing_time<NDIM>(__ldg(U + id), __ldg(U + N + id), __ldg(U + 2 * N + id),
+                                                    __ldg(U + 3 * N + id), __ldg(U + 4 * N + id), idx, idy, idz, dx,
+                                                    dy, dz, gamma));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < 8 ? sred[threadIdx.x] : -DBL_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMax(key, dti_encode(m));
+  }
+}
+
+cudaError_t calc_dti(const void *U, int nx, int ny, int nz, int g, double dx, double dy, double dz, double gamma,
+                     unsigned long long *key, cudaStream_t s)
+{
+  int ndim = 1 + (ny > 1) + (nz > 1);
+  if (nx == 1 && ny == 1 && nz == 1) ndim = 3;  // the reference's unit test drives Calc_dt_3D on a single cell
+  size_t nreal = (size_t)(nx - 2 * g) * (ndim > 1 ? ny - 2 * g : 1) * (ndim > 2 ? nz - 2 * g : 1);
+  int blocks = (int)((nreal + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  const Real *u = (const Real *)U;
+  if (ndim == 3) calc_dti_kernel<3><<<blocks, 256, 0, s>>>(u, nx, ny, nz, g, (Real)dx, (Real)dy, (Real)dz, (Real)gamma, key);
+  else if (ndim == 2) calc_dti_kernel<2><<<blocks, 256, 0, s>>>(u, nx, ny, nz, g, (Real)dx, (Real)dy, (Real)dz, (Real)gamma, key);
+  else calc_dti_kernel<1><<<blocks, 256, 0, s>>>(u, nx, ny, nz, g, (Real)dx, (Real)dy, (Real)dz, (Real)gamma, key);
+  return cudaGetLastError();
+}
+
+// Temperature_Floor_Kernel (hydro_cuda.cu:1117-1153); its guard makes it a no-op unless nz > 2*n_ghost
+__global__ void __launch_bounds__(256) tfloor_kernel(Real *U, int nx, int ny, int nz, int g, Real U_floor)
+{
+  size_t const N = (size_t)nx * ny * nz;
+  int const rx = nx - 2 * g, ry = ny - 2 * g, rz = nz - 2 * g;
+  size_t const nreal = (size_t)rx * ry * rz;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < nreal; t += (size_t)gridDim.x * blockDim.x) {
+    int const x = (int)(t % rx) + g;
+    size_t const r = t / rx;
+    int const y = (int)(r % ry) + g, z = (int)(r / ry) + g;
+    size_t const id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+    Real const d = U[id], d_inv = RC(1.0) / d;
+    Real const vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv;
+    Real const E = U[4 * N + id];
+    Real const Ekin = RC(0.5) * d * (vx * vx + vy * vy + vz * vz);
+    if ((E - Ekin) / d < U_floor) U[4 * N + id] = Ekin + d * U_floor;
+  }
+}
+
+cudaError_t tfloor(void *U, int nx, int ny, int nz, int g, double U_floor, cudaStream_t s)
+{
+  if (nx <= 2 * g || ny <= 2 * g || nz <= 2 * g) return cudaSuccess;
+  size_t nreal = (size_t)(nx - 2 * g) * (ny - 2 * g) * (nz - 2 * g);
+  int blocks = (int)((nreal + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tfloor_kernel<<<blocks, 256, 0, s>>>((Real *)U, nx, ny, nz, g, (Real)U_floor);
+  return cudaGetLastError();
+}
+
+ModeOps const ops = {sweep, calc_dti, tfloor, sizeof(Real)};
+}  // namespace
+
+ModeOps const *CHL_CAT(mode_ops_, CHL_MODE)() { return &ops; }
+}  // namespace chl

@@ -1,0 +1,379 @@
+"""Host-side mirror of the reference's `Grid3D` for the Van Leer hot path.
+
+Same method names, argument meaning and call order as the reference's host code, so that a driver written
+against `Grid3D` reads like `src/main.cpp:247-379`:
+
+    dti = G.Calc_Inverse_Timestep()
+    while G.H.t < tout:
+        G.set_dt(dti)                       # grid3D.cpp:373-409 (all-reduce MAX across ranks)
+        dti = G.Update_Hydro_Grid()         # grid3D.cpp:474-585 (VL step, temperature floor, Calc_dt)
+        G.Update_Time()
+        G.Set_Boundary_Conditions_Grid()    # boundary_conditions.cpp:19- / mpi_boundaries.cpp:29-111
+
+All arithmetic happens in libcholla_b200.so (CUDA).  PyTorch supplies device memory, the stream and
+torch.distributed (NCCL on GPUs, gloo for CPU tests of the exchange schedule); numpy is only used to stage
+initial conditions.  Multi-GPU = the reference's block decomposition (src/mpi/mpi_routines.cpp:239-532),
+one process per GPU.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import BC_MPI, BC_PERIODIC, Config, check
+
+N_FIELDS = 5
+C_CFL = 0.3  # grid3D.cpp:157
+
+
+def n_ghost_for(recon):
+    """Grid3D constructor, grid3D.cpp:52-76 (hydro)."""
+    return {_lib.PCM: 2, _lib.PLMC: 3, _lib.PPMC: 4}[recon]
+
+
+@dataclass
+class Decomposition:
+    """DomainDecompositionBLOCK (src/mpi/mpi_routines.cpp:270-532) for one rank."""
+    nproc: int
+    rank: int
+    np: List[int]              # process grid (x, y, z)
+    coords: List[int]          # this rank's (ix, iy, iz); ranks are laid out x-fastest
+    n_local: List[int]         # real cells per axis on this rank
+    offset: List[int]          # global index of the first real cell per axis
+    dest: List[int]            # neighbour ranks for faces 0..5 (periodic wrap, as in the reference)
+    flags: List[int]           # local boundary flags for faces 0..5 (5 = exchange with a neighbour)
+    global_flags: List[int]
+
+    @staticmethod
+    def build(nproc, rank, n_global, global_flags):
+        nxg, nyg, nzg = n_global
+        np_ = _lib.tile_decomposition(nproc, nxg, nyg, nzg)
+        ix = rank % np_[0]
+        iy = (rank // np_[0]) % np_[1]
+        iz = rank // (np_[0] * np_[1])
+        coords = [ix, iy, iz]
+        n_local, offset = [], []
+        for a in range(3):
+            n, o = _lib.local_extent(n_global[a], np_[a], coords[a])
+            n_local.append(n)
+            offset.append(o)
+
+        def rank_of(c):
+            return c[0] + np_[0] * (c[1] + np_[1] * c[2])
+
+        dest = []
+        for a in range(3):
+            for s in (-1, +1):
+                c = list(coords)
+                c[a] = (c[a] + s) % np_[a]
+                dest.append(rank_of(c))
+        flags = list(global_flags)
+        for a in range(3):  # mpi_routines.cpp:453-532
+            if np_[a] == 1:
+                continue
+            lo, hi = 2 * a, 2 * a + 1
+            if coords[a] == 0:
+                flags[hi] = BC_MPI
+                if flags[lo] == BC_PERIODIC:
+                    flags[lo] = BC_MPI
+            elif coords[a] == np_[a] - 1:
+                flags[lo] = BC_MPI
+                if flags[hi] == BC_PERIODIC:
+                    flags[hi] = BC_MPI
+            else:
+                flags[lo] = flags[hi] = BC_MPI
+        return Decomposition(nproc, rank, np_, coords, n_local, offset, dest, flags, list(global_flags))
+
+
+@dataclass
+class Slab:
+    """Arguments of one PackBuffers3D / UnpackBuffers3D call (cuda_boundaries.cu:11-69)."""
+    idxoffset: int
+    isize: int
+    jsize: int
+    ksize: int
+
+    @property
+    def ncells(self):
+        return self.isize * self.jsize * self.ksize
+
+
+def halo_slab(nx, ny, nz, g, face, recv):
+    """Slab sent from (recv=False) or received into (recv=True) face 0..5.
+
+    Geometry of Load_/Unload_Hydro_DeviceBuffer_{X,Y,Z}{0,1} (src/grid/mpi_boundaries.cpp:113-298): g layers
+    along the face's axis; the full extent (ghosts included) of the axes before it; the real cells of the
+    axes after it -- so edges and corners travel with the later phases.
+    """
+    n = [nx, ny, nz]
+    a, side = face // 2, face % 2
+    lo, size = [0, 0, 0], [1, 1, 1]
+    for d in range(3):
+        if n[d] == 1:
+            continue
+        if d < a:
+            lo[d], size[d] = 0, n[d]
+        elif d > a:
+            lo[d], size[d] = g, n[d] - 2 * g
+        else:
+            size[d] = g
+            if recv:
+                lo[d] = 0 if side == 0 else n[d] - g
+            else:
+                lo[d] = g if side == 0 else n[d] - 2 * g
+    return Slab(lo[0] + nx * (lo[1] + ny * lo[2]), size[0], size[1], size[2])
+
+
+@dataclass
+class Header:
+    """The subset of Grid3D::Header (grid3D.h:112-279) the hot path reads."""
+    nx: int = 1
+    ny: int = 1
+    nz: int = 1
+    nx_real: int = 1
+    ny_real: int = 1
+    nz_real: int = 1
+    n_ghost: int = 0
+    n_fields: int = N_FIELDS
+    n_cells: int = 1
+    dx: float = 1.0
+    dy: float = 1.0
+    dz: float = 1.0
+    xbound: float = 0.0
+    ybound: float = 0.0
+    zbound: float = 0.0
+    t: float = 0.0
+    dt: float = 0.0
+    n_step: int = 0
+    max_dti: float = 0.0
+
+
+class Grid3D:
+    """One rank's grid: conserved state in HBM + the chl context that advances it."""
+
+    def __init__(self, n_global, domain_len, bounds_min=(0.0, 0.0, 0.0), recon=_lib.PPMC, solver=_lib.HLLC,
+                 gamma=5.0 / 3.0, bc=(1, 1, 1, 1, 1, 1), precision=2, strict=False, density_floor=0.0,
+                 temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True):
+        import torch
+        self.torch = torch
+        self.recon, self.solver, self.gamma = recon, solver, float(gamma)
+        self.precision, self.strict, self.fused = precision, bool(strict), bool(fused)
+        self.dist_group, self.nproc, self.rank = dist_group, nproc, rank
+        n_global = [int(v) for v in n_global]
+        self.n_global = n_global
+        self.ndim = 1 + (n_global[1] > 1) + (n_global[2] > 1)
+        self.decomp = Decomposition.build(nproc, rank, n_global, list(bc))
+        g = n_ghost_for(recon)
+        H = Header()
+        H.n_ghost = g
+        H.nx_real, H.ny_real, H.nz_real = self.decomp.n_local
+        H.nx = H.nx_real + 2 * g
+        H.ny = H.ny_real + 2 * g if n_global[1] > 1 else 1
+        H.nz = H.nz_real + 2 * g if n_global[2] > 1 else 1
+        H.n_cells = H.nx * H.ny * H.nz
+        H.dx = domain_len[0] / n_global[0]
+        H.dy = domain_len[1] / n_global[1]
+        H.dz = domain_len[2] / n_global[2]
+        H.xbound, H.ybound, H.zbound = bounds_min
+        self.H = H
+        self.flags = self.decomp.flags
+        self.U_floor = float(temperature_floor_U)
+        self.dtype = torch.float64 if precision == 2 else torch.float32
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.type != "cuda":
+            raise _lib.ChollaB200Error("Grid3D needs a CUDA device: there is no CPU path")
+        torch.cuda.set_device(self.device)
+        self.C_device = torch.zeros(H.n_fields * H.n_cells, dtype=self.dtype, device=self.device)
+        cfg = Config(H.nx, H.ny, H.nz, g, H.n_fields, recon, solver, precision, int(self.strict), self.gamma,
+                     H.dx, H.dy, H.dz, float(density_floor), self.U_floor)
+        self._cfg = cfg
+        self._ctx = C.c_void_p()
+        check(_lib.lib().chl_create(C.byref(cfg), C.byref(self._ctx)), "chl_create")
+        self.gpu_launches = 0
+        self._halo_bufs = {}
+
+    # ---- plumbing ----
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            _lib.lib().chl_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ptr(self, t=None):
+        return C.c_void_p((self.C_device if t is None else t).data_ptr())
+
+    def _cflags(self):
+        return (C.c_int * 6)(*self.flags)
+
+    # ---- state in / out ----
+    def local_slices(self):
+        """numpy slices of this rank's real cells inside a global (nz, ny, nx) array."""
+        o, n = self.decomp.offset, self.decomp.n_local
+        return (slice(o[2], o[2] + n[2]), slice(o[1], o[1] + n[1]), slice(o[0], o[0] + n[0]))
+
+    def Set_Initial_Conditions(self, fields_global):
+        """fields_global: float64 array (n_fields, nz_g, ny_g, nx_g) of conserved real cells (host).  The local
+        block is copied into the real cells (initial_conditions.cpp:102-104 does the same H2D of C.host)."""
+        H, g, torch = self.H, self.H.n_ghost, self.torch
+        fields_global = np.asarray(fields_global)
+        host = np.zeros((H.n_fields, H.nz, H.ny, H.nx), dtype=np.float64)
+        sz, sy, sx = self.local_slices()
+        gz = g if H.nz > 1 else 0
+        gy = g if H.ny > 1 else 0
+        host[:, gz:gz + H.nz_real, gy:gy + H.ny_real, g:g + H.nx_real] = fields_global[:, sz, sy, sx]
+        self.C_device.copy_(torch.from_numpy(host.reshape(-1)).to(self.dtype))
+        self.H.t, self.H.n_step = 0.0, 0
+
+    def upload(self, flat_host):
+        """Copy a full local array (ghosts included, flat SoA) to the device."""
+        self.C_device.copy_(self.torch.from_numpy(np.ascontiguousarray(flat_host).reshape(-1)).to(self.dtype))
+
+    def download(self):
+        return self.C_device.detach().to("cpu", self.torch.float64).numpy().copy()
+
+    def real_cells(self):
+        H, g = self.H, self.H.n_ghost
+        a = self.download().reshape(H.n_fields, H.nz, H.ny, H.nx)
+        gz = g if H.nz > 1 else 0
+        gy = g if H.ny > 1 else 0
+        return a[:, gz:gz + H.nz_real, gy:gy + H.ny_real, g:g + H.nx_real].copy()
+
+    # ---- the hot path, reference names ----
+    def Calc_Inverse_Timestep(self):
+        """Grid3D::Calc_Inverse_Timestep (grid3D.cpp:115-120) -> Calc_dt_GPU."""
+        out = C.c_double()
+        check(_lib.lib().chl_calc_dti(self._ctx, self._ptr(), C.byref(out), self._stream()), "chl_calc_dti")
+        self.gpu_launches += 1
+        return out.value
+
+    def set_dt(self, dti):
+        """Grid3D::set_dt (grid3D.cpp:373-409): global max of the inverse time step, dt = C_cfl / max_dti."""
+        max_dti = dti
+        if self.nproc > 1:
+            dist, torch = self.torch.distributed, self.torch
+            dev = self.device if dist.get_backend(self.dist_group) == "nccl" else "cpu"
+            t = torch.tensor([dti], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.dist_group)
+            max_dti = float(t.item())
+        self.H.max_dti = max_dti
+        self.H.dt = C_CFL / max_dti
+        return self.H.dt
+
+    def Execute_Hydro_Integrator(self):
+        """Grid3D::Execute_Hydro_Integrator (grid3D.cpp:413-470) -> VL_Algorithm_{1,2,3}D_CUDA."""
+        check(_lib.lib().chl_vl_step(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step")
+        self.gpu_launches += 2
+
+    def Update_Hydro_Grid(self):
+        """Grid3D::Update_Hydro_Grid (grid3D.cpp:474-585): integrator, temperature floor, new inverse dt."""
+        L = _lib.lib()
+        if self.fused:
+            check(L.chl_vl_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step_fused")
+            self.gpu_launches += 2
+            out = C.c_double()
+            check(L.chl_dti_result(self._ctx, C.byref(out), self._stream()), "chl_dti_result")
+            return out.value
+        self.Execute_Hydro_Integrator()
+        if self.U_floor > 0.0:
+            check(L.chl_apply_temperature_floor(self._ctx, self._ptr(), self.U_floor, self._stream()),
+                  "chl_apply_temperature_floor")
+            self.gpu_launches += 1
+        return self.Calc_Inverse_Timestep()
+
+    def Update_Time(self):
+        self.H.t += self.H.dt
+        self.H.n_step += 1
+
+    def Set_Boundaries(self, direction):
+        """Grid3D::Set_Boundaries(dir, flags) (boundary_conditions.cpp:165-417) -> SetGhostCells."""
+        if direction // 2 >= self.ndim or self.flags[direction] in (_lib.BC_CUSTOM, _lib.BC_MPI):
+            return
+        check(_lib.lib().chl_set_ghost_cells(self._ctx, self._ptr(), self._cflags(), direction, self._stream()),
+              "chl_set_ghost_cells")
+        self.gpu_launches += 1
+
+    def Set_Boundary_Conditions_Grid(self):
+        """Grid3D::Set_Boundary_Conditions (boundary_conditions.cpp:54-): the six physical faces in order, or,
+        when any face is an exchange face, the x -> y -> z phased exchange of Set_Boundaries_MPI_BLOCK
+        (mpi_boundaries.cpp:29-111)."""
+        if self.nproc == 1:
+            for d in range(2 * self.ndim):
+                self.Set_Boundaries(d)
+            return
+        for axis in range(self.ndim):
+            ops = self._post_halo(axis)
+            self.Set_Boundaries(2 * axis)
+            self.Set_Boundaries(2 * axis + 1)
+            self._finish_halo(axis, ops)
+
+    # ---- halo exchange over torch.distributed (NCCL send/recv over NVLink) ----
+    def _buf(self, key, n):
+        b = self._halo_bufs.get(key)
+        if b is None or b.numel() != n:
+            b = self.torch.empty(n, dtype=self.dtype, device=self.device)
+            self._halo_bufs[key] = b
+        return b
+
+    def _post_halo(self, axis):
+        """Load_and_Send_MPI_Comm_Buffers(dir) (mpi_boundaries.cpp:300-777): pack both slabs, post the
+        receives and sends."""
+        H, L, dist = self.H, _lib.lib(), self.torch.distributed
+        lo, hi = 2 * axis, 2 * axis + 1
+        sends, recvs = [], []
+        for face in (lo, hi):
+            if self.flags[face] != BC_MPI:
+                continue
+            s = halo_slab(H.nx, H.ny, H.nz, H.n_ghost, face, recv=False)
+            sb = self._buf(("s", face), s.ncells * H.n_fields)
+            check(L.chl_pack_buffer(self._ptr(sb), self._ptr(), H.nx, H.ny, H.n_fields, H.n_cells, s.idxoffset,
+                                    s.isize, s.jsize, s.ksize, self.precision, self._stream()), "chl_pack_buffer")
+            self.gpu_launches += 1
+            rb = self._buf(("r", face), s.ncells * H.n_fields)
+            # my low slab lands in my low neighbour's HIGH ghosts (tag = receiving face), and vice versa
+            sends.append(dist.P2POp(dist.isend, sb, self.decomp.dest[face], self.dist_group, tag=face ^ 1))
+            recvs.append((face, dist.P2POp(dist.irecv, rb, self.decomp.dest[face], self.dist_group, tag=face)))
+        # a peer that is both neighbours (np = 2, periodic) sends low-then-high; what it sends first fills my
+        # HIGH ghosts, so receives are posted high-then-low to match NCCL's in-order pairing
+        recvs.sort(key=lambda fr: -fr[0])
+        ops = sends + [r for _, r in recvs]
+        works = dist.batch_isend_irecv(ops) if ops else []
+        return works
+
+    def _finish_halo(self, axis, works):
+        """Wait_and_Unload_MPI_Comm_Buffers (mpi_boundaries.cpp:779-830)."""
+        H, L = self.H, _lib.lib()
+        for w in works:
+            w.wait()
+        for face in (2 * axis, 2 * axis + 1):
+            if self.flags[face] != BC_MPI:
+                continue
+            r = halo_slab(H.nx, H.ny, H.nz, H.n_ghost, face, recv=True)
+            rb = self._buf(("r", face), r.ncells * H.n_fields)
+            check(L.chl_unpack_buffer(self._ptr(rb), self._ptr(), H.nx, H.ny, H.n_fields, H.n_cells, r.idxoffset,
+                                      r.isize, r.jsize, r.ksize, self.precision, self._stream()),
+                  "chl_unpack_buffer")
+            self.gpu_launches += 1
+
+    # ---- convenience driver: the body of main()'s loop ----
+    def advance(self, n_steps):
+        """n_steps iterations of main.cpp:247-379 (no output).  Returns the dt history."""
+        dts = []
+        dti = self.Calc_Inverse_Timestep()
+        for _ in range(n_steps):
+            self.set_dt(dti)
+            dti = self.Update_Hydro_Grid()
+            self.Update_Time()
+            self.Set_Boundary_Conditions_Grid()
+            dts.append(self.H.dt)
+        self._last_dti = dti
+        return dts

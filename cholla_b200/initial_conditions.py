@@ -1,0 +1,95 @@
+"""Closed-form initial conditions used by the tests and bench.py (host, numpy, float64).
+
+Formulas follow the reference's generators (src/grid/initial_conditions.cpp: Constant :180, Sound_Wave :244,
+Riemann :509, KH_res_ind :749, Spherical_Overpressure_3D :1203) with cell centres from the global-index rule
+of Grid3D::Get_Position (grid3D.cpp:108-110), so the fields are independent of the rank count.  Each returns
+conserved real cells as an array (5, nz, ny, nx).  They are inputs only: the same array is handed to the CUDA
+path, the CPU oracle and the compiled reference, so parity never depends on how it was generated.
+"""
+import numpy as np
+
+
+def _centres(n, length, lo):
+    d = length / n
+    return lo + np.arange(n) * d + 0.5 * d
+
+
+def _mesh(n, lengths, lo):
+    x = _centres(n[0], lengths[0], lo[0])
+    y = _centres(n[1], lengths[1], lo[1])
+    z = _centres(n[2], lengths[2], lo[2])
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    return X, Y, Z
+
+
+def _pack(d, mx, my, mz, E):
+    return np.stack([np.broadcast_to(a, d.shape).astype(np.float64) for a in (d, mx, my, mz, E)])
+
+
+def constant(n, rho=1.0, v=(0.0, 0.0, 0.0), P=1.0, gamma=5.0 / 3.0):
+    d = np.full((n[2], n[1], n[0]), rho)
+    E = P / (gamma - 1.0) + 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2)
+    return _pack(d, d * v[0], d * v[1], d * v[2], np.full_like(d, E))
+
+
+def sound_wave(n, lengths=(4.0, 4.0, 4.0), lo=(0.0, 0.0, 0.0), rho=1.0, v=(0.0, 0.0, 0.0), P=0.6, A=1e-4,
+               gamma=1.666666666666667):
+    """examples/3D/sound_wave.txt"""
+    X, _, _ = _mesh(n, lengths, lo)
+    s = A * np.sin(2.0 * np.pi * X)
+    d = rho + s
+    E = P / (gamma - 1.0) + 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2) + 1.5 * s
+    return _pack(d, rho * v[0] + s, rho * v[1] + s, rho * v[2] + s, E)
+
+
+def riemann(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0), left=(1.0, 0.0, 0.0, 0.0, 1.0),
+            right=(0.1, 0.0, 0.0, 0.0, 0.1), diaph=0.5, gamma=1.4):
+    """examples/1D/sod.txt and examples/3D/sod256.txt: (rho, vx, vy, vz, P) either side of x = diaph."""
+    X, _, _ = _mesh(n, lengths, lo)
+    L = X < diaph
+    pick = lambda i: np.where(L, left[i], right[i])
+    d, vx, vy, vz, P = (pick(i) for i in range(5))
+    E = P / (gamma - 1.0) + 0.5 * d * (vx * vx + vy * vy + vz * vz)
+    return _pack(d, d * vx, d * vy, d * vz, E)
+
+
+def spherical_overpressure(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0), gamma=1.66666667):
+    """Spherical_Overpressure_3D: rho=0.1, P=1 background; rho=1, P=11 inside r < 0.2 of the box centre."""
+    X, Y, Z = _mesh(n, lengths, lo)
+    c = [lo[i] + 0.5 * lengths[i] for i in range(3)]
+    r = np.sqrt((X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2)
+    inside = r < 0.2
+    d = np.where(inside, 1.0, 0.1)
+    P = np.where(inside, 11.0, 1.0)
+    zero = np.zeros_like(d)
+    return _pack(d, zero, zero, zero, P / (gamma - 1.0))
+
+
+def kh_res_ind(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, -0.5, -0.5), gamma=5.0 / 3.0):
+    """KH_res_ind, 3-D branch (examples/3D/KH_res_ind_3D.txt): dense cylinder along x sheared against the
+    ambient gas, resolution-independent ramp."""
+    X, Y, Z = _mesh(n, lengths, lo)
+    d1, d2, v1, v2, P, dy, A = 100.0, 1.0, 0.5, -0.5, 2.5, 0.05, 0.1
+    r = np.sqrt(Z * Z + Y * Y)
+    phi = np.arctan2(Z, Y)
+    w = np.sqrt(-2.0 * dy * dy * np.log(0.5))
+    e_m = np.exp(-0.5 * (r - 0.25 - w) ** 2 / (dy * dy))
+    e_p = np.exp(-0.5 * (r - 0.25 + w) ** 2 / (dy * dy))
+    inside = r < 0.25
+    d = np.where(inside, d1 - (d1 - d2) * e_m, d2 + (d1 - d2) * e_p)
+    mx = np.where(inside, v1 * d - d * e_m, v2 * d + d * e_p)
+    pert = d * A * np.sin(4 * np.pi * X) * np.where(inside, e_p, 1.0 - e_p)
+    my, mz = np.cos(phi) * pert, np.sin(phi) * pert
+    E = P / (gamma - 1.0) + 0.5 * (mx * mx + my * my + mz * mz) / d
+    return _pack(d, mx, my, mz, E)
+
+
+def random_smooth(n, seed=0, gamma=5.0 / 3.0):
+    """Seeded, strictly positive, smooth-ish random state that exercises every limiter branch."""
+    rng = np.random.default_rng(seed)
+    shape = (n[2], n[1], n[0])
+    d = 0.5 + rng.random(shape)
+    vx, vy, vz = (rng.random(shape) - 0.5 for _ in range(3))
+    P = 0.5 + rng.random(shape)
+    E = P / (gamma - 1.0) + 0.5 * d * (vx * vx + vy * vy + vz * vz)
+    return _pack(d, d * vx, d * vy, d * vz, E)
