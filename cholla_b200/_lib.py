@@ -63,6 +63,8 @@ def lib():
     L.chl_dti_decode.argtypes = [C.c_ulonglong]
     L.chl_dti_decode.restype = d
     L.chl_calc_dti.argtypes = [p, p, C.POINTER(d), p]
+    L.chl_set_profiling.argtypes = [p, i]
+    L.chl_stage_times.argtypes = [p, C.POINTER(d), ip]
     L.chl_apply_temperature_floor.argtypes = [p, p, d, p]
     L.chl_set_ghost_cells.argtypes = [p, p, ip, i, p]
     L.chl_set_boundaries.argtypes = [p, p, ip, p]

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/cholla_b200.h"
 #include "chl_internal.h"
@@ -47,7 +48,11 @@ struct chl_ctx {
   unsigned long long *h_key;  // pinned
   size_t n_cells;
   int ndim;
+  int profiling;                       // record events around each stage
+  std::vector<cudaEvent_t> ev;         // 3 per profiled step: before predictor, between, after corrector
+  int ev_steps;                        // steps recorded since the last chl_stage_times
 };
+static const int kMaxProfiledSteps = 256;
 
 extern "C" {
 
@@ -109,6 +114,8 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->d_half = nullptr;
   c->d_key = nullptr;
   c->h_key = nullptr;
+  c->profiling = 0;
+  c->ev_steps = 0;
   size_t const bytes = c->n_cells * cfg->n_fields * ops->real_bytes;
   cudaError_t e = cudaMalloc(&c->d_half, bytes);
   if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, sizeof(unsigned long long));
@@ -129,6 +136,7 @@ int chl_destroy(chl_ctx *c)
   if (c->d_half) cudaFree(c->d_half);
   if (c->d_key) cudaFree(c->d_key);
   if (c->h_key) cudaFreeHost(c->h_key);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
   return CHL_OK;
 }
@@ -179,7 +187,17 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
   a.U_floor = 0.0;
   a.do_dti = 0;
   a.zchunk = a.has_z ? choose_chunk(a.lo, a.hi) : 1;
+  bool const prof = c->profiling && c->ev_steps < kMaxProfiledSteps;
+  if (prof) {
+    while ((int)c->ev.size() < 3 * (c->ev_steps + 1)) {
+      cudaEvent_t e;
+      CHL_CUDA(cudaEventCreate(&e));
+      c->ev.push_back(e);
+    }
+    CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps], s));
+  }
   CHL_CUDA(c->ops->sweep(0, g.recon, g.solver, a, s));
+  if (prof) CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 1], s));
   // ---- corrector: real cells (hydro_cuda.cu:225) ----
   for (int d = 0; d < 3; d++) {
     bool const on = d == 0 || (d == 1 && a.has_y) || (d == 2 && a.has_z);
@@ -199,6 +217,36 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
   }
   a.zchunk = a.has_z ? choose_chunk(a.lo, a.hi) : 1;
   CHL_CUDA(c->ops->sweep(1, g.recon, g.solver, a, s));
+  if (prof) {
+    CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 2], s));
+    c->ev_steps++;
+  }
+  return CHL_OK;
+}
+
+int chl_set_profiling(chl_ctx *c, int enable)
+{
+  if (!c) return fail(CHL_ERR_INVALID, "chl_set_profiling: null context");
+  c->profiling = enable ? 1 : 0;
+  c->ev_steps = 0;
+  return CHL_OK;
+}
+
+int chl_stage_times(chl_ctx *c, double ms[2], int *n_steps)
+{
+  if (!c || !ms || !n_steps) return fail(CHL_ERR_INVALID, "chl_stage_times: null argument");
+  ms[0] = ms[1] = 0.0;
+  *n_steps = c->ev_steps;
+  if (c->ev_steps == 0) return CHL_OK;
+  CHL_CUDA(cudaEventSynchronize(c->ev[3 * c->ev_steps - 1]));
+  for (int i = 0; i < c->ev_steps; i++) {
+    float a = 0.f, b = 0.f;
+    CHL_CUDA(cudaEventElapsedTime(&a, c->ev[3 * i], c->ev[3 * i + 1]));
+    CHL_CUDA(cudaEventElapsedTime(&b, c->ev[3 * i + 1], c->ev[3 * i + 2]));
+    ms[0] += a;
+    ms[1] += b;
+  }
+  c->ev_steps = 0;
   return CHL_OK;
 }
 

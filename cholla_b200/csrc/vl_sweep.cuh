@@ -23,7 +23,7 @@
 #pragma once
 #include "hydro_physics.cuh"
 
-namespace chl
+namespace CHL_NS
 {
 constexpr int TX = 32;
 constexpr int TY = 8;
@@ -128,6 +128,22 @@ __device__ __forceinline__ S5 load_rot(const Real *__restrict__ a, size_t N, siz
                      __ldg(a + 4 * N + id));
 }
 
+// Half-step primitives of one cell, rotated into the sweep frame.  Product mode stores (rho, v, P).  Strict mode
+// stores (rho, v, E) and derives P here, because the reference's Load_Data sums |v|^2 in the ROTATED component
+// order (reconstruction.h:151-201 with o1,o2,o3), so the rounding of P differs between the three sweeps.
+template <int DIR>
+__device__ __forceinline__ Prim load_half(const Real *__restrict__ a, size_t N, size_t id, Real gamma)
+{
+  S5 const s = load_rot<DIR>(a, N, id);
+#if CHL_STRICT
+  Real const e = s.v[4] - RC(0.5) * s.v[0] * sq3(s.v[1], s.v[2], s.v[3]);
+  return Prim{s.v[0], s.v[1], s.v[2], s.v[3], fmax((gamma - RC(1.)) * e, kTiny)};
+#else
+  (void)gamma;
+  return Prim{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]};
+#endif
+}
+
 // Interface states of one cell along DIR: L = low side of its upper face, R = high side of its lower face.
 template <int RECON, int STAGE, int DIR>
 __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t N, size_t id, long stride, Real gamma,
@@ -143,18 +159,18 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t N
     R = L;
     return;
   }
-  Prim const wi = as_prim(load_rot<DIR>(in, N, id));
+  Prim const wi = load_half<DIR>(in, N, id, gamma);
   if (RECON == kPCM) {
     L = iface_state(wi, gamma);
     R = L;
     return;
   }
-  Prim const wm1 = as_prim(load_rot<DIR>(in, N, id - stride));
-  Prim const wp1 = as_prim(load_rot<DIR>(in, N, id + stride));
+  Prim const wm1 = load_half<DIR>(in, N, id - stride, gamma);
+  Prim const wp1 = load_half<DIR>(in, N, id + stride, gamma);
   Prim l, r;
   if (RECON == kPPMC) {
-    Prim const wm2 = as_prim(load_rot<DIR>(in, N, id - 2 * stride));
-    Prim const wp2 = as_prim(load_rot<DIR>(in, N, id + 2 * stride));
+    Prim const wm2 = load_half<DIR>(in, N, id - 2 * stride, gamma);
+    Prim const wp2 = load_half<DIR>(in, N, id + 2 * stride, gamma);
     ppmc_cell(wm2, wm1, wi, wp1, wp2, gamma, l, r);
   } else {
     plmc_cell(wm1, wi, wp1, gamma, l, r);
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 2) vl_sweep_kernel(SweepParams const
             }
             Prim const w = prim_from_cons(Cons{u[0], u[1], u[2], u[3], u[4]}, gamma);
             P.out[idm] = w.d; P.out[N + idm] = w.vx; P.out[2 * N + idm] = w.vy; P.out[3 * N + idm] = w.vz;
-            P.out[4 * N + idm] = w.p;
+            P.out[4 * N + idm] = CHL_STRICT ? u[4] : w.p;
           } else {
             if (u[0] < P.density_floor && u[0] > RC(0.)) {  // hydro_cuda.cu:279-291
               Real const d0 = u[0];
@@ -376,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 2) vl_sweep_kernel(SweepParams const
       if (STAGE == 0) {
         Prim const w = prim_from_cons(Cons{acc[0], acc[1], acc[2], acc[3], acc[4]}, gamma);
         P.out[id] = w.d; P.out[N + id] = w.vx; P.out[2 * N + id] = w.vy; P.out[3 * N + id] = w.vz;
-        P.out[4 * N + id] = w.p;
+        P.out[4 * N + id] = CHL_STRICT ? acc[4] : w.p;
       } else {
         Real u[5];
 #pragma unroll
@@ -410,4 +426,4 @@ __global__ void __launch_bounds__(kThreads, 2) vl_sweep_kernel(SweepParams const
   }
 }
 
-}  // namespace chl
+}  // namespace CHL_NS

@@ -15,8 +15,10 @@
 #define CHL_CAT2(a, b) a##b
 #define CHL_CAT(a, b) CHL_CAT2(a, b)
 
-namespace chl
+namespace CHL_NS
 {
+using chl::ModeOps;
+using chl::SweepArgs;
 namespace
 {
 template <int RECON, int SOLVER, int STAGE>
@@ -140,6 +142,10 @@ cudaError_t tfloor(void *U, int nx, int ny, int nz, int g, double U_floor, cudaS
 
 ModeOps const ops = {sweep, calc_dti, tfloor, sizeof(Real)};
 }  // namespace
+ModeOps const *get_ops() { return &ops; }
+}  // namespace CHL_NS
 
-ModeOps const *CHL_CAT(mode_ops_, CHL_MODE)() { return &ops; }
+namespace chl
+{
+ModeOps const *CHL_CAT(mode_ops_, CHL_MODE)() { return CHL_NS::get_ops(); }
 }  // namespace chl

@@ -154,7 +154,7 @@ class Grid3D:
     """One rank's grid: conserved state in HBM + the chl context that advances it."""
 
     def __init__(self, n_global, domain_len, bounds_min=(0.0, 0.0, 0.0), recon=_lib.PPMC, solver=_lib.HLLC,
-                 gamma=5.0 / 3.0, bc=(1, 1, 1, 1, 1, 1), precision=2, strict=False, density_floor=0.0,
+                 gamma=5.0 / 3.0, bc=(1, 1, 1, 1, 1, 1), precision=2, strict=True, density_floor=0.0,
                  temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True):
         import torch
         self.torch = torch
@@ -215,6 +215,15 @@ class Grid3D:
     def _cflags(self):
         return (C.c_int * 6)(*self.flags)
 
+    def set_profiling(self, on):
+        check(_lib.lib().chl_set_profiling(self._ctx, int(bool(on))), "chl_set_profiling")
+
+    def stage_times(self):
+        """(predictor_ms, corrector_ms, n_steps) summed over the steps since the last call (CUDA events)."""
+        ms, n = (C.c_double * 2)(), C.c_int()
+        check(_lib.lib().chl_stage_times(self._ctx, ms, C.byref(n)), "chl_stage_times")
+        return ms[0], ms[1], n.value
+
     # ---- state in / out ----
     def local_slices(self):
         """numpy slices of this rank's real cells inside a global (nz, ny, nx) array."""
@@ -231,6 +240,16 @@ class Grid3D:
         gz = g if H.nz > 1 else 0
         gy = g if H.ny > 1 else 0
         host[:, gz:gz + H.nz_real, gy:gy + H.ny_real, g:g + H.nx_real] = fields_global[:, sz, sy, sx]
+        self.C_device.copy_(torch.from_numpy(host.reshape(-1)).to(self.dtype))
+        self.H.t, self.H.n_step = 0.0, 0
+
+    def Set_Initial_Conditions_Local(self, fields_local):
+        """Same, from this rank's block only: (n_fields, nz_real, ny_real, nx_real)."""
+        H, g, torch = self.H, self.H.n_ghost, self.torch
+        host = np.zeros((H.n_fields, H.nz, H.ny, H.nx), dtype=np.float64)
+        gz = g if H.nz > 1 else 0
+        gy = g if H.ny > 1 else 0
+        host[:, gz:gz + H.nz_real, gy:gy + H.ny_real, g:g + H.nx_real] = fields_local
         self.C_device.copy_(torch.from_numpy(host.reshape(-1)).to(self.dtype))
         self.H.t, self.H.n_step = 0.0, 0
 

@@ -9,25 +9,53 @@ path, the CPU oracle and the compiled reference, so parity never depends on how 
 import numpy as np
 
 
-def _centres(n, length, lo):
+_BLOCK = None  # (offset_xyz, n_local_xyz): restrict the generators to one rank's block of the global grid
+
+
+class block:
+    """with block(offset, n_local): fields = sound_wave(n_global, ...)  -> only that rank's cells are built."""
+
+    def __init__(self, offset, n_local):
+        self.b = (tuple(offset), tuple(n_local))
+
+    def __enter__(self):
+        global _BLOCK
+        self.prev, _BLOCK = _BLOCK, self.b
+        return self
+
+    def __exit__(self, *a):
+        global _BLOCK
+        _BLOCK = self.prev
+
+
+def _centres(n, length, lo, axis):
     d = length / n
-    return lo + np.arange(n) * d + 0.5 * d
+    i = np.arange(n) if _BLOCK is None else _BLOCK[0][axis] + np.arange(_BLOCK[1][axis])
+    return lo + i * d + 0.5 * d  # Get_Position: bound + global_index * dx + dx/2 (grid3D.cpp:108-110)
+
+
+def _shape(n):
+    return (n[2], n[1], n[0]) if _BLOCK is None else (_BLOCK[1][2], _BLOCK[1][1], _BLOCK[1][0])
 
 
 def _mesh(n, lengths, lo):
-    x = _centres(n[0], lengths[0], lo[0])
-    y = _centres(n[1], lengths[1], lo[1])
-    z = _centres(n[2], lengths[2], lo[2])
-    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    x = _centres(n[0], lengths[0], lo[0], 0)
+    y = _centres(n[1], lengths[1], lo[1], 1)
+    z = _centres(n[2], lengths[2], lo[2], 2)
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij", sparse=True)
     return X, Y, Z
 
 
 def _pack(d, mx, my, mz, E):
-    return np.stack([np.broadcast_to(a, d.shape).astype(np.float64) for a in (d, mx, my, mz, E)])
+    shape = np.broadcast_shapes(*(np.shape(a) for a in (d, mx, my, mz, E)))
+    out = np.empty((5,) + shape, dtype=np.float64)
+    for f, a in enumerate((d, mx, my, mz, E)):
+        out[f] = a
+    return out
 
 
 def constant(n, rho=1.0, v=(0.0, 0.0, 0.0), P=1.0, gamma=5.0 / 3.0):
-    d = np.full((n[2], n[1], n[0]), rho)
+    d = np.full(_shape(n), rho)
     E = P / (gamma - 1.0) + 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2)
     return _pack(d, d * v[0], d * v[1], d * v[2], np.full_like(d, E))
 
@@ -36,7 +64,7 @@ def sound_wave(n, lengths=(4.0, 4.0, 4.0), lo=(0.0, 0.0, 0.0), rho=1.0, v=(0.0, 
                gamma=1.666666666666667):
     """examples/3D/sound_wave.txt"""
     X, _, _ = _mesh(n, lengths, lo)
-    s = A * np.sin(2.0 * np.pi * X)
+    s = A * np.sin(2.0 * np.pi * X) + 0.0 * (_mesh(n, lengths, lo)[1] + _mesh(n, lengths, lo)[2])
     d = rho + s
     E = P / (gamma - 1.0) + 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2) + 1.5 * s
     return _pack(d, rho * v[0] + s, rho * v[1] + s, rho * v[2] + s, E)
@@ -46,6 +74,7 @@ def riemann(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0), left=(1.0, 0.0, 0.0,
             right=(0.1, 0.0, 0.0, 0.0, 0.1), diaph=0.5, gamma=1.4):
     """examples/1D/sod.txt and examples/3D/sod256.txt: (rho, vx, vy, vz, P) either side of x = diaph."""
     X, _, _ = _mesh(n, lengths, lo)
+    X = X + 0.0 * (_mesh(n, lengths, lo)[1] + _mesh(n, lengths, lo)[2])
     L = X < diaph
     pick = lambda i: np.where(L, left[i], right[i])
     d, vx, vy, vz, P = (pick(i) for i in range(5))
@@ -87,7 +116,7 @@ def kh_res_ind(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, -0.5, -0.5), gamma=5.0 / 3.0
 def random_smooth(n, seed=0, gamma=5.0 / 3.0):
     """Seeded, strictly positive, smooth-ish random state that exercises every limiter branch."""
     rng = np.random.default_rng(seed)
-    shape = (n[2], n[1], n[0])
+    shape = _shape(n)
     d = 0.5 + rng.random(shape)
     vx, vy, vz = (rng.random(shape) - 0.5 for _ in range(3))
     P = 0.5 + rng.random(shape)
