@@ -116,7 +116,7 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->h_key = nullptr;
   c->profiling = 0;
   c->ev_steps = 0;
-  size_t const bytes = c->n_cells * cfg->n_fields * ops->real_bytes;
+  size_t const bytes = c->n_cells * ops->half_fields * ops->real_bytes;
   cudaError_t e = cudaMalloc(&c->d_half, bytes);
   if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, sizeof(unsigned long long));
@@ -143,7 +143,7 @@ int chl_destroy(chl_ctx *c)
 
 size_t chl_scratch_bytes(const chl_ctx *c)
 {
-  return c ? c->n_cells * c->cfg.n_fields * c->ops->real_bytes + sizeof(unsigned long long) : 0;
+  return c ? c->n_cells * c->ops->half_fields * c->ops->real_bytes + sizeof(unsigned long long) : 0;
 }
 
 static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
@@ -164,7 +164,8 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
   a.dti_key = c->d_key;
   int const n[3] = {g.nx, g.ny, g.nz};
   auto choose_chunk = [&](int const *lo, int const *hi) {
-    long const bxy = (long)((hi[0] - lo[0] + 31) / 32) * ((hi[1] - lo[1] + 7) / 8);
+    int const ty = c->ops->tile_y;
+    long const bxy = (long)((hi[0] - lo[0] + 31) / 32) * ((hi[1] - lo[1] + ty - 1) / ty);
     int const oz = hi[2] - lo[2];
     long chunks = (2368 + bxy - 1) / bxy;  // aim at >= 8 waves of 2 CTAs on 148 SMs
     if (chunks > oz / 8) chunks = oz / 8;

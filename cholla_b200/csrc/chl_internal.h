@@ -28,6 +28,8 @@ struct ModeOps {
                           double gamma, unsigned long long *key, cudaStream_t s);
   cudaError_t (*tfloor)(void *U, int nx, int ny, int nz, int n_ghost, double U_floor, cudaStream_t s);
   size_t real_bytes;
+  int half_fields;  // fields of the half-step scratch array (5, or 7 in strict mode)
+  int tile_y;       // rows of cells per CTA column
 };
 
 ModeOps const *mode_ops_f64_strict();

@@ -27,8 +27,14 @@ cudaError_t launch(SweepParams const &p, cudaStream_t s)
   int const ox = p.hi[0] - p.lo[0], oy = p.hi[1] - p.lo[1], oz = p.hi[2] - p.lo[2];
   if (ox <= 0 || oy <= 0 || oz <= 0) return cudaSuccess;
   dim3 grid((ox + TX - 1) / TX, (oy + TY - 1) / TY, p.has_z ? (oz + p.zchunk - 1) / p.zchunk : 1);
-  dim3 block(TX, TY, 1);
-  vl_sweep_kernel<RECON, SOLVER, STAGE><<<grid, block, 0, s>>>(p);
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(vl_sweep_kernel<RECON, SOLVER, STAGE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  vl_sweep_kernel<RECON, SOLVER, STAGE><<<grid, kThreads, kSmemBytes, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -40,7 +46,7 @@ cudaError_t sweep(int stage, int recon, int solver, SweepArgs const &a, cudaStre
   p.nx = a.nx; p.ny = a.ny; p.nz = a.nz;
   for (int d = 0; d < 3; d++) { p.lo[d] = a.lo[d]; p.hi[d] = a.hi[d]; }
   p.has_y = a.has_y; p.has_z = a.has_z; p.zchunk = a.zchunk;
-  p.dtodx = (Real)a.dtodx; p.dtody = (Real)a.dtody; p.dtodz = (Real)a.dtodz;
+  p.dto[0] = (Real)a.dtodx; p.dto[1] = (Real)a.dtody; p.dto[2] = (Real)a.dtodz;
   p.gamma = (Real)a.gamma; p.density_floor = (Real)a.density_floor;
   p.apply_tfloor = a.apply_tfloor; p.U_floor = (Real)a.U_floor; p.do_dti = a.do_dti;
   p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
@@ -140,7 +146,7 @@ cudaError_t tfloor(void *U, int nx, int ny, int nz, int g, double U_floor, cudaS
   return cudaGetLastError();
 }
 
-ModeOps const ops = {sweep, calc_dti, tfloor, sizeof(Real)};
+ModeOps const ops = {sweep, calc_dti, tfloor, sizeof(Real), kHalfFields, TY};
 }  // namespace
 ModeOps const *get_ops() { return &ops; }
 }  // namespace CHL_NS
