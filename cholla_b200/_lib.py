@@ -5,7 +5,8 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libcholla_b200.so")
+# CHOLLA_B200_LIB selects a tuning variant built with `make VARIANT=...` (development only)
+LIB_PATH = os.environ.get("CHOLLA_B200_LIB") or os.path.join(_HERE, "libcholla_b200.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "cholla_b200.h")
 
 CHL_OK = 0

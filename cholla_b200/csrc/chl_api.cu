@@ -3,6 +3,7 @@
 // with CHL_ERR_NO_DEVICE / CHL_ERR_CUDA.
 #include <float.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -43,7 +44,10 @@ double host_decode(unsigned long long k)
 struct chl_ctx {
   chl_config cfg;
   chl::ModeOps const *ops;
-  void *d_half;               // W at t + dt/2 (primitives), n_fields * n_cells reals
+  void *d_half;               // W at t + dt/2 (primitives), half_fields * n_cells reals
+  void *d_acc;                // direction-split sweeps: running sum of flux differences, 5 * n_cells reals
+  int split;                  // 1 = one launch per direction (default), 0 = single fused launch per stage
+  int dir_chunk;              // CHL_DIR_CHUNK override (0 = auto)
   unsigned long long *d_key;  // CFL accumulator (ordered key)
   unsigned long long *h_key;  // pinned
   size_t n_cells;
@@ -112,12 +116,21 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->n_cells = (size_t)cfg->nx * cfg->ny * cfg->nz;
   c->ndim = 1 + (cfg->ny > 1) + (cfg->nz > 1);
   c->d_half = nullptr;
+  c->d_acc = nullptr;
+  {
+    // development knobs: CHL_SWEEP_IMPL=fused|split selects the kernel family, CHL_DIR_CHUNK the marching length
+    const char *impl = getenv("CHL_SWEEP_IMPL");
+    c->split = !(impl && strcmp(impl, "fused") == 0);
+    const char *ch = getenv("CHL_DIR_CHUNK");
+    c->dir_chunk = ch ? atoi(ch) : 0;
+  }
   c->d_key = nullptr;
   c->h_key = nullptr;
   c->profiling = 0;
   c->ev_steps = 0;
   size_t const bytes = c->n_cells * ops->half_fields * ops->real_bytes;
   cudaError_t e = cudaMalloc(&c->d_half, bytes);
+  if (e == cudaSuccess && c->split) e = cudaMalloc(&c->d_acc, c->n_cells * 5 * ops->real_bytes);
   if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(c->d_half, 0, bytes);
@@ -134,6 +147,7 @@ int chl_destroy(chl_ctx *c)
 {
   if (!c) return CHL_OK;
   if (c->d_half) cudaFree(c->d_half);
+  if (c->d_acc) cudaFree(c->d_acc);
   if (c->d_key) cudaFree(c->d_key);
   if (c->h_key) cudaFreeHost(c->h_key);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -143,7 +157,7 @@ int chl_destroy(chl_ctx *c)
 
 size_t chl_scratch_bytes(const chl_ctx *c)
 {
-  return c ? c->n_cells * c->ops->half_fields * c->ops->real_bytes + sizeof(unsigned long long) : 0;
+  return c ? c->n_cells * (c->ops->half_fields + (c->split ? 5 : 0)) * c->ops->real_bytes + sizeof(unsigned long long) : 0;
 }
 
 static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
@@ -162,6 +176,9 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
   a.dy = g.dy;
   a.dz = g.dz;
   a.dti_key = c->d_key;
+  a.acc = c->d_acc;
+  a.dir_chunk = c->dir_chunk;
+  auto const sweep = c->split ? c->ops->sweep_split : c->ops->sweep;
   int const n[3] = {g.nx, g.ny, g.nz};
   auto choose_chunk = [&](int const *lo, int const *hi) {
     int const ty = c->ops->tile_y;
@@ -197,7 +214,7 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
     }
     CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps], s));
   }
-  CHL_CUDA(c->ops->sweep(0, g.recon, g.solver, a, s));
+  CHL_CUDA(sweep(0, g.recon, g.solver, a, s));
   if (prof) CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 1], s));
   // ---- corrector: real cells (hydro_cuda.cu:225) ----
   for (int d = 0; d < 3; d++) {
@@ -217,7 +234,7 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
     CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
   }
   a.zchunk = a.has_z ? choose_chunk(a.lo, a.hi) : 1;
-  CHL_CUDA(c->ops->sweep(1, g.recon, g.solver, a, s));
+  CHL_CUDA(sweep(1, g.recon, g.solver, a, s));
   if (prof) {
     CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 2], s));
     c->ev_steps++;

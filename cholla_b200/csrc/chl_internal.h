@@ -9,10 +9,12 @@ namespace chl
 struct SweepArgs {  // everything in double; each mode TU narrows to its Real
   const void *in;
   void *out;
+  void *acc;  // direction-split sweeps: running sum of the flux differences, 5 * n_cells reals
   int nx, ny, nz;
   int lo[3], hi[3];
   int has_y, has_z;
   int zchunk;
+  int dir_chunk;  // direction-split sweeps: cells per thread along the marching direction (0 = choose)
   double dtodx, dtody, dtodz, gamma, density_floor;
   int apply_tfloor;
   double U_floor;
@@ -23,7 +25,8 @@ struct SweepArgs {  // everything in double; each mode TU narrows to its Real
 
 struct ModeOps {
   // stage 0 = predictor (U -> W half), stage 1 = corrector (W half, U -> U)
-  cudaError_t (*sweep)(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s);
+  cudaError_t (*sweep)(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s);        // fused
+  cudaError_t (*sweep_split)(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s);  // per direction
   cudaError_t (*calc_dti)(const void *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz,
                           double gamma, unsigned long long *key, cudaStream_t s);
   cudaError_t (*tfloor)(void *U, int nx, int ny, int nz, int n_ghost, double U_floor, cudaStream_t s);

@@ -7,7 +7,7 @@
 #include <string.h>
 
 #include "chl_internal.h"
-#include "vl_sweep.cuh"
+#include "vl_dirsweep.cuh"
 
 #ifndef CHL_MODE
 #error "CHL_MODE must be defined (f64_strict | f64_fast | f32_fast)"
@@ -63,6 +63,81 @@ cudaError_t sweep(int stage, int recon, int solver, SweepArgs const &a, cudaStre
     case kPLMC * 2 + 1: return launch<kPLMC, kROE, 1>(p, s);
     case kPPMC * 2 + 0: return launch<kPPMC, kHLLC, 1>(p, s);
     case kPPMC * 2 + 1: return launch<kPPMC, kROE, 1>(p, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ---- direction-split sweeps (vl_dirsweep.cuh) ----
+template <int RECON, int SOLVER, int STAGE, int DIR, bool FIRST, bool LAST>
+cudaError_t launch_dir(DirParams const &p, cudaStream_t s)
+{
+  int const ox = p.hi[0] - p.lo[0], oy = p.hi[1] - p.lo[1], oz = p.hi[2] - p.lo[2];
+  if (ox <= 0 || oy <= 0 || oz <= 0) return cudaSuccess;
+  dim3 grid;
+  if (DIR == 0) grid = dim3((oy + kRowsPerCta - 1) / kRowsPerCta, oz, 1);
+  else {
+    int const om = DIR == 1 ? oy : oz;
+    grid = dim3((ox + kDirThreads - 1) / kDirThreads, DIR == 1 ? oz : oy, (om + p.chunk - 1) / p.chunk);
+  }
+  vl_dir_kernel<RECON, SOLVER, STAGE, DIR, FIRST, LAST><<<grid, kDirThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+template <int RECON, int SOLVER, int STAGE>
+cudaError_t run_dirs(DirParams p, SweepArgs const &a, cudaStream_t s)
+{
+  Real const dto[3] = {(Real)a.dtodx, (Real)a.dtody, (Real)a.dtodz};
+  auto chunk_for = [&](int d) {
+    int const o = p.hi[d] - p.lo[d];
+    if (a.dir_chunk > 0) return a.dir_chunk < o ? a.dir_chunk : o;  // caller override (tests, tuning)
+    if (o >= 128) return 64;
+    int const c = (o + 1) / 2;
+    return c < 8 ? (o < 8 ? o : 8) : c;
+  };
+  cudaError_t e;
+  if (p.ndim == 1) {
+    p.dto = dto[0];
+    return launch_dir<RECON, SOLVER, STAGE, 0, true, true>(p, s);
+  }
+  p.dto = dto[0];
+  if ((e = launch_dir<RECON, SOLVER, STAGE, 0, true, false>(p, s)) != cudaSuccess) return e;
+  p.dto   = dto[1];
+  p.chunk = chunk_for(1);
+  if (p.ndim == 2) return launch_dir<RECON, SOLVER, STAGE, 1, false, true>(p, s);
+  if ((e = launch_dir<RECON, SOLVER, STAGE, 1, false, false>(p, s)) != cudaSuccess) return e;
+  p.dto   = dto[2];
+  p.chunk = chunk_for(2);
+  return launch_dir<RECON, SOLVER, STAGE, 2, false, true>(p, s);
+}
+
+cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s)
+{
+  DirParams p;
+  p.in  = (const Real *)a.in;
+  p.U   = (const Real *)a.in;
+  p.acc = (Real *)a.acc;
+  p.out = (Real *)a.out;
+  p.nx = a.nx; p.ny = a.ny; p.nz = a.nz;
+  for (int d = 0; d < 3; d++) { p.lo[d] = a.lo[d]; p.hi[d] = a.hi[d]; }
+  p.chunk = 1;
+  p.ndim  = 1 + (a.has_y ? 1 : 0) + (a.has_z ? 1 : 0);
+  p.dto   = 0;
+  p.gamma = (Real)a.gamma; p.density_floor = (Real)a.density_floor;
+  p.apply_tfloor = a.apply_tfloor; p.U_floor = (Real)a.U_floor; p.do_dti = a.do_dti;
+  p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
+  p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
+  p.dti_key = a.dti_key;
+  if (stage == 0) {
+    if (solver == kROE) return run_dirs<kPCM, kROE, 0>(p, a, s);
+    return run_dirs<kPCM, kHLLC, 0>(p, a, s);
+  }
+  switch (recon * 2 + (solver == kROE ? 1 : 0)) {
+    case kPCM * 2 + 0: return run_dirs<kPCM, kHLLC, 1>(p, a, s);
+    case kPCM * 2 + 1: return run_dirs<kPCM, kROE, 1>(p, a, s);
+    case kPLMC * 2 + 0: return run_dirs<kPLMC, kHLLC, 1>(p, a, s);
+    case kPLMC * 2 + 1: return run_dirs<kPLMC, kROE, 1>(p, a, s);
+    case kPPMC * 2 + 0: return run_dirs<kPPMC, kHLLC, 1>(p, a, s);
+    case kPPMC * 2 + 1: return run_dirs<kPPMC, kROE, 1>(p, a, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -146,7 +221,7 @@ cudaError_t tfloor(void *U, int nx, int ny, int nz, int g, double U_floor, cudaS
   return cudaGetLastError();
 }
 
-ModeOps const ops = {sweep, calc_dti, tfloor, sizeof(Real), kHalfFields, TY};
+ModeOps const ops = {sweep, sweep_split, calc_dti, tfloor, sizeof(Real), kHalfFields, TY};
 }  // namespace
 ModeOps const *get_ops() { return &ops; }
 }  // namespace CHL_NS
