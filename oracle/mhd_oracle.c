@@ -836,3 +836,38 @@ double morc_max_divergence(const double *U, int nx, int ny, int nz, int g, doubl
       }
   return m;
 }
+
+/* ---- entry points for the reference's small-unit fiducials (reconstruction_tests.cu:51-175) ---- */
+static mprim_t prim_from8(const double p[8])
+{
+  mprim_t w;
+  w.d = p[0]; w.vx = p[1]; w.vy = p[2]; w.vz = p[3]; w.p = p[4]; w.bx = p[5]; w.by = p[6]; w.bz = p[7];
+  return w;
+}
+void morc_eigenvectors(const double prim[8], double gamma, double out[18])
+{
+  mprim_t const w = prim_from8(prim);
+  double const a = sqrt(gamma * w.p / w.d);
+  eigen_t const e = eigenvectors(w, a, a * a, gamma);
+  memcpy(out, &e, 18 * sizeof(double));
+}
+void morc_prim_to_char(const double prim[8], const double slope[8], const double eig[18], double gamma, double out[7])
+{
+  mprim_t const w = prim_from8(prim);
+  double const a = sqrt(gamma * w.p / w.d);
+  eigen_t e;
+  memcpy(&e, eig, 18 * sizeof(double));
+  mchar_t const c = to_char(w, prim_from8(slope), e, a * a);
+  memcpy(out, c.a, 7 * sizeof(double));
+}
+void morc_char_to_prim(const double prim[8], const double chr[7], const double eig[18], double gamma, double out[8])
+{
+  mprim_t const w = prim_from8(prim);
+  double const a = sqrt(gamma * w.p / w.d);
+  eigen_t e;
+  memcpy(&e, eig, 18 * sizeof(double));
+  mchar_t c;
+  memcpy(c.a, chr, 7 * sizeof(double));
+  mprim_t const o = from_char(w, c, e, a * a);
+  out[0] = o.d; out[1] = o.vx; out[2] = o.vy; out[3] = o.vz; out[4] = o.p; out[5] = 0.0; out[6] = o.by; out[7] = o.bz;
+}

@@ -652,7 +652,11 @@ void orc_boundary_extents(int dir, int nx, int ny, int nz, int g, int *imin, int
   for (int d = 0; d < 3; d++) { imin[d] = lo[d]; imax[d] = hi[d]; }
 }
 
-/* one call of Grid3D::Set_Boundaries(dir, flags) -> SetGhostCells (hydro build: diode on) */
+/* the transmissive "diode" is compiled out of MHD builds (cuda_boundaries.cu:121-147, #ifndef MHD) */
+static int g_diode = 1;
+void orc_set_mhd_build(int mhd) { g_diode = !mhd; }
+
+/* one call of Grid3D::Set_Boundaries(dir, flags) -> SetGhostCells */
 void orc_set_ghost_cells(double *U, int nx, int ny, int nz, int n_fields, int g, const int *flags, int dir)
 {
   if (flags[dir] == 4 || flags[dir] == 5) return;
@@ -670,7 +674,7 @@ void orc_set_ghost_cells(double *U, int nx, int ny, int nz, int n_fields, int g,
         if (flags[0] == 2 || flags[1] == 2) U[gidx + N] *= a[0];
         if (flags[2] == 2 || flags[3] == 2) U[gidx + 2 * N] *= a[1];
         if (flags[4] == 2 || flags[5] == 2) U[gidx + 3 * N] *= a[2];
-        if (flags[dir] == 3) {
+        if (flags[dir] == 3 && g_diode) {
           size_t m = gidx + (dir / 2 + 1) * N;
           if ((dir % 2 == 0) ? (U[m] > 0.0) : (U[m] < 0.0)) {
             U[gidx + 4 * N] -= 0.5 * (U[m] * U[m]) / U[gidx];

@@ -1,0 +1,166 @@
+"""Pin the MHD CPU oracle (oracle/mhd_oracle.c) to the reference's own MHD unit-test fiducials
+(tests/golden/mhd_*.json, extracted by tests/golden/extract_mhd_fiducials.py).
+
+Tolerances are the reference's: testing_utilities::nearlyEqualDbl = 4 ULP or 1e-14 absolute by default
+(src/utils/testing_utilities.cpp:63-75); the HLLD fixture uses 7 ULP or 2.7e-15 (hlld_cuda_tests.cu:196-197)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mhd
+from stdrandom import MT19937_64, UniformReal
+from test_oracle_golden import nearly_equal
+
+
+def load(golden_dir, name):
+    with open(os.path.join(golden_dir, name)) as fh:
+        return json.load(fh)
+
+
+def prim_to_cons(p, gamma):
+    """tMHDCalculateHLLDFluxesCUDA::Primitive_2_Conserved (hlld_cuda_tests.cu:232-262)."""
+    d, vx, vy, vz, P, bx, by, bz = p
+    E = (max(P, 1e-20) / (gamma - 1.0)) + 0.5 * d * (vx * vx + ((vy * vy) + (vz * vz)))
+    E += 0.5 * (bx * bx + ((by * by) + (bz * bz)))
+    return [d, vx * d, vy * d, vz * d, E, bx, by, bz]
+
+
+def test_hlld_all_shock_tube_fiducials(golden_dir):
+    gd = load(golden_dir, "mhd_hlld.json")
+    assert len(gd["cases"]) >= 60
+    branches = set()
+    for c in gd["cases"]:
+        l, r = prim_to_cons(c["prim_left"], c["gamma"]), prim_to_cons(c["prim_right"], c["gamma"])
+        assert l[5] == r[5]
+        f = mhd.hlld_single(l[:5] + l[6:], r[:5] + r[6:], l[5], c["gamma"])
+        assert f is not None, c
+        got = list(f[:5]) + [0.0] + list(f[5:])
+        for i, (a, b) in enumerate(zip(got, c["flux"])):
+            assert nearly_equal(a, b, ulps=7, abs_tol=2.7e-15), (c["test"], c["left"], c["right"], i, a, b)
+        branches.add(c["test"])
+    assert len(branches) >= 5  # Brio-Wu, Dai-Woodward, Ryu-Jones, Einfeldt, constant, degenerate
+
+
+def _check_sparse(arr, table, what):
+    table = {int(k): v for k, v in table.items()}
+    for i, v in enumerate(arr):
+        want = table.get(i, 0.0)
+        assert nearly_equal(float(v), want), (what, i, float(v), want)
+
+
+def test_plmc_mhd_fiducials(golden_dir):
+    gd = load(golden_dir, "mhd_plmc.json")
+    g, dist = MT19937_64(42), UniformReal(0.1, 5)
+    _dx, _dt = dist(g), dist(g)
+    n, nf = gd["nx"], gd["n_fields"]
+    U = np.array([dist(g) for _ in range(n ** 3 * nf)])
+    for d in range(3):
+        QL, QR = mhd.reconstruct(mhd.PLMC, U, n, n, n, gd["gamma"], d)
+        _check_sparse(QL, gd["left"][d], "plmc mhd L dir %d" % d)
+        _check_sparse(QR, gd["right"][d], "plmc mhd R dir %d" % d)
+
+
+def test_ppmc_vl_mhd_fiducials(golden_dir):
+    gd = load(golden_dir, "mhd_ppmc_vl.json")
+    g, dist = MT19937_64(42), UniformReal(0.1, 5)
+    n, nf = gd["nx"], gd["n_fields"]
+    U = np.array([dist(g) for _ in range(n ** 3 * nf)])
+    for d in range(3):
+        QL, QR = mhd.reconstruct(mhd.PPMC, U, n, n, n, gd["gamma"], d)
+        _check_sparse(QL, gd["left"][d], "ppmc mhd L dir %d" % d)
+        _check_sparse(QR, gd["right"][d], "ppmc mhd R dir %d" % d)
+
+
+def test_eigenvectors_and_projections(golden_dir):
+    gd = load(golden_dir, "mhd_scalars.json")
+    e = gd["eigenvectors"]
+    got = mhd.eigenvectors(e["primitive"], e["gamma"])
+    for i, (a, b) in enumerate(zip(got, e["fiducial"])):
+        assert nearly_equal(float(a), b), ("eigen", i, a, b)
+    p = gd["prim_to_char"]
+    got = mhd.prim_to_char(p["primitive"], p["slope"], p["eigen"], p["gamma"])
+    for i, (a, b) in enumerate(zip(got, p["fiducial"])):
+        assert nearly_equal(float(a), b), ("p2c", i, a, b)
+    c = gd["char_to_prim"]
+    got = mhd.char_to_prim(c["primitive"], c["characteristic"], c["eigen"], c["gamma"])
+    tol = {2: 1.34e-14, 3: 1.6e-14}  # reconstruction_tests.cu:105-106
+    for i, (a, b) in enumerate(zip(got, c["fiducial"])):
+        if i == 5:
+            continue  # magnetic_x is not produced by Characteristic_To_Primitive
+        assert nearly_equal(float(a), b, abs_tol=max(1e-14, tol.get(i, 0) * abs(b))), ("c2p", i, a, b)
+
+
+def test_ct_electric_fields_iota(golden_dir):
+    gd = load(golden_dir, "mhd_scalars.json")["ct_electric_fields"]
+    n = gd["n"]
+    N = n ** 3
+    base = np.arange(0, 7 * N * 3 + 8 * N, dtype=np.float64)
+    for name, table in gd["cases"].items():
+        Fx, Fy, Fz = base[:7 * N].copy(), base[7 * N:14 * N].copy(), base[14 * N:21 * N].copy()
+        U = base[21 * N:].copy()
+        if name == "NegativeVelocity":
+            for F in (Fx, Fy, Fz):
+                F[:N] = -F[:N]
+        elif name == "ZeroVelocity":
+            for F in (Fx, Fy, Fz):
+                F[:N] = 0.0
+        E = mhd.ct_electric_fields(Fx, Fy, Fz, U, n, n, n, fill=-999.0)
+        want = {int(k): v for k, v in table.items()}
+        for i, v in enumerate(E):
+            assert nearly_equal(float(v), want.get(i, -999.0)), (name, i, v)
+
+
+def test_magnetic_update_iota(golden_dir):
+    gd = load(golden_dir, "mhd_scalars.json")["magnetic_update"]
+    n = gd["n"]
+    N = n ** 3
+    src = np.arange(0, 8 * N, dtype=np.float64)
+    E = np.arange(8 * N, 11 * N, dtype=np.float64)
+    dst = np.full(8 * N, -999.0)
+    mhd.update_magnetic(src, dst, E, n, n, n, gd["dt"], gd["dx"], gd["dx"], gd["dx"])
+    want = {int(k): v for k, v in gd["fiducial"].items()}
+    for i, v in enumerate(dst):
+        assert nearly_equal(float(v), want.get(i, -999.0)), (i, v)
+
+
+def test_mhd_inverse_crossing_time_and_speeds(golden_dir):
+    gd = load(golden_dir, "mhd_scalars.json")
+    t = gd["mhd_inverse_crossing_time"]
+    v = mhd.mhd_inverse_crossing_time(t["energy"], t["density"], 1.0 / t["density"], t["velocityX"], t["velocityY"],
+                                      t["velocityZ"], t["magneticX"], t["magneticY"], t["magneticZ"], t["cellSizeX"],
+                                      t["cellSizeY"], t["cellSizeZ"], t["gamma"])
+    assert nearly_equal(v, t["fiducialInverseCrossingTime"])
+    u = gd["mhd_utilities"]
+    P, gamma = u["params"], u["gamma"]
+    for key, sign in (("fast_speed", 1.0), ("fast_speed_negative_density", -1.0)):
+        for i in range(3):
+            c = u[key]["coef"][i]
+            got = mhd.fast_speed(sign * c * P["density"][i], c * P["pressureGas"][i], c * P["magneticX"][i],
+                                 c * P["magneticY"][i], c * P["magneticZ"][i], gamma)
+            assert nearly_equal(got, u[key]["fiducial"][i]), (key, i, got)
+    for key, sign in (("slow_speed", 1.0), ("slow_speed_negative_density", -1.0)):
+        c = u[key]["coef"]
+        for i in range(u[key]["first_index"], 3):
+            got = mhd.slow_speed(sign * P["density"][i] * c, P["pressureGas"][i] * c, P["magneticX"][i] * c,
+                                 P["magneticY"][i] * c, P["magneticZ"][i] * c, gamma)
+            assert nearly_equal(got, u[key]["fiducial"][i]), (key, i, got)
+    for key, sign in (("alfven_speed", 1.0), ("alfven_speed_negative_density", -1.0)):
+        for i in range(3):
+            got = mhd.alfven_speed(P["magneticX"][i], sign * P["density"][i])
+            assert nearly_equal(got, u[key]["fiducial"][i]), (key, i, got)
+    cc = u["cell_centred"]
+    grid = np.arange(0, 8 * cc["n_cells"], dtype=np.float64)
+    # the reference test indexes a 125-cell field with nx = ny = 3: reproduce through a (3, 3, 125/9) view is not
+    # possible, so evaluate the three averages directly with the same index arithmetic
+    N, nx, ny = cc["n_cells"], cc["nx"], cc["ny"]
+    idc = cc["xid"] + cc["yid"] * nx + cc["zid"] * nx * ny
+    got = [0.5 * (grid[5 * N + idc] + grid[5 * N + idc - 1]), 0.5 * (grid[6 * N + idc] + grid[6 * N + idc - nx]),
+           0.5 * (grid[7 * N + idc] + grid[7 * N + idc - nx * ny])]
+    assert got == cc["fiducial"]
+    # and the oracle's routine on a consistent 5^3 grid agrees with the same formula
+    b = mhd.cell_centred_b(grid, 5, 5, 5, 2, 2, 2)
+    i5 = 2 + 5 * (2 + 5 * 2)
+    assert b[0] == 0.5 * (grid[5 * 125 + i5] + grid[5 * 125 + i5 - 1])
+    assert b[2] == 0.5 * (grid[7 * 125 + i5] + grid[7 * 125 + i5 - 25])
