@@ -11,7 +11,7 @@ HEADER_PATH = os.path.join(_ROOT, "include", "cholla_b200.h")
 
 CHL_OK = 0
 PCM, PLMC, PPMC = 0, 1, 2
-HLLC, ROE = 0, 1
+HLLC, ROE, HLLD = 0, 1, 2
 BC_PERIODIC, BC_REFLECTIVE, BC_TRANSMISSIVE, BC_CUSTOM, BC_MPI = 1, 2, 3, 4, 5
 
 
@@ -22,7 +22,7 @@ class ChollaB200Error(RuntimeError):
 class Config(C.Structure):
     """struct chl_config (include/cholla_b200.h)."""
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("n_ghost", C.c_int), ("n_fields", C.c_int),
-                ("recon", C.c_int), ("solver", C.c_int), ("precision", C.c_int), ("strict", C.c_int),
+                ("recon", C.c_int), ("solver", C.c_int), ("precision", C.c_int), ("strict", C.c_int), ("mhd", C.c_int),
                 ("gamma", C.c_double), ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
                 ("density_floor", C.c_double), ("temperature_floor_U", C.c_double)]
 
@@ -69,7 +69,7 @@ def lib():
     L.chl_apply_temperature_floor.argtypes = [p, p, d, p]
     L.chl_set_ghost_cells.argtypes = [p, p, ip, i, p]
     L.chl_set_boundaries.argtypes = [p, p, ip, p]
-    L.chl_set_ghost_cells_ext.argtypes = [p, i, i, i, i, i, i, ip, i, i, i, i, i, i, i, i, p]
+    L.chl_set_ghost_cells_ext.argtypes = [p, i, i, i, i, i, i, ip, i, i, i, i, i, i, i, i, i, p]
     L.chl_pack_buffer.argtypes = [p, p, i, i, i, l, l, i, i, i, i, p]
     L.chl_unpack_buffer.argtypes = [p, p, i, i, i, l, l, i, i, i, i, p]
     L.chl_boundary_extents.argtypes = [i, i, i, i, i, ip, ip]

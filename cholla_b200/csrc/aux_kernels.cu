@@ -12,6 +12,7 @@ struct GhostArgs {
   long n_cells;
   int flags[6];
   int isize, jsize, ksize, imin, jmin, kmin, dir;
+  int diode;  // hydro builds only (cuda_boundaries.cu:121-147 is inside #ifndef MHD)
 };
 
 // index of the source cell along one axis for ghost index `c` (FindIndex); sets refl when mirrored
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) ghost_kernel(T *__restrict__ c, GhostArgs
     if (rx && (a.flags[0] == 2 || a.flags[1] == 2)) m1 = -m1;
     if (ry && (a.flags[2] == 2 || a.flags[3] == 2)) m2 = -m2;
     if (rz && (a.flags[4] == 2 || a.flags[5] == 2)) m3 = -m3;
-    if (a.flags[a.dir] == 3) {  // transmissive "diode": no inflow through this face (hydro builds)
+    if (a.flags[a.dir] == 3 && a.diode) {  // transmissive "diode": no inflow through this face
       int const ax = a.dir / 2;
       T &mn = ax == 0 ? m1 : (ax == 1 ? m2 : m3);
       bool const inflow = (a.dir % 2 == 0) ? (mn > (T)0.0) : (mn < (T)0.0);
@@ -112,9 +113,10 @@ inline int grid_for(long n)
 
 cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields, long n_cells, int n_ghost,
                                    const int flags[6], int isize, int jsize, int ksize, int imin, int jmin, int kmin,
-                                   int dir, size_t real_bytes, cudaStream_t s)
+                                   int dir, int diode, size_t real_bytes, cudaStream_t s)
 {
   GhostArgs a;
+  a.diode = diode;
   a.nx = nx; a.ny = ny; a.nz = nz; a.n_fields = n_fields; a.g = n_ghost; a.n_cells = n_cells;
   for (int i = 0; i < 6; i++) a.flags[i] = flags[i];
   a.isize = isize; a.jsize = jsize; a.ksize = ksize; a.imin = imin; a.jmin = jmin; a.kmin = kmin; a.dir = dir;

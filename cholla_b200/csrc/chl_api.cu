@@ -46,6 +46,10 @@ struct chl_ctx {
   chl::ModeOps const *ops;
   void *d_half;               // W at t + dt/2 (primitives), half_fields * n_cells reals
   void *d_acc;                // direction-split sweeps: running sum of flux differences, 5 * n_cells reals
+  chl::MhdOps const *mhd;     // non-null in an MHD context
+  void *d_prim;               // MHD: half-step primitives + cell-centred fields
+  void *d_ctf;                // MHD: 9 * n_cells flux components kept for constrained transport
+  void *d_E;                  // MHD: 3 * n_cells edge EMFs
   int split;                  // 1 = one launch per direction (default), 0 = single fused launch per stage
   int dir_chunk;              // CHL_DIR_CHUNK override (0 = auto)
   unsigned long long *d_key;  // CFL accumulator (ordered key)
@@ -86,11 +90,19 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   *out = nullptr;
   if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 1) return fail(CHL_ERR_INVALID, "chl_create: bad grid size");
   if (cfg->ny == 1 && cfg->nz > 1) return fail(CHL_ERR_INVALID, "chl_create: nz > 1 requires ny > 1");
-  if (cfg->n_fields != 5) return fail(CHL_ERR_UNSUPPORTED, "chl_create: only n_fields = 5 (hydro) is built");
   if (cfg->recon < CHL_RECON_PCM || cfg->recon > CHL_RECON_PPMC) return fail(CHL_ERR_INVALID, "chl_create: recon");
-  if (cfg->solver < CHL_SOLVER_HLLC || cfg->solver > CHL_SOLVER_ROE)
+  if (cfg->solver < CHL_SOLVER_HLLC || cfg->solver > CHL_SOLVER_HLLD)
     return fail(CHL_ERR_INVALID, "chl_create: solver");
-  int const need_ghost = cfg->recon == CHL_RECON_PPMC ? 4 : (cfg->recon == CHL_RECON_PLMC ? 3 : 2);
+  if (cfg->mhd) {  // the reference's own constraints, src/utils/error_handling.cpp:83-118
+    if (cfg->n_fields != 8) return fail(CHL_ERR_UNSUPPORTED, "chl_create: an MHD grid has n_fields = 8");
+    if (cfg->solver != CHL_SOLVER_HLLD) return fail(CHL_ERR_INVALID, "chl_create: MHD only supports the HLLD solver");
+    if (cfg->ny == 1 || cfg->nz == 1) return fail(CHL_ERR_INVALID, "chl_create: MHD runs must be 3D");
+  } else {
+    if (cfg->n_fields != 5) return fail(CHL_ERR_UNSUPPORTED, "chl_create: a hydro grid has n_fields = 5");
+    if (cfg->solver == CHL_SOLVER_HLLD) return fail(CHL_ERR_INVALID, "chl_create: HLLD needs mhd = 1");
+  }
+  int const need_ghost =
+      (cfg->recon == CHL_RECON_PPMC ? 4 : (cfg->recon == CHL_RECON_PLMC ? 3 : 2)) + (cfg->mhd ? 1 : 0);
   if (cfg->n_ghost < need_ghost)
     return fail(CHL_ERR_INVALID, "chl_create: n_ghost too small for the reconstruction");
   if (cfg->nx <= 2 * cfg->n_ghost || (cfg->ny > 1 && cfg->ny <= 2 * cfg->n_ghost) ||
@@ -106,6 +118,11 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
     ops = chl::mode_ops_f32_fast();
   }
   if (!ops) return fail(CHL_ERR_UNSUPPORTED, "chl_create: precision not built");
+  chl::MhdOps const *mhd = nullptr;
+  if (cfg->mhd) {
+    if (cfg->precision == 1) return fail(CHL_ERR_UNSUPPORTED, "chl_create: the MHD kernels are built in fp64 only");
+    mhd = cfg->strict ? chl::mhd_ops_f64_strict() : chl::mhd_ops_f64_fast();
+  }
   if (chl_device_count() < 1)
     return fail(CHL_ERR_NO_DEVICE, "chl_create: no CUDA device (there is no CPU fallback)");
 
@@ -117,6 +134,8 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->ndim = 1 + (cfg->ny > 1) + (cfg->nz > 1);
   c->d_half = nullptr;
   c->d_acc = nullptr;
+  c->mhd = mhd;
+  c->d_prim = c->d_ctf = c->d_E = nullptr;
   {
     // development knobs: CHL_SWEEP_IMPL=fused|split selects the kernel family, CHL_DIR_CHUNK the marching length
     const char *impl = getenv("CHL_SWEEP_IMPL");
@@ -128,9 +147,18 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->h_key = nullptr;
   c->profiling = 0;
   c->ev_steps = 0;
-  size_t const bytes = c->n_cells * ops->half_fields * ops->real_bytes;
+  size_t const bytes = c->n_cells * (mhd ? 8 : ops->half_fields) * ops->real_bytes;
   cudaError_t e = cudaMalloc(&c->d_half, bytes);
-  if (e == cudaSuccess && c->split) e = cudaMalloc(&c->d_acc, c->n_cells * 5 * ops->real_bytes);
+  if (e == cudaSuccess && (c->split || mhd)) e = cudaMalloc(&c->d_acc, c->n_cells * 5 * ops->real_bytes);
+  if (mhd) {
+    size_t const w = c->n_cells * ops->real_bytes;
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_prim, mhd->prim_fields * w);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_ctf, 9 * w);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_E, 3 * w);
+    if (e == cudaSuccess) e = cudaMemset(c->d_prim, 0, mhd->prim_fields * w);
+    if (e == cudaSuccess) e = cudaMemset(c->d_ctf, 0, 9 * w);
+    if (e == cudaSuccess) e = cudaMemset(c->d_E, 0, 3 * w);
+  }
   if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(c->d_half, 0, bytes);
@@ -148,6 +176,9 @@ int chl_destroy(chl_ctx *c)
   if (!c) return CHL_OK;
   if (c->d_half) cudaFree(c->d_half);
   if (c->d_acc) cudaFree(c->d_acc);
+  if (c->d_prim) cudaFree(c->d_prim);
+  if (c->d_ctf) cudaFree(c->d_ctf);
+  if (c->d_E) cudaFree(c->d_E);
   if (c->d_key) cudaFree(c->d_key);
   if (c->h_key) cudaFreeHost(c->h_key);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -157,13 +188,43 @@ int chl_destroy(chl_ctx *c)
 
 size_t chl_scratch_bytes(const chl_ctx *c)
 {
-  return c ? c->n_cells * (c->ops->half_fields + (c->split ? 5 : 0)) * c->ops->real_bytes + sizeof(unsigned long long) : 0;
+  if (!c) return 0;
+  size_t fields = c->mhd ? 8 + 5 + c->mhd->prim_fields + 9 + 3 : c->ops->half_fields + (c->split ? 5 : 0);
+  return c->n_cells * fields * c->ops->real_bytes + sizeof(unsigned long long);
 }
 
 static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
 {
   if (!c || !U) return fail(CHL_ERR_INVALID, "chl_vl_step: null argument");
   chl_config const &g = c->cfg;
+  if (c->mhd) {
+    chl::MhdArgs m;
+    m.U = U; m.half = c->d_half; m.prim = c->d_prim; m.acc = c->d_acc; m.ctf = c->d_ctf; m.E = c->d_E;
+    m.nx = g.nx; m.ny = g.ny; m.nz = g.nz; m.n_ghost = g.n_ghost; m.recon = g.recon; m.dir_chunk = c->dir_chunk;
+    m.dx = g.dx; m.dy = g.dy; m.dz = g.dz; m.dt = dt; m.gamma = g.gamma; m.density_floor = g.density_floor;
+    bool const prof = c->profiling && c->ev_steps < kMaxProfiledSteps;
+    if (prof) {
+      while ((int)c->ev.size() < 3 * (c->ev_steps + 1)) {
+        cudaEvent_t e;
+        CHL_CUDA(cudaEventCreate(&e));
+        c->ev.push_back(e);
+      }
+      CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps], s));
+      CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 1], s));
+    }
+    CHL_CUDA(c->mhd->step(m, s));
+    if (prof) {
+      CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 2], s));
+      c->ev_steps++;
+    }
+    if (fused) {  // the same epilogue as the hydro path, as separate launches: temperature floor, then the CFL max
+      if (g.temperature_floor_U > 0.0)
+        CHL_CUDA(c->ops->tfloor(U, g.nx, g.ny, g.nz, g.n_ghost, g.temperature_floor_U, s));
+      CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
+      CHL_CUDA(c->mhd->calc_dti(U, g.nx, g.ny, g.nz, g.n_ghost, g.dx, g.dy, g.dz, g.gamma, c->d_key, s));
+    }
+    return CHL_OK;
+  }
   chl::SweepArgs a;
   a.nx = g.nx;
   a.ny = g.ny;
@@ -302,7 +363,8 @@ int chl_calc_dti(chl_ctx *c, const void *U, double *h_dti, void *stream)
   cudaStream_t s = (cudaStream_t)stream;
   chl_config const &g = c->cfg;
   CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
-  CHL_CUDA(c->ops->calc_dti(U, g.nx, g.ny, g.nz, g.n_ghost, g.dx, g.dy, g.dz, g.gamma, c->d_key, s));
+  if (c->mhd) CHL_CUDA(c->mhd->calc_dti(U, g.nx, g.ny, g.nz, g.n_ghost, g.dx, g.dy, g.dz, g.gamma, c->d_key, s));
+  else CHL_CUDA(c->ops->calc_dti(U, g.nx, g.ny, g.nz, g.n_ghost, g.dx, g.dy, g.dz, g.gamma, c->d_key, s));
   return chl_dti_result(c, h_dti, stream);
 }
 
@@ -350,12 +412,13 @@ int chl_boundary_extents(int nx, int ny, int nz, int g, int dir, int imin[3], in
 
 int chl_set_ghost_cells_ext(void *U, int nx, int ny, int nz, int n_fields, int n_cells, int n_ghost,
                             const int flags[6], int isize, int jsize, int ksize, int imin, int jmin, int kmin,
-                            int dir, int precision, void *stream)
+                            int dir, int precision, int mhd, void *stream)
 {
   if (!U || !flags || dir < 0 || dir > 5) return fail(CHL_ERR_INVALID, "chl_set_ghost_cells_ext: bad argument");
   if (n_fields < 5) return fail(CHL_ERR_INVALID, "chl_set_ghost_cells_ext: n_fields < 5");
+  if (mhd && n_fields < 8) return fail(CHL_ERR_INVALID, "chl_set_ghost_cells_ext: an MHD grid has 8 fields");
   CHL_CUDA(chl::launch_set_ghost_cells(U, nx, ny, nz, n_fields, n_cells, n_ghost, flags, isize, jsize, ksize, imin,
-                                       jmin, kmin, dir, precision == 1 ? 4 : 8, (cudaStream_t)stream));
+                                       jmin, kmin, dir, mhd ? 0 : 1, precision == 1 ? 4 : 8, (cudaStream_t)stream));
   return CHL_OK;
 }
 
@@ -368,7 +431,7 @@ int chl_set_ghost_cells(chl_ctx *c, void *U, const int flags[6], int dir, void *
   int lo[3], hi[3];
   chl_boundary_extents(g.nx, g.ny, g.nz, g.n_ghost, dir, lo, hi);
   return chl_set_ghost_cells_ext(U, g.nx, g.ny, g.nz, g.n_fields, (int)c->n_cells, g.n_ghost, flags, hi[0] - lo[0],
-                                 hi[1] - lo[1], hi[2] - lo[2], lo[0], lo[1], lo[2], dir, g.precision, stream);
+                                 hi[1] - lo[1], hi[2] - lo[2], lo[0], lo[1], lo[2], dir, g.precision, g.mhd, stream);
 }
 
 int chl_set_boundaries(chl_ctx *c, void *U, const int flags[6], void *stream)

@@ -35,6 +35,27 @@ struct ModeOps {
   int tile_y;       // rows of cells per CTA column
 };
 
+// ---- MHD (mhd_inst.cu) ----
+struct MhdArgs {
+  void *U;      // [8][N] conserved state, updated in place
+  void *half;   // [8][N] half-step conserved state
+  void *prim;   // [prim_fields][N] half-step primitives + cell-centred fields
+  void *acc;    // [5][N]
+  void *ctf;    // [3 directions][3][N] fluxes kept for constrained transport
+  void *E;      // [3][N] edge EMFs
+  int nx, ny, nz, n_ghost, recon, dir_chunk;
+  double dx, dy, dz, dt, gamma, density_floor;
+};
+struct MhdOps {
+  cudaError_t (*step)(MhdArgs const &a, cudaStream_t s);
+  cudaError_t (*calc_dti)(const void *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz,
+                          double gamma, unsigned long long *key, cudaStream_t s);
+  size_t real_bytes;
+  int prim_fields;
+};
+MhdOps const *mhd_ops_f64_strict();
+MhdOps const *mhd_ops_f64_fast();
+
 ModeOps const *mode_ops_f64_strict();
 ModeOps const *mode_ops_f64_fast();
 ModeOps const *mode_ops_f32_fast();  // nullptr when the fp32 TU is not linked
@@ -42,7 +63,7 @@ ModeOps const *mode_ops_f32_fast();  // nullptr when the fp32 TU is not linked
 // element-type-templated copy kernels (ghost cells, pack/unpack), aux_kernels.cu
 cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields, long n_cells, int n_ghost,
                                    const int flags[6], int isize, int jsize, int ksize, int imin, int jmin, int kmin,
-                                   int dir, size_t real_bytes, cudaStream_t s);
+                                   int dir, int diode, size_t real_bytes, cudaStream_t s);
 cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset,
                         int isize, int jsize, int ksize, int unpack, size_t real_bytes, cudaStream_t s);
 }  // namespace chl

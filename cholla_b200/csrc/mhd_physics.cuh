@@ -1,0 +1,451 @@
+// mhd_physics.cuh -- per-cell / per-face device arithmetic of the Van Leer MHD path (HLLD + constrained transport).
+//
+// Written from scratch for sm_100a; the *algorithms* are the reference's (cholla @ 8478c9e):
+//   mhd_utilities.h:48-236          magnetosonic / Alfven speeds, magnetic energy, total pressure, cell-centred B
+//   reconstruction.h:310-361        Compute_Eigenvectors            -> Eigen::init()
+//   reconstruction.h:378-421        Primitive_To_Characteristic     -> Eigen::project()
+//   reconstruction.h:450-481        Characteristic_To_Primitive     -> Eigen::unproject()
+//   plmc_cuda.cu:60-128,287-300     PLMC (MHD)                      -> mhd_plmc()
+//   ppmc_cuda.cu:576-684            PPMC_VL (MHD)                   -> mhd_ppmc()
+//   hlld_cuda.cu:31-509             HLLD (Miyoshi & Kusano 2005)    -> hlld_flux()
+//   ct_electric_fields.h:66-116     _ctSlope                        -> ct_slope()
+// Expressions keep the reference's association in BOTH arithmetic modes; the strict build (-fmad=false) therefore
+// reproduces the reference's bits (it calls the same CUDA math functions: sqrt, rsqrt, rhypot, copysign, fmin, fmax),
+// the product build differs only by FMA contraction.
+#pragma once
+#include "hydro_physics.cuh"
+
+namespace CHL_NS
+{
+constexpr Real kHlldSmall = RC(1.0e-8);  // hlld_cuda.h:35
+
+__device__ __forceinline__ Real dot3(Real a1, Real a2, Real a3, Real b1, Real b2, Real b3)
+{
+  return a1 * b1 + ((a2 * b2) + (a3 * b3));  // math_utilities.h:78-82
+}
+__device__ __forceinline__ Real mag_energy(Real bx, Real by, Real bz) { return RC(0.5) * dot3(bx, by, bz, bx, by, bz); }
+__device__ __forceinline__ Real total_pressure(Real p, Real bx, Real by, Real bz)
+{
+  return fmax(p + mag_energy(bx, by, bz), kTiny);
+}
+__device__ __forceinline__ Real magnetosonic(Real d, Real p, Real bx, Real by, Real bz, Real gamma, Real wave)
+{
+  Real const bx2 = bx * bx;
+  Real const b2  = bx2 + ((by * by) + (bz * bz));
+  Real const t1  = gamma * p + b2;
+  Real t2        = (t1 * t1) - RC(4.) * gamma * p * bx2;
+  t2             = sqrt(t2);
+  return sqrt((t1 + wave * t2) / (RC(2.0) * fmax(d, kTiny)));
+}
+__device__ __forceinline__ Real alfven_speed(Real bx, Real d) { return fabs(bx) / sqrt(fmax(d, kTiny)); }
+// hydro_utilities.h:34-45 / 106-118 (MHD)
+__device__ __forceinline__ Real mhd_pressure(Real E, Real d, Real vx, Real vy, Real vz, Real gamma, Real bx, Real by,
+                                             Real bz)
+{
+  Real p = E - RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
+  p -= mag_energy(bx, by, bz);
+  return fmax((gamma - RC(1.)) * p, kTiny);
+}
+__device__ __forceinline__ Real mhd_energy(Real P, Real d, Real vx, Real vy, Real vz, Real gamma, Real bx, Real by,
+                                           Real bz)
+{
+  Real e = (fmax(P, kTiny) / (gamma - RC(1.))) + RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
+  e += mag_energy(bx, by, bz);
+  return e;
+}
+
+struct MPrim {  // sweep frame; bx is the cell-centred normal field (eigenvectors only), by/bz the transverse ones
+  Real d, vx, vy, vz, p, bx, by, bz;
+};
+struct M7 {  // what travels between reconstruction and solver: (d, m1, m2, m3, E, By, Bz), sweep frame
+  Real v[7];
+};
+
+// ---- eigen-system of one cell (Stone et al. 2008, appendix A) ---------------------------------------------------
+struct Eigen {
+  Real cf, cs, cf2, cs2, alpha_f, alpha_s, beta_y, beta_z, n_fs, sign, q_f, q_s, a_f, a_s, qp_f, qp_s, ap_f, ap_s;
+  Real d, a2, isd, sqd;
+  __device__ __forceinline__ void init(MPrim const &w, Real gamma)
+  {
+    Real const a = sqrt(gamma * w.p / w.d);  // hydro_utilities::Calc_Sound_Speed
+    a2           = a * a;
+    d            = w.d;
+    cf  = magnetosonic(w.d, w.p, w.bx, w.by, w.bz, gamma, RC(1.0));
+    cs  = magnetosonic(w.d, w.p, w.bx, w.by, w.bz, gamma, RC(-1.0));
+    cf2 = cf * cf;
+    cs2 = cs * cs;
+    Real const denom = cf2 - cs2, num2 = cf2 - a2;
+    if (denom <= RC(0.0) || num2 <= RC(0.0)) {
+      alpha_f = RC(1.0);
+      alpha_s = RC(0.0);
+    } else {
+      Real const num1 = a2 - cs2;
+      if (num1 <= RC(0.0)) {
+        alpha_f = RC(0.0);
+        alpha_s = RC(1.0);
+      } else {
+        alpha_f = sqrt(num1 / denom);
+        alpha_s = sqrt(num2 / denom);
+      }
+    }
+    Real const bd = rhypot(w.by, w.bz);
+    beta_y        = isfinite(bd) ? w.by * bd : RC(1.0);
+    beta_z        = isfinite(bd) ? w.bz * bd : RC(0.0);
+    sign          = copysign(RC(1.0), w.bx);
+    n_fs          = RC(0.5) / a2;
+    qp_f          = sign * n_fs * alpha_f * cf;
+    qp_s          = sign * n_fs * alpha_s * cs;
+    q_f           = sign * alpha_f * cf;
+    q_s           = sign * alpha_s * cs;
+    sqd           = sqrt(w.d);
+    a_f           = alpha_f * a * sqd;
+    a_s           = alpha_s * a * sqd;
+    ap_f          = RC(0.5) * alpha_f / (a * sqd);
+    ap_s          = RC(0.5) * alpha_s / (a * sqd);
+    isd           = rsqrt(w.d);
+  }
+  // s = (d, vx, vy, vz, p, by, bz) of a state or of a difference
+  __device__ __forceinline__ void project(Real sd, Real svx, Real svy, Real svz, Real sp, Real sby, Real sbz,
+                                          Real (&o)[7]) const
+  {
+    o[0] = n_fs * alpha_f * (sp / d - cf * svx) + qp_s * (beta_y * svy + beta_z * svz) +
+           ap_s * (beta_y * sby + beta_z * sbz);
+    o[1] = RC(0.5) * (beta_y * (sbz * sign * isd + svz) - beta_z * (sby * sign * isd + svy));
+    o[2] = n_fs * alpha_s * (sp / d - cs * svx) - qp_f * (beta_y * svy + beta_z * svz) -
+           ap_f * (beta_y * sby + beta_z * sbz);
+    o[3] = sd - sp / a2;
+    o[4] = n_fs * alpha_s * (sp / d + cs * svx) + qp_f * (beta_y * svy + beta_z * svz) -
+           ap_f * (beta_y * sby + beta_z * sbz);
+    o[5] = RC(0.5) * (beta_y * (sbz * sign * isd - svz) - beta_z * (sby * sign * isd - svy));
+    o[6] = n_fs * alpha_f * (sp / d + cf * svx) - qp_s * (beta_y * svy + beta_z * svz) +
+           ap_s * (beta_y * sby + beta_z * sbz);
+  }
+  __device__ __forceinline__ MPrim unproject(Real const (&a)[7]) const
+  {
+    MPrim o;
+    o.d  = d * (alpha_f * (a[0] + a[6]) + alpha_s * (a[2] + a[4])) + a[3];
+    o.vx = cf * alpha_f * (a[6] - a[0]) + cs * alpha_s * (a[4] - a[2]);
+    o.vy = beta_y * (q_s * (a[0] - a[6]) + q_f * (a[4] - a[2])) + beta_z * (a[5] - a[1]);
+    o.vz = beta_z * (q_s * (a[0] - a[6]) + q_f * (a[4] - a[2])) + beta_y * (a[1] - a[5]);
+    o.p  = d * a2 * (alpha_f * (a[0] + a[6]) + alpha_s * (a[2] + a[4]));
+    o.by = beta_y * (a_s * (a[0] + a[6]) - a_f * (a[2] + a[4])) - beta_z * sign * sqd * (a[5] + a[1]);
+    o.bz = beta_z * (a_s * (a[0] + a[6]) - a_f * (a[2] + a[4])) + beta_y * sign * sqd * (a[5] + a[1]);
+    o.bx = RC(0.0);
+    return o;
+  }
+};
+
+// PPM_Single_Variable in the reference's operation order (reconstruction.h:794-901) for both modes
+__device__ __forceinline__ void ppm_single_ref(Real cm2, Real cm1, Real c0, Real cp1, Real cp2, Real &L_iph, Real &R_imh)
+{
+  Real const C2 = RC(1.25);
+  Real const sl = (c0 - cm1), sr = (cp1 - c0);
+  Real const avg_m1 = RC(0.5) * sl + RC(0.5) * (cm1 - cm2);
+  Real const avg_0  = RC(0.5) * sr + RC(0.5) * sl;
+  Real const avg_p1 = RC(0.5) * (cp2 - cp1) + RC(0.5) * sr;
+  Real R = RC(0.5) * (cm1 + c0) + (avg_m1 - avg_0) / RC(6.0);
+  Real L = RC(0.5) * (c0 + cp1) + (avg_0 - avg_p1) / RC(6.0);
+  Real const s2_m1 = cm2 + c0 - RC(2.0) * cm1;
+  Real const s2_0  = cm1 + cp1 - RC(2.0) * c0;
+  Real const s2_p1 = c0 + cp2 - RC(2.0) * cp1;
+  auto limit_face = [&](Real ci, Real cim1, Real face, Real s2_i, Real s2_im1) -> Real {
+    Real const s2_c = RC(3.0) * (cim1 + ci - RC(2.0) * face);
+    Real lim        = RC(0.0);
+    if (neg(s2_c) == neg(s2_im1) && neg(s2_c) == neg(s2_i))
+      lim = sgn1(s2_c) * fmin(C2 * fabs(s2_im1), fmin(C2 * fabs(s2_i), fabs(s2_c)));
+    if ((face - cim1) * (ci - face) < RC(0.0)) return RC(0.5) * (cim1 + ci) - lim / RC(6.0);
+    return face;
+  };
+  R = limit_face(c0, cm1, R, s2_0, s2_m1);
+  L = limit_face(cp1, c0, L, s2_p1, s2_0);
+  Real const s2_f = RC(6.0) * (R + L - RC(2.0) * c0);
+  Real s2_lim     = RC(0.0);
+  if (neg(s2_m1) == neg(s2_0) && neg(s2_m1) == neg(s2_p1) && neg(s2_m1) == neg(s2_f))
+    s2_lim = sgn1(s2_f) * fmin(fmin(C2 * fabs(s2_m1), C2 * fabs(s2_0)), fmin(C2 * fabs(s2_p1), fabs(s2_f)));
+  Real cmax = fmax(fabs(cm2), fabs(cm1));
+  cmax      = fmax(cmax, fabs(c0));
+  cmax      = fmax(cmax, fabs(cp1));
+  cmax      = fmax(cmax, fabs(cp2));
+  Real const fl = c0 - R, fr = L - c0;
+  if ((fl * fr) <= RC(0.0) || ((cp1 - c0) * (c0 - cm1)) <= RC(0.0)) {
+    Real const rho = (fabs(s2_f) > RC(1.0e-12) * cmax) ? s2_lim / s2_f : RC(0.0);
+    if (rho <= (RC(1.0) - RC(1.0e-12))) {
+      R = c0 - rho * fl;
+      L = c0 + rho * fr;
+    }
+  } else {
+    if (fabs(fl) >= RC(2.0) * fabs(fr)) R = c0 - RC(2.0) * fr;
+    if (fabs(fr) >= RC(2.0) * fabs(fl)) L = c0 + RC(2.0) * fl;
+  }
+  L_iph = L;
+  R_imh = R;
+}
+
+// ---- reconstructions on the stencil of half-step primitives -----------------------------------------------------
+// W holds per cell (rho, vx, vy, vz, P, Bcc_x, Bcc_y, Bcc_z [, P_y, P_z in strict mode]); the caller passes the
+// element offsets of the sweep-frame components (normal velocity, two transverse, pressure of this sweep, the three
+// cell-centred field components) and the cell stride along the sweep.
+struct MOff {
+  size_t v1, v2, v3, p, b1, b2, b3;
+  long s;
+};
+__device__ __forceinline__ MPrim load_mprim(const Real *__restrict__ c, MOff const &o, long k)
+{
+  const Real *q = c + k * o.s;
+  MPrim w;
+  w.d  = __ldg(q);
+  w.vx = __ldg(q + o.v1);
+  w.vy = __ldg(q + o.v2);
+  w.vz = __ldg(q + o.v3);
+  w.p  = __ldg(q + o.p);
+  w.bx = __ldg(q + o.b1);
+  w.by = __ldg(q + o.b2);
+  w.bz = __ldg(q + o.b3);
+  return w;
+}
+
+__device__ __forceinline__ void mhd_floor(MPrim &l, MPrim &r)
+{
+  r.d = fmax(r.d, kTiny);
+  l.d = fmax(l.d, kTiny);
+  r.p = fmax(r.p, kTiny);
+  l.p = fmax(l.p, kTiny);
+}
+
+__device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const &o, Real gamma, MPrim &L, MPrim &R)
+{
+  MPrim const wi = load_mprim(c, o, 0);
+  Eigen e;
+  e.init(wi, gamma);
+  Real ch[5][7];
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    MPrim const w = k == 2 ? wi : load_mprim(c, o, k - 2);
+    e.project(w.d, w.vx, w.vy, w.vz, w.p, w.by, w.bz, ch[k]);
+  }
+  Real cl[7], cr[7];
+#pragma unroll
+  for (int f = 0; f < 7; f++) ppm_single_ref(ch[0][f], ch[1][f], ch[2][f], ch[3][f], ch[4][f], cl[f], cr[f]);
+  L = e.unproject(cl);
+  R = e.unproject(cr);
+  mhd_floor(L, R);
+}
+
+__device__ __forceinline__ void mhd_plmc(const Real *__restrict__ c, MOff const &o, Real gamma, MPrim &L, MPrim &R)
+{
+  MPrim const wi = load_mprim(c, o, 0), wm = load_mprim(c, o, -1), wp = load_mprim(c, o, 1);
+  Eigen e;
+  e.init(wi, gamma);
+  Real const im[7] = {wm.d, wm.vx, wm.vy, wm.vz, wm.p, wm.by, wm.bz};
+  Real const ii[7] = {wi.d, wi.vx, wi.vy, wi.vz, wi.p, wi.by, wi.bz};
+  Real const ip[7] = {wp.d, wp.vx, wp.vy, wp.vz, wp.p, wp.by, wp.bz};
+  Real dL[7], dR[7], dC[7], dG[7];
+#pragma unroll
+  for (int f = 0; f < 7; f++) {
+    dL[f] = RC(1.0) * (ii[f] - im[f]);
+    dR[f] = RC(1.0) * (ip[f] - ii[f]);
+    dC[f] = RC(0.5) * (ip[f] - im[f]);
+    dG[f] = vl_slope(dL[f], dR[f]);
+  }
+  Real aL[7], aR[7], aC[7], aG[7], am[7];
+  e.project(dL[0], dL[1], dL[2], dL[3], dL[4], dL[5], dL[6], aL);
+  e.project(dR[0], dR[1], dR[2], dR[3], dR[4], dR[5], dR[6], aR);
+  e.project(dC[0], dC[1], dC[2], dC[3], dC[4], dC[5], dC[6], aC);
+  e.project(dG[0], dG[1], dG[2], dG[3], dG[4], dG[5], dG[6], aG);
+#pragma unroll
+  for (int f = 0; f < 7; f++) am[f] = mono_slope(aL[f], aR[f], aC[f], aG[f]);
+  MPrim const dm = e.unproject(am);
+  Real const dmv[7] = {dm.d, dm.vx, dm.vy, dm.vz, dm.p, dm.by, dm.bz};
+  Real l[7], r[7];
+#pragma unroll
+  for (int f = 0; f < 7; f++) {
+    l[f] = ii[f] + RC(1.0) * RC(0.5) * dmv[f];   // Calc_Interface_Linear: state + sign * 0.5 * slope
+    r[f] = ii[f] + RC(-1.0) * RC(0.5) * dmv[f];
+    clamp_pair(l[f], r[f], im[f], ii[f], ip[f]);
+  }
+  L = MPrim{l[0], l[1], l[2], l[3], l[4], RC(0.0), l[5], l[6]};
+  R = MPrim{r[0], r[1], r[2], r[3], r[4], RC(0.0), r[5], r[6]};
+  mhd_floor(L, R);
+}
+
+// Write_Data (reconstruction.h:918-968): interface primitives -> (d, m1, m2, m3, E, By, Bz); the energy uses the
+// FACE-centred normal field of the face the state sits on
+__device__ __forceinline__ M7 mhd_interface(MPrim const &q, Real bface, Real gamma)
+{
+  M7 s;
+  s.v[0] = q.d;
+  s.v[1] = q.d * q.vx;
+  s.v[2] = q.d * q.vy;
+  s.v[3] = q.d * q.vz;
+  s.v[4] = mhd_energy(q.p, q.d, q.vx, q.vy, q.vz, gamma, bface, q.by, q.bz);
+  s.v[5] = q.by;
+  s.v[6] = q.bz;
+  return s;
+}
+
+// ---- HLLD ----------------------------------------------------------------------------------------------------------
+struct HState {
+  Real d, vx, vy, vz, E, by, bz, pg, pt;
+};
+struct HStar {
+  Real d, vy, vz, E, by, bz;
+};
+__device__ __forceinline__ HState hlld_load(M7 const &q, Real bx, Real gamma)
+{
+  HState s;
+  s.d  = fmax(q.v[0], kTiny);
+  s.vx = q.v[1] / s.d;
+  s.vy = q.v[2] / s.d;
+  s.vz = q.v[3] / s.d;
+  s.E  = fmax(q.v[4], kTiny);
+  s.by = q.v[5];
+  s.bz = q.v[6];
+  s.pg = mhd_pressure(s.E, s.d, s.vx, s.vy, s.vz, gamma, bx, s.by, s.bz);
+  s.pt = total_pressure(s.pg, bx, s.by, s.bz);
+  return s;
+}
+__device__ __forceinline__ M7 hlld_nonstar(HState const &s, Real bx)
+{
+  M7 f;
+  f.v[0] = s.d * s.vx;
+  f.v[1] = f.v[0] * s.vx + s.pt - bx * bx;
+  f.v[2] = f.v[0] * s.vy - bx * s.by;
+  f.v[3] = f.v[0] * s.vz - bx * s.bz;
+  f.v[5] = s.by * s.vx - bx * s.vy;
+  f.v[6] = s.bz * s.vx - bx * s.vz;
+  f.v[4] = s.vx * (s.E + s.pt) - bx * (s.vx * bx + ((s.vy * s.by) + (s.vz * s.bz)));
+  return f;
+}
+__device__ __forceinline__ HStar hlld_star(HState const &s, Real S, Real SM, Real bx, Real pts)
+{
+  HStar o;
+  o.d = s.d * (S - s.vx) / (S - SM);
+  if (fabs(s.d * (S - s.vx) * (S - SM) - (bx * bx)) < pts * kHlldSmall) {
+    o.vy = s.vy;
+    o.vz = s.vz;
+    o.by = s.by;
+    o.bz = s.bz;
+  } else {
+    Real const denom = s.d * (S - s.vx) * (S - SM) - (bx * bx);
+    Real coef        = bx * (SM - s.vx) / denom;
+    o.vy             = s.vy - s.by * coef;
+    o.vz             = s.vz - s.bz * coef;
+    Real t           = (S - s.vx);
+    t                = t * t;
+    coef             = (s.d * t - (bx * bx)) / denom;
+    o.by             = s.by * coef;
+    o.bz             = s.bz * coef;
+  }
+  o.E = (s.E * (S - s.vx) - s.pt * s.vx + pts * SM +
+         bx * (dot3(s.vx, s.vy, s.vz, bx, s.by, s.bz) - dot3(SM, o.vy, o.vz, bx, o.by, o.bz))) /
+        (S - SM);
+  return o;
+}
+__device__ __forceinline__ M7 hlld_star_flux(HStar const &st, HState const &s, M7 const &f, Real SM, Real S)
+{
+  M7 o;
+  o.v[0] = f.v[0] + S * (st.d - s.d);
+  o.v[1] = f.v[1] + S * (st.d * SM - s.d * s.vx);
+  o.v[2] = f.v[2] + S * (st.d * st.vy - s.d * s.vy);
+  o.v[3] = f.v[3] + S * (st.d * st.vz - s.d * s.vz);
+  o.v[4] = f.v[4] + S * (st.E - s.E);
+  o.v[5] = f.v[5] + S * (st.by - s.by);
+  o.v[6] = f.v[6] + S * (st.bz - s.bz);
+  return o;
+}
+__device__ __forceinline__ M7 hlld_dstar_flux(Real vyd, Real vzd, Real byd, Real bzd, Real Ed, HStar const &st,
+                                              HState const &s, M7 const &f, Real SM, Real S, Real Sstar)
+{
+  M7 o;
+  Real const sd = Sstar - S;
+  o.v[0] = f.v[0] - S * s.d - sd * st.d + Sstar * st.d;
+  o.v[1] = f.v[1] - S * (s.d * s.vx) - sd * (st.d * SM) + Sstar * (st.d * SM);
+  o.v[2] = f.v[2] - S * (s.d * s.vy) - sd * (st.d * st.vy) + Sstar * (st.d * vyd);
+  o.v[3] = f.v[3] - S * (s.d * s.vz) - sd * (st.d * st.vz) + Sstar * (st.d * vzd);
+  o.v[4] = f.v[4] - S * s.E - sd * st.E + Sstar * Ed;
+  o.v[5] = f.v[5] - S * s.by - sd * st.by + Sstar * byd;
+  o.v[6] = f.v[6] - S * s.bz - sd * st.bz + Sstar * bzd;
+  return o;
+}
+
+// Calculate_HLLD_Fluxes_CUDA for one interface.  Returns false when no branch of the reference fires (NaN input);
+// the reference kernel then leaves its flux array untouched -- here the flux is zero.
+__device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, Real gamma, M7 &f)
+{
+  HState const l = hlld_load(ql, bx, gamma), r = hlld_load(qr, bx, gamma);
+  Real const cfl  = magnetosonic(l.d, l.pg, bx, l.by, l.bz, gamma, RC(1.0));
+  Real const cfr  = magnetosonic(r.d, r.pg, bx, r.by, r.bz, gamma, RC(1.0));
+  Real const cmax = fmax(cfl, cfr);
+  Real const SL = fmin(l.vx, r.vx) - cmax, SR = fmax(l.vx, r.vx) + cmax;
+  M7 const fl = hlld_nonstar(l, bx);
+  if (SL > RC(0.0)) {
+    f = fl;
+    return true;
+  }
+  M7 const fr = hlld_nonstar(r, bx);
+  if (SR < RC(0.0)) {
+    f = fr;
+    return true;
+  }
+  Real const rdiff = SR - r.vx, ldiff = SL - l.vx;
+  Real const SM  = (rdiff * r.d * r.vx - ldiff * l.d * l.vx - r.pt + l.pt) / (rdiff * r.d - ldiff * l.d);
+  Real const pts = (r.d * l.pt * (SR - r.vx) - l.d * r.pt * (SL - l.vx) +
+                    l.d * r.d * (SR - r.vx) * (SL - l.vx) * (r.vx - l.vx)) /
+                   (r.d * (SR - r.vx) - l.d * (SL - l.vx));
+  HStar const sl = hlld_star(l, SL, SM, bx, pts);
+  Real const SLs = SM + RC(-1.0) * alfven_speed(bx, sl.d);
+  if (SLs > RC(0.0) && SL <= RC(0.0)) {
+    f = hlld_star_flux(sl, l, fl, SM, SL);
+    return true;
+  }
+  HStar const sr = hlld_star(r, SR, SM, bx, pts);
+  Real const SRs = SM + RC(1.0) * alfven_speed(bx, sr.d);
+  if (SRs <= RC(0.0) && SR >= RC(0.0)) {
+    f = hlld_star_flux(sr, r, fr, SM, SR);
+    return true;
+  }
+  Real vyd, vzd, byd, bzd, EdL = RC(0.0), EdR = RC(0.0);
+  if (RC(0.5) * (bx * bx) < kHlldSmall * pts) {
+    if (SM >= RC(0.0)) {
+      vyd = sl.vy; vzd = sl.vz; byd = sl.by; bzd = sl.bz; EdL = sl.E;
+    } else {
+      vyd = sr.vy; vzd = sr.vz; byd = sr.by; bzd = sr.bz; EdR = sr.E;
+    }
+  } else {
+    Real const sdl = sqrt(sl.d), sdr = sqrt(sr.d);
+    Real const inv = RC(1.0) / (sdl + sdr);
+    Real const sg  = copysign(RC(1.0), bx);
+    vyd = inv * (sdl * sl.vy + sdr * sr.vy + sg * (sr.by - sl.by));
+    vzd = inv * (sdl * sl.vz + sdr * sr.vz + sg * (sr.bz - sl.bz));
+    byd = inv * (sdl * sr.by + sdr * sl.by + sg * (sdl * sdr) * (sr.vy - sl.vy));
+    bzd = inv * (sdl * sr.bz + sdr * sl.bz + sg * (sdl * sdr) * (sr.vz - sl.vz));
+    Real const vdb = dot3(SM, vyd, vzd, bx, byd, bzd);
+    EdL = sl.E - sdl * sg * (dot3(SM, sl.vy, sl.vz, bx, sl.by, sl.bz) - vdb);
+    EdR = sr.E + sdr * sg * (dot3(SM, sr.vy, sr.vz, bx, sr.by, sr.bz) - vdb);
+  }
+  if (SM > RC(0.0) && SLs <= RC(0.0)) {
+    f = hlld_dstar_flux(vyd, vzd, byd, bzd, EdL, sl, l, fl, SM, SL, SLs);
+    return true;
+  }
+  if (SRs > RC(0.0) && SM <= RC(0.0)) {
+    f = hlld_dstar_flux(vyd, vzd, byd, bzd, EdR, sr, r, fr, SM, SR, SRs);
+    return true;
+  }
+#pragma unroll
+  for (int k = 0; k < 7; k++) f.v[k] = RC(0.0);
+  return false;
+}
+
+// mhdInverseCrossingTime (hydro_cuda.cu:420-435)
+__device__ __forceinline__ Real mhd_inverse_crossing_time(Real E, Real d, Real vx, Real vy, Real vz, Real bx, Real by,
+                                                          Real bz, Real dx, Real dy, Real dz, Real gamma)
+{
+  Real const p  = mhd_pressure(E, d, vx, vy, vz, gamma, bx, by, bz);
+  Real const cf = magnetosonic(d, p, bx, by, bz, gamma, RC(1.0));
+  Real m        = fmax((fabs(vx) + cf) / dx, (fabs(vy) + cf) / dy);
+  m             = fmax(m, (fabs(vz) + cf) / dz);
+  m             = fmax(m, RC(0.0));
+  return m;
+}
+
+}  // namespace CHL_NS

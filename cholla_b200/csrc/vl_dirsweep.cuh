@@ -31,7 +31,10 @@ namespace CHL_NS
 #ifndef CHL_DIR_MINB
 #define CHL_DIR_MINB 4
 #endif
-constexpr int kDirThreads = 128;
+#ifndef CHL_DIR_THREADS
+#define CHL_DIR_THREADS 128
+#endif
+constexpr int kDirThreads = CHL_DIR_THREADS;
 constexpr int kRowsPerCta = kDirThreads / 32;  // x sweep: one row of cells per warp
 
 struct DirParams {

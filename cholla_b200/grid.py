@@ -28,9 +28,9 @@ N_FIELDS = 5
 C_CFL = 0.3  # grid3D.cpp:157
 
 
-def n_ghost_for(recon):
-    """Grid3D constructor, grid3D.cpp:52-76 (hydro)."""
-    return {_lib.PCM: 2, _lib.PLMC: 3, _lib.PPMC: 4}[recon]
+def n_ghost_for(recon, mhd=False):
+    """Grid3D constructor, grid3D.cpp:52-76: PCM 2, PLMC 3, PPMC 4, one more in an MHD build."""
+    return {_lib.PCM: 2, _lib.PLMC: 3, _lib.PPMC: 4}[recon] + (1 if mhd else 0)
 
 
 @dataclass
@@ -87,43 +87,7 @@ class Decomposition:
         return Decomposition(nproc, rank, np_, coords, n_local, offset, dest, flags, list(global_flags))
 
 
-@dataclass
-class Slab:
-    """Arguments of one PackBuffers3D / UnpackBuffers3D call (cuda_boundaries.cu:11-69)."""
-    idxoffset: int
-    isize: int
-    jsize: int
-    ksize: int
-
-    @property
-    def ncells(self):
-        return self.isize * self.jsize * self.ksize
-
-
-def halo_slab(nx, ny, nz, g, face, recv):
-    """Slab sent from (recv=False) or received into (recv=True) face 0..5.
-
-    Geometry of Load_/Unload_Hydro_DeviceBuffer_{X,Y,Z}{0,1} (src/grid/mpi_boundaries.cpp:113-298): g layers
-    along the face's axis; the full extent (ghosts included) of the axes before it; the real cells of the
-    axes after it -- so edges and corners travel with the later phases.
-    """
-    n = [nx, ny, nz]
-    a, side = face // 2, face % 2
-    lo, size = [0, 0, 0], [1, 1, 1]
-    for d in range(3):
-        if n[d] == 1:
-            continue
-        if d < a:
-            lo[d], size[d] = 0, n[d]
-        elif d > a:
-            lo[d], size[d] = g, n[d] - 2 * g
-        else:
-            size[d] = g
-            if recv:
-                lo[d] = 0 if side == 0 else n[d] - g
-            else:
-                lo[d] = g if side == 0 else n[d] - 2 * g
-    return Slab(lo[0] + nx * (lo[1] + ny * lo[2]), size[0], size[1], size[2])
+from .halo import HaloExchange, Slab, halo_slab  # noqa: E402,F401  (re-exported: tests import them from here)
 
 
 @dataclass
@@ -155,19 +119,23 @@ class Grid3D:
 
     def __init__(self, n_global, domain_len, bounds_min=(0.0, 0.0, 0.0), recon=_lib.PPMC, solver=_lib.HLLC,
                  gamma=5.0 / 3.0, bc=(1, 1, 1, 1, 1, 1), precision=2, strict=True, density_floor=0.0,
-                 temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True):
+                 temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True, mhd=False):
         import torch
         self.torch = torch
         self.recon, self.solver, self.gamma = recon, solver, float(gamma)
         self.precision, self.strict, self.fused = precision, bool(strict), bool(fused)
+        self.mhd = bool(mhd) or solver == _lib.HLLD
+        if self.mhd:
+            self.solver = solver = _lib.HLLD  # error_handling.cpp:93-96: MHD only supports HLLD
         self.dist_group, self.nproc, self.rank = dist_group, nproc, rank
         n_global = [int(v) for v in n_global]
         self.n_global = n_global
         self.ndim = 1 + (n_global[1] > 1) + (n_global[2] > 1)
         self.decomp = Decomposition.build(nproc, rank, n_global, list(bc))
-        g = n_ghost_for(recon)
+        g = n_ghost_for(recon, self.mhd)
         H = Header()
         H.n_ghost = g
+        H.n_fields = 8 if self.mhd else N_FIELDS
         H.nx_real, H.ny_real, H.nz_real = self.decomp.n_local
         H.nx = H.nx_real + 2 * g
         H.ny = H.ny_real + 2 * g if n_global[1] > 1 else 1
@@ -186,13 +154,13 @@ class Grid3D:
             raise _lib.ChollaB200Error("Grid3D needs a CUDA device: there is no CPU path")
         torch.cuda.set_device(self.device)
         self.C_device = torch.zeros(H.n_fields * H.n_cells, dtype=self.dtype, device=self.device)
-        cfg = Config(H.nx, H.ny, H.nz, g, H.n_fields, recon, solver, precision, int(self.strict), self.gamma,
+        cfg = Config(H.nx, H.ny, H.nz, g, H.n_fields, recon, solver, precision, int(self.strict), int(self.mhd), self.gamma,
                      H.dx, H.dy, H.dz, float(density_floor), self.U_floor)
         self._cfg = cfg
         self._ctx = C.c_void_p()
         check(_lib.lib().chl_create(C.byref(cfg), C.byref(self._ctx)), "chl_create")
         self.gpu_launches = 0
-        self._halo_bufs = {}
+        self._halo_x = None
 
     # ---- plumbing ----
     def close(self):
@@ -329,59 +297,29 @@ class Grid3D:
             for d in range(2 * self.ndim):
                 self.Set_Boundaries(d)
             return
-        for axis in range(self.ndim):
-            ops = self._post_halo(axis)
-            self.Set_Boundaries(2 * axis)
-            self.Set_Boundaries(2 * axis + 1)
-            self._finish_halo(axis, ops)
+        self._halo().exchange(self.Set_Boundaries)
 
-    # ---- halo exchange over torch.distributed (NCCL send/recv over NVLink) ----
-    def _buf(self, key, n):
-        b = self._halo_bufs.get(key)
-        if b is None or b.numel() != n:
-            b = self.torch.empty(n, dtype=self.dtype, device=self.device)
-            self._halo_bufs[key] = b
-        return b
+    # ---- halo exchange over torch.distributed (NCCL send/recv over NVLink); schedule in halo.py ----
+    def _halo(self):
+        if self._halo_x is None:
+            H, L, torch = self.H, _lib.lib(), self.torch
 
-    def _post_halo(self, axis):
-        """Load_and_Send_MPI_Comm_Buffers(dir) (mpi_boundaries.cpp:300-777): pack both slabs, post the
-        receives and sends."""
-        H, L, dist = self.H, _lib.lib(), self.torch.distributed
-        lo, hi = 2 * axis, 2 * axis + 1
-        sends, recvs = [], []
-        for face in (lo, hi):
-            if self.flags[face] != BC_MPI:
-                continue
-            s = halo_slab(H.nx, H.ny, H.nz, H.n_ghost, face, recv=False)
-            sb = self._buf(("s", face), s.ncells * H.n_fields)
-            check(L.chl_pack_buffer(self._ptr(sb), self._ptr(), H.nx, H.ny, H.n_fields, H.n_cells, s.idxoffset,
-                                    s.isize, s.jsize, s.ksize, self.precision, self._stream()), "chl_pack_buffer")
-            self.gpu_launches += 1
-            rb = self._buf(("r", face), s.ncells * H.n_fields)
-            # my low slab lands in my low neighbour's HIGH ghosts (tag = receiving face), and vice versa
-            sends.append(dist.P2POp(dist.isend, sb, self.decomp.dest[face], self.dist_group, tag=face ^ 1))
-            recvs.append((face, dist.P2POp(dist.irecv, rb, self.decomp.dest[face], self.dist_group, tag=face)))
-        # a peer that is both neighbours (np = 2, periodic) sends low-then-high; what it sends first fills my
-        # HIGH ghosts, so receives are posted high-then-low to match NCCL's in-order pairing
-        recvs.sort(key=lambda fr: -fr[0])
-        ops = sends + [r for _, r in recvs]
-        works = dist.batch_isend_irecv(ops) if ops else []
-        return works
+            def pack(face, s, buf):
+                check(L.chl_pack_buffer(self._ptr(buf), self._ptr(), H.nx, H.ny, H.n_fields, H.n_cells, s.idxoffset,
+                                        s.isize, s.jsize, s.ksize, self.precision, self._stream()), "chl_pack_buffer")
+                self.gpu_launches += 1
 
-    def _finish_halo(self, axis, works):
-        """Wait_and_Unload_MPI_Comm_Buffers (mpi_boundaries.cpp:779-830)."""
-        H, L = self.H, _lib.lib()
-        for w in works:
-            w.wait()
-        for face in (2 * axis, 2 * axis + 1):
-            if self.flags[face] != BC_MPI:
-                continue
-            r = halo_slab(H.nx, H.ny, H.nz, H.n_ghost, face, recv=True)
-            rb = self._buf(("r", face), r.ncells * H.n_fields)
-            check(L.chl_unpack_buffer(self._ptr(rb), self._ptr(), H.nx, H.ny, H.n_fields, H.n_cells, r.idxoffset,
-                                      r.isize, r.jsize, r.ksize, self.precision, self._stream()),
-                  "chl_unpack_buffer")
-            self.gpu_launches += 1
+            def unpack(face, s, buf):
+                check(L.chl_unpack_buffer(self._ptr(buf), self._ptr(), H.nx, H.ny, H.n_fields, H.n_cells, s.idxoffset,
+                                          s.isize, s.jsize, s.ksize, self.precision, self._stream()),
+                      "chl_unpack_buffer")
+                self.gpu_launches += 1
+
+            self._halo_x = HaloExchange(torch.distributed, self.dist_group, (H.nx, H.ny, H.nz), H.n_ghost, H.n_fields,
+                                        self.flags, self.decomp.dest,
+                                        lambda n: torch.empty(n, dtype=self.dtype, device=self.device), pack, unpack)
+        self._halo_x.flags = list(self.flags)
+        return self._halo_x
 
     # ---- convenience driver: the body of main()'s loop ----
     def advance(self, n_steps):

@@ -122,3 +122,91 @@ def random_smooth(n, seed=0, gamma=5.0 / 3.0):
     P = 0.5 + rng.random(shape)
     E = P / (gamma - 1.0) + 0.5 * d * (vx * vx + vy * vy + vz * vz)
     return _pack(d, d * vx, d * vy, d * vz, E)
+
+
+# ---- MHD (8 fields, face-centred magnetic field) ---------------------------------------------------------------
+# These return the FULL local array, ghost cells included, as (8, nz + 2g, ny + 2g, nx + 2g): the face-centred field is
+# the discrete curl of a vector potential sampled over the ghost zones too, so div B = 0 to round-off everywhere and
+# periodic problems need no initial ghost fill.  magnetic_x[id] sits on the +x face of cell id (grid_enum.h:57-61).
+def _mhd_mesh(n, g, lengths, lo):
+    d = [lengths[i] / n[i] for i in range(3)]
+    c = [lo[i] + (np.arange(n[i] + 2 * g) - g) * d[i] + 0.5 * d[i] for i in range(3)]  # Get_Position, ghosts included
+    Z, Y, X = np.meshgrid(c[2], c[1], c[0], indexing="ij")
+    return X, Y, Z, d
+
+
+def _curl_faces(Ax, Ay, Az, d):
+    """Init_Magnetic_Field_With_Vector_Potential (src/utils/mhd_utilities.cu:22-44): backward differences of a
+    cell-sampled potential; index 0 of every axis is left at zero like the reference."""
+    B = np.zeros((3,) + Ax.shape)
+    s = (slice(1, None),) * 3
+    zm, ym, xm = (slice(0, -1), s[1], s[2]), (s[0], slice(0, -1), s[2]), (s[0], s[1], slice(0, -1))
+    B[0][s] = (Az[s] - Az[ym]) / d[1] - (Ay[s] - Ay[zm]) / d[2]
+    B[1][s] = (Ax[s] - Ax[zm]) / d[2] - (Az[s] - Az[xm]) / d[0]
+    B[2][s] = (Ay[s] - Ay[xm]) / d[0] - (Ax[s] - Ax[ym]) / d[1]
+    return B
+
+
+def _centred(B):
+    """cellCenteredMagneticFields (mhd_utilities.h:205-236)."""
+    c = B.copy()
+    c[0][:, :, 1:] = 0.5 * (B[0][:, :, 1:] + B[0][:, :, :-1])
+    c[1][:, 1:, :] = 0.5 * (B[1][:, 1:, :] + B[1][:, :-1, :])
+    c[2][1:, :, :] = 0.5 * (B[2][1:, :, :] + B[2][:-1, :, :])
+    return c
+
+
+def _mhd_pack(d, vx, vy, vz, P, B, gamma):
+    c = _centred(B)
+    E = P / (gamma - 1.0) + 0.5 * d * (vx * vx + vy * vy + vz * vz) + 0.5 * (c[0] ** 2 + c[1] ** 2 + c[2] ** 2)
+    out = np.empty((8,) + d.shape)
+    for f, a in enumerate((d, d * vx, d * vy, d * vz, E, B[0], B[1], B[2])):
+        out[f] = a
+    return out
+
+
+def orszag_tang(n, g, gamma=1.666666666666667):
+    """Grid3D::Orszag_Tang_Vortex (initial_conditions.cpp:1926-1984, examples/3D/orszag_tang_vortex.txt)."""
+    X, Y, Z, d = _mhd_mesh(n, g, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0))
+    b0, d0, v0, p0 = 1.0 / np.sqrt(4.0 * np.pi), 25.0 / (36.0 * np.pi), 1.0, 5.0 / (12.0 * np.pi)
+    Az = b0 / (4.0 * np.pi) * (np.cos(4.0 * np.pi * X) + 2.0 * np.cos(2.0 * np.pi * Y))
+    B = _curl_faces(np.zeros_like(Az), np.zeros_like(Az), Az, d)
+    rho = np.full_like(Az, d0)
+    return _mhd_pack(rho, v0 * np.sin(2.0 * np.pi * Y), -v0 * np.sin(2.0 * np.pi * X), np.zeros_like(Az),
+                     np.full_like(Az, p0), B, gamma)
+
+
+def mhd_smooth(n, g, seed=0, gamma=5.0 / 3.0, amp=0.3, b_amp=0.5):
+    """Seeded periodic state built from a few low Fourier modes: every wave family is excited in every direction,
+    the solution stays smooth (well conditioned), and the field is the curl of a periodic potential."""
+    rng = np.random.default_rng(seed)
+    X, Y, Z, d = _mhd_mesh(n, g, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0))
+
+    def modes(scale):
+        f = np.zeros_like(X)
+        for _ in range(4):
+            k = rng.integers(-2, 3, size=3)
+            ph = rng.random() * 2.0 * np.pi
+            f = f + scale * (rng.random() - 0.5) * np.sin(2.0 * np.pi * (k[0] * X + k[1] * Y + k[2] * Z) + ph)
+        return f
+    rho = 1.0 + modes(amp)
+    P = 1.0 + modes(amp)
+    vx, vy, vz = modes(amp), modes(amp), modes(amp)
+    A = [modes(b_amp / (2.0 * np.pi)) for _ in range(3)]
+    B = _curl_faces(A[0], A[1], A[2], d)
+    B[0] += 0.3
+    B[1] += 0.2
+    B[2] += 0.1
+    return _mhd_pack(rho, vx, vy, vz, P, B, gamma)
+
+
+def mhd_blast(n, g, gamma=5.0 / 3.0):
+    """MHD_Spherical_Blast-like (initial_conditions.cpp:1865-1924): uniform oblique field, over-pressured sphere."""
+    X, Y, Z, d = _mhd_mesh(n, g, (1.0, 1.0, 1.0), (-0.5, -0.5, -0.5))
+    r = np.sqrt(X * X + Y * Y + Z * Z)
+    P = np.where(r < 0.1, 10.0, 0.1)
+    B = np.zeros((3,) + X.shape)
+    B[0] += 1.0 / np.sqrt(2.0)
+    B[1] += 1.0 / np.sqrt(2.0)
+    z = np.zeros_like(X)
+    return _mhd_pack(np.ones_like(X), z, z, z, P, B, gamma)

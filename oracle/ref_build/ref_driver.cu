@@ -19,6 +19,11 @@
 
 Real gama;
 [[noreturn]] void chexit(int code) { exit(code); }
+#ifdef MHD
+static const int kFields = 8;  // grid_enum::num_fields of an -DMHD build
+#else
+static const int kFields = 5;
+#endif
 
 static void boundary_extents(int dir, int nx, int ny, int nz, int g, int *lo, int *hi)
 {  // Grid3D::Set_Boundary_Extents lives in a host TU (boundary_conditions.cpp:419-) that needs the whole Grid3D;
@@ -84,14 +89,14 @@ double ref_advance(double *d_conserved, int nx, int ny, int nz, int n_ghost, dou
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
   }
-  double dti = Calc_dt_GPU(d_conserved, nx, ny, nz, n_ghost, 5, dx, dy, dz, gama);
+  double dti = Calc_dt_GPU(d_conserved, nx, ny, nz, n_ghost, kFields, dx, dy, dz, gama);
   if (timed_ms) cudaEventRecord(e0, 0);
   for (int s = 0; s < n_steps; s++) {
     double dt = cfl / dti;
-    ref_vl_step(d_conserved, nx, ny, nz, n_ghost, dx, dy, dz, dt, 5, density_floor);
-    Apply_Temperature_Floor(d_conserved, nx, ny, nz, n_ghost, 5, U_floor);
-    dti = Calc_dt_GPU(d_conserved, nx, ny, nz, n_ghost, 5, dx, dy, dz, gama);
-    ref_set_boundaries(d_conserved, nx, ny, nz, 5, n_ghost, flags);
+    ref_vl_step(d_conserved, nx, ny, nz, n_ghost, dx, dy, dz, dt, kFields, density_floor);
+    Apply_Temperature_Floor(d_conserved, nx, ny, nz, n_ghost, kFields, U_floor);
+    dti = Calc_dt_GPU(d_conserved, nx, ny, nz, n_ghost, kFields, dx, dy, dz, gama);
+    ref_set_boundaries(d_conserved, nx, ny, nz, kFields, n_ghost, flags);
     if (dts) dts[s] = dt;
   }
   if (timed_ms) {
@@ -108,4 +113,5 @@ double ref_advance(double *d_conserved, int nx, int ny, int nz, int n_ghost, dou
 // The reference's integrator owns its scratch through file-scope globals and Free_Memory_VL_* also frees the
 // caller's array (VL_3D_cuda.cu:362-377), so this driver never calls it: one process = one grid shape.
 int ref_last_cuda_error(void) { return (int)cudaGetLastError(); }
+int ref_n_fields(void) { return kFields; }
 }

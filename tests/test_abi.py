@@ -24,7 +24,7 @@ def test_no_silent_cpu_fallback():
     L = cb.lib()
     if L.chl_device_count() > 0:
         pytest.skip("a GPU is present; the refusal path is for CPU-only boxes")
-    cfg = cb.Config(40, 40, 40, 4, 5, cb.PPMC, cb.HLLC, 2, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)
+    cfg = cb.Config(40, 40, 40, 4, 5, cb.PPMC, cb.HLLC, 2, 0, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)
     ctx = C.c_void_p()
     rc = L.chl_create(C.byref(cfg), C.byref(ctx))
     assert rc == -3 and not ctx.value
@@ -34,11 +34,18 @@ def test_no_silent_cpu_fallback():
 def test_config_validation():
     L = cb.lib()
     ctx = C.c_void_p()
-    bad = cb.Config(40, 40, 40, 2, 5, cb.PPMC, cb.HLLC, 2, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)  # too few ghosts
+    bad = cb.Config(40, 40, 40, 2, 5, cb.PPMC, cb.HLLC, 2, 0, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)  # too few ghosts
     assert L.chl_create(C.byref(bad), C.byref(ctx)) == -1
-    bad = cb.Config(40, 40, 40, 4, 8, cb.PPMC, cb.HLLC, 2, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)  # MHD not built
+    bad = cb.Config(40, 40, 40, 4, 8, cb.PPMC, cb.HLLC, 2, 0, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)  # 8 fields = MHD
     assert L.chl_create(C.byref(bad), C.byref(ctx)) == -4
-    bad = cb.Config(40, 1, 40, 4, 5, cb.PPMC, cb.HLLC, 2, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)
+    # the reference's own MHD constraints (src/utils/error_handling.cpp:83-118): HLLD only, 3-D only, one more ghost
+    bad = cb.Config(40, 40, 40, 5, 8, cb.PPMC, cb.HLLC, 2, 0, 1, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)
+    assert L.chl_create(C.byref(bad), C.byref(ctx)) == -1
+    bad = cb.Config(40, 40, 1, 5, 8, cb.PPMC, cb.HLLD, 2, 0, 1, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)
+    assert L.chl_create(C.byref(bad), C.byref(ctx)) == -1
+    bad = cb.Config(40, 40, 40, 4, 8, cb.PPMC, cb.HLLD, 2, 0, 1, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)
+    assert L.chl_create(C.byref(bad), C.byref(ctx)) == -1
+    bad = cb.Config(40, 1, 40, 4, 5, cb.PPMC, cb.HLLC, 2, 0, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)
     assert L.chl_create(C.byref(bad), C.byref(ctx)) == -1
 
 

@@ -1,0 +1,119 @@
+"""The N>1 path on CPU: block decomposition + ghost-cell exchange schedule (cholla_b200/halo.py) over the gloo
+backend, world sizes 2, 4 and 8 (the reference's 2x1x1, 2x2x1, 2x2x2 tilings).
+
+Transport and schedule are the product's; pack/unpack and the physical faces are the oracle's CPU routines here
+(the CUDA pack kernels are checked against the same oracle routines in tests/test_gpu_parity.py).  Expected result:
+the single-domain ghost fill of the global grid, cut into each rank's block -- edges and corners included."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from cholla_b200.grid import Decomposition
+from cholla_b200.halo import HaloExchange
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_global, g, nf, flags, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D = Decomposition.build(world, rank, list(n_global), list(flags))
+        rng = np.random.default_rng(7)
+        glob = rng.random((nf, n_global[2], n_global[1], n_global[0])) + 0.5
+        glob[1:4] -= 1.0  # momenta of both signs so the transmissive diode bites on some cells
+        nl, off = D.n_local, D.offset
+        nx, ny, nz = nl[0] + 2 * g, nl[1] + 2 * g, nl[2] + 2 * g
+        N = nx * ny * nz
+        loc = np.full((nf, nz, ny, nx), -777.0)  # ghosts start as junk
+        loc[:, g:-g, g:-g, g:-g] = glob[:, off[2]:off[2] + nl[2], off[1]:off[1] + nl[1], off[0]:off[0] + nl[0]]
+        flat = np.ascontiguousarray(loc.reshape(-1))
+
+        def pack(face, s, buf):
+            buf.numpy()[:] = oracle.pack(flat, nx, ny, nf, N, s.idxoffset, s.isize, s.jsize, s.ksize)
+
+        def unpack(face, s, buf):
+            oracle.unpack(np.ascontiguousarray(buf.numpy()), flat, nx, ny, nf, N, s.idxoffset, s.isize, s.jsize, s.ksize)
+
+        def physical(face):
+            if D.flags[face] not in (4, 5):
+                oracle.set_ghost_cells(flat, nx, ny, nz, nf, g, D.flags, face)
+
+        X = HaloExchange(dist, dist.group.WORLD, (nx, ny, nz), g, nf, D.flags, D.dest,
+                         lambda n: torch.zeros(n, dtype=torch.float64), pack, unpack)
+        X.exchange(physical)
+        # the max-over-ranks reduction of Grid3D::set_dt (grid3D.cpp:394) on the same group
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert t.item() == float(world)
+        np.save(os.path.join(out_dir, "rank%d.npy" % rank), flat)
+        np.save(os.path.join(out_dir, "meta%d.npy" % rank), np.array(list(nl) + list(off) + [X.messages]))
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = [
+    (2, (16, 12, 10), [1, 1, 1, 1, 1, 1]),
+    (2, (16, 12, 10), [3, 3, 2, 2, 1, 1]),
+    (4, (16, 12, 10), [1, 1, 1, 1, 1, 1]),
+    # NB: with the hydro "diode" a transmissive face ahead of a decomposed axis is NOT rank-count invariant in the
+    # reference itself: the single-domain fill maps a corner ghost straight to the real cell (no diode), the slab
+    # exchange copies the neighbour's already-dioded x ghosts.  The schedule here follows the reference's N-rank
+    # behaviour; the single-domain comparison therefore uses reflective / periodic faces on the leading axes.
+    (8, (12, 12, 12), [2, 2, 1, 1, 3, 3]),
+    (2, (24, 10, 1), [1, 1, 1, 1, 0, 0]),
+]
+
+
+@pytest.mark.parametrize("world,n_global,flags", CASES)
+def test_exchange_reproduces_single_domain_ghost_fill(world, n_global, flags, tmp_path):
+    g, nf = 3, 5
+    if n_global[2] == 1:
+        pytest.skip("2-D decomposition keeps nz = 1 without ghosts; covered by the 3-D cases")
+    mp.spawn(_worker, args=(world, _free_port(), n_global, g, nf, flags, str(tmp_path)), nprocs=world, join=True)
+    # expected: single-domain ghost fill of the global grid
+    rng = np.random.default_rng(7)
+    glob = rng.random((nf, n_global[2], n_global[1], n_global[0])) + 0.5
+    glob[1:4] -= 1.0
+    NX, NY, NZ = [v + 2 * g for v in n_global]
+    full = np.zeros((nf, NZ, NY, NX))
+    full[:, g:-g, g:-g, g:-g] = glob
+    fflat = np.ascontiguousarray(full.reshape(-1))
+    oracle.set_boundaries(fflat, NX, NY, NZ, nf, g, flags)
+    full = fflat.reshape(nf, NZ, NY, NX)
+    total_msgs = 0
+    for r in range(world):
+        meta = np.load(os.path.join(str(tmp_path), "meta%d.npy" % r))
+        nl, off = meta[:3], meta[3:6]
+        total_msgs += int(meta[6])
+        got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % r)).reshape(nf, nl[2] + 2 * g, nl[1] + 2 * g, nl[0] + 2 * g)
+        want = full[:, off[2]:off[2] + nl[2] + 2 * g, off[1]:off[1] + nl[1] + 2 * g, off[0]:off[0] + nl[0] + 2 * g]
+        assert np.array_equal(got, want), "rank %d ghost cells differ from the single-domain fill" % r
+    assert total_msgs > 0
+
+
+def test_decomposition_matches_reference_rules():
+    # mpi_routines.cpp:373-415: remainder cells go to the low ranks; x-fastest rank order; periodic wrap of neighbours
+    D = [Decomposition.build(8, r, [13, 12, 11], [1] * 6) for r in range(8)]
+    assert D[0].np == [2, 2, 2]
+    assert [d.n_local[0] for d in D[:2]] == [7, 6] and [d.offset[0] for d in D[:2]] == [0, 7]
+    assert D[3].coords == [1, 1, 0] and D[5].coords == [1, 0, 1]
+    assert D[0].dest == [1, 1, 2, 2, 4, 4]          # two ranks per axis: both neighbours are the same peer
+    assert all(f == 5 for f in D[0].flags)          # every face of every rank exchanges
+    T = Decomposition.build(2, 0, [16, 8, 8], [3, 3, 1, 1, 1, 1])
+    assert T.flags == [3, 5, 1, 1, 1, 1]            # the outer transmissive face stays physical
+    T = Decomposition.build(2, 1, [16, 8, 8], [3, 3, 1, 1, 1, 1])
+    assert T.flags == [5, 3, 1, 1, 1, 1]
