@@ -533,4 +533,13 @@ int chl_local_extent(int n_global, int np, int coord, int *n_local, int *offset)
   return CHL_OK;
 }
 
+int chl_debug_exact_div(const double *d_a, const double *d_b, double *d_q_shared, double *d_q_plain, long n,
+                        void *stream)
+{
+  if (!d_a || !d_b || !d_q_shared || !d_q_plain || n < 0) return fail(CHL_ERR_INVALID, "chl_debug_exact_div: bad argument");
+  cudaError_t const e = chl::launch_exact_div_test(d_a, d_b, d_q_shared, d_q_plain, n, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(CHL_ERR_CUDA, "chl_debug_exact_div", e);
+  return CHL_OK;
+}
+
 }  // extern "C"

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_DIR_MINB) vl_dir_kernel(DirPa
   size_t const N = (size_t)nx * ny * P.nz;
   int const lane = threadIdx.x & 31;
   Real const gamma = P.gamma;
+  KC const kc      = make_kc(gamma);
   DirMap const m   = dir_map(DIR, N, nx, ny, (STAGE == 1 && CHL_STRICT) ? 4 + DIR : 4);
 
   // the cells this thread visits: c = c_first .. c_last along DIR at fixed `base`; it completes cells
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_DIR_MINB) vl_dir_kernel(DirPa
       size_t const id  = base + (size_t)c * (size_t)m.stride;
       S5 L, R;
       if (valid) {
-        recon_cell<RECON, STAGE>(P.in, id, m, gamma, L, R);
+        recon_cell<RECON, STAGE>(P.in, id, m, kc, L, R);
       } else {
 #pragma unroll
         for (int k = 0; k < 5; k++) L.v[k] = R.v[k] = RC(1.0);
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_DIR_MINB) vl_dir_kernel(DirPa
       bool const face = valid && c > c_first;  // face c-1/2 lies between two reconstructed cells
       Real F[5];
       if (face) {
-        Cons const f = riemann_flux<SOLVER>(to_face(Lp, gamma), to_face(R, gamma), gamma);
+        Cons const f = riemann_flux<SOLVER>(to_face(Lp, kc), to_face(R, kc), gamma);
         F[0] = f.d; F[1] = f.mx; F[2] = f.my; F[3] = f.mz; F[4] = f.E;
       } else {
 #pragma unroll

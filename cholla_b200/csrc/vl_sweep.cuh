@@ -91,21 +91,21 @@ __device__ __forceinline__ unsigned long long dti_encode(double x)
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
-__device__ __forceinline__ Face to_face(S5 const &s, Real gamma)
+__device__ __forceinline__ Face to_face(S5 const &s, KC const &k)
 {
 #if CHL_STRICT
-  return face_from_cons(Cons{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]}, gamma);
+  return face_from_cons(Cons{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]}, k.gamma);
 #else
-  return face_from_prim(Prim{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]}, gamma);
+  return face_from_prim(Prim{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]}, k);
 #endif
 }
-__device__ __forceinline__ S5 iface_state(Prim const &q, Real gamma)
+__device__ __forceinline__ S5 iface_state(Prim const &q, KC const &k)
 {
 #if CHL_STRICT
-  Cons const c = cons_from_prim(q, gamma);  // Write_Data (reconstruction.h:918-968)
+  Cons const c = cons_from_prim(q, k);  // Write_Data (reconstruction.h:918-968)
   return S5{{c.d, c.mx, c.my, c.mz, c.E}};
 #else
-  (void)gamma;
+  (void)k;
   return S5{{q.d, q.vx, q.vy, q.vz, q.p}};
 #endif
 }
@@ -133,9 +133,11 @@ __device__ __forceinline__ DirMap dir_map(int dir, size_t N, int nx, int ny, int
 // Interface states of cell `id` along the direction described by m:
 // L = low side of its upper face, R = high side of its lower face.
 template <int RECON, int STAGE>
-__device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t id, DirMap const &m, Real gamma, S5 &L,
+__device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t id, DirMap const &m, KC const &k, S5 &L,
                                            S5 &R)
 {
+  Real const gamma = k.gamma;
+  (void)gamma;
   const Real *__restrict__ c = in + id;
   if (STAGE == 0) {  // first order: both sides are the cell itself (pcm_cuda.cu); the input is conserved
     Cons const u{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)};
@@ -150,15 +152,15 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
   }
   if (RECON == kPCM) {
     Prim const wi{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)};
-    L = iface_state(wi, gamma);
+    L = iface_state(wi, k);
     R = L;
     return;
   }
   Prim l, r;
-  if (RECON == kPPMC) ppmc_stencil(c, m.o1, m.o2, m.o3, m.op, m.stride, gamma, l, r);
-  else plmc_stencil(c, m.o1, m.o2, m.o3, m.op, m.stride, gamma, l, r);
-  L = iface_state(l, gamma);
-  R = iface_state(r, gamma);
+  if (RECON == kPPMC) ppmc_stencil(c, m.o1, m.o2, m.o3, m.op, m.stride, k, l, r);
+  else plmc_stencil(c, m.o1, m.o2, m.o3, m.op, m.stride, k, l, r);
+  L = iface_state(l, k);
+  R = iface_state(r, k);
 }
 
 // Half-step state of one cell, from its conserved half-step values: what Load_Data (reconstruction.h:139-212)
@@ -175,8 +177,8 @@ __device__ __forceinline__ void store_half(Real *__restrict__ out, size_t N, siz
   // y sweep sums vy^2 + (vz^2 + vx^2), z sweep vz^2 + (vx^2 + vy^2)
   Real const ey = u[4] - RC(0.5) * w.d * sq3(w.vy, w.vz, w.vx);
   Real const ez = u[4] - RC(0.5) * w.d * sq3(w.vz, w.vx, w.vy);
-  out[5 * N + id] = fmax((gamma - RC(1.)) * ey, kTiny);
-  out[6 * N + id] = fmax((gamma - RC(1.)) * ez, kTiny);
+  out[5 * N + id] = max_s((gamma - RC(1.)) * ey, kTiny);
+  out[6 * N + id] = max_s((gamma - RC(1.)) * ez, kTiny);
 #endif
 }
 
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(kThreads, (TY <= 8 ? 2 : 1)) vl_sweep_kernel(S
   size_t const N     = (size_t)nx * ny * P.nz;
   size_t const plane = (size_t)nx * ny;
   Real const gamma   = P.gamma;
+  KC const kc        = make_kc(gamma);
   int const t = threadIdx.x, lane = t & 31, warp = t >> 5;
   int const gx0 = P.lo[0] + blockIdx.x * TX, gy0 = P.lo[1] + blockIdx.y * TY;
   int const ndir = 1 + (P.has_y ? 1 : 0) + (P.has_z ? 1 : 0);
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, (TY <= 8 ? 2 : 1)) vl_sweep_kernel(S
       if (zdir ? !active : !(full && rec[dir])) continue;
       DirMap const m = dir_map(dir, N, nx, ny, (STAGE == 1 && CHL_STRICT) ? 4 + dir : 4);
       S5 L, R;
-      recon_cell<RECON, STAGE>(P.in, id, m, gamma, L, R);
+      recon_cell<RECON, STAGE>(P.in, id, m, kc, L, R);
       if (zdir) {
         Real *const lz = myM + (size_t)(kSlotLz + 5 * (k & 1)) * kMainThreads;
 #pragma unroll
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, (TY <= 8 ? 2 : 1)) vl_sweep_kernel(S
           R.v[c] = pub[c * pub_stride];
         }
       }
-      Cons const f    = riemann_flux<SOLVER>(to_face(L, gamma), to_face(R, gamma), gamma);
+      Cons const f    = riemann_flux<SOLVER>(to_face(L, kc), to_face(R, kc), gamma);
       Real const F[5] = {f.d, f.mx, f.my, f.mz, f.E};
 #pragma unroll
       for (int c = 0; c < 5; c++) {

@@ -1,0 +1,72 @@
+"""Strict mode's shared-reciprocal division (cholla_b200/csrc/exact_div.cuh) must return the bits of the
+compiler's own IEEE division for EVERY operand pair -- it replaces the reference's `a / b` (built -fmad=false,
+Makefile:148) inside the bit-exact kernels.  Random operands over the whole exponent range plus the edge cases the
+fast-path test is about: zero / tiny numerators, denormal and infinite quotients, huge and denormal denominators,
+infinities and NaNs, signed zeros."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(a, b):
+    import torch
+    import cholla_b200 as cb
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    qs, qp = torch.empty_like(ta), torch.empty_like(ta)
+    rc = cb.lib().chl_debug_exact_div(C.c_void_p(ta.data_ptr()), C.c_void_p(tb.data_ptr()), C.c_void_p(qs.data_ptr()),
+                                      C.c_void_p(qp.data_ptr()), a.size, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return qs.cpu().numpy(), qp.cpu().numpy()
+
+
+def _same_bits(x, y):
+    xi, yi = x.view(np.uint64), y.view(np.uint64)
+    both_nan = np.isnan(x) & np.isnan(y)  # NaN payloads are not part of the contract
+    return bool(np.all((xi == yi) | both_nan))
+
+
+def test_random_operands_whole_range():
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    # uniformly random bit patterns: every exponent, both signs, denormals, infinities, NaNs
+    a = rng.integers(0, 1 << 64, n, dtype=np.uint64).view(np.float64).copy()
+    b = rng.integers(0, 1 << 64, n, dtype=np.uint64).view(np.float64).copy()
+    qs, qp = _run(a, b)
+    assert _same_bits(qs, qp)
+    with np.errstate(all="ignore"):
+        assert _same_bits(qp, a / b)  # and both are the IEEE quotient
+
+
+def test_physical_range_and_edge_cases():
+    rng = np.random.default_rng(11)
+    n = 1 << 21
+    a = (rng.standard_normal(n) * 10.0 ** rng.uniform(-12, 12, n))
+    b = (rng.standard_normal(n) * 10.0 ** rng.uniform(-12, 12, n))
+    a[::7] = 0.0
+    a[1::7] = -0.0
+    edge = np.array([0.0, -0.0, 1.0, -1.0, 6.0, 3.0, 1e-300, -1e-300, 5e-324, 2.2250738585072014e-308, 1e300, -1e300,
+                     1.7976931348623157e308, np.inf, -np.inf, np.nan, 2.0 ** -969, 2.0 ** -970, 2.0 ** 1017, 2.0 ** 1016,
+                     1.0 + 2.0 ** -52, 2.0 - 2.0 ** -52, 1.0 / 3.0])
+    A, B = np.meshgrid(edge, edge)
+    a = np.concatenate([a, A.ravel()])
+    b = np.concatenate([b, B.ravel()])
+    qs, qp = _run(a, b)
+    assert _same_bits(qs, qp)
+    with np.errstate(all="ignore"):
+        assert _same_bits(qp, a / b)
+
+
+def test_constant_denominators_of_the_path():
+    """x / 6 (PPM_Single_Variable) and x / (gamma - 1) with zero and round-off-sized numerators."""
+    rng = np.random.default_rng(3)
+    n = 1 << 20
+    a = rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 5, n)
+    a[::5] = 0.0
+    a[1::5] = -0.0
+    for den in (6.0, 1.66666667 - 1.0, 5.0 / 3.0 - 1.0, 1.4 - 1.0):
+        qs, qp = _run(a, np.full(n, den))
+        assert _same_bits(qs, qp)
