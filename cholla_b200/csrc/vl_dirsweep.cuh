@@ -31,6 +31,9 @@ namespace CHL_NS
 #ifndef CHL_DIR_MINB
 #define CHL_DIR_MINB 4
 #endif
+#ifndef CHL_DIR_MINB0  // the predictor passes (PCM + Riemann) may want a different register budget
+#define CHL_DIR_MINB0 CHL_DIR_MINB
+#endif
 #ifndef CHL_DIR_THREADS
 #define CHL_DIR_THREADS 128
 #endif
@@ -55,6 +58,58 @@ struct DirParams {
   unsigned long long *dti_key;
 };
 
+// ---- shared-memory row ring for the y / z sweeps of the corrector ---------------------------------------------
+// A thread marching along y (or z) needs, for cell c, the rows c-r .. c+r of five fields (r = 2 PPMC, 1 PLMC); at the
+// next cell four of those five rows are needed again.  Served from global memory that is 25 L2-latency loads per
+// cell (ncu, profiles/r1_prof_split_*: L1 hit 4-20 %, 38-47 % of the stall samples on the long scoreboard).  Here
+// every thread keeps its own column of a (2r+1)-row ring in shared memory -- [slot][component][thread], so a warp's
+// accesses are conflict-free and no barrier is ever needed -- and the one new row per cell is fetched by cp.async
+// (global -> shared without passing through registers) while the Riemann solve of the current cell runs.
+#ifndef CHL_DIR_RING
+#define CHL_DIR_RING 0
+#endif
+template <int RECON>
+struct RingGeom {
+  static constexpr int radius = RECON == kPPMC ? 2 : 1;
+  static constexpr int rows   = 2 * radius + 1;
+  static constexpr int slot   = 5 * kDirThreads;  // reals per row slot
+};
+template <int RADIUS>
+struct RingStencil {
+  const Real *mine;         // ring + threadIdx.x
+  int off[2 * RADIUS + 1];  // element offset of the slot holding row c + i - RADIUS
+  __device__ __forceinline__ Real operator()(int comp, int i) const { return mine[off[i + RADIUS] + comp * kDirThreads]; }
+};
+__device__ __forceinline__ void cp_async_real(Real *smem_dst, const Real *gsrc)
+{
+  unsigned const sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(Real) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// ---- staging of the update's read-modify-write operands ----------------------------------------------------
+// Completing a cell needs the running sum (and, in the last corrector pass, the old U) of that cell: five or ten
+// values the thread would otherwise load only after the Riemann solve, one exposed L2/HBM latency per cell (ncu at
+// 512^3: half of the long-scoreboard samples of the y/z passes, 90 % in the predictor).  They are fetched with
+// cp.async into a thread-private shared-memory column at the top of the iteration instead, costing no registers.
+#ifndef CHL_DIR_STAGE
+#define CHL_DIR_STAGE 1
+#endif
+// Carried values (low-side interface state, lower-face flux) parked in shared memory between iterations instead of
+// occupying 20 registers through the reconstruction (the kernels spill at 64-72 registers).
+#ifndef CHL_DIR_PARK
+#define CHL_DIR_PARK 1
+#endif
+template <int STAGE, bool FIRST, bool LAST>
+struct StageGeom {
+  static constexpr int n_sum = (STAGE == 1 && FIRST) ? 0 : 5;  // U (predictor, first pass) or the running sum
+  static constexpr int n_out = (STAGE == 1 && LAST) ? 5 : 0;   // old U, last corrector pass
+  static constexpr int n     = n_sum + n_out;
+};
+
 // value held by the cell on the low side: previous lane (x sweep) or previous iteration (y/z sweeps)
 template <int DIR>
 __device__ __forceinline__ Real from_low_side(Real v, Real &carry, int lane)
@@ -70,10 +125,44 @@ __device__ __forceinline__ Real from_low_side(Real v, Real &carry, int lane)
   return t;
 }
 
-template <int STAGE, int DIR, bool FIRST, bool LAST>
-__device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t id, Real const (&Flo)[5],
-                                            Real const (&Fhi)[5], double &dti)
+// five values at once; `park` = this thread's (y/z sweeps) or this warp's (x sweep) shared-memory slots, stride pstride
+template <int DIR>
+__device__ __forceinline__ void from_low_side5(Real const (&v)[5], Real (&carry)[5], Real (&t)[5], Real *park,
+                                               int pstride, int lane)
 {
+#if CHL_DIR_PARK
+  if (DIR == 0) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      t[k] = __shfl_up_sync(0xffffffffu, v[k], 1);
+      if (lane == 0) t[k] = park[k * pstride];
+    }
+    __syncwarp();
+    if (lane == 31) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) park[k * pstride] = v[k];
+    }
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      t[k]              = park[k * pstride];
+      park[k * pstride] = v[k];
+    }
+  }
+#else
+#pragma unroll
+  for (int k = 0; k < 5; k++) t[k] = from_low_side<DIR>(v[k], carry[k], lane);
+#endif
+}
+
+template <int STAGE, int DIR, bool FIRST, bool LAST, bool STAGED>
+__device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t id, Real const (&Flo)[5],
+                                            Real const (&Fhi)[5], double &dti, const Real *staged)
+{
+  // staged (STAGED only): this thread's shared-memory column, component k at staged[k * kDirThreads]: the five
+  // running-sum / U operands in sweep-frame order, then (last corrector pass) the five old-U values in field order
+  typedef StageGeom<STAGE, FIRST, LAST> SG;
   // sweep frame (normal, t1, t2) -> fields: (x,y,z), (y,z,x), (z,x,y)
   constexpr int field_of_comp[5] = {0, 1 + DIR, 1 + (DIR + 1) % 3, 1 + (DIR + 2) % 3, 4};
   Real u[5];
@@ -82,7 +171,8 @@ __device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t
     int const f  = field_of_comp[c];
     Real const t = P.dto * (Flo[c] - Fhi[c]);
     Real v;
-    if (STAGE == 0) v = (FIRST ? __ldg(P.U + f * N + id) : P.acc[f * N + id]) + t;
+    if (STAGED && SG::n_sum) v = staged[c * kDirThreads] + t;
+    else if (STAGE == 0) v = (FIRST ? __ldg(P.U + f * N + id) : P.acc[f * N + id]) + t;
     else v = FIRST ? t : P.acc[f * N + id] + t;
     if (!LAST) P.acc[f * N + id] = v;
     u[f] = v;
@@ -100,7 +190,7 @@ __device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t
     return;
   }
 #pragma unroll
-  for (int f = 0; f < 5; f++) u[f] = P.out[f * N + id] + u[f];
+  for (int f = 0; f < 5; f++) u[f] = (STAGED ? staged[(SG::n_sum + f) * kDirThreads] : P.out[f * N + id]) + u[f];
   if (floors) {
     if (u[0] < P.density_floor && u[0] > RC(0.)) {  // hydro_cuda.cu:279-291
       Real const d0 = u[0];
@@ -130,7 +220,7 @@ __device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t
 }
 
 template <int RECON, int SOLVER, int STAGE, int DIR, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kDirThreads, CHL_DIR_MINB) vl_dir_kernel(DirParams const P)
+__global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_DIR_MINB) vl_dir_kernel(DirParams const P)
 {
   int const nx = P.nx, ny = P.ny;
   size_t const N = (size_t)nx * ny * P.nz;
@@ -161,26 +251,84 @@ __global__ void __launch_bounds__(kDirThreads, CHL_DIR_MINB) vl_dir_kernel(DirPa
   }
   double dti = -1.7976931348623157e308;
 
+  constexpr bool kRing  = CHL_DIR_RING && STAGE == 1 && DIR != 0 && RECON != kPCM;
+  typedef RingGeom<RECON> RG;
+  typedef StageGeom<STAGE, FIRST, LAST> SG;
+  constexpr bool kStage = CHL_DIR_STAGE && SG::n > 0;
+  constexpr int kParkN  = CHL_DIR_PARK ? (DIR == 0 ? 10 * kRowsPerCta : 10 * kDirThreads) : 1;
+  __shared__ Real ring[kRing ? RG::rows * RG::slot : 1];
+  __shared__ Real stage[kStage ? SG::n * kDirThreads : 1];
+  __shared__ Real parked[kParkN];
+
   if (live) {
     Real Lc[5], Fc[5];  // carried: low-side state of the face below / flux through the face below the previous cell
 #pragma unroll
     for (int c = 0; c < 5; c++) Lc[c] = Fc[c] = RC(0.0);
     int const step = DIR == 0 ? 32 : 1;
+    constexpr int field_of_comp[5] = {0, 1 + DIR, 1 + (DIR + 1) % 3, 1 + (DIR + 2) % 3, 4};
+    Real *const park    = parked + (DIR == 0 ? (threadIdx.x >> 5) : threadIdx.x);
+    int const pstride   = DIR == 0 ? kRowsPerCta : kDirThreads;
+    Real *const staged  = stage + threadIdx.x;
+    // ring: rows c_first-r .. c_first+r into slots 0 .. 2r; `head` = slot of the oldest row
+    Real *const mine      = ring + threadIdx.x;
+    size_t const goff[5]  = {0, m.o1, m.o2, m.o3, m.op};
+    const Real *const col = P.in + base;
+    int head              = 0;
+    if (kRing) {
+#pragma unroll
+      for (int j = 0; j < RG::rows; j++) {
+        const Real *g = col + (size_t)(c_first - RG::radius + j) * (size_t)m.stride;
+#pragma unroll
+        for (int k = 0; k < 5; k++) cp_async_real(mine + j * RG::slot + k * kDirThreads, g + goff[k]);
+      }
+      cp_async_commit();
+    }
     for (int cb = c_first; cb <= c_last; cb += step) {
       int const c      = DIR == 0 ? cb + lane : cb;
       bool const valid = c <= c_last;
+      bool const face  = valid && c > c_first;  // face c-1/2 lies between two reconstructed cells
+      bool const fin   = face && c > c_first + 1;  // cell c-1 is completed by this iteration
       size_t const id  = base + (size_t)c * (size_t)m.stride;
+      if (kRing) cp_async_wait_all();  // the rows cell c needs (issued during the previous iteration) have landed
+      if (kStage) {
+        if (fin) {
+          size_t const idp = id - (size_t)m.stride;
+#pragma unroll
+          for (int k = 0; k < SG::n_sum; k++) {
+            const Real *src = (STAGE == 0 && FIRST) ? P.U : P.acc;
+            cp_async_real(staged + k * kDirThreads, src + (size_t)field_of_comp[k] * N + idp);
+          }
+#pragma unroll
+          for (int f = 0; f < SG::n_out; f++) cp_async_real(staged + (SG::n_sum + f) * kDirThreads, P.out + (size_t)f * N + idp);
+        }
+        cp_async_commit();
+      }
       S5 L, R;
-      if (valid) {
+      if (kRing) {
+        RingStencil<RG::radius> st;
+        st.mine = mine;
+#pragma unroll
+        for (int j = 0; j < RG::rows; j++) {
+          int sl = head + j;
+          sl     = sl >= RG::rows ? sl - RG::rows : sl;
+          st.off[j] = sl * RG::slot;
+        }
+        recon_from<RECON>(st, kc, L, R);
+        if (c < c_last) {  // row c-r is dead: its slot receives row c+r+1 while the Riemann solve below runs
+          const Real *g = col + (size_t)(c + RG::radius + 1) * (size_t)m.stride;
+#pragma unroll
+          for (int k = 0; k < 5; k++) cp_async_real(mine + head * RG::slot + k * kDirThreads, g + goff[k]);
+        }
+        cp_async_commit();
+        head = head + 1 == RG::rows ? 0 : head + 1;
+      } else if (valid) {
         recon_cell<RECON, STAGE>(P.in, id, m, kc, L, R);
       } else {
 #pragma unroll
         for (int k = 0; k < 5; k++) L.v[k] = R.v[k] = RC(1.0);
       }
       S5 Lp;
-#pragma unroll
-      for (int k = 0; k < 5; k++) Lp.v[k] = from_low_side<DIR>(L.v[k], Lc[k], lane);
-      bool const face = valid && c > c_first;  // face c-1/2 lies between two reconstructed cells
+      from_low_side5<DIR>(L.v, Lc, Lp.v, park, pstride, lane);
       Real F[5];
       if (face) {
         Cons const f = riemann_flux<SOLVER>(to_face(Lp, kc), to_face(R, kc), gamma);
@@ -190,9 +338,12 @@ __global__ void __launch_bounds__(kDirThreads, CHL_DIR_MINB) vl_dir_kernel(DirPa
         for (int k = 0; k < 5; k++) F[k] = RC(0.0);
       }
       Real Fp[5];
-#pragma unroll
-      for (int k = 0; k < 5; k++) Fp[k] = from_low_side<DIR>(F[k], Fc[k], lane);
-      if (face && c > c_first + 1) finish_cell<STAGE, DIR, FIRST, LAST>(P, N, id - (size_t)m.stride, Fp, F, dti);
+      from_low_side5<DIR>(F, Fc, Fp, park + 5 * pstride, pstride, lane);
+      if (kStage) {
+        if (kRing) cp_async_wait_but_newest();  // the staged operands; the ring row may still be in flight
+        else cp_async_wait_all();
+      }
+      if (fin) finish_cell<STAGE, DIR, FIRST, LAST, kStage>(P, N, id - (size_t)m.stride, Fp, F, dti, staged);
     }
   }
 

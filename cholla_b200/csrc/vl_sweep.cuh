@@ -130,6 +130,18 @@ __device__ __forceinline__ DirMap dir_map(int dir, size_t N, int nx, int ny, int
   return m;
 }
 
+// predictor (PCM on the conserved state): the interface state both faces of the cell see
+__device__ __forceinline__ void pcm_from_cons(Cons const &u, KC const &k, S5 &L)
+{
+#if CHL_STRICT
+  (void)k;
+  L = S5{{u.d, u.mx, u.my, u.mz, u.E}};
+#else
+  Prim const w = prim_from_cons(u, k.gamma);
+  L = S5{{w.d, w.vx, w.vy, w.vz, w.p}};
+#endif
+}
+
 // Interface states of cell `id` along the direction described by m:
 // L = low side of its upper face, R = high side of its lower face.
 template <int RECON, int STAGE>
@@ -140,13 +152,7 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
   (void)gamma;
   const Real *__restrict__ c = in + id;
   if (STAGE == 0) {  // first order: both sides are the cell itself (pcm_cuda.cu); the input is conserved
-    Cons const u{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)};
-#if CHL_STRICT
-    L = S5{{u.d, u.mx, u.my, u.mz, u.E}};
-#else
-    Prim const w = prim_from_cons(u, gamma);
-    L = S5{{w.d, w.vx, w.vy, w.vz, w.p}};
-#endif
+    pcm_from_cons(Cons{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)}, k, L);
     R = L;
     return;
   }
@@ -156,9 +162,21 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
     R = L;
     return;
   }
+  GlobalStencil const ld{c, {0, m.o1, m.o2, m.o3, m.op}, m.stride};
   Prim l, r;
-  if (RECON == kPPMC) ppmc_stencil(c, m.o1, m.o2, m.o3, m.op, m.stride, k, l, r);
-  else plmc_stencil(c, m.o1, m.o2, m.o3, m.op, m.stride, k, l, r);
+  if (RECON == kPPMC) ppmc_stencil(ld, k, l, r);
+  else plmc_stencil(ld, k, l, r);
+  L = iface_state(l, k);
+  R = iface_state(r, k);
+}
+
+// the same for a PLMC / PPMC stencil served by any accessor (vl_dirsweep.cuh: the shared-memory row ring)
+template <int RECON, class A>
+__device__ __forceinline__ void recon_from(A const &ld, KC const &k, S5 &L, S5 &R)
+{
+  Prim l, r;
+  if (RECON == kPPMC) ppmc_stencil(ld, k, l, r);
+  else plmc_stencil(ld, k, l, r);
   L = iface_state(l, k);
   R = iface_state(r, k);
 }

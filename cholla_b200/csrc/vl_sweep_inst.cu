@@ -79,6 +79,17 @@ cudaError_t launch_dir(DirParams const &p, cudaStream_t s)
     int const om = DIR == 1 ? oy : oz;
     grid = dim3((ox + kDirThreads - 1) / kDirThreads, DIR == 1 ? oz : oy, (om + p.chunk - 1) / p.chunk);
   }
+  if (CHL_DIR_RING && STAGE == 1 && DIR != 0 && RECON != kPCM) {
+    // the row ring needs (2r+1) x 5 x 128 reals of shared memory per CTA: ask for the largest carve-out so that the
+    // register-limited number of CTAs stays resident
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(vl_dir_kernel<RECON, SOLVER, STAGE, DIR, FIRST, LAST>,
+                                           cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+  }
   vl_dir_kernel<RECON, SOLVER, STAGE, DIR, FIRST, LAST><<<grid, kDirThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
