@@ -58,13 +58,16 @@ struct DirParams {
   unsigned long long *dti_key;
 };
 
-// ---- shared-memory row ring for the y / z sweeps of the corrector ---------------------------------------------
+// ---- shared-memory row ring for the y / z sweeps of the corrector (option, off by default) ------------------------
 // A thread marching along y (or z) needs, for cell c, the rows c-r .. c+r of five fields (r = 2 PPMC, 1 PLMC); at the
-// next cell four of those five rows are needed again.  Served from global memory that is 25 L2-latency loads per
-// cell (ncu, profiles/r1_prof_split_*: L1 hit 4-20 %, 38-47 % of the stall samples on the long scoreboard).  Here
-// every thread keeps its own column of a (2r+1)-row ring in shared memory -- [slot][component][thread], so a warp's
-// accesses are conflict-free and no barrier is ever needed -- and the one new row per cell is fetched by cp.async
-// (global -> shared without passing through registers) while the Riemann solve of the current cell runs.
+// next cell four of those five rows are needed again.  With CHL_DIR_RING=1 every thread keeps its own column of a
+// (2r+1)-row ring in shared memory -- [slot][component][thread], conflict-free, no barrier -- and the one new row per
+// cell is fetched by cp.async while the Riemann solve of the current cell runs; the 25 stencil loads become LDS with
+// immediate offsets.  Measured at 512^3 (gpurun_out/ring1.txt, stage1.txt): 35.9 vs 36.3 ms for the three corrector
+// passes alone, but 37.5 vs 36.2 ms once the update operands are staged too -- 25.6 KB per CTA forces the largest
+// shared-memory carve-out, L1 shrinks to ~28 KB and the register spills of these kernels start missing it.  The
+// stencil loads were never the exposed latency (they issue together); the update operands were.  Kept for parts
+// with a larger L1.
 #ifndef CHL_DIR_RING
 #define CHL_DIR_RING 0
 #endif
@@ -103,6 +106,8 @@ __device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.as
 #ifndef CHL_DIR_PARK
 #define CHL_DIR_PARK 1
 #endif
+// (Fetching the predictor's NEXT cell the same way, one iteration ahead into a two-slot buffer, was measured and
+// dropped: the extra 10 KB of shared memory per CTA shrinks L1 and the three predictor passes went 9.9 -> 13.3 ms.)
 template <int STAGE, bool FIRST, bool LAST>
 struct StageGeom {
   static constexpr int n_sum = (STAGE == 1 && FIRST) ? 0 : 5;  // U (predictor, first pass) or the running sum
