@@ -11,8 +11,10 @@ PPMC + HLLC, fp64; weak scaling over the reference's block decomposition (2x1x1,
 One JSON line on rank 0.  `value` = cell-updates/s with the state resident in HBM (CUDA events around K steps,
 barrier + synchronize either side, max over ranks).  `e2e` = the same through host buffers: pinned-host ->
 device copy of the state, K steps, device -> pinned-host copy of the result, all inside the timed region.
-`roofline` = the corrector kernel's algorithmic bytes (120 B/cell: read W-half, read U, write U) over its mean
-CUDA-event duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` = the CPU
+`roofline` = the step's algorithmic bytes (200 B per cell-update) over the CUDA-event time of the six
+direction sweeps that make up a step, against the measured HBM copy bandwidth in MEASURED_PEAKS.json; `traffic` =
+the DRAM bytes of those launches from the committed ncu capture (profiles/roofline_traffic.json).  `other_mode` =
+the same workload in the other arithmetic mode.  `cpu_baseline` = the CPU
 oracle (a C restatement of the reference algorithm; the reference has no CPU hydro path) on a bounded sample.
 
 --impl reference: the reference's OWN CUDA kernels, unmodified, compiled for sm_100 (oracle/_ref, built by
@@ -32,7 +34,6 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 B_ALG_STEP = 200.0       # algorithmic bytes per cell-update, fp64 hydro: 5 * NF * sizeof(Real)
-B_ALG_CORRECTOR = 120.0  # of which the corrector launch moves: read W-half (40) + read U (40) + write U (40)
 GAMMA = 1.66666667
 
 
@@ -187,25 +188,8 @@ def run_reference(args):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=512, help="cells per axis PER GPU")
-    ap.add_argument("--mode", default="strict", choices=["strict", "fast"],
-                    help="strict = bit-reproduces the reference (product default); fast = FMA + hoisted reciprocals")
-    ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
-    ap.add_argument("--ref-variant", default="shipped", choices=["shipped", "nosync"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
-    if args.impl == "reference":
-        return run_reference(args)
-
-    import numpy as np
+def run_b200(args, mode, world, rank, local, group, with_e2e):
+    """One arm of the bench: K timed steps of the hot path in `mode` arithmetic.  Returns the result dict (all ranks)."""
     import torch
     import torch.distributed as dist
 
@@ -213,20 +197,11 @@ def main():
     from cholla_b200 import initial_conditions as ic
     from cholla_b200.grid import Grid3D
 
-    world, rank, local = env_int("WORLD_SIZE", 1), env_int("RANK", 0), env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local)
-    group = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        group = dist.group.WORLD
     S = args.size
     np_grid = cb.tile_decomposition(world, S, S, S)
     n_global = [S * np_grid[0], S * np_grid[1], S * np_grid[2]]
     lengths = [float(np_grid[0]), float(np_grid[1]), float(np_grid[2])]  # unit cells, unit box per GPU
-    strict = args.mode == "strict" and args.precision == 2
+    strict = mode == "strict" and args.precision == 2
     G = Grid3D(n_global, lengths, recon=cb.PPMC, solver=cb.HLLC, gamma=GAMMA, bc=[1] * 6, precision=args.precision,
                strict=strict, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world, fused=True)
     with ic.block(G.decomp.offset, G.decomp.n_local):
@@ -280,7 +255,7 @@ def main():
 
     # ---- e2e: host buffers, copies inside the timed region ----
     e2e = None
-    if not args.no_e2e:
+    if with_e2e:
         host_in = torch.empty(G.C_device.numel(), dtype=G.C_device.dtype, pin_memory=True)
         host_out = torch.empty_like(host_in, pin_memory=True)
         host_in.copy_(G.C_device)
@@ -301,32 +276,91 @@ def main():
                "note": "pinned host -> HBM copy of the state, K steps (each returning its CFL scalar to the host), "
                        "HBM -> pinned host copy of the result, all timed; ms=%.2f" % ms2}
         del host_in, host_out
+    G.close()
+    del G
+    torch.cuda.empty_cache()
+    return dict(value=value, ms=ms, corr_ms_step=corr_ms_step, pred_ms_step=pred_ms_step, e2e=e2e, launches=launches,
+                clocks=clocks, cells_local=cells_local, n_global=n_global, np_grid=np_grid, state_bytes=state_bytes)
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="cells per axis PER GPU")
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"],
+                    help="strict = bit-reproduces the reference (headline); fast = product arithmetic (FMA, shared "
+                         "reciprocals), reported beside it")
+    ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--ref-variant", default="shipped", choices=["shipped", "nosync"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--single-mode", action="store_true", help="do not also time the other arithmetic mode")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world, rank, local = env_int("WORLD_SIZE", 1), env_int("RANK", 0), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group = dist.group.WORLD
+    S = args.size
+    mode = args.mode if args.precision == 2 else "fast"
+    r = run_b200(args, mode, world, rank, local, group, not args.no_e2e)
+    other = None
+    if not args.single_mode and args.precision == 2:
+        o = run_b200(args, "fast" if mode == "strict" else "strict", world, rank, local, group, False)
+        other = {"mode": "fast" if mode == "strict" else "strict", "value": o["value"], "unit": "cell-updates/s",
+                 "ms_per_step": o["ms"] / args.steps, "predictor_ms_per_step": o["pred_ms_step"],
+                 "corrector_ms_per_step": o["corr_ms_step"],
+                 "note": "same workload and timing in the other arithmetic mode (strict = the reference's bits; fast = "
+                         "FMA + shared reciprocals, within 1e-12 relative L1 on smooth data)"}
     if rank != 0:
         dist.destroy_process_group()
         return 0
     peak, which = measured_hbm_peak()
-    achieved = cells_local * B_ALG_CORRECTOR / (corr_ms_step * 1e-3) / 1e9 if corr_ms_step > 0 else None
-    tr = ncu_traffic()
+    sweeps_ms = r["pred_ms_step"] + r["corr_ms_step"]
+    b_alg = B_ALG_STEP if args.precision == 2 else B_ALG_STEP / 2
+    achieved = r["cells_local"] * b_alg / (sweeps_ms * 1e-3) / 1e9 if sweeps_ms > 0 else None
+    tr = (ncu_traffic() or {}).get(mode if args.precision == 2 else "f32")
     out = {
-        "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.precision == 2 else "f32", "data": "synthetic",
-        "config": {"workload": "blast %d^3 per GPU, PPMC+HLLC, periodic, VL integrator, %s arithmetic" % (S, args.mode),
-                   "global_cells": n_global, "decomposition": np_grid, "l2": "inputs larger than L2 (%.1f GB state per GPU)"
-                   % (state_bytes / 1e9), "step": "set_dt + VL step (fused T-floor/CFL) + ghost fill/halo exchange"},
-        "e2e": e2e,
-        "gpu_launches": launches,
-        "clocks": clocks,
+        "config": {"workload": "blast %d^3 per GPU, PPMC+HLLC, periodic, VL integrator, %s arithmetic" % (S, mode),
+                   "global_cells": r["n_global"], "decomposition": r["np_grid"],
+                   "l2": "inputs larger than L2 (%.1f GB state per GPU)" % (r["state_bytes"] / 1e9),
+                   "step": "set_dt + VL step (fused T-floor/CFL) + ghost fill/halo exchange"},
+        "e2e": r["e2e"],
+        "gpu_launches": r["launches"],
+        "clocks": r["clocks"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if achieved else None,
-                     "traffic": tr.get("corrector_dram_bytes_per_launch") if tr else None,
-                     "kernel": "vl_sweep_kernel<PPMC,HLLC,corrector>", "ms_per_launch": corr_ms_step,
-                     "algorithmic_bytes_per_launch": cells_local * B_ALG_CORRECTOR,
-                     "predictor_ms_per_launch": pred_ms_step,
-                     "step_frac_of_hbm_roofline": value / world * B_ALG_STEP / 1e9 / peak,
-                     "note": "peak " + which + "; this path is fp64-pipe bound, see DESIGN.md"},
+                     "traffic": tr.get("dram_bytes_per_step") if tr else None,
+                     "kernel": "vl_dir_kernel<PPMC,HLLC>: the six direction sweeps of one step (predictor x,y,z + "
+                               "corrector x,y,z), timed together by CUDA events on the launching stream",
+                     "ms_per_launch": sweeps_ms, "launches_per_step": 6,
+                     "algorithmic_bytes_per_launch": r["cells_local"] * b_alg,
+                     "predictor_ms_per_step": r["pred_ms_step"], "corrector_ms_per_step": r["corr_ms_step"],
+                     "step_frac_of_hbm_roofline": r["value"] / world * b_alg / 1e9 / peak,
+                     "fp64_pipe_busy": tr.get("fp64_pipe_busy_pct") if tr else None,
+                     "note": "achieved = %d B per cell-update (SURVEY 8d) x cells per step / time of the six sweeps; "
+                             "traffic = DRAM bytes of the same six launches from ncu (profiles/); peak " % b_alg + which +
+                             "; the sweeps are fp64-issue bound, not HBM bound, see DESIGN.md 3.1"},
     }
+    if other:
+        out["other_mode"] = other
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))

@@ -259,14 +259,18 @@ class Grid3D:
     def Execute_Hydro_Integrator(self):
         """Grid3D::Execute_Hydro_Integrator (grid3D.cpp:413-470) -> VL_Algorithm_{1,2,3}D_CUDA."""
         check(_lib.lib().chl_vl_step(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step")
-        self.gpu_launches += 2
+        self.gpu_launches += self._sweep_launches()
+
+    def _sweep_launches(self):
+        """Kernels one VL step launches: a predictor and a corrector sweep per direction (direction-split default)."""
+        return 2 * self.ndim
 
     def Update_Hydro_Grid(self):
         """Grid3D::Update_Hydro_Grid (grid3D.cpp:474-585): integrator, temperature floor, new inverse dt."""
         L = _lib.lib()
         if self.fused:
             check(L.chl_vl_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step_fused")
-            self.gpu_launches += 2
+            self.gpu_launches += self._sweep_launches()
             out = C.c_double()
             check(L.chl_dti_result(self._ctx, C.byref(out), self._stream()), "chl_dti_result")
             return out.value
