@@ -205,7 +205,12 @@ def run_b200(args, mode, world, rank, local, group, with_e2e):
     G = Grid3D(n_global, lengths, recon=cb.PPMC, solver=cb.HLLC, gamma=GAMMA, bc=[1] * 6, precision=args.precision,
                strict=strict, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world, fused=True)
     with ic.block(G.decomp.offset, G.decomp.n_local):
-        fields = ic.spherical_overpressure(n_global, lengths=lengths, gamma=GAMMA)
+        if args.workload == "kh":      # BASELINE config 3: every cell moves, two shear layers
+            fields = ic.kh_res_ind(n_global, lengths=lengths, lo=(0.0, -0.5 * lengths[1], -0.5 * lengths[2]), gamma=GAMMA)
+        elif args.workload == "noise":  # worst case: cell-to-cell noise, every limiter branch taken everywhere
+            fields = ic.random_smooth(G.decomp.n_local, seed=1 + rank, gamma=GAMMA)
+        else:                           # BASELINE config 5 (the headline): blast wave into a medium at rest
+            fields = ic.spherical_overpressure(n_global, lengths=lengths, gamma=GAMMA)
     G.Set_Initial_Conditions_Local(fields)
     del fields
     G.Set_Boundary_Conditions_Grid()
@@ -293,6 +298,9 @@ def main():
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"],
                     help="strict = bit-reproduces the reference (headline); fast = product arithmetic (FMA, shared "
                          "reciprocals), reported beside it")
+    ap.add_argument("--workload", default="blast", choices=["blast", "kh", "noise"],
+                    help="blast = BASELINE config 5 (headline); kh = Kelvin-Helmholtz (config 3 initial conditions); "
+                         "noise = random cell-to-cell state (worst case for the limiters)")
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
     ap.add_argument("--ref-variant", default="shipped", choices=["shipped", "nosync"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -338,7 +346,7 @@ def main():
         "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.precision == 2 else "f32", "data": "synthetic",
-        "config": {"workload": "blast %d^3 per GPU, PPMC+HLLC, periodic, VL integrator, %s arithmetic" % (S, mode),
+        "config": {"workload": "%s %d^3 per GPU, PPMC+HLLC, periodic, VL integrator, %s arithmetic" % (args.workload, S, mode),
                    "global_cells": r["n_global"], "decomposition": r["np_grid"],
                    "l2": "inputs larger than L2 (%.1f GB state per GPU)" % (r["state_bytes"] / 1e9),
                    "step": "set_dt + VL step (fused T-floor/CFL) + ghost fill/halo exchange"},

@@ -76,6 +76,7 @@ def lib():
     L.chl_tile_decomposition.argtypes = [i, i, i, i, ip]
     L.chl_local_extent.argtypes = [i, i, i, ip, ip]
     L.chl_debug_exact_div.argtypes = [p, p, p, p, l, p]
+    L.chl_debug_exact_sqrt.argtypes = [p, p, p, l, p]
     _lib = L
     return L
 

@@ -542,4 +542,12 @@ int chl_debug_exact_div(const double *d_a, const double *d_b, double *d_q_shared
   return CHL_OK;
 }
 
+int chl_debug_exact_sqrt(const double *d_x, double *d_r_own, double *d_r_plain, long n, void *stream)
+{
+  if (!d_x || !d_r_own || !d_r_plain || n < 0) return fail(CHL_ERR_INVALID, "chl_debug_exact_sqrt: bad argument");
+  cudaError_t e = chl::launch_exact_sqrt_test(d_x, d_r_own, d_r_plain, n, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(CHL_ERR_CUDA, "chl_debug_exact_sqrt", e);
+  return CHL_OK;
+}
+
 }  // extern "C"

@@ -69,4 +69,5 @@ cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, 
 // exact_div_test.cu: shared-reciprocal division vs the compiler's a / b
 cudaError_t launch_exact_div_test(const double *a, const double *b, double *q_shared, double *q_plain, long n,
                                   cudaStream_t s);
+cudaError_t launch_exact_sqrt_test(const double *x, double *r_own, double *r_plain, long n, cudaStream_t s);
 }  // namespace chl

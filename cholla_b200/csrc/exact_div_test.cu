@@ -1,10 +1,9 @@
-// exact_div_test.cu -- diagnostic kernel behind chl_debug_exact_div (include/cholla_b200.h): evaluates the
+// exact_div_test.cu -- diagnostic kernels behind chl_debug_exact_div / chl_debug_exact_sqrt (include/cholla_b200.h): evaluates the
 // shared-reciprocal division of exact_div.cuh and the compiler's own a / b on the same operands so that
 // tests/test_gpu_exact_div.py can compare them bit for bit.  Built -fmad=false like the strict kernels.
 #define CHL_STRICT 1
 #define CHL_MODE f64_divtest
-#define CHL_NS chl_f64_divtest
-#include "exact_div.cuh"
+#include "hydro_physics.cuh"  // exact_div.cuh + sqrt_r
 #include "chl_internal.h"
 
 namespace chl_f64_divtest
@@ -17,6 +16,14 @@ __global__ void div_kernel(const double *a, const double *b, double *q_shared, d
   q_shared[i] = qdiv(a[i], d);
   q_plain[i]  = a[i] / b[i];
 }
+// strict mode's sqrt_r (the compiler's fast-path sequence without its marshalling) against sqrt()
+__global__ void sqrt_kernel(const double *x, double *r_own, double *r_plain, long n)
+{
+  long const i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  r_own[i]   = sqrt_r(x[i]);
+  r_plain[i] = sqrt(x[i]);
+}
 }  // namespace chl_f64_divtest
 
 namespace chl
@@ -26,6 +33,12 @@ cudaError_t launch_exact_div_test(const double *a, const double *b, double *q_sh
 {
   if (n <= 0) return cudaSuccess;
   chl_f64_divtest::div_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, b, q_shared, q_plain, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_exact_sqrt_test(const double *x, double *r_own, double *r_plain, long n, cudaStream_t s)
+{
+  if (n <= 0) return cudaSuccess;
+  chl_f64_divtest::sqrt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, r_own, r_plain, n);
   return cudaGetLastError();
 }
 }  // namespace chl

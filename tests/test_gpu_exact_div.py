@@ -70,3 +70,32 @@ def test_constant_denominators_of_the_path():
     for den in (6.0, 1.66666667 - 1.0, 5.0 / 3.0 - 1.0, 1.4 - 1.0):
         qs, qp = _run(a, np.full(n, den))
         assert _same_bits(qs, qp)
+
+
+def _run_sqrt(x):
+    import torch
+    import cholla_b200 as cb
+    tx = torch.from_numpy(x).cuda()
+    ro, rp = torch.empty_like(tx), torch.empty_like(tx)
+    rc = cb.lib().chl_debug_exact_sqrt(C.c_void_p(tx.data_ptr()), C.c_void_p(ro.data_ptr()), C.c_void_p(rp.data_ptr()),
+                                       x.size, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return ro.cpu().numpy(), rp.cpu().numpy()
+
+
+def test_sqrt_whole_range_and_edges():
+    """sqrt_r (strict mode) must return the bits of sqrt() for every operand: random bit patterns (every exponent,
+    negatives, denormals, infinities, NaNs), the physical range, and the edges of the fast-path window."""
+    rng = np.random.default_rng(5)
+    n = 1 << 22
+    x = rng.integers(0, 1 << 64, n, dtype=np.uint64).view(np.float64).copy()
+    phys = np.abs(rng.standard_normal(n)) * 10.0 ** rng.uniform(-25, 25, n)
+    edge = np.array([0.0, -0.0, 1.0, 4.0, 2.0, 1e-20, 1e-300, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+                     np.inf, -np.inf, np.nan, -1.0, 2.0 ** -969, 2.0 ** -970, 2.0 ** 1000, 2.0 ** 1016, 1.0 + 2.0 ** -52,
+                     2.0 - 2.0 ** -52, 4.0 - 2.0 ** -50])
+    x = np.concatenate([x, phys, edge])
+    ro, rp = _run_sqrt(x)
+    assert _same_bits(ro, rp)
+    with np.errstate(all="ignore"):
+        assert _same_bits(rp, np.sqrt(x))
