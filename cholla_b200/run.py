@@ -1,0 +1,162 @@
+"""`python -m cholla_b200.run deck.txt [name=value ...] [--recon ppmc --solver hllc ...]` -- the body of the
+reference's `main()` (src/main.cpp:63-379) around the B200 library: read the deck, build the grid, set the initial
+conditions, fill the ghost cells, then
+
+    dti = G.Calc_Inverse_Timestep()
+    while t < tout:   set_dt(dti) -> clip dt to the next output time -> Update_Hydro_Grid -> Update_Time
+                      -> Set_Boundary_Conditions_Grid -> snapshot when t == outtime
+
+What a deck cannot say -- the reference chooses reconstruction, Riemann solver, MHD and precision at compile time
+through `builds/make.type.*` -- comes from the options, which map one-to-one to `chl_config`.  Snapshots carry the
+reference's dataset and attribute names (`density, momentum_x, momentum_y, momentum_z, Energy[, magnetic_*]`; `gamma, t,
+dt, n_step, dims, ...`, src/io/io.cpp:605-737,1350-1497) in NumPy `.npz` containers with the reference's `[i][j][k]` axis
+order: this image has no HDF5 library, so the container differs and the contents do not.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from . import _lib
+from . import initial_conditions as ic
+from .parameters import Parameters, parse_params
+
+# global.h:26-47
+MP, KB = 1.672622e-24, 1.380658e-16
+TIME_UNIT, LENGTH_UNIT = 3.15569e10, 3.08567758e21
+SP_ENERGY_UNIT = (LENGTH_UNIT / TIME_UNIT) ** 2
+
+RECON = {"pcm": _lib.PCM, "plmc": _lib.PLMC, "ppmc": _lib.PPMC}
+SOLVER = {"hllc": _lib.HLLC, "roe": _lib.ROE, "hlld": _lib.HLLD}
+
+
+def u_floor(temperature_floor, gamma):
+    """Grid3D::Update_Hydro_Grid, grid3D.cpp:493-503 (non-cosmological branch)."""
+    return temperature_floor * KB / (gamma - 1.0) / MP / SP_ENERGY_UNIT
+
+
+def initial_fields(P: Parameters, mhd=False, n_ghost=0):
+    """Grid3D::Set_Initial_Conditions (src/grid/initial_conditions.cpp:30-100): dispatch on `init`.  Hydro generators
+    return the real cells (5, nz, ny, nx) (honouring an enclosing `ic.block`); MHD ones the full local array."""
+    n = P.n_global()
+    lo, ln = P.domain()
+    ln = tuple(v if v != 0.0 else 1.0 for v in ln)
+    name = P.init
+    if name == "Constant":
+        return ic.constant(n, P.rho, (P.vx, P.vy, P.vz), P.P, P.gamma)
+    if name == "Sound_Wave":
+        return ic.sound_wave(n, ln, lo, P.rho, (P.vx, P.vy, P.vz), P.P, P.A, P.gamma)
+    if name == "Riemann":
+        return ic.riemann(n, ln, lo, (P.rho_l, P.vx_l, P.vy_l, P.vz_l, P.P_l), (P.rho_r, P.vx_r, P.vy_r, P.vz_r, P.P_r),
+                          P.diaph, P.gamma)
+    if name == "Spherical_Overpressure_3D":
+        return ic.spherical_overpressure(n, ln, lo, P.gamma)
+    if name == "KH_res_ind":
+        return ic.kh_res_ind(n, ln, lo, P.gamma)
+    if name == "Orszag_Tang_Vortex" and mhd:
+        return ic.orszag_tang(n, n_ghost, P.gamma)
+    if name == "MHD_Spherical_Blast" and mhd:
+        return ic.mhd_blast(n, n_ghost, P.gamma)
+    raise NotImplementedError("init=%s is not one of the generators of the hot-path scope (SURVEY 8d): Constant, Sound_Wave, "
+                              "Riemann, Spherical_Overpressure_3D, KH_res_ind, Orszag_Tang_Vortex, MHD_Spherical_Blast" % name)
+
+
+def snapshot(G, P: Parameters, nfile, outdir):
+    """Write_Data -> Write_Header_HDF5 + Write_Grid_HDF5 (io.cpp:605-737, 1350-1497): one file per rank,
+    `<outdir>/<nfile>/<nfile>.npz.<rank>`, datasets transposed to [i][j][k] like the reference's HDF5 buffers."""
+    H = G.H
+    real = G.real_cells()  # (nf, nz, ny, nx)
+    names = ["density", "momentum_x", "momentum_y", "momentum_z", "Energy"]
+    if H.n_fields == 8:
+        names += ["magnetic_x", "magnetic_y", "magnetic_z"]
+    data = {nm: np.ascontiguousarray(real[f].transpose(2, 1, 0)) for f, nm in enumerate(names)}
+    attrs = dict(gamma=P.gamma, t=H.t, dt=H.dt, n_step=H.n_step, n_fields=H.n_fields,
+                 dims=np.array(G.n_global), dims_local=np.array(G.decomp.n_local), offset=np.array(G.decomp.offset),
+                 nprocs=np.array(G.decomp.np), bounds=np.array([P.xmin, P.ymin, P.zmin]),
+                 domain=np.array([P.xlen, P.ylen, P.zlen]), dx=np.array([H.dx, H.dy, H.dz]))
+    d = os.path.join(outdir, str(nfile))
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "%d.npz.%d" % (nfile, G.rank))
+    with open(path, "wb") as fh:
+        np.savez(fh, **data, **{"attr_" + k: v for k, v in attrs.items()})
+    return path
+
+
+def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mhd=False, outdir=None, device=None,
+        dist_group=None, rank=0, nproc=1, max_steps=None, log=print):
+    """main.cpp:63-379.  Returns (Grid3D, list of snapshot paths)."""
+    from .grid import Grid3D, n_ghost_for
+    mhd = mhd or solver == "hlld"
+    lo, ln = P.domain()
+    ln = tuple(v if v != 0.0 else 1.0 for v in ln)
+    G = Grid3D(P.n_global(), ln, bounds_min=lo, recon=RECON[recon], solver=SOLVER[solver], gamma=P.gamma,
+               bc=P.boundary_flags(), precision=precision, strict=strict, density_floor=P.density_floor,
+               temperature_floor_U=u_floor(P.temperature_floor, P.gamma), device=device, dist_group=dist_group,
+               rank=rank, nproc=nproc, mhd=mhd)
+    if mhd:
+        if nproc != 1:
+            raise NotImplementedError("the MHD generators build the whole grid on one rank")
+        G.upload(initial_fields(P, True, n_ghost_for(RECON[recon], True)))
+    else:
+        with ic.block(G.decomp.offset, G.decomp.n_local):
+            G.Set_Initial_Conditions_Local(initial_fields(P))
+    G.Set_Boundary_Conditions_Grid()
+    outdir = outdir if outdir is not None else (P.outdir or "./")
+    files, nfile, outtime = [], P.nfile, 0.0
+    if outdir != "none":
+        files.append(snapshot(G, P, nfile, outdir))  # main.cpp:205-215: the initial state is output 0
+    nfile += 1
+    outtime += P.outstep
+    dti = G.Calc_Inverse_Timestep()
+    while G.H.t < P.tout and (max_steps is None or G.H.n_step < max_steps):
+        G.set_dt(dti)
+        nxt = min(outtime, P.tout)  # main.cpp:257-261
+        if G.H.t + G.H.dt > nxt:
+            G.H.dt = nxt - G.H.t
+        dti = G.Update_Hydro_Grid()
+        G.Update_Time()
+        G.Set_Boundary_Conditions_Grid()
+        if G.H.t == outtime:  # main.cpp:341-350
+            if outdir != "none":
+                files.append(snapshot(G, P, nfile, outdir))
+            nfile += 1
+            outtime += P.outstep
+    log("n_step: %d  sim time: %.10f  last dt: %.6e" % (G.H.n_step, G.H.t, G.H.dt))
+    return G, files
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("deck")
+    ap.add_argument("overrides", nargs="*", help="name=value pairs that override the deck (main.cpp argv handling)")
+    ap.add_argument("--recon", default="ppmc", choices=sorted(RECON))
+    ap.add_argument("--solver", default="hllc", choices=sorted(SOLVER))
+    ap.add_argument("--mhd", action="store_true")
+    ap.add_argument("--fast", action="store_true", help="product arithmetic instead of the reference's bits")
+    ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--outdir", default=None, help="overrides the deck's outdir; 'none' writes nothing")
+    ap.add_argument("--max-steps", type=int, default=None)
+    a = ap.parse_args(argv)
+    P = parse_params(a.deck, a.overrides)
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
+    group = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group = dist.group.WORLD
+    G, files = run(P, a.recon, a.solver, strict=not a.fast and a.precision == 2, precision=a.precision, mhd=a.mhd,
+                   outdir=a.outdir, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world,
+                   max_steps=a.max_steps, log=print if rank == 0 else (lambda *_: None))
+    G.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
