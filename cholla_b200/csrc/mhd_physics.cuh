@@ -11,7 +11,7 @@
 //   ct_electric_fields.h:66-116     _ctSlope                        -> ct_slope()
 // Expressions keep the reference's association in BOTH arithmetic modes; the strict build (-fmad=false) therefore
 // reproduces the reference's bits (it calls the same CUDA math functions: sqrt, rsqrt, rhypot, copysign, fmin, fmax),
-// the product build differs only by FMA contraction.
+// the product build differs by FMA contraction and the straight-line square roots / shared PPM of hydro_physics.cuh.
 #pragma once
 #include "hydro_physics.cuh"
 
@@ -34,10 +34,14 @@ __device__ __forceinline__ Real magnetosonic(Real d, Real p, Real bx, Real by, R
   Real const b2  = bx2 + ((by * by) + (bz * bz));
   Real const t1  = gamma * p + b2;
   Real t2        = (t1 * t1) - RC(4.) * gamma * p * bx2;
-  t2             = sqrt(t2);
-  return sqrt((t1 + wave * t2) / (RC(2.0) * fmax(d, kTiny)));
+#if CHL_STRICT
+  t2 = sqrt_r(t2);
+#else
+  t2 = t2 > RC(0.0) ? sqrt_r(t2) : RC(0.0);  // (gamma p - bx^2)^2 when the transverse field vanishes: can be an exact zero
+#endif
+  return sqrt_r((t1 + wave * t2) / (RC(2.0) * fmax(d, kTiny)));
 }
-__device__ __forceinline__ Real alfven_speed(Real bx, Real d) { return fabs(bx) / sqrt(fmax(d, kTiny)); }
+__device__ __forceinline__ Real alfven_speed(Real bx, Real d) { return fabs(bx) / sqrt_r(fmax(d, kTiny)); }
 // hydro_utilities.h:34-45 / 106-118 (MHD)
 __device__ __forceinline__ Real mhd_pressure(Real E, Real d, Real vx, Real vy, Real vz, Real gamma, Real bx, Real by,
                                              Real bz)
@@ -67,7 +71,7 @@ struct Eigen {
   Real d, a2, isd, sqd;
   __device__ __forceinline__ void init(MPrim const &w, Real gamma)
   {
-    Real const a = sqrt(gamma * w.p / w.d);  // hydro_utilities::Calc_Sound_Speed
+    Real const a = sqrt_r(gamma * w.p / w.d);  // hydro_utilities::Calc_Sound_Speed
     a2           = a * a;
     d            = w.d;
     cf  = magnetosonic(w.d, w.p, w.bx, w.by, w.bz, gamma, RC(1.0));
@@ -84,8 +88,8 @@ struct Eigen {
         alpha_f = RC(0.0);
         alpha_s = RC(1.0);
       } else {
-        alpha_f = sqrt(num1 / denom);
-        alpha_s = sqrt(num2 / denom);
+        alpha_f = sqrt_r(num1 / denom);
+        alpha_s = sqrt_r(num2 / denom);
       }
     }
     Real const bd = rhypot(w.by, w.bz);
@@ -97,7 +101,7 @@ struct Eigen {
     qp_s          = sign * n_fs * alpha_s * cs;
     q_f           = sign * alpha_f * cf;
     q_s           = sign * alpha_s * cs;
-    sqd           = sqrt(w.d);
+    sqd           = sqrt_r(w.d);
     a_f           = alpha_f * a * sqd;
     a_s           = alpha_s * a * sqd;
     ap_f          = RC(0.5) * alpha_f / (a * sqd);
@@ -135,52 +139,6 @@ struct Eigen {
   }
 };
 
-// PPM_Single_Variable in the reference's operation order (reconstruction.h:794-901) for both modes
-__device__ __forceinline__ void ppm_single_ref(Real cm2, Real cm1, Real c0, Real cp1, Real cp2, Real &L_iph, Real &R_imh)
-{
-  Real const C2 = RC(1.25);
-  Real const sl = (c0 - cm1), sr = (cp1 - c0);
-  Real const avg_m1 = RC(0.5) * sl + RC(0.5) * (cm1 - cm2);
-  Real const avg_0  = RC(0.5) * sr + RC(0.5) * sl;
-  Real const avg_p1 = RC(0.5) * (cp2 - cp1) + RC(0.5) * sr;
-  Real R = RC(0.5) * (cm1 + c0) + (avg_m1 - avg_0) / RC(6.0);
-  Real L = RC(0.5) * (c0 + cp1) + (avg_0 - avg_p1) / RC(6.0);
-  Real const s2_m1 = cm2 + c0 - RC(2.0) * cm1;
-  Real const s2_0  = cm1 + cp1 - RC(2.0) * c0;
-  Real const s2_p1 = c0 + cp2 - RC(2.0) * cp1;
-  auto limit_face = [&](Real ci, Real cim1, Real face, Real s2_i, Real s2_im1) -> Real {
-    Real const s2_c = RC(3.0) * (cim1 + ci - RC(2.0) * face);
-    Real lim        = RC(0.0);
-    if (neg(s2_c) == neg(s2_im1) && neg(s2_c) == neg(s2_i))
-      lim = sgn1(s2_c) * fmin(C2 * fabs(s2_im1), fmin(C2 * fabs(s2_i), fabs(s2_c)));
-    if ((face - cim1) * (ci - face) < RC(0.0)) return RC(0.5) * (cim1 + ci) - lim / RC(6.0);
-    return face;
-  };
-  R = limit_face(c0, cm1, R, s2_0, s2_m1);
-  L = limit_face(cp1, c0, L, s2_p1, s2_0);
-  Real const s2_f = RC(6.0) * (R + L - RC(2.0) * c0);
-  Real s2_lim     = RC(0.0);
-  if (neg(s2_m1) == neg(s2_0) && neg(s2_m1) == neg(s2_p1) && neg(s2_m1) == neg(s2_f))
-    s2_lim = sgn1(s2_f) * fmin(fmin(C2 * fabs(s2_m1), C2 * fabs(s2_0)), fmin(C2 * fabs(s2_p1), fabs(s2_f)));
-  Real cmax = fmax(fabs(cm2), fabs(cm1));
-  cmax      = fmax(cmax, fabs(c0));
-  cmax      = fmax(cmax, fabs(cp1));
-  cmax      = fmax(cmax, fabs(cp2));
-  Real const fl = c0 - R, fr = L - c0;
-  if ((fl * fr) <= RC(0.0) || ((cp1 - c0) * (c0 - cm1)) <= RC(0.0)) {
-    Real const rho = (fabs(s2_f) > RC(1.0e-12) * cmax) ? s2_lim / s2_f : RC(0.0);
-    if (rho <= (RC(1.0) - RC(1.0e-12))) {
-      R = c0 - rho * fl;
-      L = c0 + rho * fr;
-    }
-  } else {
-    if (fabs(fl) >= RC(2.0) * fabs(fr)) R = c0 - RC(2.0) * fr;
-    if (fabs(fr) >= RC(2.0) * fabs(fl)) L = c0 + RC(2.0) * fl;
-  }
-  L_iph = L;
-  R_imh = R;
-}
-
 // ---- reconstructions on the stencil of half-step primitives -----------------------------------------------------
 // W holds per cell (rho, vx, vy, vz, P, Bcc_x, Bcc_y, Bcc_z [, P_y, P_z in strict mode]); the caller passes the
 // element offsets of the sweep-frame components (normal velocity, two transverse, pressure of this sweep, the three
@@ -212,20 +170,22 @@ __device__ __forceinline__ void mhd_floor(MPrim &l, MPrim &r)
   l.p = fmax(l.p, kTiny);
 }
 
-__device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const &o, Real gamma, MPrim &L, MPrim &R)
+__device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const &o, KC const &k, MPrim &L, MPrim &R)
 {
-  MPrim const wi = load_mprim(c, o, 0);
+  Real const gamma = k.gamma;
+  MPrim const wi   = load_mprim(c, o, 0);
   Eigen e;
   e.init(wi, gamma);
   Real ch[5][7];
 #pragma unroll
-  for (int k = 0; k < 5; k++) {
-    MPrim const w = k == 2 ? wi : load_mprim(c, o, k - 2);
-    e.project(w.d, w.vx, w.vy, w.vz, w.p, w.by, w.bz, ch[k]);
+  for (int i = 0; i < 5; i++) {
+    MPrim const w = i == 2 ? wi : load_mprim(c, o, i - 2);
+    e.project(w.d, w.vx, w.vy, w.vz, w.p, w.by, w.bz, ch[i]);
   }
   Real cl[7], cr[7];
+  // the hydro path's PPM_Single_Variable: lazy limiters, shared x/6 reciprocal -- same values (hydro_physics.cuh)
 #pragma unroll
-  for (int f = 0; f < 7; f++) ppm_single_ref(ch[0][f], ch[1][f], ch[2][f], ch[3][f], ch[4][f], cl[f], cr[f]);
+  for (int f = 0; f < 7; f++) ppm_single(ch[0][f], ch[1][f], ch[2][f], ch[3][f], ch[4][f], cl[f], cr[f], k);
   L = e.unproject(cl);
   R = e.unproject(cr);
   mhd_floor(L, R);
@@ -412,7 +372,7 @@ __device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, R
       vyd = sr.vy; vzd = sr.vz; byd = sr.by; bzd = sr.bz; EdR = sr.E;
     }
   } else {
-    Real const sdl = sqrt(sl.d), sdr = sqrt(sr.d);
+    Real const sdl = sqrt_r(sl.d), sdr = sqrt_r(sr.d);
     Real const inv = RC(1.0) / (sdl + sdr);
     Real const sg  = copysign(RC(1.0), bx);
     vyd = inv * (sdl * sl.vy + sdr * sr.vy + sg * (sr.by - sl.by));

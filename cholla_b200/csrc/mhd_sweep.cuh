@@ -105,9 +105,23 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
   else if (DIR == 1) upd_t = xyz[2] >= P.ulo[2] && xyz[2] < P.uhi[2];
   else upd_t = xyz[1] >= P.ulo[1] && xyz[1] < P.uhi[1];
 
-  Real Lc[7], Fc[7];
+  // carried values parked in shared memory and update operands staged by cp.async, as in vl_dir_kernel
+  typedef StageGeom<STAGE, FIRST, LAST> SG;
+  constexpr bool kStage = CHL_DIR_STAGE && SG::n > 0;
+  constexpr int kParkN  = CHL_DIR_PARK ? (DIR == 0 ? 12 * kRowsPerCta : 12 * kDirThreads) : 1;
+  __shared__ Real stage[kStage ? SG::n * kDirThreads : 1];
+  __shared__ Real parked[kParkN];
+  Real *const park   = parked + (DIR == 0 ? (threadIdx.x >> 5) : threadIdx.x);
+  int const pstride  = DIR == 0 ? kRowsPerCta : kDirThreads;
+  Real *const staged = stage + threadIdx.x;
+  constexpr int field_of_comp[5] = {0, 1 + DIR, 1 + (DIR + 1) % 3, 1 + (DIR + 2) % 3, 4};
+  KC const kc = make_kc(gamma);
+
+  Real Lc[7], Fc[5];
 #pragma unroll
-  for (int k = 0; k < 7; k++) Lc[k] = Fc[k] = RC(0.0);
+  for (int k = 0; k < 7; k++) Lc[k] = RC(0.0);
+#pragma unroll
+  for (int k = 0; k < 5; k++) Fc[k] = RC(0.0);
   int const step = DIR == 0 ? 32 : 1;
   for (int cb = c_first; cb <= c_last; cb += step) {
     int const c      = DIR == 0 ? cb + lane : cb;
@@ -116,6 +130,22 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
     size_t const id  = (size_t)xyz[0] + (size_t)nx * ((size_t)xyz[1] + (size_t)ny * xyz[2]);
     bool upd_x = true;  // y/z sweeps: the thread's own x must be an updated column
     if (DIR != 0) upd_x = xyz[0] >= P.ulo[0] && xyz[0] < P.uhi[0];
+    bool const face = valid && c > c_first;  // the +face of cell c-1
+    int const u     = c - 1;                 // the cell both of whose faces are known after this iteration
+    bool const fin  = face && c > c_first + 1 && upd_t && upd_x && u >= P.ulo[DIR] && u < P.uhi[DIR];
+    if (kStage) {
+      if (fin) {
+        size_t const idu = id - o.s;
+#pragma unroll
+        for (int k = 0; k < SG::n_sum; k++) {
+          const Real *src = (STAGE == 0 && FIRST) ? P.in : P.acc;
+          cp_async_real(staged + k * kDirThreads, src + (size_t)field_of_comp[k] * N + idu);
+        }
+#pragma unroll
+        for (int f = 0; f < SG::n_out; f++) cp_async_real(staged + (SG::n_sum + f) * kDirThreads, P.out + (size_t)f * N + idu);
+      }
+      cp_async_commit();
+    }
     M7 L, R;
     if (valid) {
       if (STAGE == 0) {  // PCM_Reconstruction_3D (pcm_cuda.cu:256-424): both sides are the cell itself
@@ -140,7 +170,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
           R = L;
         } else {
           MPrim l, r;
-          if (RECON == kPPMC) mhd_ppmc(P.in + id, o, gamma, l, r);
+          if (RECON == kPPMC) mhd_ppmc(P.in + id, o, kc, l, r);
           else mhd_plmc(P.in + id, o, gamma, l, r);
           L = mhd_interface(l, bhi, gamma);
           R = mhd_interface(r, blo, gamma);
@@ -151,9 +181,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
       for (int k = 0; k < 7; k++) L.v[k] = R.v[k] = RC(1.0);
     }
     M7 Lp;
-#pragma unroll
-    for (int k = 0; k < 7; k++) Lp.v[k] = from_low_side<DIR>(L.v[k], Lc[k], lane);
-    bool const face = valid && c > c_first;  // the +face of cell c-1
+    from_low_side_n<DIR, 7>(L.v, Lc, Lp.v, park, pstride, lane);
     M7 F;
     if (face) {
       Real const bface = __ldg(P.Bsrc + (size_t)(5 + DIR) * N + id - o.s);
@@ -166,20 +194,21 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
 #pragma unroll
       for (int k = 0; k < 7; k++) F.v[k] = RC(0.0);
     }
-    Real Fp[7];
+    Real F5[5], Fp[5];
 #pragma unroll
-    for (int k = 0; k < 5; k++) Fp[k] = from_low_side<DIR>(F.v[k], Fc[k], lane);
-    int const u = c - 1;  // the cell both of whose faces are now known
-    if (face && c > c_first + 1 && upd_t && upd_x && u >= P.ulo[DIR] && u < P.uhi[DIR]) {
+    for (int k = 0; k < 5; k++) F5[k] = F.v[k];
+    from_low_side_n<DIR, 5>(F5, Fc, Fp, park + 7 * pstride, pstride, lane);
+    if (kStage) cp_async_wait_all();
+    if (fin) {
       size_t const idu = id - o.s;
-      constexpr int field_of_comp[5] = {0, 1 + DIR, 1 + (DIR + 1) % 3, 1 + (DIR + 2) % 3, 4};
       Real v[5];
 #pragma unroll
       for (int k = 0; k < 5; k++) {
         int const f  = field_of_comp[k];
         Real const t = P.dto * (Fp[k] - F.v[k]);
         Real a;
-        if (STAGE == 0) a = (FIRST ? __ldg(P.in + f * N + idu) : P.acc[f * N + idu]) + t;
+        if (kStage && SG::n_sum) a = staged[k * kDirThreads] + t;
+        else if (STAGE == 0) a = (FIRST ? __ldg(P.in + f * N + idu) : P.acc[f * N + idu]) + t;
         else a = FIRST ? t : P.acc[f * N + idu] + t;
         if (!LAST) P.acc[f * N + idu] = a;
         v[f] = a;
@@ -187,7 +216,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
       if (LAST) {
         if (STAGE == 1) {
 #pragma unroll
-          for (int f = 0; f < 5; f++) v[f] = P.out[f * N + idu] + v[f];
+          for (int f = 0; f < 5; f++) v[f] = (kStage ? staged[(SG::n_sum + f) * kDirThreads] : P.out[f * N + idu]) + v[f];
         }
         bool const fl = STAGE == 0 ? (v[0] < P.density_floor) : (v[0] < P.density_floor && v[0] > RC(0.));
         if (fl) {  // VL_3D_cuda.cu:479-493 / hydro_cuda.cu:279-291

@@ -130,35 +130,41 @@ __device__ __forceinline__ Real from_low_side(Real v, Real &carry, int lane)
   return t;
 }
 
-// five values at once; `park` = this thread's (y/z sweeps) or this warp's (x sweep) shared-memory slots, stride pstride
-template <int DIR>
-__device__ __forceinline__ void from_low_side5(Real const (&v)[5], Real (&carry)[5], Real (&t)[5], Real *park,
-                                               int pstride, int lane)
+// NV values at once; `park` = this thread's (y/z sweeps) or this warp's (x sweep) shared-memory slots, stride pstride
+template <int DIR, int NV>
+__device__ __forceinline__ void from_low_side_n(Real const (&v)[NV], Real (&carry)[NV], Real (&t)[NV], Real *park,
+                                                int pstride, int lane)
 {
 #if CHL_DIR_PARK
   if (DIR == 0) {
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < NV; k++) {
       t[k] = __shfl_up_sync(0xffffffffu, v[k], 1);
       if (lane == 0) t[k] = park[k * pstride];
     }
     __syncwarp();
     if (lane == 31) {
 #pragma unroll
-      for (int k = 0; k < 5; k++) park[k * pstride] = v[k];
+      for (int k = 0; k < NV; k++) park[k * pstride] = v[k];
     }
     __syncwarp();
   } else {
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < NV; k++) {
       t[k]              = park[k * pstride];
       park[k * pstride] = v[k];
     }
   }
 #else
 #pragma unroll
-  for (int k = 0; k < 5; k++) t[k] = from_low_side<DIR>(v[k], carry[k], lane);
+  for (int k = 0; k < NV; k++) t[k] = from_low_side<DIR>(v[k], carry[k], lane);
 #endif
+}
+template <int DIR>
+__device__ __forceinline__ void from_low_side5(Real const (&v)[5], Real (&carry)[5], Real (&t)[5], Real *park,
+                                               int pstride, int lane)
+{
+  from_low_side_n<DIR, 5>(v, carry, t, park, pstride, lane);
 }
 
 template <int STAGE, int DIR, bool FIRST, bool LAST, bool STAGED>
