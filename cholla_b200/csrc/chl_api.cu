@@ -154,10 +154,10 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
     size_t const w = c->n_cells * ops->real_bytes;
     if (e == cudaSuccess) e = cudaMalloc(&c->d_prim, mhd->prim_fields * w);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_ctf, 9 * w);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_E, 3 * w);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_E, 6 * w);  // three edge EMFs + three cell-centred reference EMFs
     if (e == cudaSuccess) e = cudaMemset(c->d_prim, 0, mhd->prim_fields * w);
     if (e == cudaSuccess) e = cudaMemset(c->d_ctf, 0, 9 * w);
-    if (e == cudaSuccess) e = cudaMemset(c->d_E, 0, 3 * w);
+    if (e == cudaSuccess) e = cudaMemset(c->d_E, 0, 6 * w);
   }
   if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, sizeof(unsigned long long));
@@ -189,7 +189,7 @@ int chl_destroy(chl_ctx *c)
 size_t chl_scratch_bytes(const chl_ctx *c)
 {
   if (!c) return 0;
-  size_t fields = c->mhd ? 8 + 5 + c->mhd->prim_fields + 9 + 3 : c->ops->half_fields + (c->split ? 5 : 0);
+  size_t fields = c->mhd ? 8 + 5 + c->mhd->prim_fields + 9 + 6 : c->ops->half_fields + (c->split ? 5 : 0);
   return c->n_cells * fields * c->ops->real_bytes + sizeof(unsigned long long);
 }
 

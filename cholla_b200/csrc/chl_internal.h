@@ -42,7 +42,7 @@ struct MhdArgs {
   void *prim;   // [prim_fields][N] half-step primitives + cell-centred fields
   void *acc;    // [5][N]
   void *ctf;    // [3 directions][3][N] fluxes kept for constrained transport
-  void *E;      // [3][N] edge EMFs
+  void *E;      // [6][N]: three edge EMFs, then three cell-centred reference EMFs
   int nx, ny, nz, n_ghost, recon, dir_chunk;
   double dx, dy, dz, dt, gamma, density_floor;
 };

@@ -54,14 +54,14 @@ cudaError_t run_mhd_dirs(MhdDirParams p, Real *ctf, size_t N, double const dto[3
   return launch_mhd_dir<RECON, STAGE, 2, false, true>(p, s);
 }
 
-cudaError_t ct_and_b(MhdArgs const &a, const Real *state, const Real *bsrc, Real *bdst, int const elo[3],
+cudaError_t ct_and_b(MhdArgs const &a, const Real *ecen, const Real *bsrc, Real *bdst, int const elo[3],
                      int const ehi[3], int const blo[3], int const bhi[3], int const clo[3], int const chi[3], double dt,
                      cudaStream_t s)
 {
   size_t const N = (size_t)a.nx * a.ny * a.nz;
   MhdCtParams c;
   for (int d = 0; d < 3; d++) c.ctf[d] = (const Real *)a.ctf + (size_t)3 * d * N;
-  c.U = state;
+  c.ecen = ecen;
   c.E = (Real *)a.E;
   c.nx = a.nx; c.ny = a.ny; c.nz = a.nz;
   for (int d = 0; d < 3; d++) { c.lo[d] = elo[d]; c.hi[d] = ehi[d]; }
@@ -86,11 +86,13 @@ cudaError_t mhd_step(MhdArgs const &a, cudaStream_t s)
   int const n[3] = {a.nx, a.ny, a.nz};
   int const g    = a.n_ghost;
   Real *U = (Real *)a.U, *H = (Real *)a.half, *W = (Real *)a.prim;
+  Real *ecen = (Real *)a.E + 3 * N;  // cell-centred EMFs live behind the three edge EMFs
   MhdDirParams p;
   p.acc = (Real *)a.acc;
   p.nx = a.nx; p.ny = a.ny; p.nz = a.nz;
   p.gamma = (Real)a.gamma; p.density_floor = (Real)a.density_floor;
   p.chunk = 1;
+  p.ecen  = ecen;
   cudaError_t e;
   // ---- predictor ----
   {
@@ -117,9 +119,9 @@ cudaError_t mhd_step(MhdArgs const &a, cudaStream_t s)
     if ((e = launch_stage0()) != cudaSuccess) return e;
     int const elo[3] = {1, 1, 1}, ehi[3] = {n[0], n[1], n[2]};
     int const blo[3] = {1, 1, 1}, bhi[3] = {n[0] - 1, n[1] - 1, n[2] - 1};
-    if ((e = ct_and_b(a, U, U, H, elo, ehi, blo, bhi, blo, bhi, h, s)) != cudaSuccess) return e;
+    if ((e = ct_and_b(a, ecen, U, H, elo, ehi, blo, bhi, blo, bhi, h, s)) != cudaSuccess) return e;
     dim3 gp((n[0] - 2 + 127) / 128, n[1] - 2, n[2] - 2);
-    mhd_prim_kernel<<<gp, 128, 0, s>>>(H, W, a.nx, a.ny, a.nz, 1, (Real)a.gamma);
+    mhd_prim_kernel<<<gp, 128, 0, s>>>(H, W, ecen, a.nx, a.ny, a.nz, 1, (Real)a.gamma);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   // ---- corrector ----
@@ -136,7 +138,7 @@ cudaError_t mhd_step(MhdArgs const &a, cudaStream_t s)
     int const elo[3] = {g, g, g}, ehi[3] = {n[0] - g + 1, n[1] - g + 1, n[2] - g + 1};
     int const blo[3] = {g - 1, g - 1, g - 1}, bhi[3] = {n[0] - g, n[1] - g, n[2] - g};
     int const clo[3] = {g, g, g};
-    if ((e = ct_and_b(a, H, U, U, elo, ehi, blo, bhi, clo, bhi, a.dt, s)) != cudaSuccess) return e;
+    if ((e = ct_and_b(a, ecen, U, U, elo, ehi, blo, bhi, clo, bhi, a.dt, s)) != cudaSuccess) return e;
   }
   return cudaSuccess;
 }

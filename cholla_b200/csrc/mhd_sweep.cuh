@@ -38,6 +38,7 @@ struct MhdDirParams {
   Real *acc;         // [5][N]
   Real *out;         // LAST: stage 0 -> U-half (hydro fields), stage 1 -> U
   Real *ctf;         // [3][N]: mass flux, induction flux slot 5, slot 6 through the +face of each cell, this direction
+  Real *ecen;        // predictor x sweep only: [3][N] cell-centred reference EMFs of the state, for constrained transport
   int nx, ny, nz;
   int flo[3], fhi[3];  // cells whose +face flux is produced: [flo, fhi) along the sweep; transverse cells [flo, fhi)
   int ulo[3], uhi[3];  // cells whose hydro fields are updated
@@ -67,6 +68,19 @@ __device__ __forceinline__ void cell_centred_b(const Real *__restrict__ U, size_
   bx = (x > 0) ? RC(0.5) * (__ldg(U + 5 * N + id) + __ldg(U + 5 * N + id - 1)) : __ldg(U + 5 * N + id);
   by = (y > 0) ? RC(0.5) * (__ldg(U + 6 * N + id) + __ldg(U + 6 * N + id - nx)) : __ldg(U + 6 * N + id);
   bz = (z > 0) ? RC(0.5) * (__ldg(U + 7 * N + id) + __ldg(U + 7 * N + id - (size_t)nx * ny)) : __ldg(U + 7 * N + id);
+}
+
+// The cell-centred reference EMFs _ctSlope subtracts from the face EMFs (ct_electric_fields.h:98-113):
+// E_c = (M3 * B2 - M2 * B3) / d with (2, 3) the two directions after c in cyclic order.  The reference recomputes each
+// of them in every one of the 24 slopes an edge triple needs (~8 times per cell, a division and seven loads each);
+// here they are computed once per cell by a kernel that visits the cell anyway -- the predictor's x sweep for the
+// state U, the half-step primitive kernel for U-half -- with the same expression, hence the same bits.
+__device__ __forceinline__ void cell_emf(Real *__restrict__ ecen, size_t N, size_t id, Real d, Real mx, Real my, Real mz,
+                                         Real bx, Real by, Real bz)
+{
+  ecen[id]         = (mz * by - my * bz) / d;
+  ecen[N + id]     = (mx * bz - mz * bx) / d;
+  ecen[2 * N + id] = (my * bx - mx * by) / d;
 }
 
 template <int RECON, int STAGE, int DIR, bool FIRST, bool LAST>
@@ -159,6 +173,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
         L.v[5] = b[T1];
         L.v[6] = b[T2];
         R      = L;
+        if (DIR == 0) cell_emf(P.ecen, N, id, L.v[0], L.v[1], L.v[2], L.v[3], b[0], b[1], b[2]);
       } else {
         Real const bhi = __ldg(P.Bsrc + (size_t)(5 + DIR) * N + id);            // +face of cell c
         Real const blo = c > 0 ? __ldg(P.Bsrc + (size_t)(5 + DIR) * N + id - o.s) : bhi;  // -face of cell c
@@ -235,28 +250,22 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
 // ---- constrained transport ----------------------------------------------------------------------------------------
 struct MhdCtParams {
   const Real *ctf[3];  // per direction [3][N]
-  const Real *U;       // the state the cell-centred reference EMF is built from: U (predictor) or U-half (corrector)
+  const Real *ecen;    // [3][N] cell-centred reference EMFs of the state (cell_emf)
   Real *E;             // [3][N]
   int nx, ny, nz;
   int lo[3], hi[3];  // EMFs are produced on [lo, hi)
 };
 
 // _ctSlope (ct_electric_fields.h:66-116): face EMF minus the cell-centred reference EMF
-__device__ __forceinline__ Real ct_slope(const Real *__restrict__ ctf, const Real *__restrict__ U, Real sign, int ctdir,
+__device__ __forceinline__ Real ct_slope(const Real *__restrict__ ctf, const Real *__restrict__ ecen, Real sign, int ctdir,
                                          int cq1, int cq2, int fq1, int fq2, int x, int y, int z, int nx, int ny,
                                          size_t N)
 {
-  int const m1 = (ctdir + 1) % 3, m2 = (ctdir + 2) % 3;
   int const xc = x - (cq1 == 0) - (cq2 == 0), yc = y - (cq1 == 1) - (cq2 == 1), zc = z - (cq1 == 2) - (cq2 == 2);
   size_t const ic  = (size_t)xc + (size_t)nx * ((size_t)yc + (size_t)ny * zc);
   size_t const ifl = (size_t)(x - (fq1 == 0) - (fq2 == 0)) +
                      (size_t)nx * ((size_t)(y - (fq1 == 1) - (fq2 == 1)) + (size_t)ny * (z - (fq1 == 2) - (fq2 == 2)));
-  size_t const st[3] = {1, (size_t)nx, (size_t)nx * ny};
-  Real const d  = __ldg(U + ic);
-  Real const M2 = __ldg(U + ic + (size_t)(m1 + 1) * N), M3 = __ldg(U + ic + (size_t)(m2 + 1) * N);
-  Real const B2 = RC(0.5) * (__ldg(U + ic + (size_t)(m1 + 5) * N) + __ldg(U + ic - st[m1] + (size_t)(m1 + 5) * N));
-  Real const B3 = RC(0.5) * (__ldg(U + ic + (size_t)(m2 + 5) * N) + __ldg(U + ic - st[m2] + (size_t)(m2 + 5) * N));
-  Real const ec = (M3 * B2 - M2 * B3) / d;
+  Real const ec = __ldg(ecen + (size_t)ctdir * N + ic);
   Real const ef = sign * __ldg(ctf + ifl + (size_t)(sign == RC(1.0) ? 2 : 1) * N);
   return ef - ec;
 }
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(128) mhd_ct_kernel(MhdCtParams const P)
   int const x = P.lo[0] + blockIdx.x * 128 + threadIdx.x, y = P.lo[1] + blockIdx.y, z = P.lo[2] + blockIdx.z;
   if (x >= P.hi[0]) return;
   const Real *Fx = P.ctf[0], *Fy = P.ctf[1], *Fz = P.ctf[2];
-  const Real *U  = P.U;
+  const Real *U  = P.ecen;
 #define CIDX(a, b, c) ((size_t)(a) + (size_t)nx * ((size_t)(b) + (size_t)ny * (size_t)(c)))
 #define SLP(fl, sg, cd, c1, c2, f1, f2) ct_slope(fl, U, RC(sg), cd, c1, c2, f1, f2, x, y, z, nx, ny, N)
   size_t const id = CIDX(x, y, z);
@@ -362,8 +371,9 @@ __global__ void __launch_bounds__(128) mhd_bupdate_kernel(MhdBParams const P)
 }
 
 // half-step primitives: Load_Data (reconstruction.h:139-212, MHD) once per cell
-__global__ void __launch_bounds__(128) mhd_prim_kernel(const Real *__restrict__ H, Real *__restrict__ W, int nx, int ny,
-                                                       int nz, int lo, Real gamma)
+__global__ void __launch_bounds__(128) mhd_prim_kernel(const Real *__restrict__ H, Real *__restrict__ W,
+                                                       Real *__restrict__ ecen, int nx, int ny, int nz, int lo,
+                                                       Real gamma)
 {
   size_t const N = (size_t)nx * ny * nz;
   int const x = lo + blockIdx.x * 128 + threadIdx.x, y = lo + blockIdx.y, z = lo + blockIdx.z;
@@ -373,6 +383,7 @@ __global__ void __launch_bounds__(128) mhd_prim_kernel(const Real *__restrict__ 
   Real const vx = H[N + id] / d, vy = H[2 * N + id] / d, vz = H[3 * N + id] / d, E = H[4 * N + id];
   Real bx, by, bz;
   cell_centred_b(H, N, id, x, y, z, nx, ny, bx, by, bz);
+  cell_emf(ecen, N, id, d, H[N + id], H[2 * N + id], H[3 * N + id], bx, by, bz);
   W[id]         = d;
   W[N + id]     = vx;
   W[2 * N + id] = vy;
