@@ -19,6 +19,20 @@ namespace CHL_NS
 {
 constexpr Real kHlldSmall = RC(1.0e-8);  // hlld_cuda.h:35
 
+// A denominator several quotients share.  Strict: exact_div.cuh's Den / qdiv (the bits of a / b).  Product mode: one
+// straight-line reciprocal and a multiplication per quotient.
+#if CHL_STRICT
+typedef Den RDen;
+__device__ __forceinline__ RDen rden(Real b) { return den(b); }
+__device__ __forceinline__ Real rdiv(Real a, RDen const &d) { return qdiv(a, d); }
+#else
+struct RDen {
+  Real y;
+};
+__device__ __forceinline__ RDen rden(Real b) { return RDen{rcp_r(b)}; }
+__device__ __forceinline__ Real rdiv(Real a, RDen const &d) { return a * d.y; }
+#endif
+
 __device__ __forceinline__ Real dot3(Real a1, Real a2, Real a3, Real b1, Real b2, Real b3)
 {
   return a1 * b1 + ((a2 * b2) + (a3 * b3));  // math_utilities.h:78-82
@@ -28,18 +42,34 @@ __device__ __forceinline__ Real total_pressure(Real p, Real bx, Real by, Real bz
 {
   return fmax(p + mag_energy(bx, by, bz), kTiny);
 }
-__device__ __forceinline__ Real magnetosonic(Real d, Real p, Real bx, Real by, Real bz, Real gamma, Real wave)
+__device__ __forceinline__ Real msonic_disc(Real p, Real bx, Real by, Real bz, Real gamma, Real &t1)
 {
   Real const bx2 = bx * bx;
   Real const b2  = bx2 + ((by * by) + (bz * bz));
-  Real const t1  = gamma * p + b2;
+  t1             = gamma * p + b2;
   Real t2        = (t1 * t1) - RC(4.) * gamma * p * bx2;
 #if CHL_STRICT
   t2 = sqrt_r(t2);
 #else
   t2 = t2 > RC(0.0) ? sqrt_r(t2) : RC(0.0);  // (gamma p - bx^2)^2 when the transverse field vanishes: can be an exact zero
 #endif
+  return t2;
+}
+// _magnetosonicSpeed (mhd_utilities.h:48-73), wave = +1 fast / -1 slow
+__device__ __forceinline__ Real magnetosonic(Real d, Real p, Real bx, Real by, Real bz, Real gamma, Real wave)
+{
+  Real t1;
+  Real const t2 = msonic_disc(p, bx, by, bz, gamma, t1);
   return sqrt_r((t1 + wave * t2) / (RC(2.0) * fmax(d, kTiny)));
+}
+// fast and slow speed of one state: the discriminant and the division by 2 rho are shared
+__device__ __forceinline__ void magnetosonic_pair(Real d, Real p, Real bx, Real by, Real bz, Real gamma, Real &cf, Real &cs)
+{
+  Real t1;
+  Real const t2 = msonic_disc(p, bx, by, bz, gamma, t1);
+  RDen const dd = rden(RC(2.0) * fmax(d, kTiny));
+  cf = sqrt_r(rdiv(t1 + RC(1.0) * t2, dd));
+  cs = sqrt_r(rdiv(t1 + RC(-1.0) * t2, dd));
 }
 __device__ __forceinline__ Real alfven_speed(Real bx, Real d) { return fabs(bx) / sqrt_r(fmax(d, kTiny)); }
 // hydro_utilities.h:34-45 / 106-118 (MHD)
@@ -69,13 +99,15 @@ struct M7 {  // what travels between reconstruction and solver: (d, m1, m2, m3, 
 struct Eigen {
   Real cf, cs, cf2, cs2, alpha_f, alpha_s, beta_y, beta_z, n_fs, sign, q_f, q_s, a_f, a_s, qp_f, qp_s, ap_f, ap_s;
   Real d, a2, isd, sqd;
+  RDen dd, da2;  // the two denominators of Primitive_To_Characteristic: rho and a^2
   __device__ __forceinline__ void init(MPrim const &w, Real gamma)
   {
-    Real const a = sqrt_r(gamma * w.p / w.d);  // hydro_utilities::Calc_Sound_Speed
+    dd           = rden(w.d);
+    Real const a = sqrt_r(rdiv(gamma * w.p, dd));  // hydro_utilities::Calc_Sound_Speed
     a2           = a * a;
+    da2          = rden(a2);
     d            = w.d;
-    cf  = magnetosonic(w.d, w.p, w.bx, w.by, w.bz, gamma, RC(1.0));
-    cs  = magnetosonic(w.d, w.p, w.bx, w.by, w.bz, gamma, RC(-1.0));
+    magnetosonic_pair(w.d, w.p, w.bx, w.by, w.bz, gamma, cf, cs);
     cf2 = cf * cf;
     cs2 = cs * cs;
     Real const denom = cf2 - cs2, num2 = cf2 - a2;
@@ -88,15 +120,16 @@ struct Eigen {
         alpha_f = RC(0.0);
         alpha_s = RC(1.0);
       } else {
-        alpha_f = sqrt_r(num1 / denom);
-        alpha_s = sqrt_r(num2 / denom);
+        RDen const dn = rden(denom);
+        alpha_f       = sqrt_r(rdiv(num1, dn));
+        alpha_s       = sqrt_r(rdiv(num2, dn));
       }
     }
     Real const bd = rhypot(w.by, w.bz);
     beta_y        = isfinite(bd) ? w.by * bd : RC(1.0);
     beta_z        = isfinite(bd) ? w.bz * bd : RC(0.0);
     sign          = copysign(RC(1.0), w.bx);
-    n_fs          = RC(0.5) / a2;
+    n_fs          = rdiv(RC(0.5), da2);
     qp_f          = sign * n_fs * alpha_f * cf;
     qp_s          = sign * n_fs * alpha_s * cs;
     q_f           = sign * alpha_f * cf;
@@ -104,24 +137,26 @@ struct Eigen {
     sqd           = sqrt_r(w.d);
     a_f           = alpha_f * a * sqd;
     a_s           = alpha_s * a * sqd;
-    ap_f          = RC(0.5) * alpha_f / (a * sqd);
-    ap_s          = RC(0.5) * alpha_s / (a * sqd);
+    RDen const das = rden(a * sqd);
+    ap_f           = rdiv(RC(0.5) * alpha_f, das);
+    ap_s           = rdiv(RC(0.5) * alpha_s, das);
     isd           = rsqrt(w.d);
   }
   // s = (d, vx, vy, vz, p, by, bz) of a state or of a difference
   __device__ __forceinline__ void project(Real sd, Real svx, Real svy, Real svz, Real sp, Real sby, Real sbz,
                                           Real (&o)[7]) const
   {
-    o[0] = n_fs * alpha_f * (sp / d - cf * svx) + qp_s * (beta_y * svy + beta_z * svz) +
+    Real const spd = rdiv(sp, dd);
+    o[0] = n_fs * alpha_f * (spd - cf * svx) + qp_s * (beta_y * svy + beta_z * svz) +
            ap_s * (beta_y * sby + beta_z * sbz);
     o[1] = RC(0.5) * (beta_y * (sbz * sign * isd + svz) - beta_z * (sby * sign * isd + svy));
-    o[2] = n_fs * alpha_s * (sp / d - cs * svx) - qp_f * (beta_y * svy + beta_z * svz) -
+    o[2] = n_fs * alpha_s * (spd - cs * svx) - qp_f * (beta_y * svy + beta_z * svz) -
            ap_f * (beta_y * sby + beta_z * sbz);
-    o[3] = sd - sp / a2;
-    o[4] = n_fs * alpha_s * (sp / d + cs * svx) + qp_f * (beta_y * svy + beta_z * svz) -
+    o[3] = sd - rdiv(sp, da2);
+    o[4] = n_fs * alpha_s * (spd + cs * svx) + qp_f * (beta_y * svy + beta_z * svz) -
            ap_f * (beta_y * sby + beta_z * sbz);
     o[5] = RC(0.5) * (beta_y * (sbz * sign * isd - svz) - beta_z * (sby * sign * isd - svy));
-    o[6] = n_fs * alpha_f * (sp / d + cf * svx) - qp_s * (beta_y * svy + beta_z * svz) +
+    o[6] = n_fs * alpha_f * (spd + cf * svx) - qp_s * (beta_y * svy + beta_z * svz) +
            ap_s * (beta_y * sby + beta_z * sbz);
   }
   __device__ __forceinline__ MPrim unproject(Real const (&a)[7]) const
@@ -254,9 +289,10 @@ __device__ __forceinline__ HState hlld_load(M7 const &q, Real bx, Real gamma)
 {
   HState s;
   s.d  = fmax(q.v[0], kTiny);
-  s.vx = q.v[1] / s.d;
-  s.vy = q.v[2] / s.d;
-  s.vz = q.v[3] / s.d;
+  RDen const dd = rden(s.d);
+  s.vx = rdiv(q.v[1], dd);
+  s.vy = rdiv(q.v[2], dd);
+  s.vz = rdiv(q.v[3], dd);
   s.E  = fmax(q.v[4], kTiny);
   s.by = q.v[5];
   s.bz = q.v[6];
@@ -279,26 +315,27 @@ __device__ __forceinline__ M7 hlld_nonstar(HState const &s, Real bx)
 __device__ __forceinline__ HStar hlld_star(HState const &s, Real S, Real SM, Real bx, Real pts)
 {
   HStar o;
-  o.d = s.d * (S - s.vx) / (S - SM);
+  RDen const dsm = rden(S - SM);
+  o.d = rdiv(s.d * (S - s.vx), dsm);
   if (fabs(s.d * (S - s.vx) * (S - SM) - (bx * bx)) < pts * kHlldSmall) {
     o.vy = s.vy;
     o.vz = s.vz;
     o.by = s.by;
     o.bz = s.bz;
   } else {
-    Real const denom = s.d * (S - s.vx) * (S - SM) - (bx * bx);
-    Real coef        = bx * (SM - s.vx) / denom;
-    o.vy             = s.vy - s.by * coef;
-    o.vz             = s.vz - s.bz * coef;
-    Real t           = (S - s.vx);
-    t                = t * t;
-    coef             = (s.d * t - (bx * bx)) / denom;
-    o.by             = s.by * coef;
-    o.bz             = s.bz * coef;
+    RDen const dn = rden(s.d * (S - s.vx) * (S - SM) - (bx * bx));
+    Real coef     = rdiv(bx * (SM - s.vx), dn);
+    o.vy          = s.vy - s.by * coef;
+    o.vz          = s.vz - s.bz * coef;
+    Real t        = (S - s.vx);
+    t             = t * t;
+    coef          = rdiv(s.d * t - (bx * bx), dn);
+    o.by          = s.by * coef;
+    o.bz          = s.bz * coef;
   }
-  o.E = (s.E * (S - s.vx) - s.pt * s.vx + pts * SM +
-         bx * (dot3(s.vx, s.vy, s.vz, bx, s.by, s.bz) - dot3(SM, o.vy, o.vz, bx, o.by, o.bz))) /
-        (S - SM);
+  o.E = rdiv(s.E * (S - s.vx) - s.pt * s.vx + pts * SM +
+                 bx * (dot3(s.vx, s.vy, s.vz, bx, s.by, s.bz) - dot3(SM, o.vy, o.vz, bx, o.by, o.bz)),
+             dsm);
   return o;
 }
 __device__ __forceinline__ M7 hlld_star_flux(HStar const &st, HState const &s, M7 const &f, Real SM, Real S)
@@ -348,10 +385,12 @@ __device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, R
     return true;
   }
   Real const rdiff = SR - r.vx, ldiff = SL - l.vx;
-  Real const SM  = (rdiff * r.d * r.vx - ldiff * l.d * l.vx - r.pt + l.pt) / (rdiff * r.d - ldiff * l.d);
-  Real const pts = (r.d * l.pt * (SR - r.vx) - l.d * r.pt * (SL - l.vx) +
-                    l.d * r.d * (SR - r.vx) * (SL - l.vx) * (r.vx - l.vx)) /
-                   (r.d * (SR - r.vx) - l.d * (SL - l.vx));
+  // (rdiff * r.d - ldiff * l.d) and (r.d * (SR - r.vx) - l.d * (SL - l.vx)) are the same products: one denominator
+  RDen const dsm = rden(rdiff * r.d - ldiff * l.d);
+  Real const SM  = rdiv(rdiff * r.d * r.vx - ldiff * l.d * l.vx - r.pt + l.pt, dsm);
+  Real const pts = rdiv(r.d * l.pt * (SR - r.vx) - l.d * r.pt * (SL - l.vx) +
+                            l.d * r.d * (SR - r.vx) * (SL - l.vx) * (r.vx - l.vx),
+                        dsm);
   HStar const sl = hlld_star(l, SL, SM, bx, pts);
   Real const SLs = SM + RC(-1.0) * alfven_speed(bx, sl.d);
   if (SLs > RC(0.0) && SL <= RC(0.0)) {
