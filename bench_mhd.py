@@ -3,7 +3,7 @@
 reference's own -DMHD kernels (oracle/_ref).  usage: bench_mhd.py [N] [steps]   (each arm in its own process: the
 reference sizes global scratch at first use)"""
 import json, os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5

@@ -40,7 +40,7 @@ __device__ __forceinline__ Real dot3(Real a1, Real a2, Real a3, Real b1, Real b2
 __device__ __forceinline__ Real mag_energy(Real bx, Real by, Real bz) { return RC(0.5) * dot3(bx, by, bz, bx, by, bz); }
 __device__ __forceinline__ Real total_pressure(Real p, Real bx, Real by, Real bz)
 {
-  return fmax(p + mag_energy(bx, by, bz), kTiny);
+  return max_s(p + mag_energy(bx, by, bz), kTiny);
 }
 __device__ __forceinline__ Real msonic_disc(Real p, Real bx, Real by, Real bz, Real gamma, Real &t1)
 {
@@ -60,30 +60,34 @@ __device__ __forceinline__ Real magnetosonic(Real d, Real p, Real bx, Real by, R
 {
   Real t1;
   Real const t2 = msonic_disc(p, bx, by, bz, gamma, t1);
-  return sqrt_r((t1 + wave * t2) / (RC(2.0) * fmax(d, kTiny)));
+  return sqrt_r(rdiv(t1 + wave * t2, rden(RC(2.0) * max_s(d, kTiny))));
 }
 // fast and slow speed of one state: the discriminant and the division by 2 rho are shared
 __device__ __forceinline__ void magnetosonic_pair(Real d, Real p, Real bx, Real by, Real bz, Real gamma, Real &cf, Real &cs)
 {
   Real t1;
   Real const t2 = msonic_disc(p, bx, by, bz, gamma, t1);
-  RDen const dd = rden(RC(2.0) * fmax(d, kTiny));
+  RDen const dd = rden(RC(2.0) * max_s(d, kTiny));
   cf = sqrt_r(rdiv(t1 + RC(1.0) * t2, dd));
   cs = sqrt_r(rdiv(t1 + RC(-1.0) * t2, dd));
 }
-__device__ __forceinline__ Real alfven_speed(Real bx, Real d) { return fabs(bx) / sqrt_r(fmax(d, kTiny)); }
+__device__ __forceinline__ Real alfven_speed(Real bx, Real d) { return rdiv(fabs(bx), rden(sqrt_r(max_s(d, kTiny)))); }
 // hydro_utilities.h:34-45 / 106-118 (MHD)
 __device__ __forceinline__ Real mhd_pressure(Real E, Real d, Real vx, Real vy, Real vz, Real gamma, Real bx, Real by,
                                              Real bz)
 {
   Real p = E - RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
   p -= mag_energy(bx, by, bz);
-  return fmax((gamma - RC(1.)) * p, kTiny);
+  return max_s((gamma - RC(1.)) * p, kTiny);
 }
-__device__ __forceinline__ Real mhd_energy(Real P, Real d, Real vx, Real vy, Real vz, Real gamma, Real bx, Real by,
+__device__ __forceinline__ Real mhd_energy(Real P, Real d, Real vx, Real vy, Real vz, KC const &k, Real bx, Real by,
                                            Real bz)
 {
-  Real e = (fmax(P, kTiny) / (gamma - RC(1.))) + RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
+#if CHL_STRICT
+  Real e = qdiv(max_s(P, kTiny), k.g1) + RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
+#else
+  Real e = (max_s(P, kTiny) * k.ig1) + RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
+#endif
   e += mag_energy(bx, by, bz);
   return e;
 }
@@ -199,10 +203,10 @@ __device__ __forceinline__ MPrim load_mprim(const Real *__restrict__ c, MOff con
 
 __device__ __forceinline__ void mhd_floor(MPrim &l, MPrim &r)
 {
-  r.d = fmax(r.d, kTiny);
-  l.d = fmax(l.d, kTiny);
-  r.p = fmax(r.p, kTiny);
-  l.p = fmax(l.p, kTiny);
+  r.d = max_s(r.d, kTiny);
+  l.d = max_s(l.d, kTiny);
+  r.p = max_s(r.p, kTiny);
+  l.p = max_s(l.p, kTiny);
 }
 
 __device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const &o, KC const &k, MPrim &L, MPrim &R)
@@ -265,14 +269,14 @@ __device__ __forceinline__ void mhd_plmc(const Real *__restrict__ c, MOff const 
 
 // Write_Data (reconstruction.h:918-968): interface primitives -> (d, m1, m2, m3, E, By, Bz); the energy uses the
 // FACE-centred normal field of the face the state sits on
-__device__ __forceinline__ M7 mhd_interface(MPrim const &q, Real bface, Real gamma)
+__device__ __forceinline__ M7 mhd_interface(MPrim const &q, Real bface, KC const &k)
 {
   M7 s;
   s.v[0] = q.d;
   s.v[1] = q.d * q.vx;
   s.v[2] = q.d * q.vy;
   s.v[3] = q.d * q.vz;
-  s.v[4] = mhd_energy(q.p, q.d, q.vx, q.vy, q.vz, gamma, bface, q.by, q.bz);
+  s.v[4] = mhd_energy(q.p, q.d, q.vx, q.vy, q.vz, k, bface, q.by, q.bz);
   s.v[5] = q.by;
   s.v[6] = q.bz;
   return s;
@@ -288,12 +292,12 @@ struct HStar {
 __device__ __forceinline__ HState hlld_load(M7 const &q, Real bx, Real gamma)
 {
   HState s;
-  s.d  = fmax(q.v[0], kTiny);
+  s.d  = max_s(q.v[0], kTiny);
   RDen const dd = rden(s.d);
   s.vx = rdiv(q.v[1], dd);
   s.vy = rdiv(q.v[2], dd);
   s.vz = rdiv(q.v[3], dd);
-  s.E  = fmax(q.v[4], kTiny);
+  s.E  = max_s(q.v[4], kTiny);
   s.by = q.v[5];
   s.bz = q.v[6];
   s.pg = mhd_pressure(s.E, s.d, s.vx, s.vy, s.vz, gamma, bx, s.by, s.bz);
@@ -412,7 +416,7 @@ __device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, R
     }
   } else {
     Real const sdl = sqrt_r(sl.d), sdr = sqrt_r(sr.d);
-    Real const inv = RC(1.0) / (sdl + sdr);
+    Real const inv = rdiv(RC(1.0), rden(sdl + sdr));
     Real const sg  = copysign(RC(1.0), bx);
     vyd = inv * (sdl * sl.vy + sdr * sr.vy + sg * (sr.by - sl.by));
     vzd = inv * (sdl * sl.vz + sdr * sr.vz + sg * (sr.bz - sl.bz));

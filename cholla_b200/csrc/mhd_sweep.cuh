@@ -78,9 +78,10 @@ __device__ __forceinline__ void cell_centred_b(const Real *__restrict__ U, size_
 __device__ __forceinline__ void cell_emf(Real *__restrict__ ecen, size_t N, size_t id, Real d, Real mx, Real my, Real mz,
                                          Real bx, Real by, Real bz)
 {
-  ecen[id]         = (mz * by - my * bz) / d;
-  ecen[N + id]     = (mx * bz - mz * bx) / d;
-  ecen[2 * N + id] = (my * bx - mx * by) / d;
+  RDen const dd    = rden(d);
+  ecen[id]         = rdiv(mz * by - my * bz, dd);
+  ecen[N + id]     = rdiv(mx * bz - mz * bx, dd);
+  ecen[2 * N + id] = rdiv(my * bx - mx * by, dd);
 }
 
 template <int RECON, int STAGE, int DIR, bool FIRST, bool LAST>
@@ -180,15 +181,15 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
         if (RECON == kPCM) {
           MPrim const w = load_mprim(P.in + id, o, 0);  // PCM corrector: interface = cell, energy from the cell state
           MPrim q       = w;
-          L             = mhd_interface(q, w.bx, gamma);
+          L             = mhd_interface(q, w.bx, kc);
           // PCM copies the conserved energy; rebuilding it from primitives with the centred field is the same sum
           R = L;
         } else {
           MPrim l, r;
           if (RECON == kPPMC) mhd_ppmc(P.in + id, o, kc, l, r);
           else mhd_plmc(P.in + id, o, gamma, l, r);
-          L = mhd_interface(l, bhi, gamma);
-          R = mhd_interface(r, blo, gamma);
+          L = mhd_interface(l, bhi, kc);
+          R = mhd_interface(r, blo, kc);
         }
       }
     } else {
@@ -380,7 +381,8 @@ __global__ void __launch_bounds__(128) mhd_prim_kernel(const Real *__restrict__ 
   if (x >= nx - lo) return;
   size_t const id = CIDX(x, y, z);
   Real const d  = H[id];
-  Real const vx = H[N + id] / d, vy = H[2 * N + id] / d, vz = H[3 * N + id] / d, E = H[4 * N + id];
+  RDen const dd = rden(d);
+  Real const vx = rdiv(H[N + id], dd), vy = rdiv(H[2 * N + id], dd), vz = rdiv(H[3 * N + id], dd), E = H[4 * N + id];
   Real bx, by, bz;
   cell_centred_b(H, N, id, x, y, z, nx, ny, bx, by, bz);
   cell_emf(ecen, N, id, d, H[N + id], H[2 * N + id], H[3 * N + id], bx, by, bz);
