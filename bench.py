@@ -321,6 +321,8 @@ def main():
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout: keep the one JSON line clean
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         group = dist.group.WORLD
     S = args.size
