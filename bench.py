@@ -139,14 +139,15 @@ def run_reference(args):
 
     from cholla_b200 import initial_conditions as ic
     from oracle import reference
-    recon, solver = 2, 0
+    recon, solver = {"pcm": 0, "plmc": 1, "ppmc": 2}[args.recon], {"hllc": 0, "roe": 1}[args.solver]
     out = {"impl": "reference", "metric": "cell-updates/s", "unit": "cell-updates/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
     nosync = args.ref_variant == "nosync"
     if not reference.available(recon, solver, nosync) or not torch.cuda.is_available():
         print(json.dumps({"impl": "reference", "unavailable":
-                          "oracle/_ref/libcholla_ref_ppmc_hllc%s.so not built or no GPU" % ("_nosync" if nosync else "")}))
+                          "oracle/_ref/libcholla_ref_%s_%s%s.so not built or no GPU"
+                          % (args.recon, args.solver, "_nosync" if nosync else "")}))
         return 0
     S, g = args.size, 4
     n = (S, S, S)
@@ -173,8 +174,8 @@ def run_reference(args):
     value = S ** 3 * args.steps / (ms * 1e-3)
     peak, which = measured_hbm_peak()
     out.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks,
-                "config": {"workload": "blast %d^3 PPMC+HLLC fp64 periodic, reference kernels%s" %
-                           (S, " (-DDISABLE_GPU_ERROR_CHECKING)" if nosync else " (as shipped: device sync after every stage)"),
+                "config": {"workload": "blast %d^3 %s+%s fp64 periodic, reference kernels%s" %
+                           (S, args.recon.upper(), args.solver.upper(), " (-DDISABLE_GPU_ERROR_CHECKING)" if nosync else " (as shipped: device sync after every stage)"),
                            "l2": "inputs larger than L2", "build": L.ref_build_flags().decode()},
                 "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "reference",
                                  "sample": "the reference has no CPU hydro path: this is its own unmodified CUDA "
@@ -202,7 +203,9 @@ def run_b200(args, mode, world, rank, local, group, with_e2e):
     n_global = [S * np_grid[0], S * np_grid[1], S * np_grid[2]]
     lengths = [float(np_grid[0]), float(np_grid[1]), float(np_grid[2])]  # unit cells, unit box per GPU
     strict = mode == "strict" and args.precision == 2
-    G = Grid3D(n_global, lengths, recon=cb.PPMC, solver=cb.HLLC, gamma=GAMMA, bc=[1] * 6, precision=args.precision,
+    recon = {"pcm": cb.PCM, "plmc": cb.PLMC, "ppmc": cb.PPMC}[args.recon]
+    solver = {"hllc": cb.HLLC, "roe": cb.ROE}[args.solver]
+    G = Grid3D(n_global, lengths, recon=recon, solver=solver, gamma=GAMMA, bc=[1] * 6, precision=args.precision,
                strict=strict, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world, fused=True)
     with ic.block(G.decomp.offset, G.decomp.n_local):
         if args.workload == "kh":      # BASELINE config 3: every cell moves, two shear layers
@@ -302,6 +305,8 @@ def main():
                     help="blast = BASELINE config 5 (headline); kh = Kelvin-Helmholtz (config 3 initial conditions); "
                          "noise = random cell-to-cell state (worst case for the limiters)")
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--recon", default="ppmc", choices=["pcm", "plmc", "ppmc"], help="headline: ppmc")
+    ap.add_argument("--solver", default="hllc", choices=["hllc", "roe"], help="headline: hllc")
     ap.add_argument("--ref-variant", default="shipped", choices=["shipped", "nosync"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -348,7 +353,8 @@ def main():
         "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.precision == 2 else "f32", "data": "synthetic",
-        "config": {"workload": "%s %d^3 per GPU, PPMC+HLLC, periodic, VL integrator, %s arithmetic" % (args.workload, S, mode),
+        "config": {"workload": "%s %d^3 per GPU, %s+%s, periodic, VL integrator, %s arithmetic"
+                               % (args.workload, S, args.recon.upper(), args.solver.upper(), mode),
                    "global_cells": r["n_global"], "decomposition": r["np_grid"],
                    "l2": "inputs larger than L2 (%.1f GB state per GPU)" % (r["state_bytes"] / 1e9),
                    "step": "set_dt + VL step (fused T-floor/CFL) + ghost fill/halo exchange"},
