@@ -106,7 +106,7 @@ def ncu_traffic():
         return None
 
 
-def cpu_baseline(sample_n=72, steps=1):
+def cpu_baseline(sample_n=192, steps=1):
     """CPU oracle (oracle/vl_oracle.c, a port) on a bounded sample of the same workload; scalar, 1 thread."""
     import numpy as np
 

@@ -8,21 +8,22 @@
 //
 // Each launch sweeps ONE direction.  A thread (y/z sweeps) or a warp (x sweep) MARCHES along that direction and
 // carries the low-side interface state and the lower-face flux from cell to cell, so every cell is reconstructed
-// once and every face is solved once -- no shared memory, no barriers, no recomputation apart from two cells at
-// the ends of a chunk:
-//     for c = first-1 .. last+1:   (L_c, R_c) = reconstruct(c)            L: low side of face c+1/2, R: high side of c-1/2
+// once and every face is solved once -- no barriers, no recomputation apart from two cells at the ends of a chunk:
+//     for c = first-1 .. last+1:   cp.async: update operands of cell c-1 -> shared memory (StageGeom)
+//                                  (L_c, R_c) = reconstruct(c)            L: low side of face c+1/2, R: high side of c-1/2
 //                                  F_{c-1/2}  = riemann(L_{c-1}, R_c)
 //                                  cell c-1  += dt/dx (F_{c-3/2} - F_{c-1/2})
 // x sweep: lanes are 32 consecutive cells, "c-1" is the lane to the left (__shfl_up) and lane 0 takes the value
-// lane 31 carried over from the previous 32 cells.  y/z sweeps: lanes are 32 consecutive x (coalesced), "c-1" is
-// the thread's own previous iteration.
+// lane 31 parked for it after the previous 32 cells.  y/z sweeps: lanes are 32 consecutive x (coalesced), "c-1" is
+// the thread's own previous iteration, parked in a thread-private shared-memory column (CHL_DIR_PARK) so that it
+// does not hold 20 registers through the reconstruction.
 //
 // The flux differences of the directions are summed in the reference's order through one accumulator array:
 //   predictor  ((U + x) + y) + z -> half-step primitives W          (VL_3D_cuda.cu:444-461)
 //   corrector  U += (x + y) + z, floors, CFL max                    (hydro_cuda.cu:236-249, 279-291, 1117-1153)
 // FIRST = this pass starts the sum, LAST = this pass completes the cell.  HBM traffic per cell-update in 3-D fp64
-// (product mode): predictor 40+40 | 40+40+40 | 40+40+40 B, corrector 40+40 | 40+40+40 | 40+40+40+40 B = 680 B,
-// i.e. 3.4x the fused kernel's 200 B and 0.37x the reference's 1.84 kB.
+// (product mode): predictor 40+40 | 40+40+40 | 40+40+40 B, corrector 40+40 | 40+40+40 | 40+40+40+40 B = 680 B by
+// design (734 B measured, profiles/roofline_traffic.json): 3.4x the fused kernel's 200 B, 0.4x the reference's 1.84 kB.
 #pragma once
 #include "vl_sweep.cuh"
 
