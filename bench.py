@@ -98,7 +98,7 @@ def measured_hbm_peak():
 
 
 def ncu_traffic():
-    """Per-launch DRAM bytes of the corrector from the committed ncu capture, if one exists."""
+    """DRAM bytes of one step's six sweeps per arithmetic mode, from the committed ncu capture (scratch/ncu_traffic.py)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
             return json.load(fh)
