@@ -145,3 +145,60 @@ def test_deck_driven_run_matches_oracle_loop(tmp_path):
     assert z["density"].shape == (100, 1, 1) and float(z["attr_t"]) == 0.2 and int(z["attr_n_step"]) == n_step
     assert np.array_equal(z["density"][:, 0, 0], got[0, 0, 0, :]) and np.array_equal(z["Energy"][:, 0, 0], got[4, 0, 0, :])
     assert os.path.basename(files[1]) == "1.npz.0" and os.path.basename(os.path.dirname(files[1])) == "1"
+
+
+OT_DECK = """# Orszag-Tang vortex, in the format of the reference's examples/3D/orszag_tang_vortex.txt (config C4), small grid
+nx=24
+ny=24
+nz=24
+tout=0.5
+outstep=0.5
+init=Orszag_Tang_Vortex
+xmin=0.0
+ymin=0.0
+zmin=0.0
+xlen=1.0
+ylen=1.0
+zlen=1.0
+xl_bcnd=1
+xu_bcnd=1
+yl_bcnd=1
+yu_bcnd=1
+zl_bcnd=1
+zu_bcnd=1
+outdir=./
+gamma=1.666666666666667
+"""
+
+
+@pytest.mark.gpu
+def test_deck_driven_mhd_run(tmp_path):
+    """run.py on an Orszag-Tang deck (PPMC + HLLD + CT): the same bytes as the MHD oracle advanced over the same number
+    of steps, div B at round-off, magnetic datasets in the snapshot."""
+    from oracle import mhd
+    import cholla_b200 as cb
+    from cholla_b200 import initial_conditions as ic, run
+    from cholla_b200.grid import n_ghost_for
+    deck = tmp_path / "ot.txt"
+    deck.write_text(OT_DECK)
+    P = pm.parse_params(str(deck), ["outdir=%s/" % tmp_path])
+    steps = 6
+    G, files = run.run(P, recon="ppmc", solver="hlld", strict=True, max_steps=steps, log=lambda *_: None)
+    got = G.download()
+    H = G.H
+    assert H.n_step == steps and H.n_fields == 8 and len(files) == 1  # only the initial snapshot: tout not reached
+    G.close()
+    g = n_ghost_for(cb.PPMC, mhd=True)
+    dims = (24 + 2 * g,) * 3
+    flat = np.ascontiguousarray(ic.orszag_tang((24, 24, 24), g, P.gamma).reshape(-1))
+    mhd.set_boundaries(flat, *dims, g, [1] * 6)
+    d = 1.0 / 24
+    mhd.advance(flat, *dims, g, d, d, d, P.gamma, cb.PPMC, [1] * 6, steps)
+    real = lambda a: a.reshape(8, dims[2], dims[1], dims[0])[:, g:-g, g:-g, g:-g]
+    a, b = real(got), real(flat)
+    groups = [[0], [1, 2, 3], [4], [5, 6, 7]]
+    err = max(sum(np.abs(a[f] - b[f]).sum() for f in q) / sum(np.abs(b[f]).sum() for f in q) for q in groups)
+    assert err <= 1e-12, err  # rsqrt / rhypot have no correctly rounded libm twin: tolerance, not bits (DESIGN 4)
+    assert mhd.max_divergence(got, *dims, g, d, d, d) <= 1e-11
+    z = np.load(files[0])
+    assert z["magnetic_x"].shape == (24, 24, 24) and int(z["attr_n_fields"]) == 8
