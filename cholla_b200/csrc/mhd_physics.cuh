@@ -209,22 +209,61 @@ __device__ __forceinline__ void mhd_floor(MPrim &l, MPrim &r)
   l.p = max_s(l.p, kTiny);
 }
 
+// PPMC_VL (MHD).  The reference projects the five cells on all seven characteristics first (35 values) and then limits
+// them; with the 22-double eigen-system that is > 60 live doubles.  Here the characteristics are produced one wave
+// family at a time -- the four magneto-sonic ones, the two Alfven ones, the entropy one -- each family reloading the few
+// primitives it needs (L1) and handing its 5-cell stencils straight to ppm_single, so the projection-only part of the
+// eigen-system dies after the first family.  Every expression keeps Eigen::project()'s association (same bits).
 __device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const &o, KC const &k, MPrim &L, MPrim &R)
 {
   Real const gamma = k.gamma;
-  MPrim const wi   = load_mprim(c, o, 0);
   Eigen e;
-  e.init(wi, gamma);
-  Real ch[5][7];
-#pragma unroll
-  for (int i = 0; i < 5; i++) {
-    MPrim const w = i == 2 ? wi : load_mprim(c, o, i - 2);
-    e.project(w.d, w.vx, w.vy, w.vz, w.p, w.by, w.bz, ch[i]);
-  }
+  e.init(load_mprim(c, o, 0), gamma);
   Real cl[7], cr[7];
-  // the hydro path's PPM_Single_Variable: lazy limiters, shared x/6 reciprocal -- same values (hydro_physics.cuh)
+  {  // fast / slow magneto-sonic pairs: characteristics 0, 6 (fast) and 2, 4 (slow)
+    Real const nf = e.n_fs * e.alpha_f, ns = e.n_fs * e.alpha_s;
+    Real t0[5], t6[5], t2[5], t4[5];
 #pragma unroll
-  for (int f = 0; f < 7; f++) ppm_single(ch[0][f], ch[1][f], ch[2][f], ch[3][f], ch[4][f], cl[f], cr[f], k);
+    for (int i = 0; i < 5; i++) {
+      const Real *q  = c + (long)(i - 2) * o.s;
+      Real const svx = __ldg(q + o.v1), svy = __ldg(q + o.v2), svz = __ldg(q + o.v3);
+      Real const sby = __ldg(q + o.b2), sbz = __ldg(q + o.b3);
+      Real const spd = rdiv(__ldg(q + o.p), e.dd);
+      Real const A = e.beta_y * svy + e.beta_z * svz, B = e.beta_y * sby + e.beta_z * sbz;
+      Real const qsA = e.qp_s * A, qfA = e.qp_f * A, asB = e.ap_s * B, afB = e.ap_f * B;
+      Real const fx = e.cf * svx, sx = e.cs * svx;
+      t0[i] = nf * (spd - fx) + qsA + asB;
+      t2[i] = ns * (spd - sx) - qfA - afB;
+      t4[i] = ns * (spd + sx) + qfA - afB;
+      t6[i] = nf * (spd + fx) - qsA + asB;
+    }
+    ppm_single(t0[0], t0[1], t0[2], t0[3], t0[4], cl[0], cr[0], k);
+    ppm_single(t6[0], t6[1], t6[2], t6[3], t6[4], cl[6], cr[6], k);
+    ppm_single(t2[0], t2[1], t2[2], t2[3], t2[4], cl[2], cr[2], k);
+    ppm_single(t4[0], t4[1], t4[2], t4[3], t4[4], cl[4], cr[4], k);
+  }
+  {  // Alfven pair: characteristics 1, 5
+    Real t1[5], t5[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const Real *q  = c + (long)(i - 2) * o.s;
+      Real const svy = __ldg(q + o.v2), svz = __ldg(q + o.v3);
+      Real const by = __ldg(q + o.b2) * e.sign * e.isd, bz = __ldg(q + o.b3) * e.sign * e.isd;
+      t1[i] = RC(0.5) * (e.beta_y * (bz + svz) - e.beta_z * (by + svy));
+      t5[i] = RC(0.5) * (e.beta_y * (bz - svz) - e.beta_z * (by - svy));
+    }
+    ppm_single(t1[0], t1[1], t1[2], t1[3], t1[4], cl[1], cr[1], k);
+    ppm_single(t5[0], t5[1], t5[2], t5[3], t5[4], cl[5], cr[5], k);
+  }
+  {  // entropy: characteristic 3
+    Real t3[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const Real *q = c + (long)(i - 2) * o.s;
+      t3[i]         = __ldg(q) - rdiv(__ldg(q + o.p), e.da2);
+    }
+    ppm_single(t3[0], t3[1], t3[2], t3[3], t3[4], cl[3], cr[3], k);
+  }
   L = e.unproject(cl);
   R = e.unproject(cr);
   mhd_floor(L, R);
