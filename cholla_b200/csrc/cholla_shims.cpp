@@ -9,7 +9,7 @@
 //
 // Signatures are the reference's, C++ linkage (src/integrators/VL_*D_cuda.h, src/hydro/hydro_cuda.h:69,87,
 // src/grid/cuda_boundaries.h).  The compile-time feature macros of builds/make.type.* select the run-time enums:
-//   -DPCM / -DPLMC / -DPPMC -> chl_config.recon      -DHLLC / -DROE / -DHLLD -> chl_config.solver
+//   -DPCM / -DPLMC / -DPPMC -> chl_config.recon      -DHLLC / -DROE / -DHLL / -DHLLD -> chl_config.solver
 //   -DPRECISION=1|2         -> Real and chl_config.precision        -DMHD -> chl_config.mhd
 // `gama` is the reference's global (src/global/global.cpp:18).  CHOLLA_B200_STRICT=0 in the environment selects the
 // product arithmetic; the default is the bit-reproducing strict mode, so a drop-in build produces the snapshots the
@@ -53,8 +53,10 @@ constexpr int kSolver = CHL_SOLVER_HLLD;
 constexpr int kSolver = CHL_SOLVER_ROE;
 #elif defined(HLLC)
 constexpr int kSolver = CHL_SOLVER_HLLC;
+#elif defined(HLL)
+constexpr int kSolver = CHL_SOLVER_HLL;
 #else
-#error "cholla_shims.cpp: build with -DHLLC, -DROE or -DHLLD (EXACT/HLL are not on the B200 path)"
+#error "cholla_shims.cpp: build with -DHLLC, -DROE, -DHLL or -DHLLD (EXACT is not on the B200 path)"
 #endif
 #ifdef MHD
 constexpr int kMhd = 1;

@@ -52,6 +52,7 @@ cudaError_t sweep(int stage, int recon, int solver, SweepArgs const &a, cudaStre
   p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
   p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
   p.dti_key = a.dti_key;
+  if (solver == kHLL) return cudaErrorNotSupported;  // the fused family instantiates HLLC and Roe only (chl_create)
   if (stage == 0) {
     if (solver == kROE) return launch<kPCM, kROE, 0>(p, s);
     return launch<kPCM, kHLLC, 0>(p, s);
@@ -141,7 +142,13 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   p.dti_key = a.dti_key;
   if (stage == 0) {
     if (solver == kROE) return run_dirs<kPCM, kROE, 0>(p, a, s);
+    if (solver == kHLL) return run_dirs<kPCM, kHLL, 0>(p, a, s);
     return run_dirs<kPCM, kHLLC, 0>(p, a, s);
+  }
+  if (solver == kHLL) {
+    if (recon == kPCM) return run_dirs<kPCM, kHLL, 1>(p, a, s);
+    if (recon == kPLMC) return run_dirs<kPLMC, kHLL, 1>(p, a, s);
+    return run_dirs<kPPMC, kHLL, 1>(p, a, s);
   }
   switch (recon * 2 + (solver == kROE ? 1 : 0)) {
     case kPCM * 2 + 0: return run_dirs<kPCM, kHLLC, 1>(p, a, s);

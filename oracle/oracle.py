@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PCM, PLMC, PPMC = 0, 1, 2
-HLLC, ROE = 0, 1
+HLLC, ROE, HLL = 0, 1, 3
 _lib = None
 
 

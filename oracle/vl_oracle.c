@@ -13,7 +13,7 @@
  *   src/reconstruction/plmc_cuda.cu          PLM, characteristic limiting
  *   src/reconstruction/ppmc_cuda.cu:540-695  PPMC_VL
  *   src/reconstruction/reconstruction.h      shared helpers (hydro branches)
- *   src/riemann_solvers/hllc_cuda.cu, roe_cuda.cu
+ *   src/riemann_solvers/hllc_cuda.cu, roe_cuda.cu, hll_cuda.cu
  *   src/hydro/hydro_cuda.cu                  conserved update, Calc_dt, temperature floor
  *   src/grid/cuda_boundaries.cu, src/grid/boundary_conditions.cpp:419-  ghost cells
  * Build with -O2 -ffp-contract=off (the reference device code is built -fmad=false,
@@ -35,7 +35,7 @@
 #define ORC_TINY 1.0e-20 /* global.h:25 */
 
 enum { ORC_PCM = 0, ORC_PLMC = 1, ORC_PPMC = 2 };
-enum { ORC_HLLC = 0, ORC_ROE = 1 };
+enum { ORC_HLLC = 0, ORC_ROE = 1, ORC_HLL = 3 }; /* 2 is HLLD (mhd_oracle.c) */
 
 typedef struct {
   double d, vx, vy, vz, p;
@@ -345,6 +345,30 @@ static cons_t hllc_flux(cons_t l, cons_t r, double gamma)
   return f;
 }
 
+/* hll_cuda.cu:62-262: Davis wave-speed bounds from the two sound speeds, single-state HLL flux */
+static cons_t hll_flux(cons_t l, cons_t r, double gamma)
+{
+  cons_t f;
+  double vxl = l.mx / l.d, vyl = l.my / l.d, vzl = l.mz / l.d;
+  double pl = (l.E - 0.5 * l.d * (vxl * vxl + vyl * vyl + vzl * vzl)) * (gamma - 1.0);
+  pl = fmax(pl, ORC_TINY);
+  double vxr = r.mx / r.d, vyr = r.my / r.d, vzr = r.mz / r.d;
+  double pr = (r.E - 0.5 * r.d * (vxr * vxr + vyr * vyr + vzr * vzr)) * (gamma - 1.0);
+  pr = fmax(pr, ORC_TINY);
+  double cfl = sqrt(gamma * pl / l.d), cfr = sqrt(gamma * pr / r.d);
+  double Sl = fmin(vxr - cfr, vxl - cfl), Sr = fmax(vxl + cfl, vxr + cfr);
+  double fdl = l.mx, fmxl = l.mx * vxl + pl, fmyl = l.my * vxl, fmzl = l.mz * vxl, fEl = (l.E + pl) * vxl;
+  double fdr = r.mx, fmxr = r.mx * vxr + pr, fmyr = r.my * vxr, fmzr = r.mz * vxr, fEr = (r.E + pr) * vxr;
+  if (Sl > 0.0) { f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl; return f; }
+  if (Sr < 0.0) { f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr; return f; }
+  f.d  = ((Sr * fdl) - (Sl * fdr) + Sl * Sr * (r.d - l.d)) / (Sr - Sl);
+  f.mx = ((Sr * fmxl) - (Sl * fmxr) + Sl * Sr * (r.mx - l.mx)) / (Sr - Sl);
+  f.my = ((Sr * fmyl) - (Sl * fmyr) + Sl * Sr * (r.my - l.my)) / (Sr - Sl);
+  f.mz = ((Sr * fmzl) - (Sl * fmzr) + Sl * Sr * (r.mz - l.mz)) / (Sr - Sl);
+  f.E  = ((Sr * fEl) - (Sl * fEr) + Sl * Sr * (r.E - l.E)) / (Sr - Sl);
+  return f;
+}
+
 /* roe_cuda.cu:105-398 (etah = 0) */
 static cons_t roe_flux(cons_t l, cons_t r, double gamma)
 {
@@ -442,7 +466,7 @@ void orc_riemann(int solver, const double *QL, const double *QR, double *F, int 
   for (long id = 0; id < (long)N; id++) {
     cons_t l = {QL[id], QL[o1 * N + id], QL[o2 * N + id], QL[o3 * N + id], QL[4 * N + id]};
     cons_t r = {QR[id], QR[o1 * N + id], QR[o2 * N + id], QR[o3 * N + id], QR[4 * N + id]};
-    cons_t f = solver == ORC_ROE ? roe_flux(l, r, gamma) : hllc_flux(l, r, gamma);
+    cons_t f = solver == ORC_ROE ? roe_flux(l, r, gamma) : (solver == ORC_HLL ? hll_flux(l, r, gamma) : hllc_flux(l, r, gamma));
     F[id] = f.d; F[o1 * N + id] = f.mx; F[o2 * N + id] = f.my; F[o3 * N + id] = f.mz; F[4 * N + id] = f.E;
   }
 }
@@ -450,7 +474,7 @@ void orc_riemann(int solver, const double *QL, const double *QR, double *F, int 
 void orc_riemann_single(int solver, const double *l5, const double *r5, double gamma, double *f5)
 {
   cons_t l = {l5[0], l5[1], l5[2], l5[3], l5[4]}, r = {r5[0], r5[1], r5[2], r5[3], r5[4]};
-  cons_t f = solver == ORC_ROE ? roe_flux(l, r, gamma) : hllc_flux(l, r, gamma);
+  cons_t f = solver == ORC_ROE ? roe_flux(l, r, gamma) : (solver == ORC_HLL ? hll_flux(l, r, gamma) : hllc_flux(l, r, gamma));
   f5[0] = f.d; f5[1] = f.mx; f5[2] = f.my; f5[3] = f.mz; f5[4] = f.E;
 }
 

@@ -46,7 +46,8 @@ def run_both(fields, recon, solver, flags, gamma, n_steps, strict, precision=2, 
     return got, ref, dims, g, dts_gpu, dts_cpu
 
 
-CASES_3D = [(cb.PPMC, cb.HLLC), (cb.PLMC, cb.HLLC), (cb.PPMC, cb.ROE), (cb.PLMC, cb.ROE), (cb.PCM, cb.HLLC)]
+CASES_3D = [(cb.PPMC, cb.HLLC), (cb.PLMC, cb.HLLC), (cb.PPMC, cb.ROE), (cb.PLMC, cb.ROE), (cb.PCM, cb.HLLC),
+            (cb.PPMC, cb.HLL), (cb.PLMC, cb.HLL)]
 
 
 @pytest.mark.parametrize("recon,solver", CASES_3D)
