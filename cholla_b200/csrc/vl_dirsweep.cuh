@@ -55,6 +55,7 @@ struct DirParams {
   int apply_tfloor;
   Real U_floor;
   int do_dti;
+  int plmp;  // predictor, strict mode: store the half-step pressures with PLMP's summation order (store_half)
   Real dx, dy, dz, idx, idy, idz;
   unsigned long long *dti_key;
 };
@@ -198,7 +199,7 @@ __device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t
 #pragma unroll
       for (int f = 1; f < 5; f++) u[f] *= (P.density_floor / d0);
     }
-    store_half(P.out, N, id, u, P.gamma);
+    store_half(P.out, N, id, u, P.gamma, P.plmp);
     return;
   }
 #pragma unroll
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
   }
   double dti = -1.7976931348623157e308;
 
-  constexpr bool kRing  = CHL_DIR_RING && STAGE == 1 && DIR != 0 && RECON != kPCM;
+  constexpr bool kRing  = CHL_DIR_RING && STAGE == 1 && DIR != 0 && (RECON == kPLMC || RECON == kPPMC);
   typedef RingGeom<RECON> RG;
   typedef StageGeom<STAGE, FIRST, LAST> SG;
   constexpr bool kStage = CHL_DIR_STAGE && SG::n > 0;

@@ -164,6 +164,18 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
   }
   GlobalStencil const ld{c, {0, m.o1, m.o2, m.o3, m.op}, m.stride};
   Prim l, r;
+  if (RECON == kPLMP) {
+    plmp_stencil(ld, k, l, r);
+#if CHL_STRICT
+    Cons const cl = cons_from_prim_plmp(l, k), cr = cons_from_prim_plmp(r, k);
+    L = S5{{cl.d, cl.mx, cl.my, cl.mz, cl.E}};
+    R = S5{{cr.d, cr.mx, cr.my, cr.mz, cr.E}};
+#else
+    L = iface_state(l, k);
+    R = iface_state(r, k);
+#endif
+    return;
+  }
   if (RECON == kPPMC) ppmc_stencil(ld, k, l, r);
   else plmc_stencil(ld, k, l, r);
   L = iface_state(l, k);
@@ -183,20 +195,35 @@ __device__ __forceinline__ void recon_from(A const &ld, KC const &k, S5 &L, S5 &
 
 // Half-step state of one cell, from its conserved half-step values: what Load_Data (reconstruction.h:139-212)
 // derives, stored once instead of being recomputed by every stencil that touches the cell.
-__device__ __forceinline__ void store_half(Real *__restrict__ out, size_t N, size_t id, Real const (&u)[5], Real gamma)
+__device__ __forceinline__ void store_half(Real *__restrict__ out, size_t N, size_t id, Real const (&u)[5], Real gamma,
+                                           int plmp)
 {
   Prim const w = prim_from_cons(Cons{u[0], u[1], u[2], u[3], u[4]}, gamma);  // P with the x-sweep association
   out[id]         = w.d;
   out[N + id]     = w.vx;
   out[2 * N + id] = w.vy;
   out[3 * N + id] = w.vz;
-  out[4 * N + id] = w.p;
 #if CHL_STRICT
+  if (plmp) {
+    // PLMP derives the stencil pressures with the plain left-to-right sum of the rotated velocities and multiplies
+    // by (gamma - 1) on the right (plmp_cuda.cu:117-118)
+    Real const ex = u[4] - RC(0.5) * w.d * (w.vx * w.vx + w.vy * w.vy + w.vz * w.vz);
+    Real const ey = u[4] - RC(0.5) * w.d * (w.vy * w.vy + w.vz * w.vz + w.vx * w.vx);
+    Real const ez = u[4] - RC(0.5) * w.d * (w.vz * w.vz + w.vx * w.vx + w.vy * w.vy);
+    out[4 * N + id] = max_s(ex * (gamma - RC(1.)), kTiny);
+    out[5 * N + id] = max_s(ey * (gamma - RC(1.)), kTiny);
+    out[6 * N + id] = max_s(ez * (gamma - RC(1.)), kTiny);
+    return;
+  }
+  out[4 * N + id] = w.p;
   // y sweep sums vy^2 + (vz^2 + vx^2), z sweep vz^2 + (vx^2 + vy^2)
   Real const ey = u[4] - RC(0.5) * w.d * sq3(w.vy, w.vz, w.vx);
   Real const ez = u[4] - RC(0.5) * w.d * sq3(w.vz, w.vx, w.vy);
   out[5 * N + id] = max_s((gamma - RC(1.)) * ey, kTiny);
   out[6 * N + id] = max_s((gamma - RC(1.)) * ez, kTiny);
+#else
+  (void)plmp;
+  out[4 * N + id] = w.p;
 #endif
 }
 
@@ -374,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, (TY <= 8 ? 2 : 1)) vl_sweep_kernel(S
 #pragma unroll
               for (int f = 1; f < 5; f++) u[f] *= (P.density_floor / d0);
             }
-            store_half(P.out, N, idm, u, gamma);
+            store_half(P.out, N, idm, u, gamma, 0);
           } else {
             if (u[0] < P.density_floor && u[0] > RC(0.)) {  // hydro_cuda.cu:279-291
               Real const d0 = u[0];
@@ -426,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, (TY <= 8 ? 2 : 1)) vl_sweep_kernel(S
           if (STAGE == 0) {
 #pragma unroll
             for (int f = 0; f < 5; f++) u[f] = acc[(size_t)f * kMainThreads];
-            store_half(P.out, N, id, u, gamma);
+            store_half(P.out, N, id, u, gamma, 0);
           } else {
 #pragma unroll
             for (int f = 0; f < 5; f++) {

@@ -52,7 +52,7 @@ cudaError_t sweep(int stage, int recon, int solver, SweepArgs const &a, cudaStre
   p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
   p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
   p.dti_key = a.dti_key;
-  if (solver == kHLL) return cudaErrorNotSupported;  // the fused family instantiates HLLC and Roe only (chl_create)
+  if (solver == kHLL || recon == kPLMP) return cudaErrorNotSupported;  // fused family: PCM/PLMC/PPMC x HLLC/Roe only
   if (stage == 0) {
     if (solver == kROE) return launch<kPCM, kROE, 0>(p, s);
     return launch<kPCM, kHLLC, 0>(p, s);
@@ -80,7 +80,7 @@ cudaError_t launch_dir(DirParams const &p, cudaStream_t s)
     int const om = DIR == 1 ? oy : oz;
     grid = dim3((ox + kDirThreads - 1) / kDirThreads, DIR == 1 ? oz : oy, (om + p.chunk - 1) / p.chunk);
   }
-  if (CHL_DIR_RING && STAGE == 1 && DIR != 0 && RECON != kPCM) {
+  if (CHL_DIR_RING && STAGE == 1 && DIR != 0 && (RECON == kPLMC || RECON == kPPMC)) {
     // the row ring needs (2r+1) x 5 x 128 reals of shared memory per CTA: ask for the largest carve-out so that the
     // register-limited number of CTAs stays resident
     static bool configured = false;  // per instantiation
@@ -140,10 +140,16 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
   p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
   p.dti_key = a.dti_key;
+  p.plmp    = recon == kPLMP ? 1 : 0;
   if (stage == 0) {
     if (solver == kROE) return run_dirs<kPCM, kROE, 0>(p, a, s);
     if (solver == kHLL) return run_dirs<kPCM, kHLL, 0>(p, a, s);
     return run_dirs<kPCM, kHLLC, 0>(p, a, s);
+  }
+  if (recon == kPLMP) {
+    if (solver == kROE) return run_dirs<kPLMP, kROE, 1>(p, a, s);
+    if (solver == kHLL) return run_dirs<kPLMP, kHLL, 1>(p, a, s);
+    return run_dirs<kPLMP, kHLLC, 1>(p, a, s);
   }
   if (solver == kHLL) {
     if (recon == kPCM) return run_dirs<kPCM, kHLL, 1>(p, a, s);

@@ -13,7 +13,7 @@
  *   src/reconstruction/plmc_cuda.cu          PLM, characteristic limiting
  *   src/reconstruction/ppmc_cuda.cu:540-695  PPMC_VL
  *   src/reconstruction/reconstruction.h      shared helpers (hydro branches)
- *   src/riemann_solvers/hllc_cuda.cu, roe_cuda.cu, hll_cuda.cu
+ *   src/riemann_solvers/hllc_cuda.cu, roe_cuda.cu, hll_cuda.cu;  src/reconstruction/plmp_cuda.cu (-DVL branch)
  *   src/hydro/hydro_cuda.cu                  conserved update, Calc_dt, temperature floor
  *   src/grid/cuda_boundaries.cu, src/grid/boundary_conditions.cpp:419-  ghost cells
  * Build with -O2 -ffp-contract=off (the reference device code is built -fmad=false,
@@ -34,7 +34,7 @@
 
 #define ORC_TINY 1.0e-20 /* global.h:25 */
 
-enum { ORC_PCM = 0, ORC_PLMC = 1, ORC_PPMC = 2 };
+enum { ORC_PCM = 0, ORC_PLMC = 1, ORC_PPMC = 2, ORC_PLMP = 3 };
 enum { ORC_HLLC = 0, ORC_ROE = 1, ORC_HLL = 3 }; /* 2 is HLLD (mhd_oracle.c) */
 
 typedef struct {
@@ -244,6 +244,68 @@ static void ppmc_cell(prim_t wm2, prim_t wm1, prim_t wi, prim_t wp1, prim_t wp2,
   r.d = fmax(r.d, ORC_TINY); l.d = fmax(l.d, ORC_TINY);
   r.p = fmax(r.p, ORC_TINY); l.p = fmax(l.p, ORC_TINY);
   *L = l; *R = r;
+}
+
+/* ---- PLMP under -DVL (plmp_cuda.cu:21-310): van Leer-limited slopes of the PRIMITIVE variables ---- */
+/* Interface_Values_PLM (plmp_cuda.cu:312-365); sgn_CUDA(0) = +1 (global_cuda.h:41-48) */
+static void plmp_interface(double qm, double qi, double qp, double *qL, double *qR)
+{
+  double dL = qi - qm, dR = qp - qi, dC = 0.5 * (qp - qm), dG;
+  if (dL * dR > 0.0) dG = 2.0 * dL * dR / (dL + dR);
+  else dG = 0.0;
+  double a = fmin(fabs(dL), fabs(dR)), b = fmin(fabs(dC), fabs(dG));
+  double m = ((dC < 0) ? -1 : 1) * fmin(2.0 * a, b);
+  *qL = qi - 0.5 * m;
+  *qR = qi + 0.5 * m;
+}
+/* the kernel's own primitive load: plain left-to-right kinetic-energy sum (plmp_cuda.cu:107-118) */
+static prim_t plmp_load(const double *U, size_t id, size_t N, int o1, int o2, int o3, double gamma)
+{
+  prim_t w;
+  w.d  = U[id];
+  w.vx = U[(size_t)o1 * N + id] / w.d;
+  w.vy = U[(size_t)o2 * N + id] / w.d;
+  w.vz = U[(size_t)o3 * N + id] / w.d;
+  w.p  = (U[4 * N + id] - 0.5 * w.d * (w.vx * w.vx + w.vy * w.vy + w.vz * w.vz)) * (gamma - 1.0);
+  w.p  = fmax(w.p, ORC_TINY);
+  return w;
+}
+static void plmp_store(prim_t q, double *Q, size_t id, size_t N, int o1, int o2, int o3, double gamma)
+{
+  Q[id]                  = q.d;
+  Q[(size_t)o1 * N + id] = q.d * q.vx;
+  Q[(size_t)o2 * N + id] = q.d * q.vy;
+  Q[(size_t)o3 * N + id] = q.d * q.vz;
+  Q[4 * N + id]          = q.p / (gamma - 1.0) + 0.5 * q.d * (q.vx * q.vx + q.vy * q.vy + q.vz * q.vz);
+}
+static void plmp_dir(const double *U, double *QL, double *QR, int nx, int ny, int nz, double gamma, int dir)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int o1, o2, o3;
+  dir_perm(dir, &o1, &o2, &o3);
+  long stride = dir == 0 ? 1 : (dir == 1 ? nx : (long)nx * ny);
+  int n[3] = {nx, ny, nz};
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        int c = dir == 0 ? x : (dir == 1 ? y : z);
+        if (c < 1 || c >= n[dir] - 2) continue; /* xs = 1, xe = nx - 2 along the sweep, every transverse cell */
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        prim_t wi = plmp_load(U, id, N, o1, o2, o3, gamma);
+        prim_t wm = plmp_load(U, id - stride, N, o1, o2, o3, gamma);
+        prim_t wp = plmp_load(U, id + stride, N, o1, o2, o3, gamma);
+        prim_t lo, hi; /* lo: the cell's low face (i-1/2), hi: its high face (i+1/2) */
+        plmp_interface(wm.d, wi.d, wp.d, &lo.d, &hi.d);
+        plmp_interface(wm.vx, wi.vx, wp.vx, &lo.vx, &hi.vx);
+        plmp_interface(wm.vy, wi.vy, wp.vy, &lo.vy, &hi.vy);
+        plmp_interface(wm.vz, wi.vz, wp.vz, &lo.vz, &hi.vz);
+        plmp_interface(wm.p, wi.p, wp.p, &lo.p, &hi.p);
+        lo.d = fmax(lo.d, ORC_TINY); hi.d = fmax(hi.d, ORC_TINY);
+        lo.p = fmax(lo.p, ORC_TINY); hi.p = fmax(hi.p, ORC_TINY);
+        plmp_store(lo, QR, id - stride, N, o1, o2, o3, gamma); /* bounds_R[i-1]: right state of face i-1/2 */
+        plmp_store(hi, QL, id, N, o1, o2, o3, gamma);          /* bounds_L[i]:   left state of face i+1/2 */
+      }
 }
 
 /* Full-grid reconstruction pass in one direction: what one launch of PLMC_cuda / PPMC_VL does.
@@ -525,6 +587,7 @@ void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, doub
   /* stage 4-5: second-order interfaces from the half-step state, then fluxes */
   for (int d = 0; d < ndim; d++) {
     if (recon == ORC_PCM) pcm_dir(Uh, QL[d], QR[d], nx, ny, nz, d);
+    else if (recon == ORC_PLMP) plmp_dir(Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
     else orc_reconstruct(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
     orc_riemann(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d);
   }
