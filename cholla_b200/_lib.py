@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CHOLLA_B200_LIB") or os.path.join(_HERE, "libcholla_b
 HEADER_PATH = os.path.join(_ROOT, "include", "cholla_b200.h")
 
 CHL_OK = 0
-PCM, PLMC, PPMC, PLMP = 0, 1, 2, 3
+PCM, PLMC, PPMC, PLMP, PPMP = 0, 1, 2, 3, 4
 HLLC, ROE, HLLD, HLL = 0, 1, 2, 3
 BC_PERIODIC, BC_REFLECTIVE, BC_TRANSMISSIVE, BC_CUSTOM, BC_MPI = 1, 2, 3, 4, 5
 

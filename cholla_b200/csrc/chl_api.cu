@@ -90,8 +90,8 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   *out = nullptr;
   if (cfg->nx < 1 || cfg->ny < 1 || cfg->nz < 1) return fail(CHL_ERR_INVALID, "chl_create: bad grid size");
   if (cfg->ny == 1 && cfg->nz > 1) return fail(CHL_ERR_INVALID, "chl_create: nz > 1 requires ny > 1");
-  if (cfg->recon < CHL_RECON_PCM || cfg->recon > CHL_RECON_PLMP) return fail(CHL_ERR_INVALID, "chl_create: recon");
-  if (cfg->mhd && cfg->recon == CHL_RECON_PLMP) return fail(CHL_ERR_INVALID, "chl_create: MHD supports PCM, PLMC and PPMC");
+  if (cfg->recon < CHL_RECON_PCM || cfg->recon > CHL_RECON_PPMP) return fail(CHL_ERR_INVALID, "chl_create: recon");
+  if (cfg->mhd && cfg->recon >= CHL_RECON_PLMP) return fail(CHL_ERR_INVALID, "chl_create: MHD supports PCM, PLMC and PPMC");
   if (cfg->solver < CHL_SOLVER_HLLC || cfg->solver > CHL_SOLVER_HLL)
     return fail(CHL_ERR_INVALID, "chl_create: solver");
   if (cfg->mhd) {  // the reference's own constraints, src/utils/error_handling.cpp:83-118
@@ -103,7 +103,8 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
     if (cfg->solver == CHL_SOLVER_HLLD) return fail(CHL_ERR_INVALID, "chl_create: HLLD needs mhd = 1");
   }
   int const need_ghost =
-      (cfg->recon == CHL_RECON_PPMC ? 4 : (cfg->recon == CHL_RECON_PCM ? 2 : 3)) + (cfg->mhd ? 1 : 0);
+      ((cfg->recon == CHL_RECON_PPMC || cfg->recon == CHL_RECON_PPMP) ? 4 : (cfg->recon == CHL_RECON_PCM ? 2 : 3)) +
+      (cfg->mhd ? 1 : 0);
   if (cfg->n_ghost < need_ghost)
     return fail(CHL_ERR_INVALID, "chl_create: n_ghost too small for the reconstruction");
   if (cfg->nx <= 2 * cfg->n_ghost || (cfg->ny > 1 && cfg->ny <= 2 * cfg->n_ghost) ||
@@ -141,7 +142,7 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
     // development knobs: CHL_SWEEP_IMPL=fused|split selects the kernel family, CHL_DIR_CHUNK the marching length
     const char *impl = getenv("CHL_SWEEP_IMPL");
     c->split = !(impl && strcmp(impl, "fused") == 0) || cfg->solver == CHL_SOLVER_HLL ||
-               cfg->recon == CHL_RECON_PLMP;  // HLL, PLMP: split sweeps only
+               cfg->recon >= CHL_RECON_PLMP;  // HLL, PLMP, PPMP: split sweeps only
     const char *ch = getenv("CHL_DIR_CHUNK");
     c->dir_chunk = ch ? atoi(ch) : 0;
   }

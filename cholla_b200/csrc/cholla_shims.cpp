@@ -9,7 +9,7 @@
 //
 // Signatures are the reference's, C++ linkage (src/integrators/VL_*D_cuda.h, src/hydro/hydro_cuda.h:69,87,
 // src/grid/cuda_boundaries.h).  The compile-time feature macros of builds/make.type.* select the run-time enums:
-//   -DPCM / -DPLMC / -DPLMP / -DPPMC -> chl_config.recon      -DHLLC / -DROE / -DHLL / -DHLLD -> chl_config.solver
+//   -DPCM / -DPLMC / -DPLMP / -DPPMP / -DPPMC -> chl_config.recon      -DHLLC / -DROE / -DHLL / -DHLLD -> chl_config.solver
 //   -DPRECISION=1|2         -> Real and chl_config.precision        -DMHD -> chl_config.mhd
 // `gama` is the reference's global (src/global/global.cpp:18).  CHOLLA_B200_STRICT=0 in the environment selects the
 // product arithmetic; the default is the bit-reproducing strict mode, so a drop-in build produces the snapshots the
@@ -44,10 +44,12 @@ constexpr int kRecon = CHL_RECON_PPMC;
 constexpr int kRecon = CHL_RECON_PLMC;
 #elif defined(PLMP)
 constexpr int kRecon = CHL_RECON_PLMP;
+#elif defined(PPMP)
+constexpr int kRecon = CHL_RECON_PPMP;
 #elif defined(PCM)
 constexpr int kRecon = CHL_RECON_PCM;
 #else
-#error "cholla_shims.cpp: build with -DPCM, -DPLMC, -DPLMP or -DPPMC (PPMP is not on the B200 path)"
+#error "cholla_shims.cpp: build with -DPCM, -DPLMC, -DPLMP, -DPPMP or -DPPMC"
 #endif
 #if defined(HLLD)
 constexpr int kSolver = CHL_SOLVER_HLLD;

@@ -55,7 +55,7 @@ struct DirParams {
   int apply_tfloor;
   Real U_floor;
   int do_dti;
-  int plmp;  // predictor, strict mode: store the half-step pressures with PLMP's summation order (store_half)
+  int plmp;  // predictor, strict mode: store the half-step pressures with PLMP's / PPMP's summation order (store_half)
   Real dx, dy, dz, idx, idy, idz;
   unsigned long long *dti_key;
 };

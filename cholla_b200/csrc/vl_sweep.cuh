@@ -164,8 +164,9 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
   }
   GlobalStencil const ld{c, {0, m.o1, m.o2, m.o3, m.op}, m.stride};
   Prim l, r;
-  if (RECON == kPLMP) {
-    plmp_stencil(ld, k, l, r);
+  if (RECON == kPLMP || RECON == kPPMP) {
+    if (RECON == kPPMP) ppmp_stencil(ld, k, l, r);
+    else plmp_stencil(ld, k, l, r);
 #if CHL_STRICT
     Cons const cl = cons_from_prim_plmp(l, k), cr = cons_from_prim_plmp(r, k);
     L = S5{{cl.d, cl.mx, cl.my, cl.mz, cl.E}};
@@ -205,8 +206,8 @@ __device__ __forceinline__ void store_half(Real *__restrict__ out, size_t N, siz
   out[3 * N + id] = w.vz;
 #if CHL_STRICT
   if (plmp) {
-    // PLMP derives the stencil pressures with the plain left-to-right sum of the rotated velocities and multiplies
-    // by (gamma - 1) on the right (plmp_cuda.cu:117-118)
+    // PLMP and PPMP derive the stencil pressures with the plain left-to-right sum of the rotated velocities and
+    // multiply by (gamma - 1) on the right (plmp_cuda.cu:117-118, ppmp_cuda.cu:168-170)
     Real const ex = u[4] - RC(0.5) * w.d * (w.vx * w.vx + w.vy * w.vy + w.vz * w.vz);
     Real const ey = u[4] - RC(0.5) * w.d * (w.vy * w.vy + w.vz * w.vz + w.vx * w.vx);
     Real const ez = u[4] - RC(0.5) * w.d * (w.vz * w.vz + w.vx * w.vx + w.vy * w.vy);

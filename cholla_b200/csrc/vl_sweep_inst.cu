@@ -52,7 +52,7 @@ cudaError_t sweep(int stage, int recon, int solver, SweepArgs const &a, cudaStre
   p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
   p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
   p.dti_key = a.dti_key;
-  if (solver == kHLL || recon == kPLMP) return cudaErrorNotSupported;  // fused family: PCM/PLMC/PPMC x HLLC/Roe only
+  if (solver == kHLL || recon == kPLMP || recon == kPPMP) return cudaErrorNotSupported;  // fused family: PCM/PLMC/PPMC x HLLC/Roe only
   if (stage == 0) {
     if (solver == kROE) return launch<kPCM, kROE, 0>(p, s);
     return launch<kPCM, kHLLC, 0>(p, s);
@@ -140,11 +140,16 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
   p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
   p.dti_key = a.dti_key;
-  p.plmp    = recon == kPLMP ? 1 : 0;
+  p.plmp    = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
   if (stage == 0) {
     if (solver == kROE) return run_dirs<kPCM, kROE, 0>(p, a, s);
     if (solver == kHLL) return run_dirs<kPCM, kHLL, 0>(p, a, s);
     return run_dirs<kPCM, kHLLC, 0>(p, a, s);
+  }
+  if (recon == kPPMP) {
+    if (solver == kROE) return run_dirs<kPPMP, kROE, 1>(p, a, s);
+    if (solver == kHLL) return run_dirs<kPPMP, kHLL, 1>(p, a, s);
+    return run_dirs<kPPMP, kHLLC, 1>(p, a, s);
   }
   if (recon == kPLMP) {
     if (solver == kROE) return run_dirs<kPLMP, kROE, 1>(p, a, s);

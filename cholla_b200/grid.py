@@ -30,7 +30,7 @@ C_CFL = 0.3  # grid3D.cpp:157
 
 def n_ghost_for(recon, mhd=False):
     """Grid3D constructor, grid3D.cpp:52-76: PCM 2, PLMP 3, PLMC 3, PPMC 4, one more in an MHD build."""
-    return {_lib.PCM: 2, _lib.PLMP: 3, _lib.PLMC: 3, _lib.PPMC: 4}[recon] + (1 if mhd else 0)
+    return {_lib.PCM: 2, _lib.PLMP: 3, _lib.PLMC: 3, _lib.PPMP: 4, _lib.PPMC: 4}[recon] + (1 if mhd else 0)
 
 
 @dataclass

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PCM, PLMC, PPMC, PLMP = 0, 1, 2, 3
+PCM, PLMC, PPMC, PLMP, PPMP = 0, 1, 2, 3, 4
 HLLC, ROE, HLL = 0, 1, 3
 _lib = None
 

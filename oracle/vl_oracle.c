@@ -13,7 +13,7 @@
  *   src/reconstruction/plmc_cuda.cu          PLM, characteristic limiting
  *   src/reconstruction/ppmc_cuda.cu:540-695  PPMC_VL
  *   src/reconstruction/reconstruction.h      shared helpers (hydro branches)
- *   src/riemann_solvers/hllc_cuda.cu, roe_cuda.cu, hll_cuda.cu;  src/reconstruction/plmp_cuda.cu (-DVL branch)
+ *   src/riemann_solvers/hllc_cuda.cu, roe_cuda.cu, hll_cuda.cu;  src/reconstruction/plmp_cuda.cu, ppmp_cuda.cu (-DVL branches)
  *   src/hydro/hydro_cuda.cu                  conserved update, Calc_dt, temperature floor
  *   src/grid/cuda_boundaries.cu, src/grid/boundary_conditions.cpp:419-  ghost cells
  * Build with -O2 -ffp-contract=off (the reference device code is built -fmad=false,
@@ -34,7 +34,7 @@
 
 #define ORC_TINY 1.0e-20 /* global.h:25 */
 
-enum { ORC_PCM = 0, ORC_PLMC = 1, ORC_PPMC = 2, ORC_PLMP = 3 };
+enum { ORC_PCM = 0, ORC_PLMC = 1, ORC_PPMC = 2, ORC_PLMP = 3, ORC_PPMP = 4 };
 enum { ORC_HLLC = 0, ORC_ROE = 1, ORC_HLL = 3 }; /* 2 is HLLD (mhd_oracle.c) */
 
 typedef struct {
@@ -305,6 +305,63 @@ static void plmp_dir(const double *U, double *QL, double *QR, int nx, int ny, in
         lo.p = fmax(lo.p, ORC_TINY); hi.p = fmax(hi.p, ORC_TINY);
         plmp_store(lo, QR, id - stride, N, o1, o2, o3, gamma); /* bounds_R[i-1]: right state of face i-1/2 */
         plmp_store(hi, QL, id, N, o1, o2, o3, gamma);          /* bounds_L[i]:   left state of face i+1/2 */
+      }
+}
+
+/* ---- PPMP under -DVL without STEEPENING / FLATTENING (ppmp_cuda.cu:28-760; no build type defines them) ---- */
+/* Calculate_Slope (ppmp_cuda.cu:677-712): the same van Leer-limited slope as Interface_Values_PLM */
+static double ppmp_slope(double qm, double qi, double qp)
+{
+  double dL = qi - qm, dR = qp - qi, dC = 0.5 * (qp - qm), dG;
+  if (dL * dR > 0.0) dG = 2.0 * dL * dR / (dL + dR);
+  else dG = 0.0;
+  double a = fmin(fabs(dL), fabs(dR)), b = fmin(fabs(dC), fabs(dG));
+  return ((dC < 0) ? -1 : 1) * fmin(2.0 * a, b);
+}
+/* Interface_Values_PPM (ppmp_cuda.cu:719-745) */
+static void ppmp_interface(double qm, double qi, double qp, double sm, double si, double sp, double *qL, double *qR)
+{
+  *qL = 0.5 * (qi + qm) - (1.0 / 6.0) * (si - sm);
+  *qR = 0.5 * (qp + qi) - (1.0 / 6.0) * (sp - si);
+  if ((*qR - qi) * (qi - *qL) <= 0) *qL = *qR = qi;
+  if (6.0 * (*qR - *qL) * (qi - 0.5 * (*qL + *qR)) > (*qR - *qL) * (*qR - *qL)) *qL = 3.0 * qi - 2.0 * (*qR);
+  if (6.0 * (*qR - *qL) * (qi - 0.5 * (*qL + *qR)) < -(*qR - *qL) * (*qR - *qL)) *qR = 3.0 * qi - 2.0 * (*qL);
+  *qL = fmax(fmin(qi, qm), *qL);
+  *qL = fmin(fmax(qi, qm), *qL);
+  *qR = fmax(fmin(qi, qp), *qR);
+  *qR = fmin(fmax(qi, qp), *qR);
+}
+static void ppmp_var(double q2m, double qm, double qi, double qp, double q2p, double *lo, double *hi)
+{
+  double sm = ppmp_slope(q2m, qm, qi), si = ppmp_slope(qm, qi, qp), sp = ppmp_slope(qi, qp, q2p);
+  ppmp_interface(qm, qi, qp, sm, si, sp, lo, hi);
+}
+static void ppmp_dir(const double *U, double *QL, double *QR, int nx, int ny, int nz, double gamma, int dir)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int o1, o2, o3;
+  dir_perm(dir, &o1, &o2, &o3);
+  long stride = dir == 0 ? 1 : (dir == 1 ? nx : (long)nx * ny);
+  int n[3] = {nx, ny, nz};
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        int c = dir == 0 ? x : (dir == 1 ? y : z);
+        if (c < 2 || c >= n[dir] - 3) continue; /* xs = 2, xe = nx - 3 along the sweep, every transverse cell */
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        prim_t w[5];
+        for (int k = 0; k < 5; k++) w[k] = plmp_load(U, id + (k - 2) * stride, N, o1, o2, o3, gamma); /* same load */
+        prim_t lo, hi;
+        ppmp_var(w[0].d, w[1].d, w[2].d, w[3].d, w[4].d, &lo.d, &hi.d);
+        ppmp_var(w[0].vx, w[1].vx, w[2].vx, w[3].vx, w[4].vx, &lo.vx, &hi.vx);
+        ppmp_var(w[0].vy, w[1].vy, w[2].vy, w[3].vy, w[4].vy, &lo.vy, &hi.vy);
+        ppmp_var(w[0].vz, w[1].vz, w[2].vz, w[3].vz, w[4].vz, &lo.vz, &hi.vz);
+        ppmp_var(w[0].p, w[1].p, w[2].p, w[3].p, w[4].p, &lo.p, &hi.p);
+        lo.d = fmax(lo.d, ORC_TINY); hi.d = fmax(hi.d, ORC_TINY);
+        lo.p = fmax(lo.p, ORC_TINY); hi.p = fmax(hi.p, ORC_TINY);
+        plmp_store(lo, QR, id - stride, N, o1, o2, o3, gamma);
+        plmp_store(hi, QL, id, N, o1, o2, o3, gamma);
       }
 }
 
@@ -588,6 +645,7 @@ void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, doub
   for (int d = 0; d < ndim; d++) {
     if (recon == ORC_PCM) pcm_dir(Uh, QL[d], QR[d], nx, ny, nz, d);
     else if (recon == ORC_PLMP) plmp_dir(Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
+    else if (recon == ORC_PPMP) ppmp_dir(Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
     else orc_reconstruct(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
     orc_riemann(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d);
   }

@@ -47,7 +47,7 @@ def run_both(fields, recon, solver, flags, gamma, n_steps, strict, precision=2, 
 
 
 CASES_3D = [(cb.PPMC, cb.HLLC), (cb.PLMC, cb.HLLC), (cb.PPMC, cb.ROE), (cb.PLMC, cb.ROE), (cb.PCM, cb.HLLC),
-            (cb.PPMC, cb.HLL), (cb.PLMC, cb.HLL), (cb.PLMP, cb.HLLC), (cb.PLMP, cb.ROE)]
+            (cb.PPMC, cb.HLL), (cb.PLMC, cb.HLL), (cb.PLMP, cb.HLLC), (cb.PLMP, cb.ROE), (cb.PPMP, cb.HLLC)]
 
 
 @pytest.mark.parametrize("recon,solver", CASES_3D)

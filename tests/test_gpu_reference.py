@@ -69,7 +69,7 @@ def _need(recon, solver):
         pytest.skip("oracle/_ref library for this combination was not built")
 
 
-@pytest.mark.parametrize("recon,solver", [(2, 0), (1, 0), (2, 1), (1, 1), (2, 3), (3, 0)])  # solver 3 = HLL (-DHLL), recon 3 = PLMP (-DPLMP)
+@pytest.mark.parametrize("recon,solver", [(2, 0), (1, 0), (2, 1), (1, 1), (2, 3), (3, 0), (4, 0)])  # solver 3 = HLL (-DHLL); recon 3 = PLMP, 4 = PPMP
 def test_reference_kernels_vs_oracle_vs_b200_3d(recon, solver):
     _need(recon, solver)
     r = run_child(recon=recon, solver=solver, n=(37, 19, 21), flags=[1, 1, 1, 1, 1, 1], gamma=5.0 / 3.0, steps=3,
