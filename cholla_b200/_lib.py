@@ -71,6 +71,7 @@ def lib():
     L.chl_set_boundaries.argtypes = [p, p, ip, p]
     L.chl_set_ghost_cells_ext.argtypes = [p, i, i, i, i, i, i, ip, i, i, i, i, i, i, i, i, i, p]
     L.chl_pack_buffer.argtypes = [p, p, i, i, i, l, l, i, i, i, i, p]
+    L.chl_pack_snapshot_field.argtypes = [p, p, i, i, i, i, i, i, i, i, i, i, p]
     L.chl_unpack_buffer.argtypes = [p, p, i, i, i, l, l, i, i, i, i, p]
     L.chl_boundary_extents.argtypes = [i, i, i, i, i, ip, ip]
     L.chl_tile_decomposition.argtypes = [i, i, i, i, ip]

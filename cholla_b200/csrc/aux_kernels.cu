@@ -109,6 +109,27 @@ inline int grid_for(long n)
   if (b < 1) b = 1;
   return (int)b;
 }
+
+// Snapshot packing (the reference's CopyReal3D_GPU_Kernel / CopyReal2D_GPU_Kernel, src/io/io_gpu.cu:21-95): the real
+// cells of one field, x fastest with ghosts, to the HDF5 buffer order out[k + n_k (j + n_j i)] -- x slowest.  A
+// transposition of the fastest axis, so a 32 x 32 shared-memory tile keeps both the loads (along i) and the stores
+// (along k) coalesced; the reference's kernel stores with a stride of n_j n_k elements.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) snapshot_pack_kernel(const Tin *__restrict__ in, Tout *__restrict__ out, int n_i,
+                                                            int n_j, int n_k, long stride_j, long stride_k)
+{
+  __shared__ Tin tile[32][33];
+  int const j = blockIdx.z, i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int const i = i0 + threadIdx.x, k = k0 + r;
+    if (i < n_i && k < n_k) tile[r][threadIdx.x] = in[i + stride_j * j + stride_k * k];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int const i = i0 + r, k = k0 + threadIdx.x;
+    if (i < n_i && k < n_k) out[k + (long)n_k * (j + (long)n_j * i)] = (Tout)tile[threadIdx.x][r];
+  }
+}
 }  // namespace
 
 cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields, long n_cells, int n_ghost,
@@ -140,6 +161,33 @@ cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, 
     if (unpack) pack_kernel<float, 1><<<g, 256, 0, s>>>((float *)buf, (float *)c, nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize);
     else pack_kernel<float, 0><<<g, 256, 0, s>>>((float *)buf, (float *)c, nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_snapshot_pack(void *out, const void *field, int nx, int ny, int nz, int n_ghost, int nx_out,
+                                 int ny_out, int nz_out, int mhd_direction, size_t in_bytes, size_t out_bytes,
+                                 cudaStream_t s)
+{
+  // first source cell of the output (io_gpu.cu:62-66: the face-centred fields start one face below the real cells)
+  long const gx = n_ghost - (mhd_direction == 0), gy = ny > 1 ? n_ghost - (mhd_direction == 1) : 0,
+             gz = nz > 1 ? n_ghost - (mhd_direction == 2) : 0;
+  long const base = gx + (long)nx * (gy + (long)ny * gz);
+  // the fastest output axis is z in 3-D, y in 2-D; a 1-D grid is a straight copy (n_k = 1)
+  int n_i = nx_out, n_j, n_k;
+  long sj, sk;
+  if (nz > 1) { n_j = ny_out; n_k = nz_out; sj = nx; sk = (long)nx * ny; }
+  else { n_j = 1; n_k = ny > 1 ? ny_out : 1; sj = 0; sk = nx; }
+  if (n_i <= 0 || n_j <= 0 || n_k <= 0) return cudaSuccess;
+  if (n_j > 65535) return cudaErrorInvalidValue;
+  dim3 const grid((n_i + 31) / 32, (n_k + 31) / 32, n_j), block(32, 8);
+  if (in_bytes == 8 && out_bytes == 8)
+    snapshot_pack_kernel<double, double><<<grid, block, 0, s>>>((const double *)field + base, (double *)out, n_i, n_j, n_k, sj, sk);
+  else if (in_bytes == 8)
+    snapshot_pack_kernel<double, float><<<grid, block, 0, s>>>((const double *)field + base, (float *)out, n_i, n_j, n_k, sj, sk);
+  else if (out_bytes == 8)
+    snapshot_pack_kernel<float, double><<<grid, block, 0, s>>>((const float *)field + base, (double *)out, n_i, n_j, n_k, sj, sk);
+  else
+    snapshot_pack_kernel<float, float><<<grid, block, 0, s>>>((const float *)field + base, (float *)out, n_i, n_j, n_k, sj, sk);
   return cudaGetLastError();
 }
 }  // namespace chl

@@ -465,6 +465,19 @@ int chl_unpack_buffer(const void *buf, void *U, int nx, int ny, int n_fields, lo
   return CHL_OK;
 }
 
+int chl_pack_snapshot_field(void *d_out, const void *d_field, int nx, int ny, int nz, int n_ghost, int nx_out, int ny_out,
+                            int nz_out, int mhd_direction, int precision, int out_precision, void *stream)
+{
+  if (!d_out || !d_field) return fail(CHL_ERR_INVALID, "chl_pack_snapshot_field: null argument");
+  if (mhd_direction < -1 || mhd_direction > 2 || nx < 1 || ny < 1 || nz < 1 || n_ghost < 1 ||
+      nx_out + n_ghost - (mhd_direction == 0) > nx || (ny > 1 && ny_out + n_ghost - (mhd_direction == 1) > ny) ||
+      (nz > 1 && nz_out + n_ghost - (mhd_direction == 2) > nz))
+    return fail(CHL_ERR_INVALID, "chl_pack_snapshot_field: extents outside the grid");
+  CHL_CUDA(chl::launch_snapshot_pack(d_out, d_field, nx, ny, nz, n_ghost, nx_out, ny_out, nz_out, mhd_direction,
+                                     precision == 1 ? 4 : 8, out_precision == 1 ? 4 : 8, (cudaStream_t)stream));
+  return CHL_OK;
+}
+
 // ---- host-only mirrors of the reference's decomposition logic (src/mpi/mpi_routines.cpp) ----
 static int greatest_prime_factor(int n)
 {

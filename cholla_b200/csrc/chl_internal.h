@@ -66,6 +66,9 @@ cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields
                                    int dir, int diode, size_t real_bytes, cudaStream_t s);
 cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset,
                         int isize, int jsize, int ksize, int unpack, size_t real_bytes, cudaStream_t s);
+cudaError_t launch_snapshot_pack(void *out, const void *field, int nx, int ny, int nz, int n_ghost, int nx_out,
+                                 int ny_out, int nz_out, int mhd_direction, size_t in_bytes, size_t out_bytes,
+                                 cudaStream_t s);
 // exact_div_test.cu: shared-reciprocal division vs the compiler's a / b
 cudaError_t launch_exact_div_test(const double *a, const double *b, double *q_shared, double *q_plain, long n,
                                   cudaStream_t s);

@@ -9,8 +9,8 @@ conditions, fill the ghost cells, then
 What a deck cannot say -- the reference chooses reconstruction, Riemann solver, MHD and precision at compile time
 through `builds/make.type.*` -- comes from the options, which map one-to-one to `chl_config`.  Snapshots carry the
 reference's dataset and attribute names (`density, momentum_x, momentum_y, momentum_z, Energy[, magnetic_*]`; `gamma, t,
-dt, n_step, dims, ...`, src/io/io.cpp:605-737,1350-1497) in NumPy `.npz` containers with the reference's `[i][j][k]` axis
-order: this image has no HDF5 library, so the container differs and the contents do not.
+dt, n_step, dims, ...`, src/io/io.cpp:605-737,1350-1497) in HDF5 files of the reference's layout (`[i][j][k]` axis order,
+big-endian types, one file per rank), written by cholla_b200/snapshot.py; `init=Read_Grid` restarts from one.
 """
 import argparse
 import os
@@ -63,24 +63,22 @@ def initial_fields(P: Parameters, mhd=False, n_ghost=0):
 
 
 def snapshot(G, P: Parameters, nfile, outdir):
-    """Write_Data -> Write_Header_HDF5 + Write_Grid_HDF5 (io.cpp:605-737, 1350-1497): one file per rank,
-    `<outdir>/<nfile>/<nfile>.npz.<rank>`, datasets transposed to [i][j][k] like the reference's HDF5 buffers."""
-    H = G.H
-    real = G.real_cells()  # (nf, nz, ny, nx)
-    names = ["density", "momentum_x", "momentum_y", "momentum_z", "Energy"]
-    if H.n_fields == 8:
-        names += ["magnetic_x", "magnetic_y", "magnetic_z"]
-    data = {nm: np.ascontiguousarray(real[f].transpose(2, 1, 0)) for f, nm in enumerate(names)}
-    attrs = dict(gamma=P.gamma, t=H.t, dt=H.dt, n_step=H.n_step, n_fields=H.n_fields,
-                 dims=np.array(G.n_global), dims_local=np.array(G.decomp.n_local), offset=np.array(G.decomp.offset),
-                 nprocs=np.array(G.decomp.np), bounds=np.array([P.xmin, P.ymin, P.zmin]),
-                 domain=np.array([P.xlen, P.ylen, P.zlen]), dx=np.array([H.dx, H.dy, H.dz]))
-    d = os.path.join(outdir, str(nfile))
-    os.makedirs(d, exist_ok=True)
-    path = os.path.join(d, "%d.npz.%d" % (nfile, G.rank))
-    with open(path, "wb") as fh:
-        np.savez(fh, **data, **{"attr_" + k: v for k, v in attrs.items()})
-    return path
+    """Write_Data -> Output_Data -> Write_Header_HDF5 + Write_Grid_HDF5 (io.cpp:92-260, 605-737, 1350-1497): one HDF5
+    file per rank, `<outdir>/<nfile>/<nfile>.h5.<rank>` -- see cholla_b200/snapshot.py."""
+    from . import snapshot as snap
+    return snap.write_data(G, P, nfile, outdir)
+
+
+def read_grid(G, P: Parameters):
+    """Grid3D::Read_Grid (io.cpp:2255-2310): `init=Read_Grid` restarts from `<indir><nfile>.h5.<rank>`; gamma, t and
+    n_step come from the file."""
+    from . import snapshot as snap
+    path = "%s%d.h5.%d" % (P.indir, P.nfile, G.rank)
+    host, gamma, t, n_step = snap.read_grid(path, G.H, G.mhd)
+    if gamma != G.gamma:
+        raise ValueError("%s was written with gamma = %r, the deck says %r" % (path, gamma, G.gamma))
+    G.upload(host)
+    G.H.t, G.H.n_step = t, n_step
 
 
 def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mhd=False, outdir=None, device=None,
@@ -94,7 +92,10 @@ def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mh
                bc=P.boundary_flags(), precision=precision, strict=strict, density_floor=P.density_floor,
                temperature_floor_U=u_floor(P.temperature_floor, P.gamma), device=device, dist_group=dist_group,
                rank=rank, nproc=nproc, mhd=mhd)
-    if mhd:
+    is_restart = P.init == "Read_Grid"  # main.cpp:89-95
+    if is_restart:
+        read_grid(G, P)
+    elif mhd:
         if nproc != 1:
             raise NotImplementedError("the MHD generators build the whole grid on one rank")
         G.upload(initial_fields(P, True, n_ghost_for(RECON[recon], True)))
@@ -104,7 +105,9 @@ def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mh
     G.Set_Boundary_Conditions_Grid()
     outdir = outdir if outdir is not None else (P.outdir or "./")
     files, nfile, outtime = [], P.nfile, 0.0
-    if outdir != "none":
+    if is_restart:
+        outtime += G.H.t  # main.cpp:124-128
+    if outdir != "none" and not is_restart:
         files.append(snapshot(G, P, nfile, outdir))  # main.cpp:205-215: the initial state is output 0
     nfile += 1
     outtime += P.outstep

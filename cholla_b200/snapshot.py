@@ -1,0 +1,217 @@
+"""The reference's HDF5 snapshot layout: writer, restart reader and the per-rank concatenation.
+
+    Write_Data / Output_Data       src/io/io.cpp:92-260      -> write_data()
+    FnameTemplate                  src/io/io.cpp:2779-2828   -> effective_output_dir_path(), format_fname()
+    Grid3D::Write_Header_HDF5      src/io/io.cpp:605-737     -> header_attributes()
+    Grid3D::Write_Grid_HDF5        src/io/io.cpp:1350-1497   -> grid_datasets()
+    CopyReal3D_GPU_Kernel          src/io/io_gpu.cu:45-95    -> the [i][j][k] transposition and the MHD face shift
+    Grid3D::Read_Grid / _HDF5      src/io/io.cpp:2255-2310, 2508-2720 -> read_grid()
+    python_scripts/concat_3d_data.py, concat_internals.py    -> concat_3d_dataset()
+
+Files are real HDF5 (cholla_b200/h5lite.py writes the format directly; this image has no libhdf5): one file per rank,
+`<outdir>/<nfile>/<nfile>.h5.<rank>`, datasets `H5T_IEEE_F64BE` (or F32BE for a PRECISION=1 build) of shape
+(nx_real, ny_real, nz_real) -- x slowest, "indexing that plays well with Python" -- and face-centred magnetic fields
+with one extra face along their own direction.  Attributes carry the reference's names, types (F64BE / I32BE /
+variable-length strings), shapes ((1,) and (3,)) and creation order.  Everything here works on host arrays, so it is
+exercised without a GPU.
+"""
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+from . import h5lite
+
+# src/global/global.h:40-48
+TIME_UNIT = 3.15569e10
+LENGTH_UNIT = 3.08567758e21
+MASS_UNIT = 1.98847e33
+DENSITY_UNIT = MASS_UNIT / (LENGTH_UNIT * LENGTH_UNIT * LENGTH_UNIT)
+VELOCITY_UNIT = LENGTH_UNIT / TIME_UNIT
+ENERGY_UNIT = DENSITY_UNIT * VELOCITY_UNIT * VELOCITY_UNIT
+MAGNETIC_FIELD_UNIT = (MASS_UNIT / LENGTH_UNIT) ** 0.5 / TIME_UNIT
+
+HYDRO_FIELDS = ["density", "momentum_x", "momentum_y", "momentum_z", "Energy"]
+MAGNETIC_FIELDS = ["magnetic_x", "magnetic_y", "magnetic_z"]
+_RECON_FLAG = {0: "-DPCM", 1: "-DPLMC", 2: "-DPPMC", 3: "-DPLMP", 4: "-DPPMP"}
+_SOLVER_FLAG = {0: "-DHLLC", 1: "-DROE", 2: "-DHLLD", 3: "-DHLL"}
+
+
+def effective_output_dir_path(outdir, nfile, legacy_flat_outdir=False):
+    """FnameTemplate::effective_output_dir_path, io.cpp:2779-2795 (always ends in '/')."""
+    if not outdir:
+        return "./"
+    if not legacy_flat_outdir:
+        return outdir + "/" + str(nfile) + "/"
+    return os.path.dirname(outdir) + "/"
+
+
+def format_fname(outdir, nfile, proc_id, pre_extension_suffix="", legacy_flat_outdir=False):
+    """FnameTemplate::format_fname, io.cpp:2807-2828, for an HDF5 build."""
+    prefix = outdir if legacy_flat_outdir else effective_output_dir_path(outdir, nfile) + "/"
+    return prefix + str(nfile) + pre_extension_suffix + ".h5" + "." + str(proc_id)
+
+
+def macro_flags(recon, solver, precision=2, mhd=False):
+    """The MACRO_FLAGS string of the equivalent reference build (Makefile:173-175, builds/make.type.hydro / .mhd)."""
+    flags = ["-DCUDA", "-DMPI_CHOLLA", "-DPRECISION=%d" % precision, _RECON_FLAG[recon], _SOLVER_FLAG[solver], "-DVL",
+             "-DDENSITY_FLOOR", "-DTEMPERATURE_FLOOR", "-DHDF5", "-DOUTPUT"]
+    if mhd:
+        flags.append("-DMHD")
+    return " ".join(flags)
+
+
+def _f64(*v):
+    return np.array(v, dtype=">f8")
+
+
+def _i32(*v):
+    return np.array(v, dtype=">i4")
+
+
+def header_attributes(H, gamma, n_global, n_local, offset, nprocs, bounds, domain, mhd=False, git_hash="",
+                      macro=""):
+    """Grid3D::Write_Header_HDF5 of an MPI_CHOLLA build, io.cpp:605-737, in creation order."""
+    a = OrderedDict()
+    a["gamma"] = _f64(gamma)
+    a["Git Commit Hash"] = h5lite.VarString(git_hash)
+    a["Macro Flags"] = h5lite.VarString(macro)
+    a["cholla"] = h5lite.VarString("")
+    a["t"] = _f64(H.t)
+    a["dt"] = _f64(H.dt)
+    a["n_step"] = _i32(H.n_step)
+    a["n_fields"] = _i32(H.n_fields)
+    a["time_unit"] = _f64(TIME_UNIT)
+    a["length_unit"] = _f64(LENGTH_UNIT)
+    a["mass_unit"] = _f64(MASS_UNIT)
+    a["velocity_unit"] = _f64(VELOCITY_UNIT)
+    a["density_unit"] = _f64(DENSITY_UNIT)
+    a["energy_unit"] = _f64(ENERGY_UNIT)
+    if mhd:
+        a["magnetic_field_unit"] = _f64(MAGNETIC_FIELD_UNIT)
+    a["dims"] = _i32(*n_global)
+    a["dims_local"] = _i32(*n_local)
+    a["offset"] = _i32(*offset)
+    a["nprocs"] = _i32(*nprocs)
+    a["bounds"] = _f64(*bounds)
+    a["domain"] = _f64(*domain)
+    a["dx"] = _f64(H.dx, H.dy, H.dz)
+    return a
+
+
+def _ghosts(H):
+    g = H.n_ghost
+    return g, (g if H.ny > 1 else 0), (g if H.nz > 1 else 0)
+
+
+def grid_datasets(H, C_host, mhd=False, precision=2):
+    """Grid3D::Write_Grid_HDF5 with Output_Complete_Data, io.cpp:1350-1497.  C_host: (n_fields, nz, ny, nx) host array,
+    ghost cells included.  1-D grids give (nx_real,), 2-D (nx_real, ny_real), 3-D (nx_real, ny_real, nz_real)."""
+    C_host = np.asarray(C_host).reshape(H.n_fields, H.nz, H.ny, H.nx)
+    gx, gy, gz = _ghosts(H)
+    dt = ">f8" if precision == 2 else ">f4"
+    ndim = 1 + (H.ny > 1) + (H.nz > 1)
+    out = OrderedDict()
+    for f, nm in enumerate(HYDRO_FIELDS):
+        real = C_host[f, gz:gz + H.nz_real, gy:gy + H.ny_real, gx:gx + H.nx_real]
+        t = real.transpose(2, 1, 0)  # [i][j][k]: dest = k + j*nz_real + i*nz_real*ny_real
+        out[nm] = np.ascontiguousarray(t.reshape(t.shape[:ndim])).astype(dt)
+    if mhd and ndim == 3:  # io.cpp:1478-1487; the face on the low side of the first real cell is part of the output
+        for d, nm in enumerate(MAGNETIC_FIELDS):
+            sx, sy, sz = (1 if d == 0 else 0), (1 if d == 1 else 0), (1 if d == 2 else 0)
+            real = C_host[5 + d, gz - sz:gz + H.nz_real, gy - sy:gy + H.ny_real, gx - sx:gx + H.nx_real]
+            out[nm] = np.ascontiguousarray(real.transpose(2, 1, 0)).astype(dt)
+    return out
+
+
+def write_snapshot(path, H, C_host, gamma, n_global, n_local, offset, nprocs, bounds, domain, mhd=False, precision=2,
+                   git_hash="", macro=""):
+    """Output_Data, io.cpp:198-260: header then grid, one file."""
+    attrs = header_attributes(H, gamma, n_global, n_local, offset, nprocs, bounds, domain, mhd, git_hash, macro)
+    h5lite.write(path, attrs, grid_datasets(H, C_host, mhd, precision))
+    return path
+
+
+def write_data(G, P, nfile, outdir):
+    """Write_Data -> Output_Data for one rank of a live Grid3D (device -> host -> file)."""
+    H = G.H
+    d = effective_output_dir_path(outdir, nfile, getattr(P, "legacy_flat_outdir", False))
+    os.makedirs(d, exist_ok=True)  # Ensure_Dir_Exists, io.cpp:2830-
+    path = format_fname(outdir, nfile, G.rank, "", getattr(P, "legacy_flat_outdir", False))
+    attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
+                              (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd))
+    dt = ">f8" if G.precision == 2 else ">f4"
+    data = OrderedDict()
+    for f, nm in enumerate(HYDRO_FIELDS):  # device-side transposition, one field at a time like the reference
+        data[nm] = G.snapshot_field(f).astype(dt)
+    if G.mhd and H.nz > 1:
+        for d, nm in enumerate(MAGNETIC_FIELDS):
+            data[nm] = G.snapshot_field(5 + d, mhd_direction=d).astype(dt)
+    h5lite.write(path, attrs, data)
+    return path
+
+
+def read_grid(path, H, mhd=False):
+    """Grid3D::Read_Grid_HDF5, io.cpp:2508-2720: returns (C_host (n_fields, nz, ny, nx) with the real cells -- and, for
+    MHD, the real faces -- filled and the ghost cells zero, gamma, t, n_step).  The caller sets the boundaries next, as
+    main.cpp does."""
+    gx, gy, gz = _ghosts(H)
+    ndim = 1 + (H.ny > 1) + (H.nz > 1)
+    out = np.zeros((H.n_fields, H.nz, H.ny, H.nx), dtype=np.float64)
+    with h5lite.File(path) as f:
+        gamma = float(f.attrs["gamma"][0])
+        t = float(f.attrs["t"][0])
+        n_step = int(f.attrs["n_step"][0])
+        want = (H.nx_real, H.ny_real, H.nz_real)[:ndim]
+        for i, nm in enumerate(HYDRO_FIELDS):
+            a = f[nm].read()
+            if a.shape != want:
+                raise ValueError("%s: dataset %s has shape %s, the grid expects %s" % (path, nm, a.shape, want))
+            a = a.reshape(a.shape + (1,) * (3 - ndim)).astype(np.float64)
+            out[i, gz:gz + H.nz_real, gy:gy + H.ny_real, gx:gx + H.nx_real] = a.transpose(2, 1, 0)
+        if mhd and ndim == 3:
+            for d, nm in enumerate(MAGNETIC_FIELDS):
+                sx, sy, sz = (1 if d == 0 else 0), (1 if d == 1 else 0), (1 if d == 2 else 0)
+                a = f[nm].read().astype(np.float64)
+                if a.shape != (H.nx_real + sx, H.ny_real + sy, H.nz_real + sz):
+                    raise ValueError("%s: dataset %s has shape %s" % (path, nm, a.shape))
+                out[5 + d, gz - sz:gz + H.nz_real, gy - sy:gy + H.ny_real, gx - sx:gx + H.nx_real] = a.transpose(2, 1, 0)
+    return out, gamma, t, n_step
+
+
+def concat_3d_dataset(source_directory, output_directory, num_processes, output_number, skip_fields=(),
+                      destination_dtype=None):
+    """python_scripts/concat_3d_data.py: merge `<src>/<n>/<n>.h5.<rank>` of all ranks into `<out>/<n>.h5`.  The header
+    is rank 0's without `dims_local` and `offset` (concat_internals.copy_header); magnetic datasets overlap by the
+    shared face."""
+    os.makedirs(output_directory, exist_ok=True)
+    dest_path = os.path.join(output_directory, "%d.h5" % output_number)
+    data, attrs = OrderedDict(), None
+    for rank in range(num_processes):
+        src = os.path.join(source_directory, str(output_number), "%d.h5.%d" % (output_number, rank))
+        with h5lite.File(src) as f:
+            if attrs is None:
+                attrs = OrderedDict((k, v) for k, v in f.attrs.items() if k not in ("dims_local", "offset"))
+                dims = tuple(int(v) for v in f.attrs["dims"])
+            nloc = [int(v) for v in f.attrs["dims_local"]]
+            off = [int(v) for v in f.attrs["offset"]]
+            for nm in f.keys():
+                if nm in skip_fields:
+                    continue
+                ds = f[nm]
+                a = ds.read()
+                extra = [1 if nm == "magnetic_" + "xyz"[d] else 0 for d in range(3)]
+                if nm not in data:
+                    shape = tuple(dims[d] + extra[d] for d in range(a.ndim))
+                    data[nm] = np.zeros(shape, dtype=destination_dtype or ds.dtype)
+                sl = tuple(slice(off[d], off[d] + nloc[d] + extra[d]) for d in range(a.ndim))
+                data[nm][sl] = a
+    out_attrs = OrderedDict()
+    for k, v in attrs.items():
+        if isinstance(v, str):
+            out_attrs[k] = h5lite.VarString(v)
+        else:
+            out_attrs[k] = np.asarray(v).astype(">f8" if np.asarray(v).dtype.kind == "f" else ">i4")
+    h5lite.write(dest_path, out_attrs, data)
+    return dest_path

@@ -298,3 +298,26 @@ def test_256_cubed_conservation_and_uniform_state():
     assert np.abs(r - r[:, :1, :1, :]).max() <= 1e-12
     G.close()
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("n,mhd", [((37, 19, 21), False), ((33, 40, 1), False), ((50, 1, 1), False), ((20, 35, 18), True)])
+def test_snapshot_pack_kernel_matches_host_layout(n, mhd):
+    """chl_pack_snapshot_field (CopyReal3D_GPU_Kernel's counterpart, io_gpu.cu:45-95) against the NumPy statement of the
+    same layout in cholla_b200/snapshot.py: every field, face-centred magnetic fields included, fp64 and -> fp32."""
+    from cholla_b200 import snapshot
+    recon = cb.PPMC
+    G = Grid3D(n, (1.0, 1.0, 1.0), recon=recon, solver=cb.HLLD if mhd else cb.HLLC, gamma=1.4, bc=[1] * 6, strict=True,
+               device="cuda:0", mhd=mhd)
+    H = G.H
+    host = np.random.default_rng(11).standard_normal(H.n_fields * H.n_cells)
+    G.upload(host)
+    want = snapshot.grid_datasets(H, host, mhd=mhd)
+    for f, nm in enumerate(snapshot.HYDRO_FIELDS):
+        got = G.snapshot_field(f)
+        assert got.shape == want[nm].shape and np.array_equal(got, want[nm].astype(np.float64)), nm
+        assert np.array_equal(G.snapshot_field(f, out_precision=1), want[nm].astype(np.float32)), nm
+    if mhd:
+        for d, nm in enumerate(snapshot.MAGNETIC_FIELDS):
+            got = G.snapshot_field(5 + d, mhd_direction=d)
+            assert got.shape == want[nm].shape and np.array_equal(got, want[nm].astype(np.float64)), nm
+    G.close()

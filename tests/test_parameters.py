@@ -141,10 +141,37 @@ def test_deck_driven_run_matches_oracle_loop(tmp_path):
         tc += dt
         steps += 1
     assert steps == n_step and np.array_equal(got, real_view(flat, dims, g))
-    z = np.load(files[1])
-    assert z["density"].shape == (100, 1, 1) and float(z["attr_t"]) == 0.2 and int(z["attr_n_step"]) == n_step
-    assert np.array_equal(z["density"][:, 0, 0], got[0, 0, 0, :]) and np.array_equal(z["Energy"][:, 0, 0], got[4, 0, 0, :])
-    assert os.path.basename(files[1]) == "1.npz.0" and os.path.basename(os.path.dirname(files[1])) == "1"
+    from cholla_b200 import h5lite
+    with h5lite.File(files[1]) as z:  # the reference's HDF5 layout: 1-D datasets of nx_real big-endian doubles
+        assert z["density"].shape == (100,) and z["density"].dtype == np.dtype(">f8")
+        assert float(z.attrs["t"][0]) == 0.2 and int(z.attrs["n_step"][0]) == n_step and z.attrs["dims"].tolist() == [100, 1, 1]
+        assert np.array_equal(z["density"].read(), got[0, 0, 0, :]) and np.array_equal(z["Energy"].read(), got[4, 0, 0, :])
+    assert os.path.basename(files[1]) == "1.h5.0" and os.path.basename(os.path.dirname(files[1])) == "1"
+
+
+@pytest.mark.gpu
+def test_restart_from_snapshot_continues_bit_for_bit(tmp_path):
+    """init=Read_Grid (io.cpp:2255-2310, main.cpp:89-128): a run restarted from its own snapshot 1 (t = 0.1) reaches
+    t = 0.2 with the bytes, step count and snapshot of the uninterrupted run."""
+    from cholla_b200 import h5lite, run
+    deck = tmp_path / "sod.txt"
+    deck.write_text(SOD_DECK)
+    P = pm.parse_params(str(deck), ["outdir=%s/a/" % tmp_path, "outstep=0.1"])
+    G, files = run.run(P, recon="plmc", solver="hllc", strict=True, log=lambda *_: None)
+    full, n_full = G.real_cells(), G.H.n_step
+    G.close()
+    assert len(files) == 3 and os.path.normpath(files[1]).endswith("/1/1.h5.0")
+    R = pm.parse_params(str(deck), ["outdir=%s/b/" % tmp_path, "outstep=0.1", "init=Read_Grid", "nfile=1",
+                                    "indir=%s/a/1/" % tmp_path])
+    G2, files2 = run.run(R, recon="plmc", solver="hllc", strict=True, log=lambda *_: None)
+    again, n_again, t_again = G2.real_cells(), G2.H.n_step, G2.H.t
+    G2.close()
+    assert t_again == 0.2 and n_again == n_full and np.array_equal(again, full)
+    assert len(files2) == 1 and os.path.normpath(files2[0]).endswith("/2/2.h5.0")  # a restart does not rewrite its input (main.cpp:198)
+    with h5lite.File(files[2]) as a, h5lite.File(files2[0]) as b:
+        for nm in a.keys():
+            assert np.array_equal(a[nm].read(), b[nm].read())
+        assert a.attrs["n_step"][0] == b.attrs["n_step"][0] and a.attrs["t"][0] == b.attrs["t"][0]
 
 
 OT_DECK = """# Orszag-Tang vortex, in the format of the reference's examples/3D/orszag_tang_vortex.txt (config C4), small grid
@@ -200,5 +227,7 @@ def test_deck_driven_mhd_run(tmp_path):
     err = max(sum(np.abs(a[f] - b[f]).sum() for f in q) / sum(np.abs(b[f]).sum() for f in q) for q in groups)
     assert err <= 1e-12, err  # rsqrt / rhypot have no correctly rounded libm twin: tolerance, not bits
     assert mhd.max_divergence(got, *dims, g, d, d, d) <= 1e-11
-    z = np.load(files[0])
-    assert z["magnetic_x"].shape == (24, 24, 24) and int(z["attr_n_fields"]) == 8
+    from cholla_b200 import h5lite
+    with h5lite.File(files[0]) as z:  # face-centred fields carry one extra face along their own direction
+        assert z["magnetic_x"].shape == (25, 24, 24) and z["magnetic_z"].shape == (24, 24, 25)
+        assert int(z.attrs["n_fields"][0]) == 8 and "magnetic_field_unit" in z.attrs and "-DMHD" in z.attrs["Macro Flags"]
