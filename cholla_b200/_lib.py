@@ -59,6 +59,8 @@ def lib():
     L.chl_scratch_bytes.restype = C.c_size_t
     L.chl_vl_step.argtypes = [p, p, d, p]
     L.chl_vl_step_fused.argtypes = [p, p, d, p]
+    L.chl_simple_step.argtypes = [p, p, d, p]
+    L.chl_simple_step_fused.argtypes = [p, p, d, p]
     L.chl_dti_result.argtypes = [p, C.POINTER(d), p]
     L.chl_dti_device_ptr.argtypes = [p, C.POINTER(p)]
     L.chl_dti_decode.argtypes = [C.c_ulonglong]

@@ -242,6 +242,7 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
   a.dti_key = c->d_key;
   a.acc = c->d_acc;
   a.dir_chunk = c->dir_chunk;
+  a.simple = 0;
   auto const sweep = c->split ? c->ops->sweep_split : c->ops->sweep;
   int const n[3] = {g.nx, g.ny, g.nz};
   auto choose_chunk = [&](int const *lo, int const *hi) {
@@ -304,6 +305,58 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
     c->ev_steps++;
   }
   return CHL_OK;
+}
+
+// Simple_Algorithm_{1,2,3}D_CUDA (src/integrators/simple_*_cuda.cu): reconstruct on U, Riemann, update over dt.
+static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
+{
+  if (!c || !U) return fail(CHL_ERR_INVALID, "chl_simple_step: null argument");
+  chl_config const &g = c->cfg;
+  if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: MHD requires the Van Leer integrator (error_handling.cpp:89)");
+  if (g.recon != CHL_RECON_PCM && g.recon != CHL_RECON_PLMC)
+    return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: PCM and PLMC only (the CTU forms of PLMP / PPMP / PPMC are not built)");
+  if (!c->d_acc) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: needs the direction-split sweeps (CHL_SWEEP_IMPL=split)");
+  chl::SweepArgs a;
+  a.nx = g.nx; a.ny = g.ny; a.nz = g.nz;
+  a.has_y = g.ny > 1;
+  a.has_z = g.nz > 1;
+  a.gamma = g.gamma;
+  a.density_floor = g.density_floor;
+  a.dx = g.dx; a.dy = g.dy; a.dz = g.dz;
+  a.dti_key = c->d_key;
+  a.acc = c->d_acc;
+  a.dir_chunk = c->dir_chunk;
+  a.simple = 1;
+  a.zchunk = 1;
+  int const n[3] = {g.nx, g.ny, g.nz};
+  for (int d = 0; d < 3; d++) {
+    bool const on = d == 0 || (d == 1 && a.has_y) || (d == 2 && a.has_z);
+    a.lo[d] = on ? g.n_ghost : 0;
+    a.hi[d] = on ? n[d] - g.n_ghost : 1;
+  }
+  a.in = c->d_half;
+  a.out = U;
+  a.dtodx = dt / g.dx;
+  a.dtody = dt / g.dy;
+  a.dtodz = dt / g.dz;
+  a.apply_tfloor = 0;
+  a.U_floor = 0.0;
+  a.do_dti = 0;
+  if (fused) {
+    a.apply_tfloor = (g.temperature_floor_U > 0.0 && c->ndim == 3) ? 1 : 0;
+    a.U_floor = g.temperature_floor_U;
+    a.do_dti = 1;
+    CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
+  }
+  CHL_CUDA(c->ops->prim_from_cons(U, c->d_half, c->n_cells, g.gamma, g.recon, s));
+  CHL_CUDA(c->ops->sweep_split(1, g.recon, g.solver, a, s));
+  return CHL_OK;
+}
+
+int chl_simple_step(chl_ctx *c, void *U, double dt, void *stream) { return simple_impl(c, U, dt, 0, (cudaStream_t)stream); }
+int chl_simple_step_fused(chl_ctx *c, void *U, double dt, void *stream)
+{
+  return simple_impl(c, U, dt, 1, (cudaStream_t)stream);
 }
 
 int chl_set_profiling(chl_ctx *c, int enable)

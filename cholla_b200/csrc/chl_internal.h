@@ -15,6 +15,7 @@ struct SweepArgs {  // everything in double; each mode TU narrows to its Real
   int has_y, has_z;
   int zchunk;
   int dir_chunk;  // direction-split sweeps: cells per thread along the marching direction (0 = choose)
+  int simple;     // 1: SIMPLE integrator -- stage 1 reconstructs with the -DSIMPLE forms (PLMC gains its tracing)
   double dtodx, dtody, dtodz, gamma, density_floor;
   int apply_tfloor;
   double U_floor;
@@ -30,6 +31,8 @@ struct ModeOps {
   cudaError_t (*calc_dti)(const void *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz,
                           double gamma, unsigned long long *key, cudaStream_t s);
   cudaError_t (*tfloor)(void *U, int nx, int ny, int nz, int n_ghost, double U_floor, cudaStream_t s);
+  // SIMPLE integrator: primitives of U for every cell -> W, then sweep_split(1, ...) with simple = 1 in SweepArgs
+  cudaError_t (*prim_from_cons)(const void *U, void *W, size_t n_cells, double gamma, int recon, cudaStream_t s);
   size_t real_bytes;
   int half_fields;  // fields of the half-step scratch array (5, or 7 in strict mode)
   int tile_y;       // rows of cells per CTA column

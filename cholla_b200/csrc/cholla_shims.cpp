@@ -126,6 +126,35 @@ void VL_Algorithm_1D_CUDA(Real *d_conserved, int nx, int x_off, int n_ghost, Rea
   if (rc != CHL_OK) die("chl_vl_step", rc);
 }
 
+// src/integrators/simple_3D_cuda.h, simple_2D_cuda.h, simple_1D_cuda.h: a -DSIMPLE build (builds/make.type.hydro:8-12) calls
+// these from Grid3D::Execute_Hydro_Integrator instead of the VL entry points; both sets are defined so one shim object
+// serves either build
+void Simple_Algorithm_3D_CUDA(Real *d_conserved, Real *d_grav_potential, int nx, int ny, int nz, int x_off, int y_off,
+                              int z_off, int n_ghost, Real dx, Real dy, Real dz, Real xbound, Real ybound, Real zbound,
+                              Real dt, int n_fields, int custom_grav, Real density_floor, Real *host_grav_potential)
+{
+  (void)d_grav_potential; (void)x_off; (void)y_off; (void)z_off; (void)xbound; (void)ybound; (void)zbound;
+  (void)custom_grav; (void)host_grav_potential;
+  int const rc = chl_simple_step(context(nx, ny, nz, n_ghost, n_fields, dx, dy, dz, density_floor), d_conserved, dt, nullptr);
+  if (rc != CHL_OK) die("chl_simple_step", rc);
+}
+
+void Simple_Algorithm_2D_CUDA(Real *d_conserved, int nx, int ny, int x_off, int y_off, int n_ghost, Real dx, Real dy,
+                              Real xbound, Real ybound, Real dt, int n_fields, int custom_grav)
+{
+  (void)x_off; (void)y_off; (void)xbound; (void)ybound; (void)custom_grav;
+  int const rc = chl_simple_step(context(nx, ny, 1, n_ghost, n_fields, dx, dy, dy, 0.0), d_conserved, dt, nullptr);
+  if (rc != CHL_OK) die("chl_simple_step", rc);
+}
+
+void Simple_Algorithm_1D_CUDA(Real *d_conserved, int nx, int x_off, int n_ghost, Real dx, Real xbound, Real dt,
+                              int n_fields, int custom_grav)
+{
+  (void)x_off; (void)xbound; (void)custom_grav;
+  int const rc = chl_simple_step(context(nx, 1, 1, n_ghost, n_fields, dx, dx, dx, 0.0), d_conserved, dt, nullptr);
+  if (rc != CHL_OK) die("chl_simple_step", rc);
+}
+
 static void free_memory()
 {
   if (g_ctx) chl_destroy(g_ctx);
@@ -134,6 +163,9 @@ static void free_memory()
 void Free_Memory_VL_1D() { free_memory(); }
 void Free_Memory_VL_2D() { free_memory(); }
 void Free_Memory_VL_3D() { free_memory(); }
+void Free_Memory_Simple_1D() { free_memory(); }
+void Free_Memory_Simple_2D() { free_memory(); }
+void Free_Memory_Simple_3D() { free_memory(); }
 
 // src/hydro/hydro_cuda.h:69
 Real Calc_dt_GPU(Real *dev_conserved, int nx, int ny, int nz, int n_ghost, int n_fields, Real dx, Real dy, Real dz,

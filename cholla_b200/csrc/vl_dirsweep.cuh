@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
   size_t const N = (size_t)nx * ny * P.nz;
   int const lane = threadIdx.x & 31;
   Real const gamma = P.gamma;
-  KC const kc      = make_kc(gamma);
+  KC kc            = make_kc(gamma);
+  kc.dtodx         = P.dto;  // read by PLMC's characteristic tracing only (SIMPLE integrator)
   DirMap const m   = dir_map(DIR, N, nx, ny, (STAGE == 1 && CHL_STRICT) ? 4 + DIR : 4);
 
   // the cells this thread visits: c = c_first .. c_last along DIR at fixed `base`; it completes cells
@@ -374,5 +375,6 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
     }
   }
 }
+
 
 }  // namespace CHL_NS

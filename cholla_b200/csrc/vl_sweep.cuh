@@ -178,7 +178,7 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
     return;
   }
   if (RECON == kPPMC) ppmc_stencil(ld, k, l, r);
-  else plmc_stencil(ld, k, l, r);
+  else plmc_stencil<RECON == kPLMCT>(ld, k, l, r);
   L = iface_state(l, k);
   R = iface_state(r, k);
 }

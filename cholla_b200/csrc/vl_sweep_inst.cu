@@ -146,6 +146,14 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
     if (solver == kHLL) return run_dirs<kPCM, kHLL, 0>(p, a, s);
     return run_dirs<kPCM, kHLLC, 0>(p, a, s);
   }
+  if (a.simple) {  // Simple_Algorithm_*_CUDA: PCM as is, PLMC with characteristic tracing; the CTU forms are not built
+    if (recon == kPLMC) {
+      if (solver == kROE) return run_dirs<kPLMCT, kROE, 1>(p, a, s);
+      if (solver == kHLL) return run_dirs<kPLMCT, kHLL, 1>(p, a, s);
+      return run_dirs<kPLMCT, kHLLC, 1>(p, a, s);
+    }
+    if (recon != kPCM) return cudaErrorNotSupported;
+  }
   if (recon == kPPMP) {
     if (solver == kROE) return run_dirs<kPPMP, kROE, 1>(p, a, s);
     if (solver == kHLL) return run_dirs<kPPMP, kHLL, 1>(p, a, s);
@@ -251,7 +259,28 @@ cudaError_t tfloor(void *U, int nx, int ny, int nz, int g, double U_floor, cudaS
   return cudaGetLastError();
 }
 
-ModeOps const ops = {sweep, sweep_split, calc_dti, tfloor, sizeof(Real), kHalfFields, TY};
+// SIMPLE integrator (simple_3D_cuda.cu): there is no predictor, the reconstruction reads U itself.  The sweeps above
+// read primitives, so one elementwise pass derives them for every cell, ghosts included (what Load_Data would do per
+// stencil access): 40 B read + 40 (56 strict) B written per cell.
+__global__ void __launch_bounds__(256) prim_from_cons_kernel(const Real *__restrict__ U, Real *__restrict__ W, size_t N,
+                                                             Real gamma, int plmp)
+{
+  for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < N; id += (size_t)gridDim.x * blockDim.x) {
+    Real const u[5] = {__ldg(U + id), __ldg(U + N + id), __ldg(U + 2 * N + id), __ldg(U + 3 * N + id), __ldg(U + 4 * N + id)};
+    store_half(W, N, id, u, gamma, plmp);
+  }
+}
+
+cudaError_t prim_from_cons(const void *U, void *W, size_t n_cells, double gamma, int recon, cudaStream_t s)
+{
+  size_t blocks = (n_cells + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  prim_from_cons_kernel<<<(unsigned)blocks, 256, 0, s>>>((const Real *)U, (Real *)W, n_cells, (Real)gamma,
+                                                        (recon == kPLMP || recon == kPPMP) ? 1 : 0);
+  return cudaGetLastError();
+}
+
+ModeOps const ops = {sweep, sweep_split, calc_dti, tfloor, prim_from_cons, sizeof(Real), kHalfFields, TY};
 }  // namespace
 ModeOps const *get_ops() { return &ops; }
 }  // namespace CHL_NS

@@ -119,9 +119,13 @@ class Grid3D:
 
     def __init__(self, n_global, domain_len, bounds_min=(0.0, 0.0, 0.0), recon=_lib.PPMC, solver=_lib.HLLC,
                  gamma=5.0 / 3.0, bc=(1, 1, 1, 1, 1, 1), precision=2, strict=True, density_floor=0.0,
-                 temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True, mhd=False):
+                 temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True, mhd=False,
+                 integrator="vl"):
         import torch
         self.torch = torch
+        if integrator not in ("vl", "simple"):  # -DVL / -DSIMPLE, builds/make.type.hydro:8-12
+            raise ValueError("integrator must be 'vl' or 'simple'")
+        self.integrator = integrator
         self.recon, self.solver, self.gamma = recon, solver, float(gamma)
         self.precision, self.strict, self.fused = precision, bool(strict), bool(fused)
         self.mhd = bool(mhd) or solver == _lib.HLLD
@@ -277,19 +281,27 @@ class Grid3D:
         return self.H.dt
 
     def Execute_Hydro_Integrator(self):
-        """Grid3D::Execute_Hydro_Integrator (grid3D.cpp:413-470) -> VL_Algorithm_{1,2,3}D_CUDA."""
-        check(_lib.lib().chl_vl_step(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step")
+        """Grid3D::Execute_Hydro_Integrator (grid3D.cpp:413-470) -> VL_Algorithm_{1,2,3}D_CUDA, or
+        Simple_Algorithm_{1,2,3}D_CUDA in a -DSIMPLE build."""
+        if self.integrator == "simple":
+            check(_lib.lib().chl_simple_step(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_simple_step")
+        else:
+            check(_lib.lib().chl_vl_step(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step")
         self.gpu_launches += self._sweep_launches()
 
     def _sweep_launches(self):
-        """Kernels one VL step launches: a predictor and a corrector sweep per direction (direction-split default)."""
-        return 2 * self.ndim
+        """Kernels one step launches: VL a predictor and a corrector sweep per direction (direction-split default);
+        SIMPLE the primitive pass and one sweep per direction."""
+        return 1 + self.ndim if self.integrator == "simple" else 2 * self.ndim
 
     def Update_Hydro_Grid(self):
         """Grid3D::Update_Hydro_Grid (grid3D.cpp:474-585): integrator, temperature floor, new inverse dt."""
         L = _lib.lib()
         if self.fused:
-            check(L.chl_vl_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step_fused")
+            if self.integrator == "simple":
+                check(L.chl_simple_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_simple_step_fused")
+            else:
+                check(L.chl_vl_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step_fused")
             self.gpu_launches += self._sweep_launches()
             out = C.c_double()
             check(L.chl_dti_result(self._ctx, C.byref(out), self._stream()), "chl_dti_result")

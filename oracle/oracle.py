@@ -33,6 +33,8 @@ def lib():
         _lib.orc_riemann.argtypes = [i, p, p, p, i, i, i, d, i]
         _lib.orc_riemann_single.argtypes = [i, p, p, d, p]
         _lib.orc_vl_step.argtypes = [p, i, i, i, i, d, d, d, d, d, i, i, d]
+        _lib.orc_simple_step.argtypes = [p, i, i, i, i, d, d, d, d, d, i, i, d]
+        _lib.orc_plmc_trace_cell.argtypes = [p, p, p, d, d, p, p]
         _lib.orc_hydro_inverse_crossing_time.argtypes = [d] * 10
         _lib.orc_hydro_inverse_crossing_time.restype = d
         _lib.orc_calc_dti.argtypes = [p, i, i, i, i, d, d, d, d]
@@ -84,6 +86,21 @@ def vl_step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, densit
     return U
 
 
+def simple_step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor=0.0):
+    """In-place Simple_Algorithm_{1,2,3}D_CUDA on U (simple_3D_cuda.cu:25-180): PCM or PLMC with characteristic tracing."""
+    if lib().orc_simple_step(_ptr(U), nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor) != 0:
+        raise NotImplementedError("the SIMPLE integrator is restated for PCM and PLMC")
+    return U
+
+
+def plmc_trace_cell(wm, wi, wp, gamma, dtodx):
+    """One PLMC cell of a -DSIMPLE build (plmc_cuda.cu:60-299): (L at i+1/2, R at i-1/2) primitives."""
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (wm, wi, wp)]
+    L, R = np.zeros(5), np.zeros(5)
+    lib().orc_plmc_trace_cell(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), gamma, dtodx, _ptr(L), _ptr(R))
+    return L, R
+
+
 def hydro_inverse_crossing_time(E, d, d_inv, vx, vy, vz, dx, dy, dz, gamma):
     return lib().orc_hydro_inverse_crossing_time(E, d, d_inv, vx, vy, vz, dx, dy, dz, gamma)
 
@@ -127,14 +144,15 @@ def unpack(buf, U, nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize):
 
 
 def advance(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_steps, cfl=0.3,
-            density_floor=0.0, U_floor=0.0):
-    """The reference's main loop body (main.cpp:247-379) without I/O: dt from the CFL reduction, VL step,
+            density_floor=0.0, U_floor=0.0, integrator="vl"):
+    """The reference's main loop body (main.cpp:247-379) without I/O: dt from the CFL reduction, VL (or SIMPLE) step,
     temperature floor, ghost fill.  Returns the list of dt used."""
     dts = []
+    step = {"vl": vl_step, "simple": simple_step}[integrator]
     dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
     for _ in range(n_steps):
         dt = cfl / dti
-        vl_step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor)
+        step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor)
         temperature_floor(U, nx, ny, nz, n_ghost, U_floor)
         dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
         set_boundaries(U, nx, ny, nz, 5, n_ghost, flags)

@@ -4,8 +4,8 @@
 // Nothing here is reference code: these are thin calls into the reference's own public host functions
 //   VL_Algorithm_{1,2,3}D_CUDA (src/integrators/VL_*_cuda.h), Calc_dt_GPU, Apply_Temperature_Floor
 //   (src/hydro/hydro_cuda.h), SetGhostCells (src/grid/cuda_boundaries.h)
-// plus the two symbols those objects need from translation units we do not build: `gama`
-// (src/global/global.cpp:19) and `chexit` (src/utils/error_handling.cpp:25).
+// plus the symbols those objects need from translation units we do not build: `gama`
+// (src/global/global.cpp:19), `chexit` (src/utils/error_handling.cpp:25) and `chprintf` (src/io/io.cpp).
 #include <cstdio>
 #include <cstdlib>
 
@@ -16,9 +16,22 @@
 #include "integrators/VL_1D_cuda.h"
 #include "integrators/VL_2D_cuda.h"
 #include "integrators/VL_3D_cuda.h"
+#include "integrators/simple_1D_cuda.h"
+#include "integrators/simple_2D_cuda.h"
+#include "integrators/simple_3D_cuda.h"
 
 Real gama;
 [[noreturn]] void chexit(int code) { exit(code); }
+// chprintf (src/io/io.h:29, defined in io.cpp: printf on the root rank): simple_*D_cuda.cu reports its allocation with it
+#include <cstdarg>
+int chprintf(const char *__restrict sdata, ...)
+{
+  va_list ap;
+  va_start(ap, sdata);
+  int const n = getenv("REF_DRIVER_VERBOSE") ? vprintf(sdata, ap) : 0;
+  va_end(ap);
+  return n;
+}
 #ifdef MHD
 static const int kFields = 8;  // grid_enum::num_fields of an -DMHD build
 #else
@@ -44,15 +57,24 @@ const char *ref_build_flags(void) { return REF_BUILD_FLAGS; }
 
 void ref_set_gamma(double g) { gama = g; }
 
-// one VL step, dimensionality from ny/nz as in Grid3D::Execute_Hydro_Integrator (grid3D.cpp:413-470)
+// one integrator step (VL, or SIMPLE in a -DSIMPLE build), dimensionality from ny/nz as in
+// Grid3D::Execute_Hydro_Integrator (grid3D.cpp:413-470)
 void ref_vl_step(double *d_conserved, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz, double dt,
                  int n_fields, double density_floor)
 {
+#ifdef SIMPLE
+  if (ny == 1 && nz == 1) Simple_Algorithm_1D_CUDA(d_conserved, nx, 0, n_ghost, dx, 0.0, dt, n_fields, 0);
+  else if (nz == 1) Simple_Algorithm_2D_CUDA(d_conserved, nx, ny, 0, 0, n_ghost, dx, dy, 0.0, 0.0, dt, n_fields, 0);
+  else
+    Simple_Algorithm_3D_CUDA(d_conserved, nullptr, nx, ny, nz, 0, 0, 0, n_ghost, dx, dy, dz, 0.0, 0.0, 0.0, dt, n_fields,
+                             0, density_floor, nullptr);
+#else
   if (ny == 1 && nz == 1) VL_Algorithm_1D_CUDA(d_conserved, nx, 0, n_ghost, dx, 0.0, dt, n_fields, 0);
   else if (nz == 1) VL_Algorithm_2D_CUDA(d_conserved, nx, ny, 0, 0, n_ghost, dx, dy, 0.0, 0.0, dt, n_fields, 0);
   else
     VL_Algorithm_3D_CUDA(d_conserved, nullptr, nx, ny, nz, 0, 0, 0, n_ghost, dx, dy, dz, 0.0, 0.0, 0.0, dt, n_fields, 0,
                          density_floor, nullptr);
+#endif
 }
 
 double ref_calc_dti(double *d_conserved, int nx, int ny, int nz, int n_ghost, int n_fields, double dx, double dy,

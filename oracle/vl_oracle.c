@@ -141,8 +141,10 @@ static prim_t prim_diff(prim_t l, prim_t r, double coef)
   return s;
 }
 
-/* one cell of PLMC_cuda (plmc_cuda.cu:60-128, 287-299; the #ifndef VL block is dead) */
-static void plmc_cell(prim_t wm, prim_t wi, prim_t wp, double gamma, prim_t *L, prim_t *R)
+/* one cell of PLMC_cuda (plmc_cuda.cu:60-128, 287-299).  trace = 0: a -DVL build, where the #ifndef VL block is dead;
+ * trace = 1: a -DSIMPLE build, which evolves the interface values over dt/2 along the characteristics
+ * (plmc_cuda.cu:130-285) with dtodx = dt / dx of the sweep direction. */
+static void plmc_cell_t(prim_t wm, prim_t wi, prim_t wp, double gamma, int trace, double dtodx, prim_t *L, prim_t *R)
 {
   double a  = sqrt(gamma * wi.p / wi.d);
   double a2 = a * a;
@@ -170,9 +172,73 @@ static void plmc_cell(prim_t wm, prim_t wi, prim_t wp, double gamma, prim_t *L, 
   clamp_pair(&l.vy, &r.vy, wm.vy, wi.vy, wp.vy);
   clamp_pair(&l.vz, &r.vz, wm.vz, wi.vz, wp.vz);
   clamp_pair(&l.p, &r.p, wm.p, wi.p, wp.p);
+  if (trace) {
+    double lm = wi.vx - a, l0 = wi.vx, lp = wi.vx + a;
+    /* integrate the linear profile over the domain of dependence of the fastest wave (plmc_cuda.cu:140-156) */
+    double qx = -0.5 * fmin(lm, 0.0) * dtodx;
+    r.d = r.d + qx * dm.d; r.vx = r.vx + qx * dm.vx; r.vy = r.vy + qx * dm.vy; r.vz = r.vz + qx * dm.vz;
+    r.p = r.p + qx * dm.p;
+    qx = 0.5 * fmax(lp, 0.0) * dtodx;
+    l.d = l.d - qx * dm.d; l.vx = l.vx - qx * dm.vx; l.vy = l.vy - qx * dm.vy; l.vz = l.vz - qx * dm.vz;
+    l.p = l.p - qx * dm.p;
+    /* characteristic tracing, Stone eqs. 42-43 (plmc_cuda.cu:170-283).  The reference also adds the terms whose
+     * wave-speed difference is identically zero (lambda_p - lambda_p, lambda_m - lambda_m): +0 for finite data */
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+    if (lm >= 0) {
+      double ld = lp - lm;
+      s0 += ld * (-wi.d * dm.vx / (2 * a) + dm.p / (2 * a2));
+      s1 += ld * (dm.vx / 2.0 - dm.p / (2 * a * wi.d));
+      s4 += ld * (-wi.d * dm.vx * a / 2.0 + dm.p / 2.0);
+    }
+    if (l0 >= 0) {
+      double ld = lp - l0;
+      s0 += ld * (dm.d - dm.p / (a2));
+      s2 += ld * dm.vy;
+      s3 += ld * dm.vz;
+    }
+    if (lp >= 0) {
+      double ld = lp - lp;
+      s0 += ld * (wi.d * dm.vx / (2 * a) + dm.p / (2 * a2));
+      s1 += ld * (dm.vx / 2.0 + dm.p / (2 * a * wi.d));
+      s4 += ld * (wi.d * dm.vx * a / 2.0 + dm.p / 2.0);
+    }
+    l.d += 0.5 * dtodx * s0; l.vx += 0.5 * dtodx * s1; l.vy += 0.5 * dtodx * s2; l.vz += 0.5 * dtodx * s3;
+    l.p += 0.5 * dtodx * s4;
+    s0 = s1 = s2 = s3 = s4 = 0;
+    if (lm <= 0) {
+      double ld = lm - lm;
+      s0 += ld * (-wi.d * dm.vx / (2 * a) + dm.p / (2 * a2));
+      s1 += ld * (dm.vx / 2.0 - dm.p / (2 * a * wi.d));
+      s4 += ld * (-wi.d * dm.vx * a / 2.0 + dm.p / 2.0);
+    }
+    if (l0 <= 0) {
+      double ld = lm - l0;
+      s0 += ld * (dm.d - dm.p / (a2));
+      s2 += ld * dm.vy;
+      s3 += ld * dm.vz;
+    }
+    if (lp <= 0) {
+      double ld = lm - lp;
+      s0 += ld * (wi.d * dm.vx / (2 * a) + dm.p / (2 * a2));
+      s1 += ld * (dm.vx / 2.0 + dm.p / (2 * a * wi.d));
+      s4 += ld * (wi.d * dm.vx * a / 2.0 + dm.p / 2.0);
+    }
+    r.d += 0.5 * dtodx * s0; r.vx += 0.5 * dtodx * s1; r.vy += 0.5 * dtodx * s2; r.vz += 0.5 * dtodx * s3;
+    r.p += 0.5 * dtodx * s4;
+  }
   r.d = fmax(r.d, ORC_TINY); l.d = fmax(l.d, ORC_TINY);
   r.p = fmax(r.p, ORC_TINY); l.p = fmax(l.p, ORC_TINY);
   *L = l; *R = r;
+}
+/* exposed for the tests: one PLMC cell with the SIMPLE build's tracing; w* = (d, vx, vy, vz, p) */
+void orc_plmc_trace_cell(const double *wm, const double *wi, const double *wp, double gamma, double dtodx, double *L,
+                         double *R)
+{
+  prim_t m = {wm[0], wm[1], wm[2], wm[3], wm[4]}, i = {wi[0], wi[1], wi[2], wi[3], wi[4]},
+         p = {wp[0], wp[1], wp[2], wp[3], wp[4]}, l, r;
+  plmc_cell_t(m, i, p, gamma, 1, dtodx, &l, &r);
+  L[0] = l.d; L[1] = l.vx; L[2] = l.vy; L[3] = l.vz; L[4] = l.p;
+  R[0] = r.d; R[1] = r.vx; R[2] = r.vy; R[3] = r.vz; R[4] = r.p;
 }
 
 /* ---- PPM_Single_Variable (reconstruction.h:794-901) ---- */
@@ -368,7 +434,14 @@ static void ppmp_dir(const double *U, double *QL, double *QR, int nx, int ny, in
 /* Full-grid reconstruction pass in one direction: what one launch of PLMC_cuda / PPMC_VL does.
  * Q_L[id] = left state at face id+1/2 (from cell id); Q_R[id - stride] = right state at
  * face id-1/2 (from cell id).  Cells outside the guard are left untouched. */
+static void reconstruct_t(int recon, const double *U, double *QL, double *QR, int nx, int ny, int nz, double gamma,
+                          int dir, int trace, double dtodx);
 void orc_reconstruct(int recon, const double *U, double *QL, double *QR, int nx, int ny, int nz, double gamma, int dir)
+{
+  reconstruct_t(recon, U, QL, QR, nx, ny, nz, gamma, dir, 0, 0.0);
+}
+static void reconstruct_t(int recon, const double *U, double *QL, double *QR, int nx, int ny, int nz, double gamma,
+                          int dir, int trace, double dtodx)
 {
   size_t N = (size_t)nx * ny * nz;
   int o1, o2, o3;
@@ -390,7 +463,7 @@ void orc_reconstruct(int recon, const double *U, double *QL, double *QR, int nx,
           prim_t wp2 = load_prim(U, id + 2 * stride, N, o1, o2, o3, gamma);
           ppmc_cell(wm2, wm, wi, wp, wp2, gamma, &L, &R);
         } else {
-          plmc_cell(wm, wi, wp, gamma, &L, &R);
+          plmc_cell_t(wm, wi, wp, gamma, trace, dtodx, &L, &R);
         }
         store_interface(L, QL, id, N, o1, o2, o3, gamma);
         store_interface(R, QR, id - stride, N, o1, o2, o3, gamma);
@@ -681,6 +754,50 @@ void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, doub
 }
 
 /* hydro_cuda.cu:404-418 */
+/* One step of the SIMPLE integrator (simple_{1,2,3}D_cuda.cu: reconstruct on U, Riemann, update over dt -- no
+ * predictor; builds/make.type.hydro selects it for cosmology builds).  PCM and PLMC (with the characteristic
+ * tracing the -DSIMPLE build of plmc_cuda.cu compiles in); the CTU forms of the other reconstructions are not restated. */
+int orc_simple_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz, double dt,
+                    double gamma, int recon, int solver, double density_floor)
+{
+  if (recon != ORC_PCM && recon != ORC_PLMC) return -1;
+  size_t N = (size_t)nx * ny * nz;
+  int ndim = 1 + (ny > 1) + (nz > 1);
+  long st[3] = {1, nx, (long)nx * ny};
+  double dto[3] = {dt / dx, dt / dy, dt / dz};
+  double *QL[3], *QR[3], *F[3];
+  for (int d = 0; d < ndim; d++) {
+    QL[d] = calloc(5 * N, sizeof(double));
+    QR[d] = calloc(5 * N, sizeof(double));
+    F[d]  = calloc(5 * N, sizeof(double));
+    if (recon == ORC_PCM) pcm_dir(U, QL[d], QR[d], nx, ny, nz, d);
+    else reconstruct_t(recon, U, QL[d], QR[d], nx, ny, nz, gamma, d, 1, dto[d]);
+    orc_riemann(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d);
+  }
+  int g = n_ghost;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        if (!(x > g - 1 && x < nx - g)) continue;
+        if (ndim > 1 && !(y > g - 1 && y < ny - g)) continue;
+        if (ndim > 2 && !(z > g - 1 && z < nz - g)) continue;
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        for (int f = 0; f < 5; f++) {
+          double s = dto[0] * (F[0][f * N + id - st[0]] - F[0][f * N + id]);
+          for (int d = 1; d < ndim; d++) s = s + dto[d] * (F[d][f * N + id - st[d]] - F[d][f * N + id]);
+          U[f * N + id] += s;
+        }
+        if (ndim == 3 && U[id] < density_floor && U[id] > 0) { /* hydro_cuda.cu:279-291 */
+          double d0 = U[id];
+          U[id] = density_floor;
+          for (int f = 1; f < 5; f++) U[f * N + id] *= (density_floor / d0);
+        }
+      }
+  for (int d = 0; d < ndim; d++) { free(QL[d]); free(QR[d]); free(F[d]); }
+  return 0;
+}
+
 double orc_hydro_inverse_crossing_time(double E, double d, double d_inv, double vx, double vy, double vz, double dx,
                                        double dy, double dz, double gamma)
 {

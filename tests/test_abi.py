@@ -102,3 +102,19 @@ def test_halo_slab_geometry_matches_reference_offsets():
     # Unload_Hydro_DeviceBuffer_X1, 2-D
     s = halo_slab(nx, ny, 1, g, 1, recv=True)
     assert (s.idxoffset, s.isize, s.jsize, s.ksize) == (nx - g + g * nx, g, ny - 2 * g, 1)
+
+
+def test_reference_builds_resolve_every_symbol():
+    """oracle/_ref/*.so (the reference's own kernels behind ref_driver.cu, and the drop-in builds) must load with
+    immediate binding: an unresolved symbol (a host function of the reference the driver forgot to supply) would
+    otherwise only show on the GPU box."""
+    import ctypes
+    import glob
+    import os
+    import pytest
+    libs = sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "*.so")))
+    if not libs:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    for f in libs:
+        L = ctypes.CDLL(f, mode=os.RTLD_NOW)
+        assert hasattr(L, "ref_advance") and hasattr(L, "ref_build_flags"), f

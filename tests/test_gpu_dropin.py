@@ -21,6 +21,7 @@ import oracle
 from cholla_b200 import initial_conditions as ic
 from helpers import ghosted
 recon, solver, n, flags, gamma, steps = %(recon)d, %(solver)d, %(n)r, %(flags)r, %(gamma)r, %(steps)d
+simple = %(simple)r  # -DSIMPLE builds: the driver calls Simple_Algorithm_3D_CUDA
 is_mhd = solver == 2
 g = {0: 2, 1: 3, 2: 4}[recon] + (1 if is_mhd else 0)
 if is_mhd:
@@ -34,17 +35,18 @@ dx, dy, dz = [1.0 / v for v in n]
 res = {}
 for dropin in (False, True):
     t = torch.from_numpy(flat.copy()).cuda()
-    dts, dti, _ = reference.advance(t, dims, g, dx, dy, dz, gamma, recon, solver, flags, steps, dropin=dropin)
+    dts, dti, _ = reference.advance(t, dims, g, dx, dy, dz, gamma, recon, solver, flags, steps, dropin=dropin, simple=simple)
     res[dropin] = (t.cpu().numpy(), dts, dti)
 a, b = res[False], res[True]
 print("RESULT " + json.dumps(dict(equal=bool(np.array_equal(a[0], b[0])), dt_equal=bool(a[1] == b[1]),
       dti_equal=bool(a[2] == b[2]), changed=bool(not np.array_equal(a[0], flat)),
-      flags=reference.lib(recon, solver, dropin=True).ref_build_flags().decode())))
+      flags=reference.lib(recon, solver, dropin=True, simple=simple).ref_build_flags().decode())))
 """
 
 
 def run_child(**kw):
     kw["root"] = ROOT
+    kw.setdefault("simple", False)
     p = subprocess.run([sys.executable, "-c", CHILD % kw], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     return json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
@@ -57,4 +59,15 @@ def test_reference_driver_runs_unchanged_on_the_b200_library(recon, solver, flag
         pytest.skip("oracle/_ref libraries for this combination were not built")
     r = run_child(recon=recon, solver=solver, n=(32, 24, 20), flags=flags, gamma=5.0 / 3.0, steps=4)
     assert r["changed"] and "cholla_shims" in r["flags"], r
+    assert r["equal"] and r["dt_equal"] and r["dti_equal"], r
+
+
+def test_simple_integrator_driver_runs_unchanged_on_the_b200_library():
+    """The same proof for a -DSIMPLE -DPLMC -DHLLC build: the driver's Simple_Algorithm_3D_CUDA call lands in
+    cholla_shims.cpp -> chl_simple_step."""
+    from oracle import reference
+    if not (reference.available(1, 0, simple=True) and reference.available(1, 0, dropin=True, simple=True)):
+        pytest.skip("oracle/_ref libraries for this combination were not built")
+    r = run_child(recon=1, solver=0, n=(32, 24, 20), flags=[3, 3, 2, 2, 1, 1], gamma=5.0 / 3.0, steps=4, simple=True)
+    assert r["changed"] and "cholla_shims" in r["flags"] and "-DSIMPLE" in r["flags"], r
     assert r["equal"] and r["dt_equal"] and r["dti_equal"], r

@@ -29,12 +29,12 @@ def make_grid(n, recon, solver, flags, gamma, strict, precision=2, lengths=(1.0,
 
 
 def run_both(fields, recon, solver, flags, gamma, n_steps, strict, precision=2, lengths=(1.0, 1.0, 1.0),
-             fused=True, U_floor=0.0):
+             fused=True, U_floor=0.0, integrator="vl"):
     nf, nz, ny, nx = fields.shape
     g = n_ghost_for(recon)
     flat, dims = ghosted(fields, g, flags)
     G = make_grid((nx, ny, nz), recon, solver, flags, gamma, strict, precision, lengths, fused,
-                  temperature_floor_U=U_floor)
+                  temperature_floor_U=U_floor, integrator=integrator)
     assert (G.H.nx, G.H.ny, G.H.nz) == dims
     G.upload(flat)
     dts_gpu = G.advance(n_steps)
@@ -42,7 +42,7 @@ def run_both(fields, recon, solver, flags, gamma, n_steps, strict, precision=2, 
     G.close()
     ref = flat.copy()
     dts_cpu = oracle.advance(ref, *dims, g, G.H.dx, G.H.dy, G.H.dz, gamma, recon, solver, flags, n_steps,
-                             U_floor=U_floor)
+                             U_floor=U_floor, integrator=integrator)
     return got, ref, dims, g, dts_gpu, dts_cpu
 
 
@@ -320,4 +320,37 @@ def test_snapshot_pack_kernel_matches_host_layout(n, mhd):
         for d, nm in enumerate(snapshot.MAGNETIC_FIELDS):
             got = G.snapshot_field(5 + d, mhd_direction=d)
             assert got.shape == want[nm].shape and np.array_equal(got, want[nm].astype(np.float64)), nm
+    G.close()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("solver", [cb.HLLC, cb.ROE, cb.HLL])
+@pytest.mark.parametrize("shape", [(37, 19, 21), (45, 23, 1), (90, 1, 1)])
+def test_simple_integrator_plmc_strict_is_bit_exact(shape, solver, fused):
+    """chl_simple_step(_fused) (Simple_Algorithm_{1,2,3}D_CUDA, -DSIMPLE): PLMC with characteristic tracing against the
+    oracle, every solver, 1-/2-/3-D, with the temperature floor and the CFL reduction in the epilogue or as passes."""
+    fields = ic.random_smooth(shape, seed=7)
+    flags = [1, 1] + ([1, 1] if shape[1] > 1 else [0, 0]) + ([1, 1] if shape[2] > 1 else [0, 0])
+    got, ref, dims, g, dts_gpu, dts_cpu = run_both(fields, cb.PLMC, solver, flags, 1.4, 4, strict=True, fused=fused,
+                                                   U_floor=1e-3, integrator="simple")
+    assert dts_gpu == dts_cpu
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("recon,solver", [(cb.PLMC, cb.HLLC), (cb.PLMC, cb.ROE), (cb.PCM, cb.HLLC)])
+def test_simple_integrator_fast_mode_within_tolerance(recon, solver):
+    fields = ic.random_smooth((37, 19, 21), seed=8)
+    got, ref, dims, g, dts_gpu, dts_cpu = run_both(fields, recon, solver, PERIODIC, 5.0 / 3.0, 3, strict=False,
+                                                   integrator="simple")
+    assert rel_l1(real_view(got, dims, g), real_view(ref, dims, g)).max() <= TOL_F64
+    assert np.allclose(dts_gpu, dts_cpu, rtol=1e-13, atol=0)
+
+
+def test_simple_integrator_rejects_what_it_does_not_build():
+    """PPMC under -DSIMPLE is PPMC_CTU, which is not on the path: the call fails loudly instead of running PPMC_VL."""
+    G = make_grid((24, 24, 24), cb.PPMC, cb.HLLC, PERIODIC, 1.4, True, integrator="simple")
+    G.upload(ghosted(ic.random_smooth((24, 24, 24), seed=1), n_ghost_for(cb.PPMC), PERIODIC)[0])
+    G.H.dt = 1e-3
+    with pytest.raises(cb.ChollaB200Error):
+        G.Execute_Hydro_Integrator()
     G.close()

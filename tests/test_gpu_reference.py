@@ -25,6 +25,7 @@ from cholla_b200.grid import Grid3D, n_ghost_for
 from helpers import ghosted, real_view, rel_l1, max_ulp
 
 recon, solver, n, flags, gamma, steps, icname = %(recon)d, %(solver)d, %(n)r, %(flags)r, %(gamma)r, %(steps)d, %(ic)r
+integ = %(integ)r  # "vl" or "simple" (-DSIMPLE reference build, chl_simple_step, oracle.simple_step)
 fields = getattr(ic, icname)(n) if icname != "random_smooth" else ic.random_smooth(n, seed=4)
 g = n_ghost_for(recon)
 flat, dims = ghosted(fields, g, flags)
@@ -32,15 +33,15 @@ lengths = (1.0, 1.0, 1.0)
 dx, dy, dz = [lengths[i] / n[i] for i in range(3)]
 # arm 1: the reference's kernels
 t = torch.from_numpy(flat.copy()).cuda()
-dts_ref, dti_ref, _ = reference.advance(t, dims, g, dx, dy, dz, gamma, recon, solver, flags, steps)
+dts_ref, dti_ref, _ = reference.advance(t, dims, g, dx, dy, dz, gamma, recon, solver, flags, steps, simple=integ == "simple")
 ref = t.cpu().numpy()
 # arm 2: CPU oracle
 orc = flat.copy()
-dts_orc = oracle.advance(orc, *dims, g, dx, dy, dz, gamma, recon, solver, flags, steps)
+dts_orc = oracle.advance(orc, *dims, g, dx, dy, dz, gamma, recon, solver, flags, steps, integrator=integ)
 # arm 3/4: B200-native kernels, strict and product mode
 out = {}
 for strict in (True, False):
-    G = Grid3D(n, lengths, recon=recon, solver=solver, gamma=gamma, bc=flags, strict=strict)
+    G = Grid3D(n, lengths, recon=recon, solver=solver, gamma=gamma, bc=flags, strict=strict, integrator=integ)
     G.upload(flat)
     dts = G.advance(steps)
     got = G.download(); G.close()
@@ -50,22 +51,23 @@ for strict in (True, False):
         dt_equal=bool(dts == dts_ref), whole_array_equal=bool(np.array_equal(got, ref)))
 out["oracle"] = dict(ulp=max_ulp(real_view(orc, dims, g), real_view(ref, dims, g)), dt_equal=bool(dts_orc == dts_ref),
                      whole_array_equal=bool(np.array_equal(orc, ref)))
-out["flags"] = reference.lib(recon, solver).ref_build_flags().decode()
+out["flags"] = reference.lib(recon, solver, simple=integ == "simple").ref_build_flags().decode()
 print("RESULT " + json.dumps(out))
 """
 
 
 def run_child(**kw):
     kw["root"] = ROOT
+    kw.setdefault("integ", "vl")
     p = subprocess.run([sys.executable, "-c", CHILD % kw], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
     return json.loads(line[7:])
 
 
-def _need(recon, solver):
+def _need(recon, solver, simple=False):
     from oracle import reference
-    if not reference.available(recon, solver):
+    if not reference.available(recon, solver, simple=simple):
         pytest.skip("oracle/_ref library for this combination was not built")
 
 
@@ -104,3 +106,30 @@ def test_reference_kernels_2d():
     r = run_child(recon=2, solver=0, n=(45, 23, 1), flags=[1, 1, 1, 1, 0, 0], gamma=1.4, steps=4, ic="random_smooth")
     assert r["oracle"]["ulp"] == 0 and r["strict"]["ulp"] == 0, r
     assert r["fast"]["l1"] <= 1e-12, r
+
+
+@pytest.mark.parametrize("n,flags,icname,steps", [((37, 19, 21), [1, 1, 1, 1, 1, 1], "random_smooth", 3),
+                                                  ((40, 32, 24), [3, 3, 2, 2, 1, 1], "spherical_overpressure", 4),
+                                                  ((45, 23, 1), [1, 1, 1, 1, 0, 0], "random_smooth", 4),
+                                                  ((100, 1, 1), [3, 3, 0, 0, 0, 0], "riemann", 30)])
+def test_simple_integrator_plmc_reference_vs_oracle_vs_b200(n, flags, icname, steps):
+    """-DSIMPLE -DPLMC -DHLLC (builds/make.type.hydro with the cosmology integrator): Simple_Algorithm_{1,2,3}D_CUDA with
+    PLMC's characteristic tracing, reference kernels == oracle == strict kernels, bit for bit."""
+    _need(1, 0, simple=True)
+    r = run_child(recon=1, solver=0, n=n, flags=flags, gamma=5.0 / 3.0 if icname != "riemann" else 1.4, steps=steps,
+                  ic=icname, integ="simple")
+    assert "-DSIMPLE" in r["flags"] and "-DVL" not in r["flags"]
+    assert r["oracle"]["ulp"] == 0 and r["oracle"]["dt_equal"], r
+    assert r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], r
+    if icname == "random_smooth":
+        assert r["fast"]["l1"] <= 1e-12, r
+
+
+def test_simple_integrator_pcm_roe_reference():
+    """-DSIMPLE -DPCM -DROE: first-order update.  The oracle copies the conserved state like PCM_Reconstruction_3D and is
+    bit-exact; the kernels reconstruct from primitives, so they carry prim -> cons round-off (like the VL PCM corrector)."""
+    _need(0, 1, simple=True)
+    r = run_child(recon=0, solver=1, n=(37, 19, 21), flags=[1, 1, 1, 1, 1, 1], gamma=5.0 / 3.0, steps=3,
+                  ic="random_smooth", integ="simple")
+    assert r["oracle"]["ulp"] == 0 and r["oracle"]["dt_equal"], r
+    assert r["strict"]["l1"] <= 1e-12 and r["fast"]["l1"] <= 1e-12, r
