@@ -144,7 +144,8 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
     nosync = args.ref_variant == "nosync"
-    if not reference.available(recon, solver, nosync) or not torch.cuda.is_available():
+    simple = args.integrator == "simple"
+    if not reference.available(recon, solver, nosync, simple=simple) or not torch.cuda.is_available():
         print(json.dumps({"impl": "reference", "unavailable":
                           "oracle/_ref/libcholla_ref_%s_%s%s.so not built or no GPU"
                           % (args.recon, args.solver, "_nosync" if nosync else "")}))
@@ -160,22 +161,22 @@ def run_reference(args):
     d = 1.0 / S
     flags = [1] * 6
     # ghost fill + warm-up (also sizes the reference's global scratch: 55 doubles per cell)
-    L = reference.lib(recon, solver, nosync)
+    L = reference.lib(recon, solver, nosync, simple=simple)
     L.ref_set_gamma(GAMMA)
     import ctypes as C
     L.ref_set_boundaries(C.c_void_p(U.data_ptr()), *dims, 5, g, (C.c_int * 6)(*flags))
-    reference.advance(U, dims, g, d, d, d, GAMMA, recon, solver, flags, max(args.warmup, 1), nosync=nosync)
+    reference.advance(U, dims, g, d, d, d, GAMMA, recon, solver, flags, max(args.warmup, 1), nosync=nosync, simple=simple)
     sampler = ClockSampler(0)
     sampler.start()
     torch.cuda.synchronize()
-    _, _, ms = reference.advance(U, dims, g, d, d, d, GAMMA, recon, solver, flags, args.steps, nosync=nosync, timed=True)
+    _, _, ms = reference.advance(U, dims, g, d, d, d, GAMMA, recon, solver, flags, args.steps, nosync=nosync, timed=True, simple=simple)
     torch.cuda.synchronize()
     clocks = sampler.finish()
     value = S ** 3 * args.steps / (ms * 1e-3)
     peak, which = measured_hbm_peak()
     out.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks,
-                "config": {"workload": "blast %d^3 %s+%s fp64 periodic, reference kernels%s" %
-                           (S, args.recon.upper(), args.solver.upper(), " (-DDISABLE_GPU_ERROR_CHECKING)" if nosync else " (as shipped: device sync after every stage)"),
+                "config": {"workload": "blast %d^3 %s+%s fp64 periodic, %s integrator, reference kernels%s" %
+                           (S, args.recon.upper(), args.solver.upper(), args.integrator.upper(), " (-DDISABLE_GPU_ERROR_CHECKING)" if nosync else " (as shipped: device sync after every stage)"),
                            "l2": "inputs larger than L2", "build": L.ref_build_flags().decode()},
                 "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "reference",
                                  "sample": "the reference has no CPU hydro path: this is its own unmodified CUDA "
@@ -206,7 +207,8 @@ def run_b200(args, mode, world, rank, local, group, with_e2e):
     recon = {"pcm": cb.PCM, "plmc": cb.PLMC, "ppmc": cb.PPMC, "plmp": cb.PLMP, "ppmp": cb.PPMP}[args.recon]
     solver = {"hllc": cb.HLLC, "roe": cb.ROE, "hll": cb.HLL}[args.solver]
     G = Grid3D(n_global, lengths, recon=recon, solver=solver, gamma=GAMMA, bc=[1] * 6, precision=args.precision,
-               strict=strict, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world, fused=True)
+               strict=strict, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world, fused=True,
+               integrator=args.integrator)
     with ic.block(G.decomp.offset, G.decomp.n_local):
         if args.workload == "kh":      # BASELINE config 3: every cell moves, two shear layers
             fields = ic.kh_res_ind(n_global, lengths=lengths, lo=(0.0, -0.5 * lengths[1], -0.5 * lengths[2]), gamma=GAMMA)
@@ -307,6 +309,8 @@ def main():
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
     ap.add_argument("--recon", default="ppmc", choices=["pcm", "plmc", "ppmc", "plmp", "ppmp"], help="headline: ppmc")
     ap.add_argument("--solver", default="hllc", choices=["hllc", "roe", "hll"], help="headline: hllc")
+    ap.add_argument("--integrator", default="vl", choices=["vl", "simple"],
+                    help="headline: vl; simple = the reference's -DSIMPLE integrator (PCM / PLMC only)")
     ap.add_argument("--ref-variant", default="shipped", choices=["shipped", "nosync"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -353,11 +357,11 @@ def main():
         "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.precision == 2 else "f32", "data": "synthetic",
-        "config": {"workload": "%s %d^3 per GPU, %s+%s, periodic, VL integrator, %s arithmetic"
-                               % (args.workload, S, args.recon.upper(), args.solver.upper(), mode),
+        "config": {"workload": "%s %d^3 per GPU, %s+%s, periodic, %s integrator, %s arithmetic"
+                               % (args.workload, S, args.recon.upper(), args.solver.upper(), args.integrator.upper(), mode),
                    "global_cells": r["n_global"], "decomposition": r["np_grid"],
                    "l2": "inputs larger than L2 (%.1f GB state per GPU)" % (r["state_bytes"] / 1e9),
-                   "step": "set_dt + VL step (fused T-floor/CFL) + ghost fill/halo exchange"},
+                   "step": "set_dt + %s step (fused T-floor/CFL) + ghost fill/halo exchange" % args.integrator.upper()},
         "e2e": r["e2e"],
         "gpu_launches": r["launches"],
         "clocks": r["clocks"],

@@ -82,7 +82,7 @@ def read_grid(G, P: Parameters):
 
 
 def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mhd=False, outdir=None, device=None,
-        dist_group=None, rank=0, nproc=1, max_steps=None, log=print):
+        dist_group=None, rank=0, nproc=1, max_steps=None, log=print, integrator="vl"):
     """main.cpp:63-379.  Returns (Grid3D, list of snapshot paths)."""
     from .grid import Grid3D, n_ghost_for
     mhd = mhd or solver == "hlld"
@@ -91,7 +91,7 @@ def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mh
     G = Grid3D(P.n_global(), ln, bounds_min=lo, recon=RECON[recon], solver=SOLVER[solver], gamma=P.gamma,
                bc=P.boundary_flags(), precision=precision, strict=strict, density_floor=P.density_floor,
                temperature_floor_U=u_floor(P.temperature_floor, P.gamma), device=device, dist_group=dist_group,
-               rank=rank, nproc=nproc, mhd=mhd)
+               rank=rank, nproc=nproc, mhd=mhd, integrator=integrator)
     is_restart = P.init == "Read_Grid"  # main.cpp:89-95
     if is_restart:
         read_grid(G, P)
@@ -136,6 +136,7 @@ def main(argv=None):
     ap.add_argument("--recon", default="ppmc", choices=sorted(RECON))
     ap.add_argument("--solver", default="hllc", choices=sorted(SOLVER))
     ap.add_argument("--mhd", action="store_true")
+    ap.add_argument("--integrator", default="vl", choices=["vl", "simple"], help="-DVL / -DSIMPLE (make.type.hydro:8-12)")
     ap.add_argument("--fast", action="store_true", help="product arithmetic instead of the reference's bits")
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
     ap.add_argument("--outdir", default=None, help="overrides the deck's outdir; 'none' writes nothing")
@@ -153,7 +154,7 @@ def main(argv=None):
         group = dist.group.WORLD
     G, files = run(P, a.recon, a.solver, strict=not a.fast and a.precision == 2, precision=a.precision, mhd=a.mhd,
                    outdir=a.outdir, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world,
-                   max_steps=a.max_steps, log=print if rank == 0 else (lambda *_: None))
+                   max_steps=a.max_steps, log=print if rank == 0 else (lambda *_: None), integrator=a.integrator)
     G.close()
     if world > 1:
         import torch.distributed as dist

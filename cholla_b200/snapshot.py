@@ -52,9 +52,9 @@ def format_fname(outdir, nfile, proc_id, pre_extension_suffix="", legacy_flat_ou
     return prefix + str(nfile) + pre_extension_suffix + ".h5" + "." + str(proc_id)
 
 
-def macro_flags(recon, solver, precision=2, mhd=False):
+def macro_flags(recon, solver, precision=2, mhd=False, integrator="vl"):
     """The MACRO_FLAGS string of the equivalent reference build (Makefile:173-175, builds/make.type.hydro / .mhd)."""
-    flags = ["-DCUDA", "-DMPI_CHOLLA", "-DPRECISION=%d" % precision, _RECON_FLAG[recon], _SOLVER_FLAG[solver], "-DVL",
+    flags = ["-DCUDA", "-DMPI_CHOLLA", "-DPRECISION=%d" % precision, _RECON_FLAG[recon], _SOLVER_FLAG[solver], "-DSIMPLE" if integrator == "simple" else "-DVL",
              "-DDENSITY_FLOOR", "-DTEMPERATURE_FLOOR", "-DHDF5", "-DOUTPUT"]
     if mhd:
         flags.append("-DMHD")
@@ -140,7 +140,7 @@ def write_data(G, P, nfile, outdir):
     path = format_fname(outdir, nfile, G.rank, "", getattr(P, "legacy_flat_outdir", False))
     attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
                               (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
-                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd))
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl")))
     dt = ">f8" if G.precision == 2 else ">f4"
     data = OrderedDict()
     for f, nm in enumerate(HYDRO_FIELDS):  # device-side transposition, one field at a time like the reference
