@@ -139,7 +139,7 @@ def run_reference(args):
 
     from cholla_b200 import initial_conditions as ic
     from oracle import reference
-    recon, solver = {"pcm": 0, "plmc": 1, "ppmc": 2, "plmp": 3, "ppmp": 4}[args.recon], {"hllc": 0, "roe": 1, "hll": 3}[args.solver]
+    recon, solver = {"pcm": 0, "plmc": 1, "ppmc": 2, "plmp": 3, "ppmp": 4}[args.recon], {"hllc": 0, "roe": 1, "hll": 3, "exact": 4}[args.solver]
     out = {"impl": "reference", "metric": "cell-updates/s", "unit": "cell-updates/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
@@ -205,7 +205,7 @@ def run_b200(args, mode, world, rank, local, group, with_e2e):
     lengths = [float(np_grid[0]), float(np_grid[1]), float(np_grid[2])]  # unit cells, unit box per GPU
     strict = mode == "strict" and args.precision == 2
     recon = {"pcm": cb.PCM, "plmc": cb.PLMC, "ppmc": cb.PPMC, "plmp": cb.PLMP, "ppmp": cb.PPMP}[args.recon]
-    solver = {"hllc": cb.HLLC, "roe": cb.ROE, "hll": cb.HLL}[args.solver]
+    solver = {"hllc": cb.HLLC, "roe": cb.ROE, "hll": cb.HLL, "exact": cb.EXACT}[args.solver]
     G = Grid3D(n_global, lengths, recon=recon, solver=solver, gamma=GAMMA, bc=[1] * 6, precision=args.precision,
                strict=strict, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world, fused=True,
                integrator=args.integrator)
@@ -308,7 +308,7 @@ def main():
                          "noise = random cell-to-cell state (worst case for the limiters)")
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
     ap.add_argument("--recon", default="ppmc", choices=["pcm", "plmc", "ppmc", "plmp", "ppmp"], help="headline: ppmc")
-    ap.add_argument("--solver", default="hllc", choices=["hllc", "roe", "hll"], help="headline: hllc")
+    ap.add_argument("--solver", default="hllc", choices=["hllc", "roe", "hll", "exact"], help="headline: hllc")
     ap.add_argument("--integrator", default="vl", choices=["vl", "simple"],
                     help="headline: vl; simple = the reference's -DSIMPLE integrator (PCM / PLMC only)")
     ap.add_argument("--ref-variant", default="shipped", choices=["shipped", "nosync"])

@@ -11,7 +11,7 @@ HEADER_PATH = os.path.join(_ROOT, "include", "cholla_b200.h")
 
 CHL_OK = 0
 PCM, PLMC, PPMC, PLMP, PPMP = 0, 1, 2, 3, 4
-HLLC, ROE, HLLD, HLL = 0, 1, 2, 3
+HLLC, ROE, HLLD, HLL, EXACT = 0, 1, 2, 3, 4
 BC_PERIODIC, BC_REFLECTIVE, BC_TRANSMISSIVE, BC_CUSTOM, BC_MPI = 1, 2, 3, 4, 5
 
 

@@ -92,7 +92,7 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   if (cfg->ny == 1 && cfg->nz > 1) return fail(CHL_ERR_INVALID, "chl_create: nz > 1 requires ny > 1");
   if (cfg->recon < CHL_RECON_PCM || cfg->recon > CHL_RECON_PPMP) return fail(CHL_ERR_INVALID, "chl_create: recon");
   if (cfg->mhd && cfg->recon >= CHL_RECON_PLMP) return fail(CHL_ERR_INVALID, "chl_create: MHD supports PCM, PLMC and PPMC");
-  if (cfg->solver < CHL_SOLVER_HLLC || cfg->solver > CHL_SOLVER_HLL)
+  if (cfg->solver < CHL_SOLVER_HLLC || cfg->solver > CHL_SOLVER_EXACT)
     return fail(CHL_ERR_INVALID, "chl_create: solver");
   if (cfg->mhd) {  // the reference's own constraints, src/utils/error_handling.cpp:83-118
     if (cfg->n_fields != 8) return fail(CHL_ERR_UNSUPPORTED, "chl_create: an MHD grid has n_fields = 8");
@@ -141,8 +141,8 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   {
     // development knobs: CHL_SWEEP_IMPL=fused|split selects the kernel family, CHL_DIR_CHUNK the marching length
     const char *impl = getenv("CHL_SWEEP_IMPL");
-    c->split = !(impl && strcmp(impl, "fused") == 0) || cfg->solver == CHL_SOLVER_HLL ||
-               cfg->recon >= CHL_RECON_PLMP;  // HLL, PLMP, PPMP: split sweeps only
+    c->split = !(impl && strcmp(impl, "fused") == 0) || cfg->solver >= CHL_SOLVER_HLL ||
+               cfg->recon >= CHL_RECON_PLMP;  // HLL, exact, PLMP, PPMP: split sweeps only
     const char *ch = getenv("CHL_DIR_CHUNK");
     c->dir_chunk = ch ? atoi(ch) : 0;
   }

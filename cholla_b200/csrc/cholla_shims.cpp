@@ -59,8 +59,10 @@ constexpr int kSolver = CHL_SOLVER_ROE;
 constexpr int kSolver = CHL_SOLVER_HLLC;
 #elif defined(HLL)
 constexpr int kSolver = CHL_SOLVER_HLL;
+#elif defined(EXACT)
+constexpr int kSolver = CHL_SOLVER_EXACT;
 #else
-#error "cholla_shims.cpp: build with -DHLLC, -DROE, -DHLL or -DHLLD (EXACT is not on the B200 path)"
+#error "cholla_shims.cpp: build with -DHLLC, -DROE, -DHLL, -DEXACT or -DHLLD"
 #endif
 #ifdef MHD
 constexpr int kMhd = 1;

@@ -52,7 +52,7 @@ cudaError_t sweep(int stage, int recon, int solver, SweepArgs const &a, cudaStre
   p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
   p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
   p.dti_key = a.dti_key;
-  if (solver == kHLL || recon == kPLMP || recon == kPPMP) return cudaErrorNotSupported;  // fused family: PCM/PLMC/PPMC x HLLC/Roe only
+  if (solver == kHLL || solver == kEXACT || recon == kPLMP || recon == kPPMP) return cudaErrorNotSupported;  // fused family: PCM/PLMC/PPMC x HLLC/Roe only
   if (stage == 0) {
     if (solver == kROE) return launch<kPCM, kROE, 0>(p, s);
     return launch<kPCM, kHLLC, 0>(p, s);
@@ -144,7 +144,15 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   if (stage == 0) {
     if (solver == kROE) return run_dirs<kPCM, kROE, 0>(p, a, s);
     if (solver == kHLL) return run_dirs<kPCM, kHLL, 0>(p, a, s);
+    if (solver == kEXACT) return run_dirs<kPCM, kEXACT, 0>(p, a, s);
     return run_dirs<kPCM, kHLLC, 0>(p, a, s);
+  }
+  if (solver == kEXACT) {  // -DEXACT: PCM, PLMC and PPMC under the Van Leer integrator, PCM and PLMC under SIMPLE
+    if (recon == kPLMP || recon == kPPMP || (a.simple && recon == kPPMC)) return cudaErrorNotSupported;
+    if (a.simple && recon == kPLMC) return run_dirs<kPLMCT, kEXACT, 1>(p, a, s);
+    if (recon == kPCM) return run_dirs<kPCM, kEXACT, 1>(p, a, s);
+    if (recon == kPLMC) return run_dirs<kPLMC, kEXACT, 1>(p, a, s);
+    return run_dirs<kPPMC, kEXACT, 1>(p, a, s);
   }
   if (a.simple) {  // Simple_Algorithm_*_CUDA: PCM as is, PLMC with characteristic tracing; the CTU forms are not built
     if (recon == kPLMC) {

@@ -28,7 +28,7 @@ TIME_UNIT, LENGTH_UNIT = 3.15569e10, 3.08567758e21
 SP_ENERGY_UNIT = (LENGTH_UNIT / TIME_UNIT) ** 2
 
 RECON = {"pcm": _lib.PCM, "plmc": _lib.PLMC, "ppmc": _lib.PPMC, "plmp": _lib.PLMP, "ppmp": _lib.PPMP}
-SOLVER = {"hllc": _lib.HLLC, "roe": _lib.ROE, "hll": _lib.HLL, "hlld": _lib.HLLD}
+SOLVER = {"hllc": _lib.HLLC, "roe": _lib.ROE, "hll": _lib.HLL, "hlld": _lib.HLLD, "exact": _lib.EXACT}
 
 
 def u_floor(temperature_floor, gamma):

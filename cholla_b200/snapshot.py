@@ -34,7 +34,7 @@ MAGNETIC_FIELD_UNIT = (MASS_UNIT / LENGTH_UNIT) ** 0.5 / TIME_UNIT
 HYDRO_FIELDS = ["density", "momentum_x", "momentum_y", "momentum_z", "Energy"]
 MAGNETIC_FIELDS = ["magnetic_x", "magnetic_y", "magnetic_z"]
 _RECON_FLAG = {0: "-DPCM", 1: "-DPLMC", 2: "-DPPMC", 3: "-DPLMP", 4: "-DPPMP"}
-_SOLVER_FLAG = {0: "-DHLLC", 1: "-DROE", 2: "-DHLLD", 3: "-DHLL"}
+_SOLVER_FLAG = {0: "-DHLLC", 1: "-DROE", 2: "-DHLLD", 3: "-DHLL", 4: "-DEXACT"}
 
 
 def effective_output_dir_path(outdir, nfile, legacy_flat_outdir=False):

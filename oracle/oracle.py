@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PCM, PLMC, PPMC, PLMP, PPMP = 0, 1, 2, 3, 4
-HLLC, ROE, HLL = 0, 1, 3
+HLLC, ROE, HLL, EXACT = 0, 1, 3, 4
 _lib = None
 
 

@@ -71,9 +71,15 @@ void ref_vl_step(double *d_conserved, int nx, int ny, int nz, int n_ghost, doubl
 #else
   if (ny == 1 && nz == 1) VL_Algorithm_1D_CUDA(d_conserved, nx, 0, n_ghost, dx, 0.0, dt, n_fields, 0);
   else if (nz == 1) VL_Algorithm_2D_CUDA(d_conserved, nx, ny, 0, 0, n_ghost, dx, dy, 0.0, 0.0, dt, n_fields, 0);
-  else
+  else {
+  #ifdef REF_NO_VL3D  // the reference's VL_3D_cuda.cu does not compile in this configuration (see the Makefile)
+    fprintf(stderr, "ref_driver: this reference build has no 3-D Van Leer integrator\n");
+    chexit(-1);
+  #else
     VL_Algorithm_3D_CUDA(d_conserved, nullptr, nx, ny, nz, 0, 0, 0, n_ghost, dx, dy, dz, 0.0, 0.0, 0.0, dt, n_fields, 0,
                          density_floor, nullptr);
+  #endif
+  }
 #endif
 }
 

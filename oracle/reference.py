@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(_HERE, "_ref")
 _NAMES = {0: "pcm", 1: "plmc", 2: "ppmc", 3: "plmp", 4: "ppmp"}
-_SOLV = {0: "hllc", 1: "roe", 2: "hlld", 3: "hll"}
+_SOLV = {0: "hllc", 1: "roe", 2: "hlld", 3: "hll", 4: "exact"}
 _libs = {}
 
 

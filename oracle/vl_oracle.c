@@ -35,7 +35,7 @@
 #define ORC_TINY 1.0e-20 /* global.h:25 */
 
 enum { ORC_PCM = 0, ORC_PLMC = 1, ORC_PPMC = 2, ORC_PLMP = 3, ORC_PPMP = 4 };
-enum { ORC_HLLC = 0, ORC_ROE = 1, ORC_HLL = 3 }; /* 2 is HLLD (mhd_oracle.c) */
+enum { ORC_HLLC = 0, ORC_ROE = 1, ORC_HLL = 3, ORC_EXACT = 4 }; /* 2 is HLLD (mhd_oracle.c) */
 
 typedef struct {
   double d, vx, vy, vz, p;
@@ -648,6 +648,103 @@ static cons_t roe_flux(cons_t l, cons_t r, double gamma)
 }
 
 /* one launch of Calculate_{HLLC,Roe}_Fluxes_CUDA: every cell, F[id] = flux(Q_L[id], Q_R[id]) */
+/* exact_cuda.cu:21-334 (Toro 1999, 4.9).  PARITY UNPINNED ON THE CPU: the reference evaluates its powers with the
+ * device's powf (single precision, not correctly rounded) and no CPU libm reproduces those bits, so this restatement
+ * agrees with the reference's kernels to float round-off (~1e-7) only.  The bit-level check of the CUDA path for this
+ * solver is the reference's own -DEXACT build in tests/test_gpu_reference.py. */
+static double exact_pow(double a, double b) { return (double)powf((float)a, (float)b); }
+static void exact_prefun(double *f, double *fd, double p, double dk, double pk, double ck, double gamma)
+{
+  if (p <= pk) {
+    *f  = (2.0 / (gamma - 1.0)) * ck * (exact_pow(p / pk, (gamma - 1.0) / (2.0 * gamma)) - 1.0);
+    *fd = (1.0 / (dk * ck)) * exact_pow((p / pk), -((gamma + 1.0) / (2.0 * gamma)));
+  } else {
+    double qrt = sqrt(((2.0 / (gamma + 1.0)) / dk) / ((((gamma - 1.0) / (gamma + 1.0)) * pk) + p));
+    *f  = (p - pk) * qrt;
+    *fd = (1.0 - 0.5 * (p - pk) / ((((gamma - 1.0) / (gamma + 1.0)) * pk) + p)) * qrt;
+  }
+}
+static cons_t exact_flux(cons_t l, cons_t r, double gamma)
+{
+  double dl = l.d, vxl = l.mx / dl, vyl = l.my / dl, vzl = l.mz / dl;
+  double pl = fmax((l.E - 0.5 * dl * (vxl * vxl + vyl * vyl + vzl * vzl)) * (gamma - 1.0), ORC_TINY);
+  double dr = r.d, vxr = r.mx / dr, vyr = r.my / dr, vzr = r.mz / dr;
+  double pr = fmax((r.E - 0.5 * dr * (vxr * vxr + vyr * vyr + vzr * vzr)) * (gamma - 1.0), ORC_TINY);
+  double cl = sqrt(gamma * pl / dl), cr = sqrt(gamma * pr / dr);
+  const double TOL = 1.0e-6;
+  /* guessp_CUDA */
+  double ppv = 0.5 * (pl + pr) + 0.125 * (vxl - vxr) * (dl + dr) * (cl + cr);
+  if (ppv < 0.0) ppv = 0.0;
+  double gl = sqrt((2.0 / ((gamma + 1.0) * dl)) / (((gamma - 1.0) / (gamma + 1.0)) * pl + ppv));
+  double gr = sqrt((2.0 / ((gamma + 1.0) * dr)) / (((gamma - 1.0) / (gamma + 1.0)) * pr + ppv));
+  double pold = (gl * pl + gr * pr - (vxr - vxl)) / (gl + gr);
+  if (pold < 0.0) pold = TOL;
+  /* starpv_CUDA */
+  double pm = pold, fl = 0, fld = 0, fr = 0, frd = 0;
+  for (int i = 0; i <= 20; i++) {
+    exact_prefun(&fl, &fld, pold, dl, pl, cl, gamma);
+    exact_prefun(&fr, &frd, pold, dr, pr, cr, gamma);
+    pm = pold - (fl + fr + vxr - vxl) / (fld + frd);
+    double change = 2.0 * fabs((pm - pold) / (pm + pold));
+    if (change <= TOL) break;
+    if (pm < 0.0) pm = TOL;
+    pold = pm;
+  }
+  double vm = 0.5 * (vxl + vxr + fr - fl);
+  /* sample_CUDA */
+  double ds, vs, ps, c;
+  double g1 = (gamma - 1.0) / (gamma + 1.0);
+  if (vm >= 0) {
+    if (pm <= pl) {
+      if (vxl - cl >= 0) { ds = dl; vs = vxl; ps = pl; }
+      else if (vm - cl * exact_pow(pm / pl, (gamma - 1.0) / (2.0 * gamma)) < 0) {
+        ds = dl * exact_pow(pm / pl, 1.0 / gamma); vs = vm; ps = pm;
+      } else {
+        c  = (2.0 / (gamma + 1.0)) * (cl + ((gamma - 1.0) / 2.0) * vxl);
+        vs = c;
+        ds = dl * exact_pow(c / cl, 2.0 / (gamma - 1.0));
+        ps = pl * exact_pow(c / cl, 2.0 * gamma / (gamma - 1.0));
+      }
+    } else {
+      double sl = vxl - cl * sqrt(((gamma + 1.0) / (2.0 * gamma)) * (pm / pl) + ((gamma - 1.0) / (2.0 * gamma)));
+      if (sl >= 0) { ds = dl; vs = vxl; ps = pl; }
+      else { ds = dl * (pm / pl + g1) / ((pm / pl) * g1 + 1.0); vs = vm; ps = pm; }
+    }
+  } else {
+    if (pm > pr) {
+      double sr = vxr + cr * sqrt(((gamma + 1.0) / (2.0 * gamma)) * (pm / pr) + ((gamma - 1.0) / (2.0 * gamma)));
+      if (sr <= 0) { ds = dr; vs = vxr; ps = pr; }
+      else { ds = dr * (pm / pr + g1) / ((pm / pr) * g1 + 1.0); vs = vm; ps = pm; }
+    } else {
+      if (vxr + cr <= 0) { ds = dr; vs = vxr; ps = pr; }
+      else if (vm + cr * exact_pow(pm / pr, (gamma - 1.0) / (2.0 * gamma)) >= 0) {
+        ds = dr * exact_pow(pm / pr, (1.0 / gamma)); vs = vm; ps = pm;
+      } else {
+        c  = (2.0 / (gamma + 1.0)) * (cr - ((gamma - 1.0) / 2.0) * vxr);
+        vs = -c;
+        ds = dr * exact_pow(c / cr, 2.0 / (gamma - 1.0));
+        ps = pr * exact_pow(c / cr, 2.0 * gamma / (gamma - 1.0));
+      }
+    }
+  }
+  double vy = vs >= 0 ? vyl : vyr, vz = vs >= 0 ? vzl : vzr;
+  cons_t f;
+  f.d  = ds * vs;
+  f.mx = ds * vs * vs + ps;
+  f.my = ds * vs * vy;
+  f.mz = ds * vs * vz;
+  double Es = (ps / (gamma - 1.0)) + 0.5 * ds * (vs * vs + vy * vy + vz * vz);
+  f.E = (Es + ps) * vs;
+  return f;
+}
+static cons_t flux_of(int solver, cons_t l, cons_t r, double gamma)
+{
+  if (solver == ORC_ROE) return roe_flux(l, r, gamma);
+  if (solver == ORC_HLL) return hll_flux(l, r, gamma);
+  if (solver == ORC_EXACT) return exact_flux(l, r, gamma);
+  return hllc_flux(l, r, gamma);
+}
+
 void orc_riemann(int solver, const double *QL, const double *QR, double *F, int nx, int ny, int nz, double gamma,
                  int dir)
 {
@@ -658,7 +755,7 @@ void orc_riemann(int solver, const double *QL, const double *QR, double *F, int 
   for (long id = 0; id < (long)N; id++) {
     cons_t l = {QL[id], QL[o1 * N + id], QL[o2 * N + id], QL[o3 * N + id], QL[4 * N + id]};
     cons_t r = {QR[id], QR[o1 * N + id], QR[o2 * N + id], QR[o3 * N + id], QR[4 * N + id]};
-    cons_t f = solver == ORC_ROE ? roe_flux(l, r, gamma) : (solver == ORC_HLL ? hll_flux(l, r, gamma) : hllc_flux(l, r, gamma));
+    cons_t f = flux_of(solver, l, r, gamma);
     F[id] = f.d; F[o1 * N + id] = f.mx; F[o2 * N + id] = f.my; F[o3 * N + id] = f.mz; F[4 * N + id] = f.E;
   }
 }
@@ -666,7 +763,7 @@ void orc_riemann(int solver, const double *QL, const double *QR, double *F, int 
 void orc_riemann_single(int solver, const double *l5, const double *r5, double gamma, double *f5)
 {
   cons_t l = {l5[0], l5[1], l5[2], l5[3], l5[4]}, r = {r5[0], r5[1], r5[2], r5[3], r5[4]};
-  cons_t f = solver == ORC_ROE ? roe_flux(l, r, gamma) : (solver == ORC_HLL ? hll_flux(l, r, gamma) : hllc_flux(l, r, gamma));
+  cons_t f = flux_of(solver, l, r, gamma);
   f5[0] = f.d; f5[1] = f.mx; f5[2] = f.my; f5[3] = f.mz; f5[4] = f.E;
 }
 

@@ -354,3 +354,14 @@ def test_simple_integrator_rejects_what_it_does_not_build():
     with pytest.raises(cb.ChollaB200Error):
         G.Execute_Hydro_Integrator()
     G.close()
+
+
+@pytest.mark.parametrize("recon", [cb.PCM, cb.PLMC, cb.PPMC])
+@pytest.mark.parametrize("strict", [True, False])
+def test_exact_solver_against_oracle(recon, strict):
+    """chl_config.solver = CHL_SOLVER_EXACT against the CPU restatement: float round-off apart (the device's powf has no
+    CPU twin -- the bit-level check is tests/test_gpu_reference.py::test_exact_solver_reference_vs_b200)."""
+    fields = ic.random_smooth((37, 19, 21), seed=3)
+    got, ref, dims, g, dts_gpu, dts_cpu = run_both(fields, recon, cb.EXACT, PERIODIC, 1.4, 3, strict=strict)
+    assert rel_l1(real_view(got, dims, g), real_view(ref, dims, g)).max() <= 1e-5
+    assert np.allclose(dts_gpu, dts_cpu, rtol=1e-5, atol=0)

@@ -50,6 +50,7 @@ for strict in (True, False):
         l1=float(rel_l1(real_view(got, dims, g), real_view(ref, dims, g)).max()),
         dt_equal=bool(dts == dts_ref), whole_array_equal=bool(np.array_equal(got, ref)))
 out["oracle"] = dict(ulp=max_ulp(real_view(orc, dims, g), real_view(ref, dims, g)), dt_equal=bool(dts_orc == dts_ref),
+                     l1=float(rel_l1(real_view(orc, dims, g), real_view(ref, dims, g)).max()),
                      whole_array_equal=bool(np.array_equal(orc, ref)))
 out["flags"] = reference.lib(recon, solver, simple=integ == "simple").ref_build_flags().decode()
 print("RESULT " + json.dumps(out))
@@ -133,3 +134,21 @@ def test_simple_integrator_pcm_roe_reference():
                   ic="random_smooth", integ="simple")
     assert r["oracle"]["ulp"] == 0 and r["oracle"]["dt_equal"], r
     assert r["strict"]["l1"] <= 1e-12 and r["fast"]["l1"] <= 1e-12, r
+
+
+@pytest.mark.parametrize("recon,n,flags,icname,steps,integ", [
+    (2, (45, 23, 1), [1, 1, 1, 1, 0, 0], "random_smooth", 4, "vl"),
+    (1, (100, 1, 1), [3, 3, 0, 0, 0, 0], "riemann", 30, "vl"),
+    (1, (37, 19, 21), [1, 1, 1, 1, 1, 1], "random_smooth", 3, "simple"),
+    (1, (40, 32, 24), [3, 3, 2, 2, 1, 1], "spherical_overpressure", 4, "simple")])
+def test_exact_solver_reference_vs_b200(recon, n, flags, icname, steps, integ):
+    """-DEXACT (exact_cuda.cu, Toro's solver with powf powers and a 1e-6 Newton tolerance): the strict kernels, built
+    without FMA contraction and calling the same device powf, reproduce the reference's kernels bit for bit.  The CPU
+    oracle and the product arithmetic can only follow to float round-off: powf is not correctly rounded on the device
+    and has no CPU twin, and a one-ulp operand change can flip a float rounding.  The reference's 3-D Van Leer
+    integrator does not compile with -DEXACT (VL_3D_cuda.cu:148-149), so its 3-D arm is the -DSIMPLE build."""
+    _need(recon, 4, simple=integ == "simple")
+    r = run_child(recon=recon, solver=4, n=n, flags=flags, gamma=1.4, steps=steps, ic=icname, integ=integ)
+    assert "-DEXACT" in r["flags"]
+    assert r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], r
+    assert r["oracle"]["l1"] <= 1e-5 and r["fast"]["l1"] <= 1e-5, r
