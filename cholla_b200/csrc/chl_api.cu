@@ -348,8 +348,22 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
     a.do_dti = 1;
     CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
   }
+  bool const prof = c->profiling && c->ev_steps < kMaxProfiledSteps;  // "predictor" = the primitive pass here
+  if (prof) {
+    while ((int)c->ev.size() < 3 * (c->ev_steps + 1)) {
+      cudaEvent_t e;
+      CHL_CUDA(cudaEventCreate(&e));
+      c->ev.push_back(e);
+    }
+    CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps], s));
+  }
   CHL_CUDA(c->ops->prim_from_cons(U, c->d_half, c->n_cells, g.gamma, g.recon, s));
+  if (prof) CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 1], s));
   CHL_CUDA(c->ops->sweep_split(1, g.recon, g.solver, a, s));
+  if (prof) {
+    CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 2], s));
+    c->ev_steps++;
+  }
   return CHL_OK;
 }
 
