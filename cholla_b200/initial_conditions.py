@@ -1,7 +1,8 @@
 """Closed-form initial conditions used by the tests and bench.py (host, numpy, float64).
 
 Formulas follow the reference's generators (src/grid/initial_conditions.cpp: Constant :180, Sound_Wave :244,
-Riemann :509, KH_res_ind :749, Spherical_Overpressure_3D :1203) with cell centres from the global-index rule
+Linear_Wave :302, Square_Wave :437, Riemann :509, Shu_Osher :597, Blast_1D :635, KH :677, KH_res_ind :749,
+Gresho :932, Implosion_2D :1033, Spherical_Overpressure_3D :1203) with cell centres from the global-index rule
 of Grid3D::Get_Position (grid3D.cpp:108-110), so the fields are independent of the rank count.  Each returns
 conserved real cells as an array (5, nz, ny, nx).  They are inputs only: the same array is handed to the CUDA
 path, the CPU oracle and the compiled reference, so parity never depends on how it was generated.
@@ -113,6 +114,102 @@ def kh_res_ind(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, -0.5, -0.5), gamma=5.0 / 3.0
     return _pack(d, mx, my, mz, E)
 
 
+def _full(a, n, lengths, lo):
+    """Broadcast a sparse-mesh expression to the block's full (nz, ny, nx) shape."""
+    X, Y, Z = _mesh(n, lengths, lo)
+    return a + 0.0 * (X + Y + Z)
+
+
+def square_wave(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0), rho=1.0, v=(1.0, 0.0, 0.0), P=0.01, A=2.0,
+                gamma=1.4):
+    """Grid3D::Square_Wave (initial_conditions.cpp:437-502, examples/1D/square_wave.txt): density rho * A between a
+    quarter and three quarters of the x extent, pressure equilibrium."""
+    X, _, _ = _mesh(n, lengths, lo)
+    X = _full(X, n, lengths, lo)
+    d = np.where((X > 0.25 * lengths[0]) & (X < 0.75 * lengths[0]), rho * A, rho)
+    E = P / (gamma - 1.0) + 0.5 * d * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+    return _pack(d, d * v[0], d * v[1], d * v[2], E)
+
+
+def shu_osher(n, lengths=(2.0, 1.0, 1.0), lo=(-1.0, 0.0, 0.0), gamma=1.4):
+    """Grid3D::Shu_Osher (initial_conditions.cpp:597-630, examples/1D/Shu_Osher.txt): Mach-3 shock into a sinusoidal
+    density field.  1-D."""
+    X, _, _ = _mesh(n, lengths, lo)
+    X = _full(X, n, lengths, lo)
+    shocked = X < -0.8
+    d = np.where(shocked, 3.857143, 1.0 + 0.2 * np.sin(5.0 * np.pi * X))
+    vx = np.where(shocked, 2.629369, 0.0)
+    P = np.where(shocked, 10.33333, 1.0)
+    z = np.zeros_like(d)
+    return _pack(d, d * vx, z, z, P / (gamma - 1.0) + 0.5 * d * vx * vx)
+
+
+def blast_1d(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0), gamma=1.4):
+    """Grid3D::Blast_1D (initial_conditions.cpp:635-672, examples/1D/blast_1D.txt): two interacting blast waves (Stone
+    2008, 8.1); the deck closes the tube with reflective boundaries."""
+    X, _, _ = _mesh(n, lengths, lo)
+    X = _full(X, n, lengths, lo)
+    P = np.where(X < 0.1, 1000.0, np.where(X > 0.9, 100.0, 0.01))
+    d = np.ones_like(P)
+    z = np.zeros_like(P)
+    return _pack(d, z, z, z, P / (gamma - 1.0))
+
+
+def kh(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0), gamma=5.0 / 3.0):
+    """Grid3D::KH (initial_conditions.cpp:677-744, examples/2D/KH_discontinuous_2D.txt): discontinuous shear layers at a
+    quarter and three quarters of the y extent, d = 2 / 1, vx = +-0.5, vy = 0.1 sin(4 pi x), P = 2.5."""
+    X, Y, _ = _mesh(n, lengths, lo)
+    X, Y = _full(X, n, lengths, lo), _full(Y, n, lengths, lo)
+    outer = (Y <= 1.0 * lengths[1] / 4.0) | (Y >= 3.0 * lengths[1] / 4.0)
+    d = np.where(outer, 1.0, 2.0)
+    mx = np.where(outer, -0.5, 0.5) * d
+    my = d * 0.1 * np.sin(4 * np.pi * X)
+    E = 2.5 / (gamma - 1.0) + 0.5 * (mx * mx + my * my) / d
+    return _pack(d, mx, my, np.zeros_like(d), E)
+
+
+def gresho(n, lengths=(1.0, 1.0, 1.0), lo=(-0.5, -0.5, 0.0), gamma=1.4):
+    """Grid3D::Gresho (initial_conditions.cpp:932-1028, examples/2D/Gresho.txt): the stationary triangular vortex, point
+    values at the cell centres."""
+    X, Y, _ = _mesh(n, lengths, lo)
+    X, Y = _full(X, n, lengths, lo), _full(Y, n, lengths, lo)
+    r, phi = np.sqrt(X * X + Y * Y), np.arctan2(Y, X)
+    inner, mid = r < 0.2, (r >= 0.2) & (r < 0.4)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p_mid = 9.0 - 4.0 * np.log(0.2) + 0.5 * 25.0 * r * r - 20.0 * r + 4.0 * np.log(r)
+    vt = np.where(inner, 5.0 * r, np.where(mid, 2.0 - 5.0 * r, 0.0))
+    P = np.where(inner, 5.0 + 0.5 * 25.0 * r * r, np.where(mid, p_mid, 3.0 + 4.0 * np.log(2.0)))
+    vx, vy = -np.sin(phi) * vt, np.cos(phi) * vt
+    d = np.ones_like(r)
+    return _pack(d, d * vx, d * vy, np.zeros_like(d), P / (gamma - 1.0) + 0.5 * d * (vx * vx + vy * vy))
+
+
+def implosion_2d(n, lengths=(0.3, 0.3, 1.0), lo=(0.0, 0.0, 0.0), gamma=1.4):
+    """Grid3D::Implosion_2D (initial_conditions.cpp:1033-1071, examples/2D/Implosion_2D.txt; Liska & Wendroff 2003): low
+    density and pressure below the diagonal x + y = 0.15."""
+    X, Y, _ = _mesh(n, lengths, lo)
+    X, Y = _full(X, n, lengths, lo), _full(Y, n, lengths, lo)
+    low = Y < (0.1500001 - X)
+    d = np.where(low, 0.125, 1.0)
+    P = np.where(low, 0.14, 1.0)
+    z = np.zeros_like(d)
+    return _pack(d, z, z, z, P / (gamma - 1.0))
+
+
+def linear_wave(n, lengths, lo, rho, vx, P, A, eigenvector, wave_length=1.0, pitch=0.0, yaw=0.0, gamma=5.0 / 3.0):
+    """Grid3D::Linear_Wave, hydro build (initial_conditions.cpp:302-432): background (rho, vx, P) plus A sin(k x') times
+    the right eigenvector (rho, momentum x / y / z, E) of the wave, x' rotated by pitch and yaw."""
+    X, Y, Z = _mesh(n, lengths, lo)
+    sy, cy, sp, cp = np.sin(yaw), np.cos(yaw), np.sin(pitch), np.cos(pitch)
+    xr = cp * (X * cy + Y * sy) + Z * sp
+    sine = _full(np.sin(xr * (2.0 * np.pi / wave_length)), n, lengths, lo)
+    e_rho, e_mx, e_my, e_mz, e_E = eigenvector
+    d = rho + A * e_rho * sine
+    mx, my, mz = rho * vx + A * e_mx * sine, A * e_my * sine, A * e_mz * sine
+    E = P / (gamma - 1.0) + 0.5 * rho * vx * vx + A * sine * e_E
+    return _pack(d, mx * cp * cy - my * sy - mz * sp * cy, mx * cp * sy + my * cy - mz * sp * sy, mx * sp + mz * cp, E)
+
+
 def random_smooth(n, seed=0, gamma=5.0 / 3.0):
     """Seeded, strictly positive, smooth-ish random state that exercises every limiter branch."""
     rng = np.random.default_rng(seed)
@@ -210,3 +307,40 @@ def mhd_blast(n, g, gamma=5.0 / 3.0):
     B[1] += 1.0 / np.sqrt(2.0)
     z = np.zeros_like(X)
     return _mhd_pack(np.ones_like(X), z, z, z, P, B, gamma)
+
+
+def mhd_riemann(n, g, lengths, lo, left, right, diaph, gamma):
+    """Grid3D::Riemann, -DMHD build (initial_conditions.cpp:509-592; examples/3D/Brio_and_Wu.txt, Dai_and_Woodward.txt,
+    Ryu_and_Jones_*.txt, Einfeldt_Strong_Rarefaction.txt): (rho, vx, vy, vz, P, Bx, By, Bz) either side of x = diaph.
+    A face takes the side of the CENTRE of the cell it is stored with, and the energy uses the given field, not a
+    face average -- both as in the reference."""
+    X, Y, Z, d = _mhd_mesh(n, g, lengths, lo)
+    L = X < diaph
+    pick = lambda i: np.where(L, left[i], right[i])
+    rho, vx, vy, vz, P, bx, by, bz = (pick(i) for i in range(8))
+    E = np.maximum(P, 1e-20) / (gamma - 1.0) + 0.5 * rho * (vx * vx + ((vy * vy) + (vz * vz))) + 0.5 * (bx * bx + ((by * by) + (bz * bz)))
+    out = np.empty((8,) + X.shape)
+    for f, a in enumerate((rho, rho * vx, rho * vy, rho * vz, E, bx, by, bz)):
+        out[f] = a
+    return out
+
+
+def mhd_linear_wave(n, g, lengths, lo, rho, vx, P, B0, A, eigenvector, wave_length=1.0, gamma=5.0 / 3.0):
+    """Grid3D::Linear_Wave, -DMHD build, grid-aligned (pitch = yaw = 0; the reference's rotated set-up is commented out
+    as unstable, initial_conditions.cpp:312-358): examples/3D/alfven_wave.txt, fast_magnetosonic.txt,
+    slow_magnetosonic.txt, mhd_contact_wave.txt.  eigenvector = (rho, mx, my, mz, E, Bx, By, Bz).  The face fields are
+    evaluated at the cell-centre abscissa like the reference's; the box is periodic, so the ghost zones are generated
+    too."""
+    X, Y, Z, d = _mhd_mesh(n, g, lengths, lo)
+    sine = np.sin(X * (2.0 * np.pi / wave_length)) + 0.0 * (Y + Z)
+    e_rho, e_mx, e_my, e_mz, e_E, e_bx, e_by, e_bz = eigenvector
+    out = np.empty((8,) + sine.shape)
+    out[0] = rho + A * e_rho * sine
+    out[1] = rho * vx + A * e_mx * sine
+    out[2] = A * e_my * sine
+    out[3] = A * e_mz * sine
+    out[4] = P / (gamma - 1.0) + 0.5 * rho * vx * vx + A * sine * e_E + 0.5 * (B0[0] * B0[0] + B0[1] * B0[1] + B0[2] * B0[2])
+    out[5] = B0[0] + A * e_bx * sine
+    out[6] = B0[1] + A * e_by * sine
+    out[7] = B0[2] + A * e_bz * sine
+    return out

@@ -60,6 +60,7 @@ class Parameters:
     zl_bcnd: int = 0
     zu_bcnd: int = 0
     custom_bcnd: str = ""
+    legacy_flat_outdir: int = 0
     outdir: str = ""
     indir: str = ""
     rho: float = 0.0
@@ -91,6 +92,17 @@ class Parameters:
     radius: float = 0.0
     P_blast: float = 0.0
     wave_length: float = 1.0
+    pitch: float = 0.0
+    yaw: float = 0.0
+    polarization: float = 0.0
+    rEigenVec_rho: float = 0.0
+    rEigenVec_MomentumX: float = 0.0
+    rEigenVec_MomentumY: float = 0.0
+    rEigenVec_MomentumZ: float = 0.0
+    rEigenVec_E: float = 0.0
+    rEigenVec_Bx: float = 0.0
+    rEigenVec_By: float = 0.0
+    rEigenVec_Bz: float = 0.0
     prng_seed: int = 0
     temperature_floor: float = 0.0
     density_floor: float = 0.0
@@ -115,9 +127,7 @@ class Parameters:
 _IGNORED = {"n_particle", "n_projection", "n_rotated_projection", "n_slice", "n_out_float32", "out_float32_density",
             "out_float32_momentum_x", "out_float32_momentum_y", "out_float32_momentum_z", "out_float32_Energy",
             "out_float32_GasEnergy", "out_float32_magnetic_x", "out_float32_magnetic_y", "out_float32_magnetic_z",
-            "legacy_flat_outdir", "custom_grav", "rEigenVec_rho", "rEigenVec_MomentumX", "rEigenVec_MomentumY",
-            "rEigenVec_MomentumZ", "rEigenVec_E", "rEigenVec_Bx", "rEigenVec_By", "rEigenVec_Bz", "pitch", "yaw",
-            "polarization", "snr_filename", "scale_outputs_file", "Omega_b", "bc_potential_type", "UVB_rates_file"}
+            "custom_grav", "snr_filename", "scale_outputs_file", "Omega_b", "bc_potential_type", "UVB_rates_file"}
 # optionalParams, global.cpp:104-108
 _OPTIONAL = {"flag_delta", "ddelta_dt", "n_delta", "Lz", "Lx", "phi", "theta", "delta", "nzr", "nxr", "H0", "Omega_M",
              "Omega_L", "Init_redshift", "End_redshift", "tile_length", "n_proc_x", "n_proc_y", "n_proc_z"}
