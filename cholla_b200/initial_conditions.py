@@ -344,3 +344,57 @@ def mhd_linear_wave(n, g, lengths, lo, rho, vx, P, B0, A, eigenvector, wave_leng
     out[6] = B0[1] + A * e_by * sine
     out[7] = B0[2] + A * e_bz * sine
     return out
+
+
+def _mhd_pack_momentum(rho, mx, my, mz, P, B, gamma):
+    """Calc_Energy_Conserved with the cell-centred field (hydro_utilities.h:120-135)."""
+    c = _centred(B)
+    E = np.maximum(P, 1e-20) / (gamma - 1.0) + 0.5 * (mx * mx + ((my * my) + (mz * mz))) / rho + 0.5 * (c[0] ** 2 + ((c[1] ** 2) + (c[2] ** 2)))
+    out = np.empty((8,) + np.shape(B[0]))
+    for f, a in enumerate((rho, mx, my, mz, E, B[0], B[1], B[2])):
+        out[f] = a
+    return out
+
+
+def circularly_polarized_alfven_wave(n, g, lengths, lo, polarization=1.0, vx=0.0, pitch=0.0, yaw=0.0, gamma=5.0 / 3.0):
+    """Grid3D::Circularly_Polarized_Alfven_Wave (initial_conditions.cpp:1680-1797,
+    examples/3D/circularly_polarized_alfven_wave.txt): rho = 1, P = 0.1, B_x = 1, transverse amplitude 0.1, unit
+    wavelength along the (pitch, yaw)-rotated x axis; vx = 0 travelling, 1 standing.  The field is the curl of a
+    potential sampled on the cell edges, as in the reference."""
+    X, Y, Z, d = _mhd_mesh(n, g, lengths, lo)
+    X, Y, Z = X + 0.0 * (Y + Z), Y + 0.0 * (X + Z), Z + 0.0 * (X + Y)
+    sy, cy, sp, cp = np.sin(yaw), np.cos(yaw), np.sin(pitch), np.cos(pitch)
+    amp, k, bx0, rho, P = 0.1, 2.0 * np.pi, 1.0, 1.0, 0.1
+
+    def potential(x, y, z):
+        x_rot = x * cp * cy + y * cp * sy + z * sp
+        y_rot = -x * sy + y * cy
+        return polarization * (amp / k) * np.sin(k * x_rot), (amp / k) * np.cos(k * x_rot) + bx0 * y_rot
+
+    ay, az = potential(X, Y + d[1] / 2.0, Z + d[2] / 2.0)
+    Ax = -ay * sy - az * sp * cy
+    ay, az = potential(X + d[0] / 2.0, Y, Z + d[2] / 2.0)
+    Ay = ay * cy - az * sp * sy
+    ay, az = potential(X + d[0] / 2.0, Y + d[1] / 2.0, Z)
+    Az = az * cp
+    B = _curl_faces(Ax, Ay, Az, d)
+    x_rot = X * cp * cy + Y * cp * sy + Z * sp
+    mx = rho * vx + 0.0 * X
+    my = -polarization * rho * amp * np.sin(k * x_rot)
+    mz = -rho * amp * np.cos(k * x_rot)
+    return _mhd_pack_momentum(np.full_like(X, rho), mx * cp * cy - my * sy - mz * sp * cy,
+                              mx * cp * sy + my * cy - mz * sp * sy, mx * sp + mz * cp, P, B, gamma)
+
+
+def advecting_field_loop(n, g, lengths, lo, rho=1.0, v=(1.0, 1.0, 2.0), P=1.0, A=1e-3, radius=0.3, gamma=5.0 / 3.0):
+    """Grid3D::Advecting_Field_Loop (initial_conditions.cpp:1799-1863, examples/3D/advecting_field_loop.txt): a weak field
+    loop, A_y = A_z = A (R - r) inside r < R, advected diagonally through a periodic box centred on the origin."""
+    X, Y, Z, d = _mhd_mesh(n, g, lengths, lo)
+    X, Y, Z = X + 0.0 * (Y + Z), Y + 0.0 * (X + Z), Z + 0.0 * (X + Y)
+    r = np.sqrt((X + d[0] / 2.0) ** 2 + Y ** 2 + (Z + d[2] / 2.0) ** 2)
+    Ay = np.where(r < radius, A * (radius - r), 0.0)
+    r = np.sqrt((X + d[0] / 2.0) ** 2 + (Y + d[1] / 2.0) ** 2 + Z ** 2)
+    Az = np.where(r < radius, A * (radius - r), 0.0)
+    B = _curl_faces(np.zeros_like(Ay), Ay, Az, d)
+    one = np.ones_like(X)
+    return _mhd_pack_momentum(rho * one, rho * v[0] * one, rho * v[1] * one, rho * v[2] * one, P, B, gamma)

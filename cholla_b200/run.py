@@ -53,6 +53,10 @@ def initial_fields(P: Parameters, mhd=False, n_ghost=0):
         return ic.mhd_linear_wave(n, n_ghost, ln, lo, P.rho, P.vx, P.P, (P.Bx, P.By, P.Bz), P.A,
                                   (P.rEigenVec_rho, P.rEigenVec_MomentumX, P.rEigenVec_MomentumY, P.rEigenVec_MomentumZ,
                                    P.rEigenVec_E, P.rEigenVec_Bx, P.rEigenVec_By, P.rEigenVec_Bz), P.wave_length, P.gamma)
+    if mhd and name == "Circularly_Polarized_Alfven_Wave":
+        return ic.circularly_polarized_alfven_wave(n, n_ghost, ln, lo, P.polarization, P.vx, P.pitch, P.yaw, P.gamma)
+    if mhd and name == "Advecting_Field_Loop":
+        return ic.advecting_field_loop(n, n_ghost, ln, lo, P.rho, (P.vx, P.vy, P.vz), P.P, P.A, P.radius, P.gamma)
     if name == "Constant":
         return ic.constant(n, P.rho, (P.vx, P.vy, P.vz), P.P, P.gamma)
     if name == "Sound_Wave":
@@ -86,7 +90,8 @@ def initial_fields(P: Parameters, mhd=False, n_ghost=0):
         return ic.mhd_blast(n, n_ghost, P.gamma)
     raise NotImplementedError("init=%s is not one of the generators of the hot-path scope (SURVEY 8d): Constant, Sound_Wave, "
                               "Riemann, Square_Wave, Shu_Osher, Blast_1D, KH, KH_res_ind, Gresho, Implosion_2D, Linear_Wave, "
-                              "Spherical_Overpressure_3D, Orszag_Tang_Vortex, MHD_Spherical_Blast" % name)
+                              "Spherical_Overpressure_3D, Orszag_Tang_Vortex, MHD_Spherical_Blast, Circularly_Polarized_Alfven_Wave, "
+                              "Advecting_Field_Loop" % name)
 
 
 def snapshot(G, P: Parameters, nfile, outdir):

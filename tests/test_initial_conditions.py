@@ -136,7 +136,8 @@ def test_shipped_decks_build_their_initial_state():
         pytest.skip("reference tree not present")
     hydro = {"Constant", "Sound_Wave", "Riemann", "Square_Wave", "Shu_Osher", "Blast_1D", "KH", "KH_res_ind", "Gresho",
              "Implosion_2D", "Spherical_Overpressure_3D"}
-    mhd_only = {"Orszag_Tang_Vortex", "MHD_Spherical_Blast", "Linear_Wave"}
+    mhd_only = {"Orszag_Tang_Vortex", "MHD_Spherical_Blast", "Linear_Wave", "Circularly_Polarized_Alfven_Wave",
+                "Advecting_Field_Loop"}
     built = 0
     for deck in sorted(glob.glob(root + "/[123]D/*.txt")):
         P = pm.parse_params(deck, [])
@@ -148,4 +149,31 @@ def test_shipped_decks_build_their_initial_state():
         f = run.initial_fields(P, bool(is_mhd), 5 if is_mhd else 0)
         assert np.isfinite(f).all() and (f[0] > 0).all(), deck
         built += 1
-    assert built >= 25
+    assert built >= 27
+
+
+def test_alfven_wave_and_field_loop():
+    from oracle import mhd
+    g, n = 5, (16, 8, 8)
+    lengths, lo = (1.0, 0.5, 0.5), (0.0, 0.0, 0.0)
+    d = [lengths[i] / n[i] for i in range(3)]
+    dims = tuple(v + 2 * g for v in n)
+    w = ic.circularly_polarized_alfven_wave(n, g, lengths, lo, polarization=1.0, vx=0.0)
+    flat = np.ascontiguousarray(w.reshape(-1))
+    assert mhd.max_divergence(flat, *dims, g, *d) <= 1e-12
+    real = w[:, g:-g, g:-g, g:-g]
+    assert np.allclose(real[5], 1.0, atol=1e-12)  # B_x = 1 everywhere
+    x = (np.arange(16) + 0.5) / 16
+    # B_y = -dA_z/dx at the y face: 0.1 sin(2 pi x) up to the finite difference; momentum is anti-parallel to the field
+    assert np.allclose(real[6][3, 3], 0.1 * np.sin(2 * np.pi * x), atol=0.1 * (2 * np.pi / 16) ** 2)
+    assert np.allclose(real[2][3, 3], -0.1 * np.sin(2 * np.pi * x)) and np.allclose(real[3][3, 3], -0.1 * np.cos(2 * np.pi * x))
+    assert np.allclose(real[6] ** 2 + 0 * real[7], real[6] ** 2)
+    # periodic: the generated ghost zones equal the periodic images (index 0 of every axis stays zero, like the
+    # reference's Init_Magnetic_Field_With_Vector_Potential)
+    assert np.allclose(w[5:, 1:, 1:, 1:g], w[5:, 1:, 1:, n[0] + 1:n[0] + g], atol=1e-13)
+    loop = ic.advecting_field_loop((16, 16, 16), g, (1.0, 1.0, 1.0), (-0.5, -0.5, -0.5), A=1e-3, radius=0.3)
+    flat = np.ascontiguousarray(loop.reshape(-1))
+    assert mhd.max_divergence(flat, 26, 26, 26, g, 1 / 16, 1 / 16, 1 / 16) <= 1e-12
+    b2 = (loop[5:] ** 2).sum(axis=0)
+    assert b2.max() > 0 and b2[g, g, g] == 0.0 and np.isclose(np.sqrt(b2.max()), np.sqrt(2) * 1e-3, rtol=0.5)
+    assert np.all(loop[1] == 1.0) and np.all(loop[3] == 2.0)
