@@ -239,7 +239,7 @@ class Grid3D:
         gy = g if H.ny > 1 else 0
         return a[:, gz:gz + H.nz_real, gy:gy + H.ny_real, g:g + H.nx_real].copy()
 
-    def snapshot_field(self, field, mhd_direction=-1, out_precision=None):
+    def snapshot_field(self, field, mhd_direction=-1, out_precision=None, extra=0):
         """Write_Grid_HDF5_Field_GPU / Write_HDF5_Field_3D (io.cpp:1318-1324, io_gpu.cu:97-140): the real cells of one
         field transposed on the device into the snapshot's [i][j][k] order, then copied to the host.  Face-centred
         magnetic fields (mhd_direction 0/1/2) carry one extra face along their own axis."""
@@ -248,12 +248,14 @@ class Grid3D:
         ext = [H.nx_real, H.ny_real, H.nz_real]
         if mhd_direction >= 0:
             ext[mhd_direction] += 1
+        if extra:  # Output_Float32's magnetic datasets (io.cpp:347-362): one more cell on the low side of every axis
+            ext = [e + extra for e in ext]
         ndim = 1 + (H.ny > 1) + (H.nz > 1)
         buf = torch.empty(ext[0] * ext[1] * ext[2], dtype=torch.float64 if out_precision == 2 else torch.float32,
                           device=self.device)
         esz = 8 if self.precision == 2 else 4
         src = C.c_void_p(self.C_device.data_ptr() + field * H.n_cells * esz)
-        check(_lib.lib().chl_pack_snapshot_field(self._ptr(buf), src, H.nx, H.ny, H.nz, H.n_ghost, ext[0], ext[1],
+        check(_lib.lib().chl_pack_snapshot_field(self._ptr(buf), src, H.nx, H.ny, H.nz, H.n_ghost - extra, ext[0], ext[1],
                                                  ext[2], mhd_direction, self.precision, out_precision, self._stream()),
               "chl_pack_snapshot_field")
         self.gpu_launches += 1

@@ -46,6 +46,15 @@ class Parameters:
     init: str = ""
     nfile: int = 0
     n_hydro: int = 1
+    n_out_float32: int = 0
+    out_float32_density: int = 0
+    out_float32_momentum_x: int = 0
+    out_float32_momentum_y: int = 0
+    out_float32_momentum_z: int = 0
+    out_float32_Energy: int = 0
+    out_float32_magnetic_x: int = 0
+    out_float32_magnetic_y: int = 0
+    out_float32_magnetic_z: int = 0
     output_always: int = 0
     xmin: float = 0.0
     ymin: float = 0.0
@@ -124,9 +133,7 @@ class Parameters:
 
 
 # names the reference accepts that have no meaning for this path (other physics, output selection): parsed, not stored
-_IGNORED = {"n_particle", "n_projection", "n_rotated_projection", "n_slice", "n_out_float32", "out_float32_density",
-            "out_float32_momentum_x", "out_float32_momentum_y", "out_float32_momentum_z", "out_float32_Energy",
-            "out_float32_GasEnergy", "out_float32_magnetic_x", "out_float32_magnetic_y", "out_float32_magnetic_z",
+_IGNORED = {"n_particle", "n_projection", "n_rotated_projection", "n_slice", "out_float32_GasEnergy",
             "custom_grav", "snr_filename", "scale_outputs_file", "Omega_b", "bc_potential_type", "UVB_rates_file"}
 # optionalParams, global.cpp:104-108
 _OPTIONAL = {"flag_delta", "ddelta_dt", "n_delta", "Lz", "Lx", "phi", "theta", "delta", "nzr", "nxr", "H0", "Omega_M",

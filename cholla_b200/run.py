@@ -98,7 +98,11 @@ def snapshot(G, P: Parameters, nfile, outdir):
     """Write_Data -> Output_Data -> Write_Header_HDF5 + Write_Grid_HDF5 (io.cpp:92-260, 605-737, 1350-1497): one HDF5
     file per rank, `<outdir>/<nfile>/<nfile>.h5.<rank>` -- see cholla_b200/snapshot.py."""
     from . import snapshot as snap
-    return snap.write_data(G, P, nfile, outdir)
+    path = None
+    if nfile % max(P.n_hydro, 1) == 0:  # io.cpp:126-130
+        path = snap.write_data(G, P, nfile, outdir)
+    f32 = snap.write_float32(G, P, nfile, outdir)  # io.cpp:133-137: n_out_float32 and the out_float32_* selection
+    return path if path is not None else f32
 
 
 def read_grid(G, P: Parameters):

@@ -152,6 +152,55 @@ def write_data(G, P, nfile, outdir):
     return path
 
 
+FLOAT32_SELECT = [("density", 0, "out_float32_density"), ("momentum_x", 1, "out_float32_momentum_x"),
+                  ("momentum_y", 2, "out_float32_momentum_y"), ("momentum_z", 3, "out_float32_momentum_z"),
+                  ("Energy", 4, "out_float32_Energy")]
+FLOAT32_SELECT_MHD = [("magnetic_x", 5, "out_float32_magnetic_x"), ("magnetic_y", 6, "out_float32_magnetic_y"),
+                      ("magnetic_z", 7, "out_float32_magnetic_z")]
+
+
+def float32_datasets(H, C_host, P, mhd=False):
+    """Output_Float32 (io.cpp:266-375): the fields the deck selects with out_float32_<name> > 0, as H5T_IEEE_F32BE.  3-D
+    only.  In an MHD build the magnetic datasets have the reference's "different output format": (n+1)^3 cells starting
+    one below the real cells on EVERY axis (io.cpp:347-362 passes n_ghost - 1 and no direction)."""
+    C_host = np.asarray(C_host).reshape(H.n_fields, H.nz, H.ny, H.nx)
+    g = H.n_ghost
+    out = OrderedDict()
+    for nm, f, key in FLOAT32_SELECT:
+        if getattr(P, key, 0) > 0:
+            out[nm] = np.ascontiguousarray(C_host[f, g:g + H.nz_real, g:g + H.ny_real, g:g + H.nx_real].transpose(2, 1, 0)).astype(">f4")
+    if mhd:
+        for nm, f, key in FLOAT32_SELECT_MHD:
+            if getattr(P, key, 0) > 0:
+                out[nm] = np.ascontiguousarray(C_host[f, g - 1:g + H.nz_real, g - 1:g + H.ny_real, g - 1:g + H.nx_real].transpose(2, 1, 0)).astype(">f4")
+    return out
+
+
+def write_float32(G, P, nfile, outdir):
+    """Write_Data's Output_Float32 leg for one rank of a live Grid3D: `<outdir>/<n>/<n>.float32.h5.<rank>`; returns the
+    path, or None where the reference returns without writing (1-D / 2-D grids, n_out_float32 unset or not dividing
+    nfile)."""
+    H = G.H
+    if H.ny_real == 1 or H.nz_real == 1 or not P.n_out_float32 or nfile % P.n_out_float32 != 0:
+        return None
+    flat = getattr(P, "legacy_flat_outdir", False)
+    os.makedirs(effective_output_dir_path(outdir, nfile, flat), exist_ok=True)
+    path = format_fname(outdir, nfile, G.rank, ".float32", flat)
+    attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
+                              (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl")))
+    data = OrderedDict()
+    for nm, f, key in FLOAT32_SELECT:
+        if getattr(P, key, 0) > 0:
+            data[nm] = G.snapshot_field(f, out_precision=1).astype(">f4")
+    if G.mhd:
+        for nm, f, key in FLOAT32_SELECT_MHD:
+            if getattr(P, key, 0) > 0:
+                data[nm] = G.snapshot_field(f, out_precision=1, extra=1).astype(">f4")
+    h5lite.write(path, attrs, data)
+    return path
+
+
 def read_grid(path, H, mhd=False):
     """Grid3D::Read_Grid_HDF5, io.cpp:2508-2720: returns (C_host (n_fields, nz, ny, nx) with the real cells -- and, for
     MHD, the real faces -- filled and the ghost cells zero, gamma, t, n_step).  The caller sets the boundaries next, as

@@ -90,3 +90,30 @@ def test_mhd_deck_matches_the_oracle_loop(tmp_path, init, bc, extra):
     assert mhd.max_divergence(got, *dims, g, H.dx, H.dy, H.dz) <= 1e-11
     with h5lite.File(files[0]) as f:
         assert f["magnetic_x"].shape == (n[0] + 1, n[1], n[2])
+
+
+@pytest.mark.parametrize("mhd", [False, True])
+def test_float32_output_files(tmp_path, mhd):
+    """n_out_float32 / out_float32_* (Output_Float32, io.cpp:266-375): `<n>.float32.h5.<rank>` beside the full snapshot,
+    transposed and narrowed on the device; the MHD datasets in the reference's (n+1)^3 format."""
+    import os
+    from cholla_b200 import snapshot
+    init = "Orszag_Tang_Vortex" if mhd else "Sound_Wave"
+    extra = dict(n_out_float32=1, out_float32_density=1, out_float32_Energy=1, rho=1.0, P=0.6, A=0.01)
+    if mhd:
+        extra.update(out_float32_magnetic_x=1, out_float32_magnetic_z=1)
+    P = deck(tmp_path, init, (24, 16, 12), [1] * 6, 5.0 / 3.0, **extra)
+    G, files = run.run(P, recon="plmc", solver="hlld" if mhd else "hllc", strict=True, max_steps=2, log=lambda *_: None)
+    G.close()
+    path = os.path.join(os.path.dirname(files[0]), "0.float32.h5.0")
+    with h5lite.File(files[0]) as full, h5lite.File(path) as f32:
+        want = ["density", "Energy"] + (["magnetic_x", "magnetic_z"] if mhd else [])
+        assert sorted(f32.keys()) == sorted(want) and list(f32.attrs) == list(full.attrs)
+        for nm in ("density", "Energy"):
+            assert f32[nm].dtype == np.dtype(">f4") and np.array_equal(f32[nm].read(), full[nm].read().astype(np.float32))
+        if mhd:
+            bx, bz = f32["magnetic_x"].read(), f32["magnetic_z"].read()
+            assert bx.shape == (25, 17, 13) and bz.shape == (25, 17, 13)
+            # the real faces are a sub-block of the float32 box: x faces start at the same x index, one further in y and z
+            assert np.array_equal(bx[:, 1:, 1:], full["magnetic_x"].read().astype(np.float32))
+            assert np.array_equal(bz[1:, 1:, :], full["magnetic_z"].read().astype(np.float32))

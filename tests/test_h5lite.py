@@ -245,3 +245,19 @@ def test_concat_of_rank_files(tmp_path):
             assert np.array_equal(f[nm].read(), cells[i].transpose(2, 1, 0))
         for d, nm in enumerate(snapshot.MAGNETIC_FIELDS):
             assert np.array_equal(f[nm].read(), faces[d].transpose(2, 1, 0))
+
+
+def test_float32_output_selection_and_mhd_format():
+    """Output_Float32 (io.cpp:266-375): only the selected fields, big-endian floats; the MHD datasets cover (n+1)^3 cells
+    from one below the real cells on every axis."""
+    n_real, g = (6, 5, 4), 5
+    H = _header(n_real, g, 8)
+    C = np.random.default_rng(2).standard_normal((8, H.nz, H.ny, H.nx))
+    P = SimpleNamespace(out_float32_density=1, out_float32_momentum_x=0, out_float32_momentum_y=0, out_float32_momentum_z=0,
+                        out_float32_Energy=1, out_float32_magnetic_x=0, out_float32_magnetic_y=1, out_float32_magnetic_z=0)
+    d = snapshot.float32_datasets(H, C, P, mhd=True)
+    assert list(d) == ["density", "Energy", "magnetic_y"] and all(v.dtype == np.dtype(">f4") for v in d.values())
+    assert d["density"].shape == n_real and d["magnetic_y"].shape == (7, 6, 5)
+    assert d["Energy"][2, 3, 1] == np.float32(C[4, 1 + g, 3 + g, 2 + g])
+    assert d["magnetic_y"][0, 0, 0] == np.float32(C[6, g - 1, g - 1, g - 1]) and d["magnetic_y"][6, 5, 4] == np.float32(C[6, g + 3, g + 4, g + 5])
+    assert snapshot.format_fname("out", 4, 0, ".float32") == "out/4//4.float32.h5.0"
