@@ -102,6 +102,7 @@ def snapshot(G, P: Parameters, nfile, outdir):
     if nfile % max(P.n_hydro, 1) == 0:  # io.cpp:126-130
         path = snap.write_data(G, P, nfile, outdir)
     f32 = snap.write_float32(G, P, nfile, outdir)  # io.cpp:133-137: n_out_float32 and the out_float32_* selection
+    snap.write_slices(G, P, nfile, outdir)  # io.cpp:152-156: n_slice
     return path if path is not None else f32
 
 

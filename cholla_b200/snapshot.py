@@ -201,6 +201,59 @@ def write_float32(G, P, nfile, outdir):
     return path
 
 
+def slice_datasets(H, get, n_global, offset, mhd=False, precision=2):
+    """Grid3D::Write_Slices_HDF5, 3-D MPI_CHOLLA branch (io.cpp:1835-2250): the xy, xz and yz planes through the middle
+    of the GLOBAL grid (index n_global / 2), real cells only, as d_/mx_/my_/mz_/E_<plane> (+ cell-centred
+    magnetic_{x,y,z}_<plane> in an MHD build).  A rank the plane does not cross writes zeros.  `get(f, ks, js, is_)`
+    returns field f over the given local index slices as a numpy array, so the planes can come straight from device
+    memory."""
+    g = H.n_ghost
+    dt = ">f8" if precision == 2 else ">f4"
+    n_local = (H.nx_real, H.ny_real, H.nz_real)
+    real = [slice(g, g + H.nx_real), slice(g, g + H.ny_real), slice(g, g + H.nz_real)]
+    names = [("d", 0), ("mx", 1), ("my", 2), ("mz", 3), ("E", 4)]
+    out = OrderedDict()
+    for plane, axis in (("xy", 2), ("xz", 1), ("yz", 0)):
+        mid = n_global[axis] // 2
+        inside = offset[axis] <= mid < offset[axis] + n_local[axis]
+        loc = mid - offset[axis] + g
+        keep = [a for a in (0, 1, 2) if a != axis]
+        shape = tuple(n_local[a] for a in keep)
+
+        def plane_of(f, shift=(0, 0, 0)):
+            sl = [slice(real[a].start - shift[a], real[a].stop - shift[a]) for a in range(3)]
+            sl[axis] = slice(loc - shift[axis], loc - shift[axis] + 1)
+            a = np.asarray(get(f, sl[2], sl[1], sl[0]))  # (nz, ny, nx) with one axis of length 1
+            return np.squeeze(a, axis=2 - axis).T  # -> [first kept axis][second kept axis], x before y before z
+
+        for nm, f in names:
+            out["%s_%s" % (nm, plane)] = (plane_of(f) if inside else np.zeros(shape)).astype(dt)
+        if mhd:
+            for d, nm in enumerate(MAGNETIC_FIELDS):
+                sh = tuple(1 if a == d else 0 for a in range(3))
+                v = 0.5 * (plane_of(5 + d) + plane_of(5 + d, sh)) if inside else np.zeros(shape)
+                out["%s_%s" % (nm, plane)] = v.astype(dt)
+    return out
+
+
+def write_slices(G, P, nfile, outdir):
+    """Output_Slices (io.cpp:518-552): `<outdir>/<n>/<n>_slice.h5.<rank>`, header + the three mid-planes.  Only the cells
+    of the planes leave the device.  3-D grids; returns None when n_slice is unset or does not divide nfile."""
+    H = G.H
+    if not getattr(P, "n_slice", 0) or nfile % P.n_slice != 0 or H.nz_real == 1 or H.ny_real == 1:
+        return None
+    flat = getattr(P, "legacy_flat_outdir", False)
+    os.makedirs(effective_output_dir_path(outdir, nfile, flat), exist_ok=True)
+    path = format_fname(outdir, nfile, G.rank, "_slice", flat)
+    C4 = G.C_device.view(H.n_fields, H.nz, H.ny, H.nx)
+    get = lambda f, ks, js, is_: C4[f, ks, js, is_].to("cpu", G.torch.float64).numpy()
+    attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
+                              (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl")))
+    h5lite.write(path, attrs, slice_datasets(H, get, G.n_global, G.decomp.offset, G.mhd, G.precision))
+    return path
+
+
 def read_grid(path, H, mhd=False):
     """Grid3D::Read_Grid_HDF5, io.cpp:2508-2720: returns (C_host (n_fields, nz, ny, nx) with the real cells -- and, for
     MHD, the real faces -- filled and the ghost cells zero, gamma, t, n_step).  The caller sets the boundaries next, as

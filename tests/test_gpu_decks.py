@@ -117,3 +117,23 @@ def test_float32_output_files(tmp_path, mhd):
             # the real faces are a sub-block of the float32 box: x faces start at the same x index, one further in y and z
             assert np.array_equal(bx[:, 1:, 1:], full["magnetic_x"].read().astype(np.float32))
             assert np.array_equal(bz[1:, 1:, :], full["magnetic_z"].read().astype(np.float32))
+
+
+@pytest.mark.parametrize("mhd", [False, True])
+def test_slice_output_files(tmp_path, mhd):
+    """n_slice (Output_Slices / Write_Slices_HDF5, io.cpp:518-552, 1835-2250): `<n>_slice.h5.<rank>` holds the three global
+    mid-planes of the state the full snapshot holds."""
+    import os
+    init = "Orszag_Tang_Vortex" if mhd else "Sound_Wave"
+    P = deck(tmp_path, init, (24, 16, 12), [1] * 6, 5.0 / 3.0, n_slice=1, rho=1.0, P=0.6, A=0.01)
+    G, files = run.run(P, recon="plmc", solver="hlld" if mhd else "hllc", strict=True, max_steps=2, log=lambda *_: None)
+    G.close()
+    with h5lite.File(files[0]) as full, h5lite.File(os.path.join(os.path.dirname(files[0]), "0_slice.h5.0")) as s:
+        assert list(s.attrs) == list(full.attrs)
+        for nm, ds in (("d", "density"), ("mx", "momentum_x"), ("E", "Energy")):
+            a = full[ds].read()
+            assert np.array_equal(s[nm + "_xy"].read(), a[:, :, 6]) and np.array_equal(s[nm + "_xz"].read(), a[:, 8, :])
+            assert np.array_equal(s[nm + "_yz"].read(), a[12, :, :])
+        if mhd:
+            bx = full["magnetic_x"].read()  # faces 0 .. 24: cell i lies between faces i and i + 1
+            assert np.array_equal(s["magnetic_x_xy"].read(), 0.5 * (bx[1:, :, 6] + bx[:-1, :, 6]))

@@ -261,3 +261,26 @@ def test_float32_output_selection_and_mhd_format():
     assert d["Energy"][2, 3, 1] == np.float32(C[4, 1 + g, 3 + g, 2 + g])
     assert d["magnetic_y"][0, 0, 0] == np.float32(C[6, g - 1, g - 1, g - 1]) and d["magnetic_y"][6, 5, 4] == np.float32(C[6, g + 3, g + 4, g + 5])
     assert snapshot.format_fname("out", 4, 0, ".float32") == "out/4//4.float32.h5.0"
+
+
+@pytest.mark.parametrize("mhd", [False, True])
+def test_slice_datasets(mhd):
+    """Write_Slices_HDF5 (io.cpp:1835-2250): global mid-planes, [x][y] / [x][z] / [y][z] order, zeros on ranks the plane
+    misses, cell-centred magnetic fields."""
+    g, nf = (5 if mhd else 4), (8 if mhd else 5)
+    n_glob, n_loc, off = (12, 10, 8), (6, 10, 8), (6, 0, 0)  # the upper-x rank of a 2 x 1 x 1 decomposition
+    H = _header(n_loc, g, nf)
+    C = np.random.default_rng(4).standard_normal((nf, H.nz, H.ny, H.nx))
+    get = lambda f, ks, js, is_: C[f, ks, js, is_]
+    d = snapshot.slice_datasets(H, get, n_glob, off, mhd)
+    want = ["%s_%s" % (a, p) for p in ("xy", "xz", "yz") for a in (["d", "mx", "my", "mz", "E"] + (["magnetic_x", "magnetic_y", "magnetic_z"] if mhd else []))]
+    assert list(d) == want
+    assert d["d_xy"].shape == (6, 10) and d["E_xz"].shape == (6, 8) and d["mx_yz"].shape == (10, 8)
+    assert d["d_xy"][2, 3] == C[0, 4 + g, 3 + g, 2 + g]        # z = 8 / 2 = 4
+    assert d["E_xz"][1, 7] == C[4, 7 + g, 5 + g, 1 + g]        # y = 10 / 2 = 5
+    assert d["mx_yz"][9, 0] == C[1, g, 9 + g, 0 + g]           # x = 12 / 2 = 6 -> local 0 on this rank
+    lower = snapshot.slice_datasets(H, get, n_glob, (0, 0, 0), mhd)  # the lower-x rank: the yz plane is not its own
+    assert not lower["d_yz"].any() and lower["d_xy"].any()
+    if mhd:
+        assert d["magnetic_x_xy"][2, 3] == 0.5 * (C[5, 4 + g, 3 + g, 2 + g] + C[5, 4 + g, 3 + g, 1 + g])
+        assert d["magnetic_z_yz"][4, 2] == 0.5 * (C[7, 2 + g, 4 + g, g] + C[7, 1 + g, 4 + g, g])
