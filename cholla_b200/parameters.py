@@ -48,6 +48,7 @@ class Parameters:
     n_hydro: int = 1
     n_out_float32: int = 0
     n_slice: int = 0
+    n_projection: int = 0
     out_float32_density: int = 0
     out_float32_momentum_x: int = 0
     out_float32_momentum_y: int = 0
@@ -134,7 +135,7 @@ class Parameters:
 
 
 # names the reference accepts that have no meaning for this path (other physics, output selection): parsed, not stored
-_IGNORED = {"n_particle", "n_projection", "n_rotated_projection", "out_float32_GasEnergy",
+_IGNORED = {"n_particle", "n_rotated_projection", "out_float32_GasEnergy",
             "custom_grav", "snr_filename", "scale_outputs_file", "Omega_b", "bc_potential_type", "UVB_rates_file"}
 # optionalParams, global.cpp:104-108
 _OPTIONAL = {"flag_delta", "ddelta_dt", "n_delta", "Lz", "Lx", "phi", "theta", "delta", "nzr", "nxr", "H0", "Omega_M",

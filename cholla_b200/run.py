@@ -103,6 +103,7 @@ def snapshot(G, P: Parameters, nfile, outdir):
         path = snap.write_data(G, P, nfile, outdir)
     f32 = snap.write_float32(G, P, nfile, outdir)  # io.cpp:133-137: n_out_float32 and the out_float32_* selection
     snap.write_slices(G, P, nfile, outdir)  # io.cpp:152-156: n_slice
+    snap.write_projection(G, P, nfile, outdir)  # io.cpp:140-144: n_projection
     return path if path is not None else f32
 
 

@@ -254,6 +254,59 @@ def write_slices(G, P, nfile, outdir):
     return path
 
 
+MP, KB = 1.672622e-24, 1.380658e-16  # global.h:26-27
+PRESSURE_UNIT = DENSITY_UNIT * VELOCITY_UNIT * VELOCITY_UNIT
+
+
+def projection_datasets(H, C4, gamma, mhd=False, precision=2):
+    """Grid3D::Write_Projection_HDF5, 3-D branch without DE / DUST (io.cpp:1502-1660): column density along z and along y,
+    d_xy = sum_k d dz, d_xz = sum_j d dy, and the density-weighted temperature T_xy = sum_k T d dz, T_xz = sum_j T d dy
+    with T = P PRESSURE_UNIT / (n KB), n = d DENSITY_UNIT / (mu MP), mu = 0.6 (hydro_utilities.h:60-88).  C4 is the
+    (n_fields, nz, ny, nx) state as a numpy array or a torch tensor: only arithmetic, slicing and sums are used, so the
+    reduction runs where the data lives and four small planes come back.  (The sums associate differently from the
+    reference's sequential loops: equal to round-off.)"""
+    g, mu, tiny = H.n_ghost, 0.6, 1e-20
+    r = (slice(g, g + H.nz_real), slice(g, g + H.ny_real), slice(g, g + H.nx_real))
+    d, mx, my, mz, E = (C4[f][r] for f in range(5))
+    e = E - 0.5 * (mx * mx + my * my + mz * mz) / d
+    if mhd:  # cellCenteredMagneticFields: average of the two faces of the cell
+        lo = [(slice(g, g + H.nz_real), slice(g, g + H.ny_real), slice(g - 1, g - 1 + H.nx_real)),
+              (slice(g, g + H.nz_real), slice(g - 1, g - 1 + H.ny_real), slice(g, g + H.nx_real)),
+              (slice(g - 1, g - 1 + H.nz_real), slice(g, g + H.ny_real), slice(g, g + H.nx_real))]
+        for a in range(3):
+            b = 0.5 * (C4[5 + a][r] + C4[5 + a][lo[a]])
+            e = e - 0.5 * b * b
+    P = e * (gamma - 1.0)
+    P = P * (P > tiny) + tiny * (P <= tiny)  # fmax(P, TINY_NUMBER), hydro_utilities.h:48-58
+    n = d * DENSITY_UNIT / (mu * MP)
+    Td = (P * PRESSURE_UNIT / (n * KB)) * d
+    dt = ">f8" if precision == 2 else ">f4"
+    host = lambda a: np.asarray(a.cpu() if hasattr(a, "cpu") else a, dtype=np.float64).T.astype(dt)  # -> [x][y] / [x][z]
+    out = OrderedDict()
+    out["d_xy"] = host(d.sum(0) * H.dz)
+    out["d_xz"] = host(d.sum(1) * H.dy)
+    out["T_xy"] = host(Td.sum(0) * H.dz)
+    out["T_xz"] = host(Td.sum(1) * H.dy)
+    return out
+
+
+def write_projection(G, P, nfile, outdir):
+    """Output_Projected_Data (io.cpp:380-430): `<outdir>/<n>/<n>_proj.h5.<rank>`, header + the four projections, reduced on
+    the device.  3-D grids; None when n_projection is unset or does not divide nfile."""
+    H = G.H
+    if not getattr(P, "n_projection", 0) or nfile % P.n_projection != 0 or H.nz_real == 1 or H.ny_real == 1:
+        return None
+    flat = getattr(P, "legacy_flat_outdir", False)
+    os.makedirs(effective_output_dir_path(outdir, nfile, flat), exist_ok=True)
+    path = format_fname(outdir, nfile, G.rank, "_proj", flat)
+    attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
+                              (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl")))
+    C4 = G.C_device.view(H.n_fields, H.nz, H.ny, H.nx).to(G.torch.float64)
+    h5lite.write(path, attrs, projection_datasets(H, C4, P.gamma, G.mhd, G.precision))
+    return path
+
+
 def read_grid(path, H, mhd=False):
     """Grid3D::Read_Grid_HDF5, io.cpp:2508-2720: returns (C_host (n_fields, nz, ny, nx) with the real cells -- and, for
     MHD, the real faces -- filled and the ghost cells zero, gamma, t, n_step).  The caller sets the boundaries next, as

@@ -125,9 +125,16 @@ def test_slice_output_files(tmp_path, mhd):
     mid-planes of the state the full snapshot holds."""
     import os
     init = "Orszag_Tang_Vortex" if mhd else "Sound_Wave"
-    P = deck(tmp_path, init, (24, 16, 12), [1] * 6, 5.0 / 3.0, n_slice=1, rho=1.0, P=0.6, A=0.01)
+    P = deck(tmp_path, init, (24, 16, 12), [1] * 6, 5.0 / 3.0, n_slice=1, n_projection=1, rho=1.0, P=0.6, A=0.01)
     G, files = run.run(P, recon="plmc", solver="hlld" if mhd else "hllc", strict=True, max_steps=2, log=lambda *_: None)
     G.close()
+    # n_projection (Output_Projected_Data, io.cpp:380-430): column densities and density-weighted temperatures, reduced on
+    # the device
+    with h5lite.File(files[0]) as full, h5lite.File(os.path.join(os.path.dirname(files[0]), "0_proj.h5.0")) as pr:
+        d = full["density"].read()
+        assert sorted(pr.keys()) == ["T_xy", "T_xz", "d_xy", "d_xz"] and pr["d_xy"].shape == (24, 16) and pr["T_xz"].shape == (24, 12)
+        assert np.allclose(pr["d_xy"].read(), d.sum(axis=2) / 12.0, rtol=1e-13) and np.allclose(pr["d_xz"].read(), d.sum(axis=1) / 16.0, rtol=1e-13)
+        assert (pr["T_xy"].read() > 0).all()
     with h5lite.File(files[0]) as full, h5lite.File(os.path.join(os.path.dirname(files[0]), "0_slice.h5.0")) as s:
         assert list(s.attrs) == list(full.attrs)
         for nm, ds in (("d", "density"), ("mx", "momentum_x"), ("E", "Energy")):
