@@ -226,8 +226,13 @@ def random_smooth(n, seed=0, gamma=5.0 / 3.0):
 # the discrete curl of a vector potential sampled over the ghost zones too, so div B = 0 to round-off everywhere and
 # periodic problems need no initial ghost fill.  magnetic_x[id] sits on the +x face of cell id (grid_enum.h:57-61).
 def _mhd_mesh(n, g, lengths, lo):
+    """Cell centres of the local array, ghost zones included.  Inside `with block(offset, n_local)` only that rank's
+    block (plus its ghost zones) of the global grid is built, from the same global-index rule, so the cells a rank
+    owns do not depend on the rank count."""
     d = [lengths[i] / n[i] for i in range(3)]
-    c = [lo[i] + (np.arange(n[i] + 2 * g) - g) * d[i] + 0.5 * d[i] for i in range(3)]  # Get_Position, ghosts included
+    off, nl = ((0, 0, 0), n) if _BLOCK is None else _BLOCK
+    # Get_Position: bound + global_index * dx + dx / 2 (grid3D.cpp:108-110), ghosts included
+    c = [lo[i] + (off[i] + np.arange(nl[i] + 2 * g) - g) * d[i] + 0.5 * d[i] for i in range(3)]
     Z, Y, X = np.meshgrid(c[2], c[1], c[0], indexing="ij")
     return X, Y, Z, d
 

@@ -145,8 +145,14 @@ def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mh
     files, nfile, outtime = [], P.nfile, 0.0
     if is_restart:
         outtime += G.H.t  # main.cpp:124-128
+
+    def output(n):
+        path = snapshot(G, P, n, outdir)
+        if path is not None:  # n_hydro may skip the full snapshot of this output number (io.cpp:126-130)
+            files.append(path)
+
     if outdir != "none" and not is_restart:
-        files.append(snapshot(G, P, nfile, outdir))  # main.cpp:205-215: the initial state is output 0
+        output(nfile)  # main.cpp:205-215: the initial state is output 0
     nfile += 1
     outtime += P.outstep
     dti = G.Calc_Inverse_Timestep()
@@ -160,7 +166,7 @@ def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mh
         G.Set_Boundary_Conditions_Grid()
         if G.H.t == outtime:  # main.cpp:341-350
             if outdir != "none":
-                files.append(snapshot(G, P, nfile, outdir))
+                output(nfile)
             nfile += 1
             outtime += P.outstep
     log("n_step: %d  sim time: %.10f  last dt: %.6e" % (G.H.n_step, G.H.t, G.H.dt))

@@ -135,8 +135,8 @@ def write_snapshot(path, H, C_host, gamma, n_global, n_local, offset, nprocs, bo
 def write_data(G, P, nfile, outdir):
     """Write_Data -> Output_Data for one rank of a live Grid3D (device -> host -> file)."""
     H = G.H
-    d = effective_output_dir_path(outdir, nfile, getattr(P, "legacy_flat_outdir", False))
-    os.makedirs(d, exist_ok=True)  # Ensure_Dir_Exists, io.cpp:2830-
+    os.makedirs(effective_output_dir_path(outdir, nfile, getattr(P, "legacy_flat_outdir", False)),
+                exist_ok=True)  # Ensure_Dir_Exists, io.cpp:2830-
     path = format_fname(outdir, nfile, G.rank, "", getattr(P, "legacy_flat_outdir", False))
     attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
                               (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,

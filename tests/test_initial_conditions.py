@@ -177,3 +177,31 @@ def test_alfven_wave_and_field_loop():
     b2 = (loop[5:] ** 2).sum(axis=0)
     assert b2.max() > 0 and b2[g, g, g] == 0.0 and np.isclose(np.sqrt(b2.max()), np.sqrt(2) * 1e-3, rtol=0.5)
     assert np.all(loop[1] == 1.0) and np.all(loop[3] == 2.0)
+
+
+@pytest.mark.parametrize("gen", ["orszag_tang", "mhd_riemann", "cpaw", "loop"])
+def test_mhd_generators_are_rank_count_independent(gen):
+    """Inside ic.block(offset, n_local) an MHD generator builds one rank's array (ghost zones included) from the global
+    index rule of Get_Position: the cells and faces a rank owns equal the single-domain ones, so a run does not depend
+    on the decomposition."""
+    from cholla_b200 import _lib
+    g, n = 5, (16, 12, 8)
+    lengths, lo = (1.0, 1.0, 1.0), (-0.5, -0.5, -0.5)
+    make = {"orszag_tang": lambda: ic.orszag_tang(n, g),
+            "mhd_riemann": lambda: ic.mhd_riemann(n, g, lengths, lo, (1.0, 0, 0, 0, 1.0, 0.75, 1.0, 0.0),
+                                                  (0.125, 0, 0, 0, 0.1, 0.75, -1.0, 0.0), 0.0, 2.0),
+            "cpaw": lambda: ic.circularly_polarized_alfven_wave(n, g, lengths, lo),
+            "loop": lambda: ic.advecting_field_loop(n, g, lengths, lo, radius=0.3)}[gen]
+    whole = make()
+    np_grid = _lib.tile_decomposition(4, *n)
+    for rank in range(4):
+        coords = (rank % np_grid[0], (rank // np_grid[0]) % np_grid[1], rank // (np_grid[0] * np_grid[1]))
+        ext = [_lib.local_extent(n[a], np_grid[a], coords[a]) for a in range(3)]
+        nl, off = [e[0] for e in ext], [e[1] for e in ext]
+        with ic.block(off, nl):
+            part = make()
+        assert part.shape == (8, nl[2] + 2 * g, nl[1] + 2 * g, nl[0] + 2 * g)
+        # what the rank owns -- its real cells and the faces around them -- and all but the two outermost ghost layers
+        # (the curl helper leaves index 0 at zero and the energy of index 1 averages with it; the exchange refills both)
+        want = whole[:, off[2] + 2:off[2] + nl[2] + 2 * g, off[1] + 2:off[1] + nl[1] + 2 * g, off[0] + 2:off[0] + nl[0] + 2 * g]
+        assert np.array_equal(part[:, 2:, 2:, 2:], want), rank
