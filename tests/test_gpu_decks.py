@@ -144,3 +144,44 @@ def test_slice_output_files(tmp_path, mhd):
         if mhd:
             bx = full["magnetic_x"].read()  # faces 0 .. 24: cell i lies between faces i and i + 1
             assert np.array_equal(s["magnetic_x_xy"].read(), 0.5 * (bx[1:, :, 6] + bx[:-1, :, 6]))
+
+
+WAVES = {  # hydro_system_tests.cpp:205-258: eigenvector (rho, mx, my, mz, E), vx, fiducial number of time steps, L1 factor
+    "SoundWaveRightMoving": ((1.0, 1.0, 1.0, 1.0, 1.5), 0.0, 214, 2.0),
+    "SoundWaveLeftMoving": ((1.0, -1.0, 1.0, 1.0, 1.5), 0.0, 214, 2.0),
+    "HydroContactWave": ((1.0, 1.0, 0.0, 0.0, 0.5), 1.0, 427, 1.0),
+}
+
+
+@pytest.mark.parametrize("recon,allowed", [("plmc", 1e-7), ("ppmc", 2.7e-8)])
+@pytest.mark.parametrize("wave", sorted(WAVES))
+def test_reference_linear_wave_system_tests(tmp_path, wave, recon, allowed):
+    """tHYDROtMHDSYSTEMLinearWavesParameterizedMpi (hydro_system_tests.cpp:142-258) with the reference's pass criteria,
+    deck-driven on the GPU: one period on 64 x 32 x 32, the fiducial number of time steps, L1 error against the initial
+    snapshot inside the Gardiner & Stone bound of the reconstruction (tests/test_system_tests.py runs the same on the
+    CPU oracle)."""
+    from cholla_b200 import system_test
+    ev, vx, steps, factor = WAVES[wave]
+    P = deck(tmp_path, "Linear_Wave", (64, 32, 32), [1] * 6, 5.0 / 3.0, ln=(1.0, 0.5, 0.5), rho=1.0, vx=vx, vy=0.0, vz=0.0,
+             P=1.0 / (5.0 / 3.0), A=1e-6, rEigenVec_rho=ev[0], rEigenVec_MomentumX=ev[1], rEigenVec_MomentumY=ev[2],
+             rEigenVec_MomentumZ=ev[3], rEigenVec_E=ev[4])
+    P = pm.parse_params(str(tmp_path / "Linear_Wave.txt"), ["outdir=%s" % tmp_path, "tout=1.0", "outstep=1.0"])
+    G, files = run.run(P, recon=recon, solver="hllc", strict=True, log=lambda *_: None)
+    G.close()
+    assert len(files) == 2
+    fails, info = system_test.l1_error_test(str(tmp_path), factor * allowed, allowed, expected_n_steps=steps)
+    assert not fails, (fails, info)
+
+
+def test_reference_sound_wave_3d_system_test(tmp_path):
+    """tHYDROtMHDSYSTEMSoundWave3D (hydro_system_tests.cpp:96-128): 64^3 to t = 0.05, analytic sine to 1e-7."""
+    from cholla_b200 import system_test
+    deck(tmp_path, "Linear_Wave", (64, 64, 64), [1] * 6, 1.666666666666667, rho=1.0, vx=0.0, vy=0.0, vz=0.0, P=0.6, A=1e-5,
+         rEigenVec_rho=1.0, rEigenVec_MomentumX=1.0, rEigenVec_MomentumY=1.0, rEigenVec_MomentumZ=1.0, rEigenVec_E=1.5)
+    P = pm.parse_params(str(tmp_path / "Linear_Wave.txt"), ["outdir=%s" % tmp_path, "tout=0.05", "outstep=0.05"])
+    G, files = run.run(P, recon="plmc", solver="hllc", strict=True, log=lambda *_: None)
+    G.close()
+    kx = 2 * np.pi / 64.0
+    phase = kx * 0.5 - 1.0 * 0.05 * 2 * np.pi
+    assert system_test.analytic_sine(str(tmp_path), "density", 1.0, 1e-5, kx, 0.0, 0.0, phase, 1e-7)
+    assert system_test.analytic_sine(str(tmp_path), "momentum_x", 0.0, 1e-5, kx, 0.0, 0.0, phase, 1e-7)
