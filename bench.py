@@ -2,6 +2,8 @@
 """bench.py -- cell-updates/s of the Van Leer hydro hot path (3-D, PPMC + HLLC, fp64) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S] [--mode strict|fast]
+                    [--recon pcm|plmc|ppmc|plmp|ppmp] [--solver hllc|roe|hll|exact] [--integrator vl|simple]
+                    [--workload blast|kh|noise] [--precision 1|2]        (defaults = the headline: PPMC + HLLC, VL, fp64)
 
 A "step" is one pass of the hot path over the local grid: the reference's main-loop body (main.cpp:247-379)
     set_dt (all-reduce MAX) -> VL step (+ temperature floor, CFL max) -> ghost fill / halo exchange.
