@@ -370,3 +370,43 @@ def concat_3d_dataset(source_directory, output_directory, num_processes, output_
             out_attrs[k] = np.asarray(v).astype(">f8" if np.asarray(v).dtype.kind == "f" else ">i4")
     h5lite.write(dest_path, out_attrs, data)
     return dest_path
+
+
+def concat_2d_dataset(source_directory, output_directory, num_processes, output_number, dataset_kind, skip_fields=(),
+                      destination_dtype=None):
+    """python_scripts/concat_2d_data.py for `slice` and `proj` outputs: `<src>/<n>/<n>_<kind>.h5.<rank>` of all ranks into
+    `<out>/<n>_<kind>.h5`.  A rank's plane is ADDED at its offset -- projections of ranks stacked along the line of sight
+    sum, slices of ranks the plane misses are zeros (and, like the script, are skipped)."""
+    if dataset_kind not in ("slice", "proj"):
+        raise ValueError("dataset_kind can only be 'slice' or 'proj' (rotated projections are not written)")
+    os.makedirs(output_directory, exist_ok=True)
+    dest_path = os.path.join(output_directory, "%d_%s.h5" % (output_number, dataset_kind))
+    data, attrs = OrderedDict(), None
+    axes = {"xy": (0, 1, 2), "yz": (1, 2, 0), "xz": (0, 2, 1)}  # the two kept axes, then the one through the plane
+    for rank in range(num_processes):
+        src = os.path.join(source_directory, str(output_number), "%d_%s.h5.%d" % (output_number, dataset_kind, rank))
+        with h5lite.File(src) as f:
+            if attrs is None:
+                attrs = OrderedDict((k, v) for k, v in f.attrs.items() if k not in ("dims_local", "offset"))
+            dims = [int(v) for v in f.attrs["dims"]]
+            nloc = [int(v) for v in f.attrs["dims_local"]]
+            off = [int(v) for v in f.attrs["offset"]]
+            for nm in f.keys():
+                if nm in skip_fields:
+                    continue
+                a0, a1, ax = axes[nm[-2:]]
+                ds = f[nm]
+                if nm not in data:
+                    data[nm] = np.zeros((dims[a0], dims[a1]), dtype=destination_dtype or ds.dtype)
+                if dataset_kind == "slice" and not (off[ax] <= dims[ax] // 2 <= off[ax] + nloc[ax]):
+                    continue
+                data[nm][off[a0]:off[a0] + nloc[a0], off[a1]:off[a1] + nloc[a1]] += ds.read().astype(data[nm].dtype)
+    out_attrs = OrderedDict()
+    for k, v in attrs.items():
+        if isinstance(v, str):
+            out_attrs[k] = h5lite.VarString(v)
+        else:
+            out_attrs[k] = np.asarray(v).astype(">f8" if np.asarray(v).dtype.kind == "f" else ">i4")
+    h5lite.write(dest_path, out_attrs, data)
+    return dest_path
+

@@ -319,3 +319,42 @@ def test_projection_datasets_numpy_and_torch(mhd):
     t = snapshot.projection_datasets(H, torch.from_numpy(C), gamma, mhd)
     for k in d:
         assert np.allclose(t[k].astype(np.float64), d[k].astype(np.float64), rtol=1e-14)
+
+
+def test_concat_2d_slices_and_projections(tmp_path):
+    """python_scripts/concat_2d_data.py: slice and projection files of a 2 x 2 x 1 decomposition back to the planes of the
+    single-domain state (projections of ranks along the line of sight add up)."""
+    from cholla_b200 import _lib
+    n_glob, g, nf, gamma = (8, 6, 4), 4, 5, 5.0 / 3.0
+    rng = np.random.default_rng(8)
+    cells = rng.random((5, n_glob[2], n_glob[1], n_glob[0])) + 0.5
+    cells[4] += 3.0
+    np_grid = _lib.tile_decomposition(4, *n_glob)
+    Hg = _header(n_glob, g, nf)
+    Cg = np.zeros((nf, Hg.nz, Hg.ny, Hg.nx))
+    Cg[:, g:-g, g:-g, g:-g] = cells
+    whole_slices = snapshot.slice_datasets(Hg, lambda f, ks, js, is_: Cg[f, ks, js, is_], n_glob, (0, 0, 0))
+    whole_proj = snapshot.projection_datasets(Hg, Cg, gamma)
+    for rank in range(4):
+        cx, cy = rank % 2, rank // 2
+        ext = [_lib.local_extent(n_glob[a], np_grid[a], c) for a, c in zip(range(3), (cx, cy, 0))]
+        nloc, off = [e[0] for e in ext], [e[1] for e in ext]
+        H = _header(nloc, g, nf)
+        H.dx, H.dy, H.dz = Hg.dx, Hg.dy, Hg.dz
+        C = np.zeros((nf, H.nz, H.ny, H.nx))
+        C[:, g:-g, g:-g, g:-g] = cells[:, off[2]:off[2] + nloc[2], off[1]:off[1] + nloc[1], off[0]:off[0] + nloc[0]]
+        attrs = snapshot.header_attributes(H, gamma, n_glob, nloc, off, np_grid, (0, 0, 0), (1, 1, 1))
+        os.makedirs(tmp_path / "raw" / "3", exist_ok=True)
+        h5lite.write(str(tmp_path / "raw" / "3" / ("3_slice.h5.%d" % rank)), attrs,
+                     snapshot.slice_datasets(H, lambda f, ks, js, is_, C=C: C[f, ks, js, is_], n_glob, off))
+        h5lite.write(str(tmp_path / "raw" / "3" / ("3_proj.h5.%d" % rank)), attrs, snapshot.projection_datasets(H, C, gamma))
+    s = snapshot.concat_2d_dataset(str(tmp_path / "raw"), str(tmp_path / "cat"), 4, 3, "slice")
+    p = snapshot.concat_2d_dataset(str(tmp_path / "raw"), str(tmp_path / "cat"), 4, 3, "proj")
+    assert os.path.basename(s) == "3_slice.h5" and os.path.basename(p) == "3_proj.h5"
+    with h5lite.File(s) as f:
+        assert "offset" not in f.attrs
+        for nm, want in whole_slices.items():
+            assert np.array_equal(f[nm].read(), want), nm
+    with h5lite.File(p) as f:
+        for nm, want in whole_proj.items():
+            assert np.allclose(f[nm].read(), want, rtol=1e-13), nm
