@@ -78,9 +78,14 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("world,n_global,flags", CASES)
-def test_exchange_reproduces_single_domain_ghost_fill(world, n_global, flags, tmp_path):
-    g, nf = 3, 5
+# eight fields = an MHD build's slabs (density, momenta, energy, three face-centred field components: the exchange moves
+# n_ghost layers of every field alike, mpi_boundaries.cpp:113-298); periodic faces, where the fill rule is field-agnostic
+CASES_NF = [c + (5,) for c in CASES] + [(2, (16, 12, 10), [1] * 6, 8), (8, (12, 12, 12), [1] * 6, 8)]
+
+
+@pytest.mark.parametrize("world,n_global,flags,nf", CASES_NF)
+def test_exchange_reproduces_single_domain_ghost_fill(world, n_global, flags, nf, tmp_path):
+    g = 3 if nf == 5 else 5
     if n_global[2] == 1:
         pytest.skip("2-D decomposition keeps nz = 1 without ghosts; covered by the 3-D cases")
     mp.spawn(_worker, args=(world, _free_port(), n_global, g, nf, flags, str(tmp_path)), nprocs=world, join=True)
