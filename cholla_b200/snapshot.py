@@ -410,3 +410,33 @@ def concat_2d_dataset(source_directory, output_directory, num_processes, output_
     h5lite.write(dest_path, out_attrs, data)
     return dest_path
 
+
+def main(argv=None):
+    """`python -m cholla_b200.snapshot -s <source dir> -o <output dir> -n <ranks> -c <outputs> [-d slice|proj]`: the
+    command lines of python_scripts/concat_3d_data.py and concat_2d_data.py (concat_internals.common_cli: -c takes single
+    numbers and inclusive ranges, e.g. `-c 0 4-6`)."""
+    import argparse
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("-s", "--source-directory", required=True)
+    ap.add_argument("-o", "--output-directory", required=True)
+    ap.add_argument("-n", "--num-processes", type=int, required=True)
+    ap.add_argument("-c", "--concat-outputs", nargs="+", required=True)
+    ap.add_argument("-d", "--dataset-kind", choices=["slice", "proj"], default=None, help="2-D outputs; default: the 3-D snapshot")
+    ap.add_argument("--skip-fields", nargs="*", default=[])
+    a = ap.parse_args(argv)
+    outputs = []
+    for tok in a.concat_outputs:
+        lo, _, hi = tok.partition("-")
+        outputs.extend(range(int(lo), int(hi or lo) + 1))
+    for n in outputs:
+        if a.dataset_kind:
+            print(concat_2d_dataset(a.source_directory, a.output_directory, a.num_processes, n, a.dataset_kind, a.skip_fields))
+        else:
+            print(concat_3d_dataset(a.source_directory, a.output_directory, a.num_processes, n, a.skip_fields))
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())
+

@@ -348,6 +348,8 @@ def test_concat_2d_slices_and_projections(tmp_path):
         h5lite.write(str(tmp_path / "raw" / "3" / ("3_slice.h5.%d" % rank)), attrs,
                      snapshot.slice_datasets(H, lambda f, ks, js, is_, C=C: C[f, ks, js, is_], n_glob, off))
         h5lite.write(str(tmp_path / "raw" / "3" / ("3_proj.h5.%d" % rank)), attrs, snapshot.projection_datasets(H, C, gamma))
+    assert snapshot.main(["-s", str(tmp_path / "raw"), "-o", str(tmp_path / "cli"), "-n", "4", "-c", "3-3", "-d", "proj"]) == 0
+    assert os.path.exists(tmp_path / "cli" / "3_proj.h5")
     s = snapshot.concat_2d_dataset(str(tmp_path / "raw"), str(tmp_path / "cat"), 4, 3, "slice")
     p = snapshot.concat_2d_dataset(str(tmp_path / "raw"), str(tmp_path / "cat"), 4, 3, "proj")
     assert os.path.basename(s) == "3_slice.h5" and os.path.basename(p) == "3_proj.h5"
