@@ -80,6 +80,18 @@ def lib():
     L.chl_local_extent.argtypes = [i, i, i, ip, ip]
     L.chl_debug_exact_div.argtypes = [p, p, p, p, l, p]
     L.chl_debug_exact_sqrt.argtypes = [p, p, p, l, p]
+    L.chl_debug_exact_div_flagged.argtypes = [p, p, p, p, i, l, p]
+    L.chl_bad_cells.argtypes = [p, C.POINTER(C.c_ulonglong), p]
+    L.chl_set_tuning.argtypes = [p, i]
+    L.chl_halo_blob_bytes.restype = C.c_size_t
+    L.chl_halo_create.argtypes = [p, ip, i, C.POINTER(p)]
+    L.chl_halo_destroy.argtypes = [p]
+    L.chl_halo_export.argtypes = [p, p]
+    L.chl_halo_connect.argtypes = [p, i, p]
+    L.chl_halo_exchange.argtypes = [p, p, p]
+    L.chl_halo_error.argtypes = [p, p]
+    L.chl_vl_step_exchange.argtypes = [p, p, p, d, p]
+    L.chl_dti_copy_key.argtypes = [p, p, p]
     _lib = L
     return L
 

@@ -1,7 +1,7 @@
 // aux_kernels.cu -- ghost-cell fill and halo pack/unpack: pure copies, HBM-bound, element type agnostic.
 // Behaviour follows src/grid/cuda_boundaries.cu:11-303 of the reference (SetGhostCellsKernel,
 // SetBoundaryMapping, FindIndex, Pack/UnpackBuffers3DKernel); the code is new.
-#include "chl_internal.h"
+#include "chl_aux.h"
 
 namespace chl
 {

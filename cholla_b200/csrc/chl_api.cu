@@ -11,6 +11,7 @@
 
 #include "../../include/cholla_b200.h"
 #include "chl_internal.h"
+#include "chl_aux.h"
 
 namespace
 {
@@ -50,10 +51,9 @@ struct chl_ctx {
   void *d_prim;               // MHD: half-step primitives + cell-centred fields
   void *d_ctf;                // MHD: 9 * n_cells flux components kept for constrained transport
   void *d_E;                  // MHD: 3 * n_cells edge EMFs
-  int split;                  // 1 = one launch per direction (default), 0 = single fused launch per stage
-  int dir_chunk;              // CHL_DIR_CHUNK override (0 = auto)
-  unsigned long long *d_key;  // CFL accumulator (ordered key)
-  unsigned long long *h_key;  // pinned
+  int dir_chunk;              // marching length override (0 = auto), chl_set_tuning
+  unsigned long long *d_key;  // [0] CFL accumulator (ordered key), [1] count of cells with density <= 0
+  unsigned long long *h_key;  // pinned, 2 words
   size_t n_cells;
   int ndim;
   int profiling;                       // record events around each stage
@@ -138,21 +138,14 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->d_acc = nullptr;
   c->mhd = mhd;
   c->d_prim = c->d_ctf = c->d_E = nullptr;
-  {
-    // development knobs: CHL_SWEEP_IMPL=fused|split selects the kernel family, CHL_DIR_CHUNK the marching length
-    const char *impl = getenv("CHL_SWEEP_IMPL");
-    c->split = !(impl && strcmp(impl, "fused") == 0) || cfg->solver >= CHL_SOLVER_HLL ||
-               cfg->recon >= CHL_RECON_PLMP;  // HLL, exact, PLMP, PPMP: split sweeps only
-    const char *ch = getenv("CHL_DIR_CHUNK");
-    c->dir_chunk = ch ? atoi(ch) : 0;
-  }
+  c->dir_chunk = 0;
   c->d_key = nullptr;
   c->h_key = nullptr;
   c->profiling = 0;
   c->ev_steps = 0;
   size_t const bytes = c->n_cells * (mhd ? 8 : ops->half_fields) * ops->real_bytes;
   cudaError_t e = cudaMalloc(&c->d_half, bytes);
-  if (e == cudaSuccess && (c->split || mhd)) e = cudaMalloc(&c->d_acc, c->n_cells * 5 * ops->real_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_acc, c->n_cells * 5 * ops->real_bytes);
   if (mhd) {
     size_t const w = c->n_cells * ops->real_bytes;
     if (e == cudaSuccess) e = cudaMalloc(&c->d_prim, mhd->prim_fields * w);
@@ -162,10 +155,10 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
     if (e == cudaSuccess) e = cudaMemset(c->d_ctf, 0, 9 * w);
     if (e == cudaSuccess) e = cudaMemset(c->d_E, 0, 6 * w);
   }
-  if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(c->d_half, 0, bytes);
-  if (e == cudaSuccess) e = cudaMemset(c->d_key, 0, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(c->d_key, 0, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     chl_destroy(c);
     return fail(CHL_ERR_CUDA, "chl_create: allocation", e);
@@ -192,11 +185,18 @@ int chl_destroy(chl_ctx *c)
 size_t chl_scratch_bytes(const chl_ctx *c)
 {
   if (!c) return 0;
-  size_t fields = c->mhd ? 8 + 5 + c->mhd->prim_fields + 9 + 6 : c->ops->half_fields + (c->split ? 5 : 0);
-  return c->n_cells * fields * c->ops->real_bytes + sizeof(unsigned long long);
+  size_t fields = c->mhd ? 8 + 5 + c->mhd->prim_fields + 9 + 6 : c->ops->half_fields + 5;
+  return c->n_cells * fields * c->ops->real_bytes + 2 * sizeof(unsigned long long);
 }
 
-static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
+struct chl_halo;
+static int halo_exchange_impl(chl_halo *h, void *U, cudaStream_t s);
+static int halo_fork(chl_halo *h, cudaStream_t main, cudaStream_t *side);
+static int halo_join(chl_halo *h, cudaStream_t main);
+
+// halo != nullptr: the last corrector pass completes the boundary shell first, the ghost-cell exchange then runs on the
+// halo's own stream while the interior of that pass runs on `s`; both are joined on `s` before returning.
+static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, chl_halo *halo = nullptr)
 {
   if (!c || !U) return fail(CHL_ERR_INVALID, "chl_vl_step: null argument");
   chl_config const &g = c->cfg;
@@ -240,20 +240,14 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
   a.dy = g.dy;
   a.dz = g.dz;
   a.dti_key = c->d_key;
+  a.bad_cells = c->d_key + 1;
   a.acc = c->d_acc;
   a.dir_chunk = c->dir_chunk;
   a.simple = 0;
-  auto const sweep = c->split ? c->ops->sweep_split : c->ops->sweep;
+  a.part = 0;
+  a.shell = 0;
+  auto const sweep = c->ops->sweep_split;
   int const n[3] = {g.nx, g.ny, g.nz};
-  auto choose_chunk = [&](int const *lo, int const *hi) {
-    int const ty = c->ops->tile_y;
-    long const bxy = (long)((hi[0] - lo[0] + 31) / 32) * ((hi[1] - lo[1] + ty - 1) / ty);
-    int const oz = hi[2] - lo[2];
-    long chunks = (2368 + bxy - 1) / bxy;  // aim at >= 8 waves of 2 CTAs on 148 SMs
-    if (chunks > oz / 8) chunks = oz / 8;
-    if (chunks < 1) chunks = 1;
-    return (int)((oz + chunks - 1) / chunks);
-  };
   // ---- predictor: every cell but the outermost ring (VL_3D_cuda.cu:408) ----
   for (int d = 0; d < 3; d++) {
     bool const on = d == 0 || (d == 1 && a.has_y) || (d == 2 && a.has_z);
@@ -269,7 +263,6 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
   a.apply_tfloor = 0;
   a.U_floor = 0.0;
   a.do_dti = 0;
-  a.zchunk = a.has_z ? choose_chunk(a.lo, a.hi) : 1;
   bool const prof = c->profiling && c->ev_steps < kMaxProfiledSteps;
   if (prof) {
     while ((int)c->ev.size() < 3 * (c->ev_steps + 1)) {
@@ -298,8 +291,26 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s)
     a.do_dti = 1;
     CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
   }
-  a.zchunk = a.has_z ? choose_chunk(a.lo, a.hi) : 1;
-  CHL_CUDA(sweep(1, g.recon, g.solver, a, s));
+  if (halo && c->ndim == 3) {
+    a.part  = 1;
+    a.shell = g.n_ghost;
+    CHL_CUDA(sweep(1, g.recon, g.solver, a, s));  // x and y passes, then the boundary shell of the z pass
+    cudaStream_t side;
+    int r = halo_fork(halo, s, &side);
+    if (r != CHL_OK) return r;
+    r = halo_exchange_impl(halo, U, side);        // reads shell cells, writes ghost cells
+    if (r != CHL_OK) return r;
+    a.part = 2;
+    CHL_CUDA(sweep(1, g.recon, g.solver, a, s));  // interior of the z pass: touches neither
+    r = halo_join(halo, s);
+    if (r != CHL_OK) return r;
+  } else {
+    CHL_CUDA(sweep(1, g.recon, g.solver, a, s));
+    if (halo) {
+      int const r = halo_exchange_impl(halo, U, s);
+      if (r != CHL_OK) return r;
+    }
+  }
   if (prof) {
     CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 2], s));
     c->ev_steps++;
@@ -315,7 +326,6 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
   if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: MHD requires the Van Leer integrator (error_handling.cpp:89)");
   if (g.recon != CHL_RECON_PCM && g.recon != CHL_RECON_PLMC)
     return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: PCM and PLMC only (the CTU forms of PLMP / PPMP / PPMC are not built)");
-  if (!c->d_acc) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: needs the direction-split sweeps (CHL_SWEEP_IMPL=split)");
   chl::SweepArgs a;
   a.nx = g.nx; a.ny = g.ny; a.nz = g.nz;
   a.has_y = g.ny > 1;
@@ -324,10 +334,12 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
   a.density_floor = g.density_floor;
   a.dx = g.dx; a.dy = g.dy; a.dz = g.dz;
   a.dti_key = c->d_key;
+  a.bad_cells = c->d_key + 1;
   a.acc = c->d_acc;
   a.dir_chunk = c->dir_chunk;
   a.simple = 1;
-  a.zchunk = 1;
+  a.part = 0;
+  a.shell = 0;
   int const n[3] = {g.nx, g.ny, g.nz};
   for (int d = 0; d < 3; d++) {
     bool const on = d == 0 || (d == 1 && a.has_y) || (d == 2 && a.has_z);
@@ -415,6 +427,24 @@ int chl_dti_result(chl_ctx *c, double *h_dti, void *stream)
   CHL_CUDA(cudaMemcpyAsync(c->h_key, c->d_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CHL_CUDA(cudaStreamSynchronize(s));
   *h_dti = host_decode(*c->h_key);
+  return CHL_OK;
+}
+
+int chl_bad_cells(chl_ctx *c, unsigned long long *h_count, void *stream)
+{
+  if (!c || !h_count) return fail(CHL_ERR_INVALID, "chl_bad_cells: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CHL_CUDA(cudaMemcpyAsync(c->h_key + 1, c->d_key + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CHL_CUDA(cudaMemsetAsync(c->d_key + 1, 0, sizeof(unsigned long long), s));
+  CHL_CUDA(cudaStreamSynchronize(s));
+  *h_count = c->h_key[1];
+  return CHL_OK;
+}
+
+int chl_set_tuning(chl_ctx *c, int dir_chunk)
+{
+  if (!c || dir_chunk < 0) return fail(CHL_ERR_INVALID, "chl_set_tuning: bad argument");
+  c->dir_chunk = dir_chunk;
   return CHL_OK;
 }
 
@@ -545,7 +575,264 @@ int chl_pack_snapshot_field(void *d_out, const void *d_field, int nx, int ny, in
   return CHL_OK;
 }
 
+}  // extern "C"
+
+// ---- native ghost-cell exchange between the ranks of one box (halo_p2p.cu) -----------------------------------------
+namespace
+{
+struct HaloLayout {  // this rank's receive block, as its neighbours need to know it
+  unsigned long long buf_off[6][2];  // byte offset of the receive buffer of face f, exchange parity p
+  unsigned long long buf_bytes[6];
+  unsigned long long flag_off;       // 6 arrival words (unsigned long long)
+  unsigned long long block_bytes;
+};
+struct HaloBlob {  // what a rank publishes to its neighbours (chl_halo_export)
+  cudaIpcMemHandle_t mem;
+  HaloLayout lay;
+  int rank, device;
+  unsigned long long magic;
+};
+constexpr unsigned long long kHaloMagic = 0x63686c68616c6f31ull;  // "chlhalo1"
+
+struct Slab {
+  long idxoffset;
+  int isize, jsize, ksize;
+};
+// Load_/Unload_Hydro_DeviceBuffer_{X,Y,Z}{0,1} geometry (mpi_boundaries.cpp:113-298): g layers along the face's axis, the
+// full extent (ghosts included) of the axes before it, the real cells of the axes after it
+Slab halo_slab(int nx, int ny, int nz, int g, int face, bool recv)
+{
+  int const n[3] = {nx, ny, nz};
+  int const ax = face / 2, side = face % 2;
+  int lo[3] = {0, 0, 0}, size[3] = {1, 1, 1};
+  for (int d = 0; d < 3; d++) {
+    if (n[d] == 1) continue;
+    if (d < ax) {
+      lo[d]   = 0;
+      size[d] = n[d];
+    } else if (d > ax) {
+      lo[d]   = g;
+      size[d] = n[d] - 2 * g;
+    } else {
+      size[d] = g;
+      lo[d]   = recv ? (side == 0 ? 0 : n[d] - g) : (side == 0 ? g : n[d] - 2 * g);
+    }
+  }
+  return Slab{lo[0] + (long)nx * (lo[1] + (long)ny * lo[2]), size[0], size[1], size[2]};
+}
+}  // namespace
+
+struct chl_halo {
+  chl_ctx *ctx;
+  int flags[6];
+  int rank;
+  char *d_block;                 // this rank's receive buffers + arrival words + send counters + error word
+  HaloLayout lay;
+  unsigned *d_counter;           // 6 last-block counters of this rank's send launches
+  unsigned *d_err;
+  unsigned *h_err;               // pinned
+  char *peer_base[6];            // neighbour behind face f: its block mapped here
+  HaloLayout peer_lay[6];
+  std::vector<std::pair<int, char *>> opened;  // (peer rank, mapped base): one mapping per distinct peer
+  unsigned long long seq;        // exchanges done
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+};
+
+static int halo_fork(chl_halo *h, cudaStream_t main, cudaStream_t *side)
+{
+  CHL_CUDA(cudaEventRecord(h->ev_fork, main));
+  CHL_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  *side = h->side;
+  return CHL_OK;
+}
+static int halo_join(chl_halo *h, cudaStream_t main)
+{
+  CHL_CUDA(cudaEventRecord(h->ev_join, h->side));
+  CHL_CUDA(cudaStreamWaitEvent(main, h->ev_join, 0));
+  return CHL_OK;
+}
+
+// Grid3D::Set_Boundaries_MPI_BLOCK (mpi_boundaries.cpp:29-111): per axis -- send both slabs, fill the physical faces of
+// the axis, receive both slabs
+static int halo_exchange_impl(chl_halo *h, void *U, cudaStream_t s)
+{
+  chl_ctx *c = h->ctx;
+  chl_config const &g = c->cfg;
+  size_t const rb = c->ops->real_bytes;
+  unsigned long long const seq = ++h->seq;
+  int const par = (int)(seq & 1ull);
+  for (int ax = 0; ax < c->ndim; ax++) {
+    for (int face = 2 * ax; face < 2 * ax + 2; face++) {
+      if (h->flags[face] != CHL_BC_MPI) continue;
+      if (!h->peer_base[face]) return fail(CHL_ERR_INVALID, "chl_halo_exchange: a neighbour is not connected");
+      Slab const sl = halo_slab(g.nx, g.ny, g.nz, g.n_ghost, face, false);
+      int const pf = face ^ 1;  // my low slab fills the neighbour's HIGH ghosts and vice versa
+      HaloLayout const &pl = h->peer_lay[face];
+      size_t const bytes = (size_t)sl.isize * sl.jsize * sl.ksize * g.n_fields * rb;
+      if (bytes != pl.buf_bytes[pf]) return fail(CHL_ERR_INVALID, "chl_halo_exchange: slab size differs from the neighbour's");
+      CHL_CUDA(chl::launch_halo_send(h->peer_base[face] + pl.buf_off[pf][par], U, g.nx, g.ny, g.n_fields, (long)c->n_cells,
+                                     sl.idxoffset, sl.isize, sl.jsize, sl.ksize, h->d_counter + face,
+                                     (unsigned long long *)(h->peer_base[face] + pl.flag_off) + pf, seq, rb, s));
+    }
+    for (int face = 2 * ax; face < 2 * ax + 2; face++) {
+      int const r = chl_set_ghost_cells(c, U, h->flags, face, (void *)s);  // skips exchange and custom faces
+      if (r != CHL_OK) return r;
+    }
+    for (int face = 2 * ax; face < 2 * ax + 2; face++) {
+      if (h->flags[face] != CHL_BC_MPI) continue;
+      Slab const sl = halo_slab(g.nx, g.ny, g.nz, g.n_ghost, face, true);
+      CHL_CUDA(chl::launch_halo_recv(h->d_block + h->lay.buf_off[face][par], U, g.nx, g.ny, g.n_fields, (long)c->n_cells,
+                                     sl.idxoffset, sl.isize, sl.jsize, sl.ksize,
+                                     (const unsigned long long *)(h->d_block + h->lay.flag_off) + face, seq, h->d_err, rb, s));
+    }
+  }
+  return CHL_OK;
+}
+
+extern "C" {
+
+size_t chl_halo_blob_bytes(void) { return sizeof(HaloBlob); }
+
+int chl_halo_create(chl_ctx *c, const int flags[6], int rank, chl_halo **out)
+{
+  if (!c || !flags || !out) return fail(CHL_ERR_INVALID, "chl_halo_create: null argument");
+  *out = nullptr;
+  chl_halo *h = new chl_halo();
+  h->ctx = c;
+  h->rank = rank;
+  h->d_block = nullptr;
+  h->d_counter = h->d_err = h->h_err = nullptr;
+  h->seq = 0;
+  h->side = nullptr;
+  h->ev_fork = h->ev_join = nullptr;
+  chl_config const &g = c->cfg;
+  size_t off = 0;
+  for (int f = 0; f < 6; f++) {
+    h->flags[f] = flags[f];
+    h->peer_base[f] = nullptr;
+    size_t bytes = 0;
+    if (flags[f] == CHL_BC_MPI && f / 2 < c->ndim) {
+      Slab const sl = halo_slab(g.nx, g.ny, g.nz, g.n_ghost, f, true);
+      bytes = (size_t)sl.isize * sl.jsize * sl.ksize * g.n_fields * c->ops->real_bytes;
+    }
+    h->lay.buf_bytes[f] = bytes;
+    for (int p = 0; p < 2; p++) {
+      h->lay.buf_off[f][p] = off;
+      off += (bytes + 255) / 256 * 256;
+    }
+  }
+  h->lay.flag_off = off;
+  off += 256;
+  h->lay.block_bytes = off;
+  cudaError_t e = cudaMalloc((void **)&h->d_block, off);
+  if (e == cudaSuccess) e = cudaMemset(h->d_block + h->lay.flag_off, 0, 256);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_counter, 8 * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(h->d_counter, 0, 8 * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_err, sizeof(unsigned));
+  if (e == cudaSuccess) {
+    h->d_err = h->d_counter + 6;
+    int lo = 0, hi = 0;
+    e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    // highest priority: the exchange's few CTAs go ahead of the interior update's queue of CTAs
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    chl_halo_destroy(h);
+    return fail(CHL_ERR_CUDA, "chl_halo_create", e);
+  }
+  *out = h;
+  return CHL_OK;
+}
+
+int chl_halo_destroy(chl_halo *h)
+{
+  if (!h) return CHL_OK;
+  cudaDeviceSynchronize();
+  for (auto &p : h->opened) cudaIpcCloseMemHandle(p.second);
+  if (h->d_block) cudaFree(h->d_block);
+  if (h->d_counter) cudaFree(h->d_counter);
+  if (h->h_err) cudaFreeHost(h->h_err);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  delete h;
+  return CHL_OK;
+}
+
+int chl_halo_export(chl_halo *h, void *blob)
+{
+  if (!h || !blob) return fail(CHL_ERR_INVALID, "chl_halo_export: null argument");
+  HaloBlob b;
+  memset(&b, 0, sizeof b);
+  CHL_CUDA(cudaIpcGetMemHandle(&b.mem, h->d_block));
+  b.lay = h->lay;
+  b.rank = h->rank;
+  CHL_CUDA(cudaGetDevice(&b.device));
+  b.magic = kHaloMagic;
+  memcpy(blob, &b, sizeof b);
+  return CHL_OK;
+}
+
+int chl_halo_connect(chl_halo *h, int face, const void *peer_blob)
+{
+  if (!h || !peer_blob || face < 0 || face > 5) return fail(CHL_ERR_INVALID, "chl_halo_connect: bad argument");
+  HaloBlob b;
+  memcpy(&b, peer_blob, sizeof b);
+  if (b.magic != kHaloMagic) return fail(CHL_ERR_INVALID, "chl_halo_connect: not a chl_halo_export blob");
+  if (b.rank == h->rank) return fail(CHL_ERR_INVALID, "chl_halo_connect: a rank cannot be its own neighbour (use a periodic face)");
+  char *base = nullptr;
+  for (auto &p : h->opened)
+    if (p.first == b.rank) base = p.second;
+  if (!base) {
+    CHL_CUDA(cudaIpcOpenMemHandle((void **)&base, b.mem, cudaIpcMemLazyEnablePeerAccess));
+    h->opened.push_back(std::make_pair(b.rank, base));
+  }
+  h->peer_base[face] = base;
+  h->peer_lay[face]  = b.lay;
+  return CHL_OK;
+}
+
+int chl_halo_exchange(chl_halo *h, void *U, void *stream)
+{
+  if (!h || !U) return fail(CHL_ERR_INVALID, "chl_halo_exchange: null argument");
+  return halo_exchange_impl(h, U, (cudaStream_t)stream);
+}
+
+int chl_halo_error(chl_halo *h, void *stream)
+{
+  if (!h) return fail(CHL_ERR_INVALID, "chl_halo_error: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CHL_CUDA(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  CHL_CUDA(cudaStreamSynchronize(s));
+  if (*h->h_err) return fail(CHL_ERR_CUDA, "chl_halo: a receive waited 20 s for its neighbour's slab and gave up");
+  return CHL_OK;
+}
+
+int chl_vl_step_exchange(chl_ctx *c, chl_halo *h, void *U, double dt, void *stream)
+{
+  if (!h || h->ctx != c) return fail(CHL_ERR_INVALID, "chl_vl_step_exchange: the halo belongs to another context");
+  if (c->mhd) {  // the MHD step is one block of launches: exchange after it, same stream
+    int const r = step_impl(c, U, dt, 1, (cudaStream_t)stream);
+    return r != CHL_OK ? r : halo_exchange_impl(h, U, (cudaStream_t)stream);
+  }
+  return step_impl(c, U, dt, 1, (cudaStream_t)stream, h);
+}
+
+int chl_dti_copy_key(chl_ctx *c, void *d_dst, void *stream)
+{
+  if (!c || !d_dst) return fail(CHL_ERR_INVALID, "chl_dti_copy_key: null argument");
+  CHL_CUDA(cudaMemcpyAsync(d_dst, c->d_key, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return CHL_OK;
+}
+
+}  // extern "C"
+
 // ---- host-only mirrors of the reference's decomposition logic (src/mpi/mpi_routines.cpp) ----
+extern "C" {
 static int greatest_prime_factor(int n)
 {
   int best = 1;
@@ -622,6 +909,15 @@ int chl_debug_exact_div(const double *d_a, const double *d_b, double *d_q_shared
   if (!d_a || !d_b || !d_q_shared || !d_q_plain || n < 0) return fail(CHL_ERR_INVALID, "chl_debug_exact_div: bad argument");
   cudaError_t const e = chl::launch_exact_div_test(d_a, d_b, d_q_shared, d_q_plain, n, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(CHL_ERR_CUDA, "chl_debug_exact_div", e);
+  return CHL_OK;
+}
+
+int chl_debug_exact_div_flagged(const double *d_a, const double *d_b, double *d_q, int *d_flag, int zero_ok, long n,
+                                void *stream)
+{
+  if (!d_a || !d_b || !d_q || !d_flag || n < 0) return fail(CHL_ERR_INVALID, "chl_debug_exact_div_flagged: bad argument");
+  cudaError_t const e = chl::launch_exact_div_flag_test(d_a, d_b, d_q, d_flag, zero_ok, n, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(CHL_ERR_CUDA, "chl_debug_exact_div_flagged", e);
   return CHL_OK;
 }
 

@@ -1,0 +1,33 @@
+// chl_aux.h -- launchers of the element-type-agnostic kernels (ghost cells, pack / unpack, snapshot transposition, halo
+// exchange, arithmetic diagnostics) for the C-ABI TU.  Kept apart from chl_internal.h so that the large per-mode sweep TUs do
+// not depend on it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace chl
+{
+// element-type-templated copy kernels (ghost cells, pack/unpack), aux_kernels.cu
+cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields, long n_cells, int n_ghost,
+                                   const int flags[6], int isize, int jsize, int ksize, int imin, int jmin, int kmin,
+                                   int dir, int diode, size_t real_bytes, cudaStream_t s);
+cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset,
+                        int isize, int jsize, int ksize, int unpack, size_t real_bytes, cudaStream_t s);
+cudaError_t launch_snapshot_pack(void *out, const void *field, int nx, int ny, int nz, int n_ghost, int nx_out,
+                                 int ny_out, int nz_out, int mhd_direction, size_t in_bytes, size_t out_bytes,
+                                 cudaStream_t s);
+// halo_p2p.cu: slab -> the neighbour's peer-mapped receive buffer (+ arrival word), and wait + buffer -> ghost slab
+cudaError_t launch_halo_send(void *remote, const void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset,
+                             int isize, int jsize, int ksize, unsigned *counter, unsigned long long *remote_flag,
+                             unsigned long long seq, size_t real_bytes, cudaStream_t s);
+cudaError_t launch_halo_recv(const void *buf, void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset, int isize,
+                             int jsize, int ksize, const unsigned long long *flag, unsigned long long seq, unsigned *err,
+                             size_t real_bytes, cudaStream_t s);
+// exact_div_test.cu: shared-reciprocal division vs the compiler's a / b
+cudaError_t launch_exact_div_test(const double *a, const double *b, double *q_shared, double *q_plain, long n,
+                                  cudaStream_t s);
+// the branch-free form: the raw quotient and sqrt plus the sticky flag each raised (flag bit 0: quotient, bit 1: sqrt of a)
+cudaError_t launch_exact_div_flag_test(const double *a, const double *b, double *q, int *flag, int zero_ok, long n,
+                                       cudaStream_t s);
+cudaError_t launch_exact_sqrt_test(const double *x, double *r_own, double *r_plain, long n, cudaStream_t s);
+}  // namespace chl

@@ -1,10 +1,11 @@
 // vl_dirsweep.cuh -- direction-split Van Leer sweeps: one launch per (stage, direction).
 //
-// Why: the fused single-launch sweep (vl_sweep.cuh) moves the algorithmic minimum of HBM bytes but ncu shows it
-// is nowhere near HBM-bound -- it is bound by fp64 issue latency at 21 resident warps/SM (fp64 pipe 37 % busy,
-// top stalls: fixed-latency wait, barrier, local-memory spills, instruction-cache misses; profiles/r1_*).  With
-// >90 % of HBM bandwidth idle, the cheaper trade on B200 is the opposite one: spend a few more bytes per cell and
-// make every launch a small, barrier-free, spill-free loop that keeps the fp64 pipe fed.
+// Why: a single launch per stage that exchanges every interface state through shared memory (round 1's fused sweep,
+// removed) moves the algorithmic minimum of HBM bytes but was nowhere near HBM-bound -- fp64 issue latency at 21
+// resident warps/SM (fp64 pipe 37 % busy; top stalls: fixed-latency wait, barrier, local-memory spills, instruction
+// cache misses; profiles/r1_*).  With most of the HBM bandwidth idle, the cheaper trade on B200 for the CORRECTOR is
+// the opposite one: spend a few more bytes per cell and make every launch a small, barrier-free loop that keeps the
+// fp64 pipe fed.  (The predictor -- PCM, one-cell stencil -- is a single fused launch again: vl_predictor.cuh.)
 //
 // Each launch sweeps ONE direction.  A thread (y/z sweeps) or a warp (x sweep) MARCHES along that direction and
 // carries the low-side interface state and the lower-face flux from cell to cell, so every cell is reconstructed
@@ -25,7 +26,7 @@
 // (product mode): predictor 40+40 | 40+40+40 | 40+40+40 B, corrector 40+40 | 40+40+40 | 40+40+40+40 B = 680 B by
 // design (734 B measured, profiles/roofline_traffic.json): 3.4x the fused kernel's 200 B, 0.4x the reference's 1.84 kB.
 #pragma once
-#include "vl_sweep.cuh"
+#include "sweep_common.cuh"
 
 namespace CHL_NS
 {
@@ -58,33 +59,10 @@ struct DirParams {
   int plmp;  // predictor, strict mode: store the half-step pressures with PLMP's / PPMP's summation order (store_half)
   Real dx, dy, dz, idx, idy, idz;
   unsigned long long *dti_key;
+  unsigned long long *bad_cells;  // last corrector pass: running count of cells whose density came out <= 0
+  int xw_log2;                    // y / z sweeps: log2 of the CTA's extent along x (7 = 128 x 1 threads, 2 = 4 x 32)
 };
 
-// ---- shared-memory row ring for the y / z sweeps of the corrector (option, off by default) ------------------------
-// A thread marching along y (or z) needs, for cell c, the rows c-r .. c+r of five fields (r = 2 PPMC, 1 PLMC); at the
-// next cell four of those five rows are needed again.  With CHL_DIR_RING=1 every thread keeps its own column of a
-// (2r+1)-row ring in shared memory -- [slot][component][thread], conflict-free, no barrier -- and the one new row per
-// cell is fetched by cp.async while the Riemann solve of the current cell runs; the 25 stencil loads become LDS with
-// immediate offsets.  Measured at 512^3 (gpurun_out/ring1.txt, stage1.txt): 35.9 vs 36.3 ms for the three corrector
-// passes alone, but 37.5 vs 36.2 ms once the update operands are staged too -- 25.6 KB per CTA forces the largest
-// shared-memory carve-out, L1 shrinks to ~28 KB and the register spills of these kernels start missing it.  The
-// stencil loads were never the exposed latency (they issue together); the update operands were.  Kept for parts
-// with a larger L1.
-#ifndef CHL_DIR_RING
-#define CHL_DIR_RING 0
-#endif
-template <int RECON>
-struct RingGeom {
-  static constexpr int radius = RECON == kPPMC ? 2 : 1;
-  static constexpr int rows   = 2 * radius + 1;
-  static constexpr int slot   = 5 * kDirThreads;  // reals per row slot
-};
-template <int RADIUS>
-struct RingStencil {
-  const Real *mine;         // ring + threadIdx.x
-  int off[2 * RADIUS + 1];  // element offset of the slot holding row c + i - RADIUS
-  __device__ __forceinline__ Real operator()(int comp, int i) const { return mine[off[i + RADIUS] + comp * kDirThreads]; }
-};
 __device__ __forceinline__ void cp_async_real(Real *smem_dst, const Real *gsrc)
 {
   unsigned const sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -93,7 +71,6 @@ __device__ __forceinline__ void cp_async_real(Real *smem_dst, const Real *gsrc)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // ---- staging of the update's read-modify-write operands ----------------------------------------------------
 // Completing a cell needs the running sum (and, in the last corrector pass, the old U) of that cell: five or ten
@@ -170,8 +147,8 @@ __device__ __forceinline__ void from_low_side5(Real const (&v)[5], Real (&carry)
 }
 
 template <int STAGE, int DIR, bool FIRST, bool LAST, bool STAGED>
-__device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t id, Real const (&Flo)[5],
-                                            Real const (&Fhi)[5], double &dti, const Real *staged)
+__device__ __forceinline__ void finish_cell(DirParams const &P, KH const &k, size_t N, size_t id, Real const (&Flo)[5],
+                                            Real const (&Fhi)[5], double &dti, int &n_bad, const Real *staged)
 {
   // staged (STAGED only): this thread's shared-memory column, component k at staged[k * kDirThreads]: the five
   // running-sum / U operands in sweep-frame order, then (last corrector pass) the five old-U values in field order
@@ -199,7 +176,7 @@ __device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t
 #pragma unroll
       for (int f = 1; f < 5; f++) u[f] *= (P.density_floor / d0);
     }
-    store_half(P.out, N, id, u, P.gamma, P.plmp);
+    store_half(P.out, N, id, half_state_checked(u, k, P.plmp));
     return;
   }
 #pragma unroll
@@ -211,25 +188,15 @@ __device__ __forceinline__ void finish_cell(DirParams const &P, size_t N, size_t
 #pragma unroll
       for (int f = 1; f < 5; f++) u[f] *= (P.density_floor / d0);
     }
-    if (P.apply_tfloor) {  // Temperature_Floor_Kernel, hydro_cuda.cu:1117-1153
-      Real const d_inv = RC(1.0) / u[0];
-      Real const vx = u[1] * d_inv, vy = u[2] * d_inv, vz = u[3] * d_inv;
-      Real const Ekin = RC(0.5) * u[0] * (vx * vx + vy * vy + vz * vz);
-      if ((u[4] - Ekin) / u[0] < P.U_floor) u[4] = Ekin + u[0] * P.U_floor;
-    }
   }
+  // a cell whose density came out non-positive is counted (chl_bad_cells): the reference averages its neighbours inside
+  // the in-place update, a race with no bits to match (hydro_cuda.cu:292-297), and leaves the decision to the host
+  if (!(u[0] > RC(0.))) n_bad++;
+  Real const v = cell_epilogue_checked(u, k, floors && P.apply_tfloor, P.U_floor, P.do_dti, P.ndim, P.idx, P.idy, P.idz,
+                                       P.dx, P.dy, P.dz);
 #pragma unroll
   for (int f = 0; f < 5; f++) P.out[f * N + id] = u[f];
-  if (P.do_dti) {
-    Real v;
-    if (P.ndim == 3)
-      v = inverse_crossing_time<3>(u[0], u[1], u[2], u[3], u[4], P.idx, P.idy, P.idz, P.dx, P.dy, P.dz, P.gamma);
-    else if (P.ndim == 2)
-      v = inverse_crossing_time<2>(u[0], u[1], u[2], u[3], u[4], P.idx, P.idy, P.idz, P.dx, P.dy, P.dz, P.gamma);
-    else
-      v = inverse_crossing_time<1>(u[0], u[1], u[2], u[3], u[4], P.idx, P.idy, P.idz, P.dx, P.dy, P.dz, P.gamma);
-    dti = fmax(dti, (double)v);
-  }
+  if (P.do_dti) dti = fmax(dti, (double)v);
 }
 
 template <int RECON, int SOLVER, int STAGE, int DIR, bool FIRST, bool LAST>
@@ -238,10 +205,9 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
   int const nx = P.nx, ny = P.ny;
   size_t const N = (size_t)nx * ny * P.nz;
   int const lane = threadIdx.x & 31;
-  Real const gamma = P.gamma;
-  KC kc            = make_kc(gamma);
-  kc.dtodx         = P.dto;  // read by PLMC's characteristic tracing only (SIMPLE integrator)
-  DirMap const m   = dir_map(DIR, N, nx, ny, (STAGE == 1 && CHL_STRICT) ? 4 + DIR : 4);
+  KH kc    = make_kct<KH>(P.gamma);
+  kc.dtodx = P.dto;  // read by PLMC's characteristic tracing only (SIMPLE integrator)
+  DirMap const m = dir_map(DIR, N, nx, ny, (STAGE == 1 && CHL_STRICT) ? 4 + DIR : 4);
 
   // the cells this thread visits: c = c_first .. c_last along DIR at fixed `base`; it completes cells
   // [c_first + 1, c_last - 1]
@@ -255,22 +221,24 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
     c_first = P.lo[0] - 1;
     c_last  = P.hi[0];
   } else {
-    int const x = P.lo[0] + blockIdx.x * kDirThreads + threadIdx.x;
-    int const o = DIR == 1 ? P.lo[2] + blockIdx.y : P.lo[1] + blockIdx.y;  // the other fixed coordinate
-    live        = x < P.hi[0];
-    base        = DIR == 1 ? (size_t)x + (size_t)nx * ny * o : (size_t)x + (size_t)nx * o;
-    int const b = P.lo[DIR] + blockIdx.z * P.chunk;
-    c_first     = b - 1;
-    c_last      = min(b + P.chunk, P.hi[DIR]);
+    // a CTA covers 2^xw_log2 cells along x and 128 / 2^xw_log2 along the other fixed axis: 128 x 1 for ordinary boxes,
+    // 4 x 32 for the four-cell-wide x shells of the boundary-first last pass (same sectors per warp either way)
+    int const tx = threadIdx.x & ((1 << P.xw_log2) - 1), to = threadIdx.x >> P.xw_log2;
+    int const x  = P.lo[0] + (blockIdx.x << P.xw_log2) + tx;
+    int const od = DIR == 1 ? 2 : 1;  // the other fixed axis
+    int const o  = P.lo[od] + blockIdx.y * (kDirThreads >> P.xw_log2) + to;
+    live         = x < P.hi[0] && o < P.hi[od];
+    base         = DIR == 1 ? (size_t)x + (size_t)nx * ny * o : (size_t)x + (size_t)nx * o;
+    int const b  = P.lo[DIR] + blockIdx.z * P.chunk;
+    c_first      = b - 1;
+    c_last       = min(b + P.chunk, P.hi[DIR]);
   }
   double dti = -1.7976931348623157e308;
+  int n_bad  = 0;
 
-  constexpr bool kRing  = CHL_DIR_RING && STAGE == 1 && DIR != 0 && (RECON == kPLMC || RECON == kPPMC);
-  typedef RingGeom<RECON> RG;
   typedef StageGeom<STAGE, FIRST, LAST> SG;
   constexpr bool kStage = CHL_DIR_STAGE && SG::n > 0;
   constexpr int kParkN  = CHL_DIR_PARK ? (DIR == 0 ? 10 * kRowsPerCta : 10 * kDirThreads) : 1;
-  __shared__ Real ring[kRing ? RG::rows * RG::slot : 1];
   __shared__ Real stage[kStage ? SG::n * kDirThreads : 1];
   __shared__ Real parked[kParkN];
 
@@ -280,30 +248,15 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
     for (int c = 0; c < 5; c++) Lc[c] = Fc[c] = RC(0.0);
     int const step = DIR == 0 ? 32 : 1;
     constexpr int field_of_comp[5] = {0, 1 + DIR, 1 + (DIR + 1) % 3, 1 + (DIR + 2) % 3, 4};
-    Real *const park    = parked + (DIR == 0 ? (threadIdx.x >> 5) : threadIdx.x);
-    int const pstride   = DIR == 0 ? kRowsPerCta : kDirThreads;
-    Real *const staged  = stage + threadIdx.x;
-    // ring: rows c_first-r .. c_first+r into slots 0 .. 2r; `head` = slot of the oldest row
-    Real *const mine      = ring + threadIdx.x;
-    size_t const goff[5]  = {0, m.o1, m.o2, m.o3, m.op};
-    const Real *const col = P.in + base;
-    int head              = 0;
-    if (kRing) {
-#pragma unroll
-      for (int j = 0; j < RG::rows; j++) {
-        const Real *g = col + (size_t)(c_first - RG::radius + j) * (size_t)m.stride;
-#pragma unroll
-        for (int k = 0; k < 5; k++) cp_async_real(mine + j * RG::slot + k * kDirThreads, g + goff[k]);
-      }
-      cp_async_commit();
-    }
+    Real *const park   = parked + (DIR == 0 ? (threadIdx.x >> 5) : threadIdx.x);
+    int const pstride  = DIR == 0 ? kRowsPerCta : kDirThreads;
+    Real *const staged = stage + threadIdx.x;
     for (int cb = c_first; cb <= c_last; cb += step) {
       int const c      = DIR == 0 ? cb + lane : cb;
       bool const valid = c <= c_last;
       bool const face  = valid && c > c_first;  // face c-1/2 lies between two reconstructed cells
       bool const fin   = face && c > c_first + 1;  // cell c-1 is completed by this iteration
       size_t const id  = base + (size_t)c * (size_t)m.stride;
-      if (kRing) cp_async_wait_all();  // the rows cell c needs (issued during the previous iteration) have landed
       if (kStage) {
         if (fin) {
           size_t const idp = id - (size_t)m.stride;
@@ -318,25 +271,8 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
         cp_async_commit();
       }
       S5 L, R;
-      if (kRing) {
-        RingStencil<RG::radius> st;
-        st.mine = mine;
-#pragma unroll
-        for (int j = 0; j < RG::rows; j++) {
-          int sl = head + j;
-          sl     = sl >= RG::rows ? sl - RG::rows : sl;
-          st.off[j] = sl * RG::slot;
-        }
-        recon_from<RECON>(st, kc, L, R);
-        if (c < c_last) {  // row c-r is dead: its slot receives row c+r+1 while the Riemann solve below runs
-          const Real *g = col + (size_t)(c + RG::radius + 1) * (size_t)m.stride;
-#pragma unroll
-          for (int k = 0; k < 5; k++) cp_async_real(mine + head * RG::slot + k * kDirThreads, g + goff[k]);
-        }
-        cp_async_commit();
-        head = head + 1 == RG::rows ? 0 : head + 1;
-      } else if (valid) {
-        recon_cell<RECON, STAGE>(P.in, id, m, kc, L, R);
+      if (valid) {
+        recon_cell_checked<RECON, STAGE>(P.in, id, m, kc, L, R);
       } else {
 #pragma unroll
         for (int k = 0; k < 5; k++) L.v[k] = R.v[k] = RC(1.0);
@@ -345,7 +281,7 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
       from_low_side5<DIR>(L.v, Lc, Lp.v, park, pstride, lane);
       Real F[5];
       if (face) {
-        Cons const f = riemann_flux<SOLVER>(to_face(Lp, kc), to_face(R, kc), gamma);
+        Cons const f = riemann_checked<SOLVER>(Lp, R, kc);
         F[0] = f.d; F[1] = f.mx; F[2] = f.my; F[3] = f.mz; F[4] = f.E;
       } else {
 #pragma unroll
@@ -353,28 +289,36 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
       }
       Real Fp[5];
       from_low_side5<DIR>(F, Fc, Fp, park + 5 * pstride, pstride, lane);
-      if (kStage) {
-        if (kRing) cp_async_wait_but_newest();  // the staged operands; the ring row may still be in flight
-        else cp_async_wait_all();
-      }
-      if (fin) finish_cell<STAGE, DIR, FIRST, LAST, kStage>(P, N, id - (size_t)m.stride, Fp, F, dti, staged);
+      if (kStage) cp_async_wait_all();
+      if (fin) finish_cell<STAGE, DIR, FIRST, LAST, kStage>(P, kc, N, id - (size_t)m.stride, Fp, F, dti, n_bad, staged);
     }
   }
 
-  if (STAGE == 1 && LAST && P.do_dti) {  // warp shuffle -> one value per warp -> one atomic per CTA
+  if (STAGE == 1 && LAST) {  // warp shuffle -> one value per warp -> one atomic per CTA
     __shared__ double sred[kDirThreads / 32];
+    __shared__ int sbad[kDirThreads / 32];
     double mx = dti;
+    int nb    = n_bad;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    if (lane == 0) sred[threadIdx.x >> 5] = mx;
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+      nb += __shfl_down_sync(0xffffffffu, nb, o);
+    }
+    if (lane == 0) {
+      sred[threadIdx.x >> 5] = mx;
+      sbad[threadIdx.x >> 5] = nb;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int w = 1; w < kDirThreads / 32; w++) mx = fmax(mx, sred[w]);
-      atomicMax(P.dti_key, dti_encode(mx));
+      for (int w = 1; w < kDirThreads / 32; w++) {
+        mx = fmax(mx, sred[w]);
+        nb += sbad[w];
+      }
+      if (P.do_dti) atomicMax(P.dti_key, dti_encode(mx));
+      if (nb) atomicAdd(P.bad_cells, (unsigned long long)nb);
     }
   }
 }
-
 
 }  // namespace CHL_NS

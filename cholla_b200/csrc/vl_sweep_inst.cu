@@ -1,4 +1,4 @@
-// vl_sweep_inst.cu -- instantiates the fused sweep kernels for ONE arithmetic mode.  The build compiles this
+// vl_sweep_inst.cu -- instantiates the hydro sweep kernels for ONE arithmetic mode.  The build compiles this
 // file three times:   -DCHL_STRICT=1 -DCHL_REAL=double -fmad=false   (mode f64_strict)
 //                     -DCHL_STRICT=0 -DCHL_REAL=double               (mode f64_fast)
 //                     -DCHL_STRICT=0 -DCHL_REAL=float                (mode f32_fast)
@@ -21,53 +21,6 @@ using chl::ModeOps;
 using chl::SweepArgs;
 namespace
 {
-template <int RECON, int SOLVER, int STAGE>
-cudaError_t launch(SweepParams const &p, cudaStream_t s)
-{
-  int const ox = p.hi[0] - p.lo[0], oy = p.hi[1] - p.lo[1], oz = p.hi[2] - p.lo[2];
-  if (ox <= 0 || oy <= 0 || oz <= 0) return cudaSuccess;
-  dim3 grid((ox + TX - 1) / TX, (oy + TY - 1) / TY, p.has_z ? (oz + p.zchunk - 1) / p.zchunk : 1);
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(vl_sweep_kernel<RECON, SOLVER, STAGE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  vl_sweep_kernel<RECON, SOLVER, STAGE><<<grid, kThreads, kSmemBytes, s>>>(p);
-  return cudaGetLastError();
-}
-
-cudaError_t sweep(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s)
-{
-  SweepParams p;
-  p.in  = (const Real *)a.in;
-  p.out = (Real *)a.out;
-  p.nx = a.nx; p.ny = a.ny; p.nz = a.nz;
-  for (int d = 0; d < 3; d++) { p.lo[d] = a.lo[d]; p.hi[d] = a.hi[d]; }
-  p.has_y = a.has_y; p.has_z = a.has_z; p.zchunk = a.zchunk;
-  p.dto[0] = (Real)a.dtodx; p.dto[1] = (Real)a.dtody; p.dto[2] = (Real)a.dtodz;
-  p.gamma = (Real)a.gamma; p.density_floor = (Real)a.density_floor;
-  p.apply_tfloor = a.apply_tfloor; p.U_floor = (Real)a.U_floor; p.do_dti = a.do_dti;
-  p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
-  p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
-  p.dti_key = a.dti_key;
-  if (solver == kHLL || solver == kEXACT || recon == kPLMP || recon == kPPMP) return cudaErrorNotSupported;  // fused family: PCM/PLMC/PPMC x HLLC/Roe only
-  if (stage == 0) {
-    if (solver == kROE) return launch<kPCM, kROE, 0>(p, s);
-    return launch<kPCM, kHLLC, 0>(p, s);
-  }
-  switch (recon * 2 + (solver == kROE ? 1 : 0)) {
-    case kPCM * 2 + 0: return launch<kPCM, kHLLC, 1>(p, s);
-    case kPCM * 2 + 1: return launch<kPCM, kROE, 1>(p, s);
-    case kPLMC * 2 + 0: return launch<kPLMC, kHLLC, 1>(p, s);
-    case kPLMC * 2 + 1: return launch<kPLMC, kROE, 1>(p, s);
-    case kPPMC * 2 + 0: return launch<kPPMC, kHLLC, 1>(p, s);
-    case kPPMC * 2 + 1: return launch<kPPMC, kROE, 1>(p, s);
-  }
-  return cudaErrorInvalidValue;
-}
-
 // ---- direction-split sweeps (vl_dirsweep.cuh) ----
 template <int RECON, int SOLVER, int STAGE, int DIR, bool FIRST, bool LAST>
 cudaError_t launch_dir(DirParams const &p, cudaStream_t s)
@@ -77,19 +30,9 @@ cudaError_t launch_dir(DirParams const &p, cudaStream_t s)
   dim3 grid;
   if (DIR == 0) grid = dim3((oy + kRowsPerCta - 1) / kRowsPerCta, oz, 1);
   else {
-    int const om = DIR == 1 ? oy : oz;
-    grid = dim3((ox + kDirThreads - 1) / kDirThreads, DIR == 1 ? oz : oy, (om + p.chunk - 1) / p.chunk);
-  }
-  if (CHL_DIR_RING && STAGE == 1 && DIR != 0 && (RECON == kPLMC || RECON == kPPMC)) {
-    // the row ring needs (2r+1) x 5 x 128 reals of shared memory per CTA: ask for the largest carve-out so that the
-    // register-limited number of CTAs stays resident
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(vl_dir_kernel<RECON, SOLVER, STAGE, DIR, FIRST, LAST>,
-                                           cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (e != cudaSuccess) return e;
-      configured = true;
-    }
+    int const om = DIR == 1 ? oy : oz, oo = DIR == 1 ? oz : oy;
+    int const xw = 1 << p.xw_log2, ow = kDirThreads >> p.xw_log2;
+    grid = dim3((ox + xw - 1) / xw, (oo + ow - 1) / ow, (om + p.chunk - 1) / p.chunk);
   }
   vl_dir_kernel<RECON, SOLVER, STAGE, DIR, FIRST, LAST><<<grid, kDirThreads, 0, s>>>(p);
   return cudaGetLastError();
@@ -108,19 +51,46 @@ cudaError_t run_dirs(DirParams p, SweepArgs const &a, cudaStream_t s)
     return c < 8 ? (o < 8 ? o : 8) : c;
   };
   cudaError_t e;
-  if (p.ndim == 1) {
+  // a.part (3-D only; 1-D / 2-D grids run whole in part 1): 0 = the whole stage; 1 = every pass except the interior box
+  // of the last one -- the last pass then completes the boundary shell (the `shell` outermost layers of the output
+  // region, the cells a neighbouring rank's ghost layers mirror) as six thin boxes; 2 = the interior box of the last
+  // pass.  The caller starts the halo exchange between part 1 and part 2 (chl_api.cu, overlapped step).
+  bool const split = a.part != 0 && p.ndim == 3 && a.shell > 0 && p.hi[0] - p.lo[0] > 2 * a.shell &&
+                     p.hi[1] - p.lo[1] > 2 * a.shell && p.hi[2] - p.lo[2] > 2 * a.shell;
+  if (a.part == 2 && !split) return cudaSuccess;
+  if (a.part != 2) {
+    if (p.ndim == 1) {
+      p.dto = dto[0];
+      return launch_dir<RECON, SOLVER, STAGE, 0, true, true>(p, s);
+    }
     p.dto = dto[0];
-    return launch_dir<RECON, SOLVER, STAGE, 0, true, true>(p, s);
+    if ((e = launch_dir<RECON, SOLVER, STAGE, 0, true, false>(p, s)) != cudaSuccess) return e;
+    p.dto   = dto[1];
+    p.chunk = chunk_for(1);
+    if (p.ndim == 2) return launch_dir<RECON, SOLVER, STAGE, 1, false, true>(p, s);
+    if ((e = launch_dir<RECON, SOLVER, STAGE, 1, false, false>(p, s)) != cudaSuccess) return e;
   }
-  p.dto = dto[0];
-  if ((e = launch_dir<RECON, SOLVER, STAGE, 0, true, false>(p, s)) != cudaSuccess) return e;
-  p.dto   = dto[1];
-  p.chunk = chunk_for(1);
-  if (p.ndim == 2) return launch_dir<RECON, SOLVER, STAGE, 1, false, true>(p, s);
-  if ((e = launch_dir<RECON, SOLVER, STAGE, 1, false, false>(p, s)) != cudaSuccess) return e;
-  p.dto   = dto[2];
-  p.chunk = chunk_for(2);
-  return launch_dir<RECON, SOLVER, STAGE, 2, false, true>(p, s);
+  p.dto = dto[2];
+  if (!split) {
+    p.chunk = chunk_for(2);
+    return launch_dir<RECON, SOLVER, STAGE, 2, false, true>(p, s);
+  }
+  int const lo[3] = {p.lo[0], p.lo[1], p.lo[2]}, hi[3] = {p.hi[0], p.hi[1], p.hi[2]}, sh = a.shell;
+  auto box = [&](int x0, int x1, int y0, int y1, int z0, int z1, int xw_log2) {
+    p.lo[0] = x0; p.hi[0] = x1; p.lo[1] = y0; p.hi[1] = y1; p.lo[2] = z0; p.hi[2] = z1;
+    p.xw_log2 = xw_log2;
+    p.chunk   = chunk_for(2);
+    return launch_dir<RECON, SOLVER, STAGE, 2, false, true>(p, s);
+  };
+  if (a.part == 2) return box(lo[0] + sh, hi[0] - sh, lo[1] + sh, hi[1] - sh, lo[2] + sh, hi[2] - sh, 7);
+  int xs = 0;
+  while ((1 << xs) < sh) xs++;  // the x shells are `sh` cells wide: 2^xs x (128 >> xs) threads per CTA
+  if ((e = box(lo[0], hi[0], lo[1], hi[1], lo[2], lo[2] + sh, 7)) != cudaSuccess) return e;                  // -z
+  if ((e = box(lo[0], hi[0], lo[1], hi[1], hi[2] - sh, hi[2], 7)) != cudaSuccess) return e;                  // +z
+  if ((e = box(lo[0], hi[0], lo[1], lo[1] + sh, lo[2] + sh, hi[2] - sh, 7)) != cudaSuccess) return e;        // -y
+  if ((e = box(lo[0], hi[0], hi[1] - sh, hi[1], lo[2] + sh, hi[2] - sh, 7)) != cudaSuccess) return e;        // +y
+  if ((e = box(lo[0], lo[0] + sh, lo[1] + sh, hi[1] - sh, lo[2] + sh, hi[2] - sh, xs)) != cudaSuccess) return e;  // -x
+  return box(hi[0] - sh, hi[0], lo[1] + sh, hi[1] - sh, lo[2] + sh, hi[2] - sh, xs);                         // +x
 }
 
 cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s)
@@ -139,8 +109,15 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   p.apply_tfloor = a.apply_tfloor; p.U_floor = (Real)a.U_floor; p.do_dti = a.do_dti;
   p.dx = (Real)a.dx; p.dy = (Real)a.dy; p.dz = (Real)a.dz;
   p.idx = (Real)(1.0 / a.dx); p.idy = (Real)(1.0 / a.dy); p.idz = (Real)(1.0 / a.dz);
-  p.dti_key = a.dti_key;
-  p.plmp    = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
+  p.dti_key   = a.dti_key;
+  p.bad_cells = a.bad_cells;
+  p.xw_log2   = 7;
+  p.plmp      = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
+#ifdef CHL_DEV_SUBSET  // development builds (make VARIANT=... EXTRA=-DCHL_DEV_SUBSET): the headline combination only
+  if (solver != kHLLC || recon != kPPMC) return cudaErrorNotSupported;
+  if (stage == 0) return run_dirs<kPCM, kHLLC, 0>(p, a, s);
+  return run_dirs<kPPMC, kHLLC, 1>(p, a, s);
+#else
   if (stage == 0) {
     if (solver == kROE) return run_dirs<kPCM, kROE, 0>(p, a, s);
     if (solver == kHLL) return run_dirs<kPCM, kHLL, 0>(p, a, s);
@@ -186,6 +163,7 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
     case kPPMC * 2 + 1: return run_dirs<kPPMC, kROE, 1>(p, a, s);
   }
   return cudaErrorInvalidValue;
+#endif
 }
 
 // Calc_dt_{1,2,3}D (hydro_cuda.cu:437-560): grid-stride max over real cells, warp shuffle, one atomic per CTA
@@ -199,6 +177,7 @@ __global__ void __launch_bounds__(256) calc_dti_kernel(const Real *__restrict__ 
   int const rx = nx - 2 * g, ry = NDIM > 1 ? ny - 2 * g : 1, rz = NDIM > 2 ? nz - 2 * g : 1;
   size_t const nreal = (size_t)rx * ry * rz;
   Real const idx = RC(1.0) / dx, idy = RC(1.0) / dy, idz = RC(1.0) / dz;
+  KC const kc = make_kc(gamma);
   double m = -DBL_MAX;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < nreal; t += (size_t)gridDim.x * blockDim.x) {
     int const x = (int)(t % rx) + g;
@@ -208,7 +187,7 @@ __global__ void __launch_bounds__(256) calc_dti_kernel(const Real *__restrict__ 
     size_t const id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
     m = fmax(m, (double)inverse_crossing_time<NDIM>(__ldg(U + id), __ldg(U + N + id), __ldg(U + 2 * N + id),
                                                     __ldg(U + 3 * N + id), __ldg(U + 4 * N + id), idx, idy, idz, dx,
-                                                    dy, dz, gamma));
+                                                    dy, dz, kc));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
@@ -273,9 +252,10 @@ cudaError_t tfloor(void *U, int nx, int ny, int nz, int g, double U_floor, cudaS
 __global__ void __launch_bounds__(256) prim_from_cons_kernel(const Real *__restrict__ U, Real *__restrict__ W, size_t N,
                                                              Real gamma, int plmp)
 {
+  KH const kc = make_kct<KH>(gamma);
   for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < N; id += (size_t)gridDim.x * blockDim.x) {
     Real const u[5] = {__ldg(U + id), __ldg(U + N + id), __ldg(U + 2 * N + id), __ldg(U + 3 * N + id), __ldg(U + 4 * N + id)};
-    store_half(W, N, id, u, gamma, plmp);
+    store_half(W, N, id, half_state_checked(u, kc, plmp));
   }
 }
 
@@ -288,7 +268,7 @@ cudaError_t prim_from_cons(const void *U, void *W, size_t n_cells, double gamma,
   return cudaGetLastError();
 }
 
-ModeOps const ops = {sweep, sweep_split, calc_dti, tfloor, prim_from_cons, sizeof(Real), kHalfFields, TY};
+ModeOps const ops = {sweep_split, calc_dti, tfloor, prim_from_cons, sizeof(Real), kHalfFields};
 }  // namespace
 ModeOps const *get_ops() { return &ops; }
 }  // namespace CHL_NS

@@ -120,7 +120,7 @@ class Grid3D:
     def __init__(self, n_global, domain_len, bounds_min=(0.0, 0.0, 0.0), recon=_lib.PPMC, solver=_lib.HLLC,
                  gamma=5.0 / 3.0, bc=(1, 1, 1, 1, 1, 1), precision=2, strict=True, density_floor=0.0,
                  temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True, mhd=False,
-                 integrator="vl"):
+                 integrator="vl", halo_transport="p2p", overlap=True):
         import torch
         self.torch = torch
         if integrator not in ("vl", "simple"):  # -DVL / -DSIMPLE, builds/make.type.hydro:8-12
@@ -165,9 +165,24 @@ class Grid3D:
         check(_lib.lib().chl_create(C.byref(cfg), C.byref(self._ctx)), "chl_create")
         self.gpu_launches = 0
         self._halo_x = None
+        # multi-rank: "p2p" = the library's own exchange (peer-mapped stores over NVLink, chl_halo_*), optionally
+        # overlapped with the interior of the last corrector pass; "nccl" = torch.distributed send / recv (halo.py)
+        if halo_transport not in ("p2p", "nccl"):
+            raise ValueError("halo_transport must be 'p2p' or 'nccl'")
+        self.halo_transport = halo_transport if nproc > 1 else "none"
+        self.overlap = bool(overlap) and self.halo_transport == "p2p" and self.integrator == "vl" and self.fused
+        self._halo_h = None          # chl_halo*
+        self._exchanged = False      # the step just taken already exchanged the ghost cells
+        self._dti_is_global = False  # the dti just returned is already the maximum over ranks
+        self._key_t = None
+        if self.halo_transport == "p2p":
+            self._halo_p2p_setup()
 
     # ---- plumbing ----
     def close(self):
+        if getattr(self, "_halo_h", None) is not None and self._halo_h.value:
+            _lib.lib().chl_halo_destroy(self._halo_h)
+            self._halo_h = None
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             _lib.lib().chl_destroy(self._ctx)
             self._ctx = C.c_void_p()
@@ -272,7 +287,9 @@ class Grid3D:
     def set_dt(self, dti):
         """Grid3D::set_dt (grid3D.cpp:373-409): global max of the inverse time step, dt = C_cfl / max_dti."""
         max_dti = dti
-        if self.nproc > 1:
+        if self.nproc > 1 and self._dti_is_global:
+            self._dti_is_global = False  # Update_Hydro_Grid reduced the CFL keys across ranks on the device
+        elif self.nproc > 1:
             dist, torch = self.torch.distributed, self.torch
             dev = self.device if dist.get_backend(self.dist_group) == "nccl" else "cpu"
             t = torch.tensor([dti], dtype=torch.float64, device=dev)
@@ -302,9 +319,25 @@ class Grid3D:
         if self.fused:
             if self.integrator == "simple":
                 check(L.chl_simple_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_simple_step_fused")
+            elif self.overlap:
+                # step + ghost-cell exchange in one call: boundary shell first, exchange overlapped with the interior
+                check(L.chl_vl_step_exchange(self._ctx, self._halo_h, self._ptr(), self.H.dt, self._stream()),
+                      "chl_vl_step_exchange")
+                self._exchanged = True
+                self.gpu_launches += self._exchange_launches() + (6 if self.ndim == 3 and not self.mhd else 0)
             else:
                 check(L.chl_vl_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step_fused")
             self.gpu_launches += self._sweep_launches()
+            if self.nproc > 1 and self.torch.distributed.get_backend(self.dist_group) == "nccl":
+                # MAX over ranks of the ordered CFL keys, on the device; one host read per step.  (The key of a
+                # non-negative value has its top bit set, so as int64 the keys keep their order.)
+                torch, dist = self.torch, self.torch.distributed
+                if self._key_t is None:
+                    self._key_t = torch.zeros(1, dtype=torch.int64, device=self.device)
+                check(L.chl_dti_copy_key(self._ctx, self._ptr(self._key_t), self._stream()), "chl_dti_copy_key")
+                dist.all_reduce(self._key_t, op=dist.ReduceOp.MAX, group=self.dist_group)
+                self._dti_is_global = True
+                return L.chl_dti_decode(C.c_ulonglong(int(self._key_t.item()) & 0xFFFFFFFFFFFFFFFF))
             out = C.c_double()
             check(L.chl_dti_result(self._ctx, C.byref(out), self._stream()), "chl_dti_result")
             return out.value
@@ -314,6 +347,13 @@ class Grid3D:
                   "chl_apply_temperature_floor")
             self.gpu_launches += 1
         return self.Calc_Inverse_Timestep()
+
+    def bad_cells(self):
+        """Cells whose density came out <= 0 (or NaN) in the corrector since the last call (chl_bad_cells): the host-side
+        stand-in for the reference's device printf + neighbour averaging (hydro_cuda.cu:292-297) -- abort or repair here."""
+        n = C.c_ulonglong()
+        check(_lib.lib().chl_bad_cells(self._ctx, C.byref(n), self._stream()), "chl_bad_cells")
+        return int(n.value)
 
     def Update_Time(self):
         self.H.t += self.H.dt
@@ -335,7 +375,41 @@ class Grid3D:
             for d in range(2 * self.ndim):
                 self.Set_Boundaries(d)
             return
+        if self._exchanged:  # chl_vl_step_exchange did it, overlapped with the interior update
+            self._exchanged = False
+            return
+        if self.halo_transport == "p2p":
+            check(_lib.lib().chl_halo_exchange(self._halo_h, self._ptr(), self._stream()), "chl_halo_exchange")
+            self.gpu_launches += self._exchange_launches()
+            return
         self._halo().exchange(self.Set_Boundaries)
+
+    # ---- the library's own exchange: set-up (the only host-side communication it needs) ----
+    def _halo_p2p_setup(self):
+        L, dist = _lib.lib(), self.torch.distributed
+        h = C.c_void_p()
+        check(L.chl_halo_create(self._ctx, self._cflags(), self.rank, C.byref(h)), "chl_halo_create")
+        self._halo_h = h
+        blob = C.create_string_buffer(L.chl_halo_blob_bytes())
+        check(L.chl_halo_export(h, blob), "chl_halo_export")
+        blobs = [None] * self.nproc
+        dist.all_gather_object(blobs, bytes(blob.raw), group=self.dist_group)  # MPI_Allgather in a Cholla build
+        for face in range(2 * self.ndim):
+            if self.flags[face] == BC_MPI:
+                check(L.chl_halo_connect(h, face, blobs[self.decomp.dest[face]]), "chl_halo_connect")
+        dist.barrier(group=self.dist_group)  # every rank has mapped its neighbours before anyone sends
+
+    def _exchange_launches(self):
+        n_mpi = sum(1 for f in range(2 * self.ndim) if self.flags[f] == BC_MPI)
+        return 2 * n_mpi + (2 * self.ndim - n_mpi)
+
+    def halo_kind(self):
+        return self.halo_transport
+
+    def halo_check(self):
+        """Raises if a receive gave up waiting for its neighbour (chl_halo_error); synchronises the stream."""
+        if self._halo_h is not None:
+            check(_lib.lib().chl_halo_error(self._halo_h, self._stream()), "chl_halo_error")
 
     # ---- halo exchange over torch.distributed (NCCL send/recv over NVLink); schedule in halo.py ----
     def _halo(self):
@@ -371,4 +445,5 @@ class Grid3D:
             self.Set_Boundary_Conditions_Grid()
             dts.append(self.H.dt)
         self._last_dti = dti
+        self.halo_check()
         return dts

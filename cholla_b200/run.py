@@ -134,12 +134,6 @@ def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mh
     if is_restart:
         read_grid(G, P)
     elif mhd:
-        if nproc != 1 and os.environ.get("CHOLLA_B200_MHD_MULTIRANK") != "1":
-            # every piece is checked on its own -- rank-local MHD generators (tests/test_initial_conditions.py), the
-            # 8-field slab exchange over gloo (tests/test_halo_gloo.py) -- but the assembled path has not run on more
-            # than one GPU yet, so it is opt-in rather than silently trusted
-            raise NotImplementedError("multi-rank MHD runs have not been validated on >1 GPU: set "
-                                      "CHOLLA_B200_MHD_MULTIRANK=1 to run one anyway")
         with ic.block(G.decomp.offset, G.decomp.n_local):
             G.upload(initial_fields(P, True, n_ghost_for(RECON[recon], True)))
     else:

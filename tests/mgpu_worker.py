@@ -23,20 +23,34 @@ def main():
     n, steps, gamma = (64, 48, 40), 6, 1.66666667
     flags = [int(v) for v in os.environ.get("MGPU_FLAGS", "1,1,1,1,1,1").split(",")]
     strict = os.environ.get("MGPU_STRICT", "1") == "1"
-    fields = ic.spherical_overpressure(n, gamma=gamma)
-    G = Grid3D(n, (1.0, 1.0, 1.0), recon=cb.PPMC, solver=cb.HLLC, gamma=gamma, bc=flags, strict=strict,
-               device="cuda:%d" % local, dist_group=dist.group.WORLD, rank=rank, nproc=world)
-    G.Set_Initial_Conditions(fields)
+    mhd = os.environ.get("MGPU_MHD", "0") == "1"      # Orszag-Tang, PPMC + HLLD + CT (BASELINE config 4, reduced size)
+    overlap = os.environ.get("MGPU_OVERLAP", "1") == "1"
+    transport = os.environ.get("MGPU_TRANSPORT", "p2p")
+    nf = 8 if mhd else 5
+    solver = cb.HLLD if mhd else cb.HLLC
+    if mhd:
+        n, steps, gamma = (64, 64, 64), 5, 1.666666666666667
+    kw = dict(recon=cb.PPMC, solver=solver, gamma=gamma, bc=flags, strict=strict, mhd=mhd)
+    G = Grid3D(n, (1.0, 1.0, 1.0), device="cuda:%d" % local, dist_group=dist.group.WORLD, rank=rank, nproc=world,
+               halo_transport=transport, overlap=overlap, **kw)
+    if mhd:
+        from cholla_b200.grid import n_ghost_for
+        with ic.block(G.decomp.offset, G.decomp.n_local):
+            G.upload(ic.orszag_tang(n, n_ghost_for(cb.PPMC, True), gamma=gamma).reshape(-1))
+    else:
+        fields = ic.spherical_overpressure(n, gamma=gamma)
+        G.Set_Initial_Conditions(fields)
     G.Set_Boundary_Conditions_Grid()
     dts = G.advance(steps)
     mine = torch.from_numpy(G.real_cells()).cuda()
+    halo_kind = G.halo_kind()
     # gather every rank's block on rank 0
     out = None
     if rank == 0:
-        out = np.zeros((5, n[2], n[1], n[0]))
+        out = np.zeros((nf, n[2], n[1], n[0]))
     for r in range(world):
         D = type(G.decomp).build(world, r, list(n), flags)
-        shape = (5, D.n_local[2], D.n_local[1], D.n_local[0])
+        shape = (nf, D.n_local[2], D.n_local[1], D.n_local[0])
         buf = mine if r == rank else torch.empty(shape, dtype=torch.float64, device="cuda")
         if r != 0:
             if rank == r:
@@ -48,15 +62,19 @@ def main():
             out[:, o[2]:o[2] + shape[1], o[1]:o[1] + shape[2], o[0]:o[0] + shape[3]] = (mine if r == 0 else buf).cpu().numpy()
     G.close()
     if rank == 0:
-        S = Grid3D(n, (1.0, 1.0, 1.0), recon=cb.PPMC, solver=cb.HLLC, gamma=gamma, bc=flags, strict=strict, device="cuda:0")
-        S.Set_Initial_Conditions(fields)
+        S = Grid3D(n, (1.0, 1.0, 1.0), device="cuda:0", **kw)
+        if mhd:
+            S.upload(ic.orszag_tang(n, S.H.n_ghost, gamma=gamma).reshape(-1))
+        else:
+            S.Set_Initial_Conditions(fields)
         S.Set_Boundary_Conditions_Grid()
         dts1 = S.advance(steps)
         one = S.real_cells()
         S.close()
         err = float(np.abs(out - one).sum() / np.abs(one).sum())
         print("RESULT " + json.dumps(dict(world=world, equal=bool(np.array_equal(out, one)), dt_equal=bool(dts == dts1),
-                                          rel_l1=err, decomposition=G.decomp.np)))
+                                          rel_l1=err, decomposition=G.decomp.np, mhd=mhd, halo=halo_kind,
+                                          overlap=overlap)))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -99,3 +99,57 @@ def test_sqrt_whole_range_and_edges():
     assert _same_bits(ro, rp)
     with np.errstate(all="ignore"):
         assert _same_bits(rp, np.sqrt(x))
+
+
+def _run_flagged(a, b, zero_ok=True):
+    import torch
+    import cholla_b200 as cb
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    q = torch.empty_like(ta)
+    fl = torch.empty(a.size, dtype=torch.int32, device="cuda")
+    rc = cb.lib().chl_debug_exact_div_flagged(C.c_void_p(ta.data_ptr()), C.c_void_p(tb.data_ptr()), C.c_void_p(q.data_ptr()),
+                                              C.c_void_p(fl.data_ptr()), int(zero_ok), a.size, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return q.cpu().numpy(), fl.cpu().numpy()
+
+
+def test_branch_free_policy_flag_clear_means_exact():
+    """kDivFlag (the hydro sweeps): whenever the sticky flag stays clear the raw quotient carries the bits of a / b and
+    the raw square root those of sqrt(a); the flag never comes up on the operands the path actually sees (normal
+    magnitudes and exact zeros of either sign), so the IEEE redo stays out of the hot loop."""
+    rng = np.random.default_rng(23)
+    n = 1 << 22
+    a = rng.integers(0, 1 << 64, n, dtype=np.uint64).view(np.float64).copy()
+    b = rng.integers(0, 1 << 64, n, dtype=np.uint64).view(np.float64).copy()
+    edge = np.array([0.0, -0.0, 1.0, -1.0, 6.0, 3.0, 1e-300, -1e-300, 5e-324, 2.2250738585072014e-308, 1e300, -1e300,
+                     1.7976931348623157e308, np.inf, -np.inf, np.nan, 2.0 ** -969, 2.0 ** -970, 2.0 ** 1017, 2.0 ** 1016,
+                     2.0 ** -1016, 2.0 ** -1017, 2.0 ** -1022, 1.0 + 2.0 ** -52, 2.0 - 2.0 ** -52, 1.0 / 3.0])
+    A, B = np.meshgrid(edge, edge)
+    a = np.concatenate([a, A.ravel()])
+    b = np.concatenate([b, B.ravel()])
+    for zero_ok in (True, False):
+        q, fl = _run_flagged(a, b, zero_ok)
+        with np.errstate(all="ignore"):
+            want = a / b
+        clear = (fl & 1) == 0
+        assert clear.sum() > 0.2 * a.size  # random bit patterns: a sizeable share stays in the fast-path window
+        assert _same_bits(q[clear], want[clear])
+        assert not np.any(fl & 4)          # clear sqrt flag => the bits of sqrt(a)
+    # the physical range, exact zeros of both signs included: no flag at all
+    m = 1 << 21
+    a = rng.standard_normal(m) * 10.0 ** rng.uniform(-30, 30, m)
+    b = rng.standard_normal(m) * 10.0 ** rng.uniform(-30, 30, m)
+    a[::5] = 0.0
+    a[1::5] = -0.0
+    q, fl = _run_flagged(a, b, True)
+    assert not np.any(fl & 1)
+    with np.errstate(all="ignore"):
+        assert _same_bits(q, a / b)
+    # the nonzero hint: a zero numerator only raises the flag (the block is redone), it never passes silently
+    q, fl = _run_flagged(a, b, False)
+    z = a == 0.0
+    assert np.all(fl[z] & 1) and not np.any(fl[~z] & 1)
+    pos = np.abs(a) + 1e-250               # inside the square root's fast-path window (2^-969 ... 2^1016)
+    _, fl = _run_flagged(pos, b, True)
+    assert not np.any(fl & 2)              # positive normal arguments never flag the square root

@@ -365,3 +365,40 @@ def test_exact_solver_against_oracle(recon, strict):
     got, ref, dims, g, dts_gpu, dts_cpu = run_both(fields, recon, cb.EXACT, PERIODIC, 1.4, 3, strict=strict)
     assert rel_l1(real_view(got, dims, g), real_view(ref, dims, g)).max() <= 1e-5
     assert np.allclose(dts_gpu, dts_cpu, rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("recon,solver", [(cb.PPMC, cb.HLLC), (cb.PLMC, cb.ROE), (cb.PPMC, cb.HLL)])
+def test_strict_ieee_redo_path_extreme_operands(recon, solver):
+    """The strict sweeps evaluate their quotients branch-free and redo a block with IEEE divisions when a quotient
+    leaves the fast-path window (csrc/exact_div.cuh, kDivFlag).  Ordinary data never gets there; this state does, in
+    most cells: velocities of 1e-300 (numerators below 2^-969, denormal quotients) on top of a smooth state, plus a
+    slab at rest (exact zeros, which must NOT need the redo).  Same bits as the oracle either way."""
+    rng = np.random.default_rng(5)
+    fields = ic.random_smooth((24, 20, 18), seed=3)
+    d = fields[0].copy()
+    v = rng.standard_normal((3,) + d.shape) * 1e-300
+    v[:, :, :6, :] = 0.0
+    p = fields[4] - 0.5 * (fields[1] ** 2 + fields[2] ** 2 + fields[3] ** 2) / d
+    for a in range(3):
+        fields[1 + a] = d * v[a]
+    fields[4] = p  # the kinetic energy underflows: E = e_int
+    got, ref, dims, g, dts_gpu, dts_cpu = run_both(fields, recon, solver, PERIODIC, 5.0 / 3.0, 2, strict=True)
+    assert dts_gpu == dts_cpu
+    assert np.array_equal(got, ref)
+
+
+def test_bad_cell_counter():
+    """chl_bad_cells: a corrector result with density <= 0 is counted (the reference prints and averages neighbours
+    in place, a race -- hydro_cuda.cu:292-297); healthy data counts zero."""
+    fields = ic.random_smooth((20, 16, 12), seed=4)
+    G = make_grid((20, 16, 12), cb.PLMC, cb.HLLC, PERIODIC, 5.0 / 3.0, True)
+    G.Set_Initial_Conditions(fields)
+    G.Set_Boundary_Conditions_Grid()
+    G.advance(2)
+    assert G.bad_cells() == 0
+    # an absurd time step drives densities negative
+    G.H.dt = 50.0 * G.H.dt
+    G.Update_Hydro_Grid()
+    assert G.bad_cells() > 0
+    assert G.bad_cells() == 0  # reading resets the counter
+    G.close()
