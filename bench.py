@@ -1,27 +1,35 @@
 #!/usr/bin/env python3
-"""bench.py -- cell-updates/s of the Van Leer hydro hot path (3-D, PPMC + HLLC, fp64) on N B200s.
+"""bench.py -- cell-updates/s of the Van Leer hot path (3-D, PPMC + HLLC, fp64) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S] [--mode strict|fast]
-                    [--recon pcm|plmc|ppmc|plmp|ppmp] [--solver hllc|roe|hll|exact] [--integrator vl|simple]
-                    [--workload blast|kh|noise] [--precision 1|2]        (defaults = the headline: PPMC + HLLC, VL, fp64)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|dropin]
+                    [--size S | --global-size G] [--mode strict|fast] [--workload blast|kh|noise|sound|sod|ot]
+                    [--recon pcm|plmc|ppmc|plmp|ppmp] [--solver hllc|roe|hll|exact|hlld] [--integrator vl|simple]
+                    [--precision 1|2] [--no-configs] [--no-parity] ...     (defaults = the headline: PPMC + HLLC, VL, fp64)
 
 A "step" is one pass of the hot path over the local grid: the reference's main-loop body (main.cpp:247-379)
-    set_dt (all-reduce MAX) -> VL step (+ temperature floor, CFL max) -> ghost fill / halo exchange.
-Workload (BASELINE.json metric, config 5): spherical blast wave, S^3 cells PER GPU (default 512^3), periodic,
-PPMC + HLLC, fp64; weak scaling over the reference's block decomposition (2x1x1, 2x2x1, 2x2x2).
+    set_dt (MAX over ranks) -> VL step (+ temperature floor, CFL max) -> ghost fill / halo exchange.
+Headline workload (BASELINE.json metric, config 5): spherical blast wave, S^3 cells PER GPU (default 512^3), periodic,
+PPMC + HLLC, fp64, strict arithmetic (the reference's bits); weak scaling over the reference's block decomposition
+(2x1x1, 2x2x1, 2x2x2) with the library's own peer-to-peer halo exchange overlapped with the interior update.
 
-One JSON line on rank 0.  `value` = cell-updates/s with the state resident in HBM (CUDA events around K steps,
-barrier + synchronize either side, max over ranks).  `e2e` = the same through host buffers: pinned-host ->
-device copy of the state, K steps, device -> pinned-host copy of the result, all inside the timed region.
-`roofline` = the step's algorithmic bytes (200 B per cell-update) over the CUDA-event time of the six
-direction sweeps that make up a step, against the measured HBM copy bandwidth in MEASURED_PEAKS.json; `traffic` =
-the DRAM bytes of those launches from the committed ncu capture (profiles/roofline_traffic.json).  `other_mode` =
-the same workload in the other arithmetic mode.  `cpu_baseline` = the CPU
-oracle (a C restatement of the reference algorithm; the reference has no CPU hydro path) on a bounded sample.
+One JSON line on rank 0:
+  value      cell-updates/s with the state resident in HBM (CUDA events around K steps, barrier + synchronize either side,
+             max over ranks)
+  e2e        the same through host buffers: pinned-host -> device copy of the state, K steps, device -> pinned-host copy
+  roofline   algorithmic bytes (200 B per cell-update) over the CUDA-event time of the sweeps of a step against
+             the measured HBM copy bandwidth (MEASURED_PEAKS.json); `traffic` = DRAM bytes of those launches from the
+             committed ncu capture; `secondary` = the ceilings that actually bind (fp64 pipe, issue slots)
+  parity     N = 1: the reference's own kernels (oracle/_ref) run on the same initial conditions for the same number of
+             steps in a child process; position-weighted checksums of the two final states must agree (bit equality)
+  configs    BASELINE.json configs 2-5 measured the same way (fixed step counts), each with its reference-kernel number
+             and parity flag at N = 1 and a rank-count-independent checksum at every N
+  other_mode the headline in the other arithmetic mode;  cpu_baseline: the CPU oracle (a C port) on a bounded sample.
 
 --impl reference: the reference's OWN CUDA kernels, unmodified, compiled for sm_100 (oracle/_ref, built by
-oracle/ref_build/Makefile), same workload, same loop, on rank 0's GPU.  The reference has no CPU hydro
-implementation and needs MPI (absent from this image) for multi-GPU, so this arm is single-GPU by construction.
+oracle/ref_build/Makefile), same workload, same loop, on rank 0's GPU (the reference has no CPU hydro path and needs
+MPI, absent from this image, for multi-GPU: single-GPU by construction).  --impl dropin: the same driver linked against
+cholla_b200/csrc/cholla_shims.cpp + libcholla_b200.so -- the path a Cholla maintainer gets (un-fused VL step, separate
+temperature floor and Calc_dt_GPU).
 """
 import argparse
 import json
@@ -35,8 +43,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-B_ALG_STEP = 200.0       # algorithmic bytes per cell-update, fp64 hydro: 5 * NF * sizeof(Real)
-GAMMA = 1.66666667
+GAMMA_BLAST = 1.66666667
+RECONS = {"pcm": 0, "plmc": 1, "ppmc": 2, "plmp": 3, "ppmp": 4}
+SOLVERS = {"hllc": 0, "roe": 1, "hlld": 2, "hll": 3, "exact": 4}
+GHOSTS = {"pcm": 2, "plmc": 3, "plmp": 3, "ppmc": 4, "ppmp": 4}
+CONFIG_STEPS, CONFIG_WARMUP = 5, 3  # fixed, so that the checksums of a config are comparable across runs and GPU counts
 
 
 def env_int(name, default):
@@ -100,12 +111,74 @@ def measured_hbm_peak():
 
 
 def ncu_traffic():
-    """DRAM bytes of one step's six sweeps per arithmetic mode, from the committed ncu capture (scratch/ncu_traffic.py)."""
+    """Per arithmetic mode: DRAM bytes, fp64-pipe and issue-slot utilisation of one step's sweeps, from the committed
+    ncu capture of this command (profiles/roofline_traffic.json, written by tools/ncu_traffic.py)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
             return json.load(fh)
     except Exception:
         return None
+
+
+# ---- workloads ---------------------------------------------------------------------------------------------------
+def workload(name, size, global_size, np_grid):
+    """-> dict(n_global, lengths, lo, flags, gamma, mhd, weak).  `size` = cells per axis per GPU (weak scaling: the box
+    grows with the process grid); `global_size` = cells per axis of the whole problem (fixed box, BASELINE configs 2-4)."""
+    weak = global_size is None
+    if weak:
+        n_global = [size * np_grid[0], size * np_grid[1], size * np_grid[2]]
+        lengths = [float(v) for v in np_grid]  # a unit box per GPU
+    else:
+        n_global, lengths = [global_size] * 3, [1.0, 1.0, 1.0]
+    w = dict(name=name, n_global=n_global, lengths=lengths, lo=(0.0, 0.0, 0.0), flags=[1] * 6, gamma=GAMMA_BLAST,
+             mhd=False, weak=weak)
+    if name == "kh":       # BASELINE config 3 (examples/3D/KH_res_ind_3D.txt): every cell moves
+        w.update(lo=(0.0, -0.5 * lengths[1], -0.5 * lengths[2]), gamma=5.0 / 3.0 if not weak else GAMMA_BLAST)
+    elif name == "sound":  # BASELINE config 2b (examples/3D/sound_wave.txt): L = 4
+        w.update(lengths=[4.0 * v for v in lengths], gamma=1.666666666666667)
+    elif name == "sod":    # BASELINE config 2a (examples/3D/sod256.txt): transmissive faces
+        w.update(flags=[3] * 6, gamma=1.4)
+    elif name == "ot":     # BASELINE config 4 (examples/3D/orszag_tang_vortex.txt)
+        w.update(mhd=True, gamma=1.666666666666667)
+    return w
+
+
+def build_fields(w, ic, n_ghost, n_local, rank):
+    """Host initial conditions of this rank's block (call inside ic.block): real cells (5, nz, ny, nx), or for MHD the
+    full ghosted local array (8, nz+2g, ny+2g, nx+2g)."""
+    n, L, lo, gamma = w["n_global"], w["lengths"], w["lo"], w["gamma"]
+    if w["name"] == "kh":
+        return ic.kh_res_ind(n, lengths=L, lo=lo, gamma=gamma)
+    if w["name"] == "noise":  # worst case: cell-to-cell noise, every limiter branch taken everywhere
+        return ic.random_smooth(n_local, seed=1 + rank, gamma=gamma)
+    if w["name"] == "sound":
+        return ic.sound_wave(n, lengths=L, lo=lo, gamma=gamma)
+    if w["name"] == "sod":
+        return ic.riemann(n, lengths=L, lo=lo, gamma=gamma)
+    if w["name"] == "ot":
+        return ic.orszag_tang(n, n_ghost, gamma=gamma)
+    return ic.spherical_overpressure(n, lengths=L, lo=lo, gamma=gamma)
+
+
+def checksum(torch, C_device, H, n_fields, offset, n_global, group=None):
+    """Position-weighted wrapping sum of the bit patterns of every real cell: sum over fields f and cells of
+    bits(f, cell) * (2 * (gid + f * N_global) + 1) mod 2^64, gid = the cell's GLOBAL linear index.  Integer arithmetic,
+    so it does not depend on the summation order or on how the grid is split across ranks; equal checksums <=> (to
+    2^-64) bit-identical fields."""
+    g = H.n_ghost
+    a = C_device.view(n_fields, H.nz, H.ny, H.nx)[:, g:H.nz - g, g:H.ny - g, g:H.nx - g].contiguous().view(torch.int64)
+    dev = a.device
+    ix = torch.arange(H.nx_real, device=dev, dtype=torch.int64) + offset[0]
+    iy = torch.arange(H.ny_real, device=dev, dtype=torch.int64) + offset[1]
+    iz = torch.arange(H.nz_real, device=dev, dtype=torch.int64) + offset[2]
+    gid = ix[None, None, :] + n_global[0] * (iy[None, :, None] + n_global[1] * iz[:, None, None])
+    ncell = n_global[0] * n_global[1] * n_global[2]
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    for f in range(n_fields):
+        total += (a[f] * (2 * (gid + f * ncell) + 1)).sum()
+    if group is not None:
+        torch.distributed.all_reduce(total, op=torch.distributed.ReduceOp.SUM, group=group)
+    return "%016x" % (int(total.item()) & 0xFFFFFFFFFFFFFFFF)
 
 
 def cpu_baseline(sample_n=192, steps=1):
@@ -116,14 +189,14 @@ def cpu_baseline(sample_n=192, steps=1):
     from cholla_b200 import initial_conditions as ic
     n = (sample_n,) * 3
     g = 4
-    f = ic.spherical_overpressure(n, gamma=GAMMA)
+    f = ic.spherical_overpressure(n, gamma=GAMMA_BLAST)
     a = np.zeros((5, n[2] + 2 * g, n[1] + 2 * g, n[0] + 2 * g))
     a[:, g:-g, g:-g, g:-g] = f
     flat = np.ascontiguousarray(a.reshape(-1))
     dims = (n[0] + 2 * g,) * 3
     oracle.set_boundaries(flat, *dims, 5, g, [1] * 6)
     t0 = time.perf_counter()
-    oracle.advance(flat, *dims, g, 1.0 / sample_n, 1.0 / sample_n, 1.0 / sample_n, GAMMA, oracle.PPMC, oracle.HLLC,
+    oracle.advance(flat, *dims, g, 1.0 / sample_n, 1.0 / sample_n, 1.0 / sample_n, GAMMA_BLAST, oracle.PPMC, oracle.HLLC,
                    [1] * 6, steps)
     dt = time.perf_counter() - t0
     return {"value": sample_n ** 3 * steps / dt, "unit": "cell-updates/s", "cores": 1, "kind": "port",
@@ -131,98 +204,144 @@ def cpu_baseline(sample_n=192, steps=1):
                       % (sample_n, steps, dt)}
 
 
+# ---- the reference's own kernels (and the drop-in build of the same driver) ---------------------------------------
 def run_reference(args):
-    """The reference's own kernels (oracle/_ref) on rank 0's GPU.  Other ranks exit without work."""
-    rank = env_int("RANK", 0)
-    if rank != 0:
+    """oracle/_ref on rank 0's GPU: warm-up W steps, K timed steps, checksum of the final state.  Other ranks exit."""
+    if env_int("RANK", 0) != 0:
         return 0
+    import ctypes as C
+
     import numpy as np
     import torch
 
     from cholla_b200 import initial_conditions as ic
+    from cholla_b200.grid import Header
     from oracle import reference
-    recon, solver = {"pcm": 0, "plmc": 1, "ppmc": 2, "plmp": 3, "ppmp": 4}[args.recon], {"hllc": 0, "roe": 1, "hll": 3, "exact": 4}[args.solver]
-    out = {"impl": "reference", "metric": "cell-updates/s", "unit": "cell-updates/s", "n_gpus": args.gpus,
+    dropin = args.impl == "dropin"
+    recon, solver = RECONS[args.recon], SOLVERS[args.solver]
+    out = {"impl": args.impl, "metric": "cell-updates/s", "unit": "cell-updates/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
     nosync = args.ref_variant == "nosync"
     simple = args.integrator == "simple"
-    if not reference.available(recon, solver, nosync, simple=simple) or not torch.cuda.is_available():
-        print(json.dumps({"impl": "reference", "unavailable":
-                          "oracle/_ref/libcholla_ref_%s_%s%s.so not built or no GPU"
-                          % (args.recon, args.solver, "_nosync" if nosync else "")}))
+    if not reference.available(recon, solver, nosync, dropin=dropin, simple=simple) or not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "unavailable": "%s not built or no GPU"
+                          % os.path.basename(reference.lib_path(recon, solver, nosync, dropin, simple))}))
         return 0
-    S, g = args.size, {"pcm": 2, "plmc": 3, "plmp": 3, "ppmc": 4, "ppmp": 4}[args.recon]
-    n = (S, S, S)
-    dims = (S + 2 * g,) * 3
+    w = workload(args.workload, args.size, args.global_size, [1, 1, 1])
+    mhd = w["mhd"]
+    g = GHOSTS[args.recon] + (1 if mhd else 0)
+    n = w["n_global"]
+    nf = 8 if mhd else 5
+    dims = tuple(v + 2 * g for v in n)
     torch.cuda.set_device(0)
-    host = np.zeros((5,) + dims[::-1])
-    host[:, g:-g, g:-g, g:-g] = ic.spherical_overpressure(n, gamma=GAMMA)
-    U = torch.from_numpy(host.reshape(-1)).cuda()
+    if mhd:
+        host = build_fields(w, ic, g, n, 0)
+    else:
+        host = np.zeros((5,) + dims[::-1])
+        host[:, g:-g, g:-g, g:-g] = build_fields(w, ic, g, n, 0)
+    U = torch.from_numpy(np.ascontiguousarray(host).reshape(-1)).cuda()
     del host
-    d = 1.0 / S
-    flags = [1] * 6
-    # ghost fill + warm-up (also sizes the reference's global scratch: 55 doubles per cell)
-    L = reference.lib(recon, solver, nosync, simple=simple)
-    L.ref_set_gamma(GAMMA)
-    import ctypes as C
-    L.ref_set_boundaries(C.c_void_p(U.data_ptr()), *dims, 5, g, (C.c_int * 6)(*flags))
-    reference.advance(U, dims, g, d, d, d, GAMMA, recon, solver, flags, max(args.warmup, 1), nosync=nosync, simple=simple)
+    d = [w["lengths"][a] / n[a] for a in range(3)]
+    flags, gamma = w["flags"], w["gamma"]
+    L = reference.lib(recon, solver, nosync, dropin=dropin, simple=simple)
+    L.ref_set_gamma(gamma)
+    L.ref_set_boundaries(C.c_void_p(U.data_ptr()), *dims, nf, g, (C.c_int * 6)(*flags))
+    kw = dict(nosync=nosync, dropin=dropin, simple=simple)
+    # warm-up (also sizes the reference's global scratch: 55 doubles per cell)
+    reference.advance(U, dims, g, d[0], d[1], d[2], gamma, recon, solver, flags, max(args.warmup, 1), **kw)
     sampler = ClockSampler(0)
     sampler.start()
     torch.cuda.synchronize()
-    _, _, ms = reference.advance(U, dims, g, d, d, d, GAMMA, recon, solver, flags, args.steps, nosync=nosync, timed=True, simple=simple)
+    _, _, ms = reference.advance(U, dims, g, d[0], d[1], d[2], gamma, recon, solver, flags, args.steps, timed=True, **kw)
     torch.cuda.synchronize()
     clocks = sampler.finish()
-    value = S ** 3 * args.steps / (ms * 1e-3)
+    cells = n[0] * n[1] * n[2]
+    value = cells * args.steps / (ms * 1e-3)
+    H = Header()
+    H.nx, H.ny, H.nz = dims
+    H.nx_real, H.ny_real, H.nz_real = n
+    H.n_ghost = g
+    cs = checksum(torch, U, H, nf, (0, 0, 0), n)
     peak, which = measured_hbm_peak()
-    out.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks,
-                "config": {"workload": "blast %d^3 %s+%s fp64 periodic, %s integrator, reference kernels%s" %
-                           (S, args.recon.upper(), args.solver.upper(), args.integrator.upper(), " (-DDISABLE_GPU_ERROR_CHECKING)" if nosync else " (as shipped: device sync after every stage)"),
+    b_alg = 40.0 * nf
+    kind = ("the same driver linked against cholla_shims.cpp + libcholla_b200.so (strict arithmetic, un-fused entry points)"
+            if dropin else "reference kernels" + (" (-DDISABLE_GPU_ERROR_CHECKING)" if nosync
+                                                  else " (as shipped: device sync after every stage)"))
+    out.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "checksum": cs,
+                "total_steps": max(args.warmup, 1) + args.steps,
+                "config": {"workload": "%s %s^3 %s+%s fp64, %s integrator, %s" %
+                           (args.workload, n[0], args.recon.upper(), args.solver.upper(), args.integrator.upper(), kind),
                            "l2": "inputs larger than L2", "build": L.ref_build_flags().decode()},
                 "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "reference",
                                  "sample": "the reference has no CPU hydro path: this is its own unmodified CUDA "
                                            "build (oracle/_ref) on one B200, full workload, 1 host thread"},
                 "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "roofline": {"bound": "hbm", "achieved": value * B_ALG_STEP / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": value * B_ALG_STEP / 1e9 / peak, "traffic": None,
-                             "note": "whole step at the 200 B/cell algorithmic figure; peak " + which},
+                "roofline": {"bound": "hbm", "achieved": value * b_alg / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": value * b_alg / 1e9 / peak, "traffic": None,
+                             "note": "whole step at the %d B/cell algorithmic figure; peak " % b_alg + which},
                 "gpu_launches": 0})
     print(json.dumps(out))
     return 0
 
 
-def run_b200(args, mode, world, rank, local, group, with_e2e):
-    """One arm of the bench: K timed steps of the hot path in `mode` arithmetic.  Returns the result dict (all ranks)."""
+def reference_child(spec, steps, warmup, impl="reference", variant="shipped", timeout=900):
+    """Run one --impl reference / dropin measurement in a child process (the reference keeps its 55-doubles-per-cell
+    scratch in process-wide globals it never frees) and return its JSON line, or {'unavailable': ...}."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", impl, "--workload", spec["workload"], "--recon",
+           spec["recon"], "--solver", spec["solver"], "--steps", str(steps), "--warmup", str(warmup), "--ref-variant", variant]
+    cmd += ["--global-size", str(spec["global_size"])] if spec.get("global_size") else ["--size", str(spec["size"])]
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        for line in reversed(p.stdout.splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"unavailable": "child failed: " + (p.stderr or p.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": "child failed: %r" % (e,)}
+
+
+# ---- this library ----------------------------------------------------------------------------------------------------
+def run_b200(spec, mode, steps, warmup, ctx, with_e2e=False, keep_state=False):
+    """K timed steps of the hot path for one workload spec in `mode` arithmetic.  Returns a result dict on every rank."""
     import torch
     import torch.distributed as dist
 
     import cholla_b200 as cb
     from cholla_b200 import initial_conditions as ic
-    from cholla_b200.grid import Grid3D
+    from cholla_b200.grid import Grid3D, n_ghost_for
 
-    S = args.size
-    np_grid = cb.tile_decomposition(world, S, S, S)
-    n_global = [S * np_grid[0], S * np_grid[1], S * np_grid[2]]
-    lengths = [float(np_grid[0]), float(np_grid[1]), float(np_grid[2])]  # unit cells, unit box per GPU
-    strict = mode == "strict" and args.precision == 2
-    recon = {"pcm": cb.PCM, "plmc": cb.PLMC, "ppmc": cb.PPMC, "plmp": cb.PLMP, "ppmp": cb.PPMP}[args.recon]
-    solver = {"hllc": cb.HLLC, "roe": cb.ROE, "hll": cb.HLL, "exact": cb.EXACT}[args.solver]
-    G = Grid3D(n_global, lengths, recon=recon, solver=solver, gamma=GAMMA, bc=[1] * 6, precision=args.precision,
-               strict=strict, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world, fused=True,
-               integrator=args.integrator)
+    world, rank, local, group = ctx["world"], ctx["rank"], ctx["local"], ctx["group"]
+    precision = spec.get("precision", 2)
+    g_size = spec.get("global_size")
+    probe = g_size if g_size else spec["size"]
+    np_grid = cb.tile_decomposition(world, probe, probe, probe)
+    w = workload(spec["workload"], spec.get("size"), g_size, np_grid)
+    strict = mode == "strict" and precision == 2
+    recon = getattr(cb, spec["recon"].upper())
+    solver = cb.HLLD if w["mhd"] else getattr(cb, spec["solver"].upper())
+    G = Grid3D(w["n_global"], w["lengths"], bounds_min=w["lo"], recon=recon, solver=solver, gamma=w["gamma"],
+               bc=w["flags"], precision=precision, strict=strict, device="cuda:%d" % local, dist_group=group, rank=rank,
+               nproc=world, fused=True, integrator=spec.get("integrator", "vl"), mhd=w["mhd"],
+               halo_transport=os.environ.get("CHOLLA_TRANSPORT", "p2p"), overlap=os.environ.get("CHOLLA_OVERLAP", "1") == "1")
+    if os.environ.get("CHOLLA_FUSED_PREDICTOR") == "1":  # measurement: the single-launch predictor (slower on B200)
+        G.set_tuning(0, True)
     with ic.block(G.decomp.offset, G.decomp.n_local):
-        if args.workload == "kh":      # BASELINE config 3: every cell moves, two shear layers
-            fields = ic.kh_res_ind(n_global, lengths=lengths, lo=(0.0, -0.5 * lengths[1], -0.5 * lengths[2]), gamma=GAMMA)
-        elif args.workload == "noise":  # worst case: cell-to-cell noise, every limiter branch taken everywhere
-            fields = ic.random_smooth(G.decomp.n_local, seed=1 + rank, gamma=GAMMA)
-        else:                           # BASELINE config 5 (the headline): blast wave into a medium at rest
-            fields = ic.spherical_overpressure(n_global, lengths=lengths, gamma=GAMMA)
-    G.Set_Initial_Conditions_Local(fields)
+        fields = build_fields(w, ic, n_ghost_for(recon, w["mhd"]), G.decomp.n_local, rank)
+    if w["mhd"]:
+        G.upload(fields.reshape(-1))
+    else:
+        G.Set_Initial_Conditions_Local(fields)
     del fields
     G.Set_Boundary_Conditions_Grid()
     cells_local = G.H.nx_real * G.H.ny_real * G.H.nz_real
-    cells_total = cells_local * world
+    t = torch.tensor([cells_local], dtype=torch.int64, device=G.device)
+    if world > 1:
+        dist.all_reduce(t, group=group)
+    cells_total = int(t.item())
     state_bytes = G.C_device.numel() * G.C_device.element_size()
 
     def barrier():
@@ -238,20 +357,18 @@ def run_b200(args, mode, world, rank, local, group, with_e2e):
             G.Set_Boundary_Conditions_Grid()
         return dti
 
-    # ---- warm-up ----
     dti = G.Calc_Inverse_Timestep()
-    dti = step_loop(args.warmup, dti)
-    # ---- timed region: K steps, state resident in HBM ----
+    dti = step_loop(warmup, dti)
     G.set_profiling(True)
     G.gpu_launches = 0
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and spec.get("clocks") else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    dti = step_loop(args.steps, dti)
+    dti = step_loop(steps, dti)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -259,15 +376,18 @@ def run_b200(args, mode, world, rank, local, group, with_e2e):
     launches = G.gpu_launches
     pred_ms, corr_ms, nprof = G.stage_times()
     G.set_profiling(False)
-    t = torch.tensor([ms, corr_ms / max(nprof, 1), pred_ms / max(nprof, 1)], dtype=torch.float64, device=G.device)
+    G.halo_check()
+    bad = G.bad_cells()
+    t = torch.tensor([ms, corr_ms / max(nprof, 1), pred_ms / max(nprof, 1), float(bad)], dtype=torch.float64, device=G.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    ms, corr_ms_step, pred_ms_step = [float(v) for v in t.tolist()]
-    value = cells_total * args.steps / (ms * 1e-3)
+    ms, corr_ms_step, pred_ms_step, bad = [float(v) for v in t.tolist()]
+    value = cells_total * steps / (ms * 1e-3)
+    cs = checksum(torch, G.C_device, G.H, G.H.n_fields, G.decomp.offset, w["n_global"], group) if precision == 2 else None
+    state = G.C_device.clone() if keep_state else None
 
-    # ---- e2e: host buffers, copies inside the timed region ----
     e2e = None
-    if with_e2e:
+    if with_e2e:  # host buffers, copies inside the timed region
         host_in = torch.empty(G.C_device.numel(), dtype=G.C_device.dtype, pin_memory=True)
         host_out = torch.empty_like(host_in, pin_memory=True)
         host_in.copy_(G.C_device)
@@ -275,7 +395,7 @@ def run_b200(args, mode, world, rank, local, group, with_e2e):
         e0.record()
         G.C_device.copy_(host_in, non_blocking=True)
         d2 = G.Calc_Inverse_Timestep()
-        d2 = step_loop(args.steps, d2)
+        d2 = step_loop(steps, d2)
         host_out.copy_(G.C_device, non_blocking=True)
         e1.record()
         barrier()
@@ -283,16 +403,89 @@ def run_b200(args, mode, world, rank, local, group, with_e2e):
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX, group=group)
         ms2 = float(t2.item())
-        e2e = {"value": cells_total * args.steps / (ms2 * 1e-3), "unit": "cell-updates/s",
-               "h2d_bytes_per_step": state_bytes / args.steps, "d2h_bytes_per_step": state_bytes / args.steps + 8,
+        e2e = {"value": cells_total * steps / (ms2 * 1e-3), "unit": "cell-updates/s",
+               "h2d_bytes_per_step": state_bytes / steps, "d2h_bytes_per_step": state_bytes / steps + 8,
                "note": "pinned host -> HBM copy of the state, K steps (each returning its CFL scalar to the host), "
                        "HBM -> pinned host copy of the result, all timed; ms=%.2f" % ms2}
         del host_in, host_out
+    r = dict(value=value, ms=ms, ms_per_step=ms / steps, corr_ms_step=corr_ms_step, pred_ms_step=pred_ms_step, e2e=e2e,
+             launches=launches, clocks=clocks, cells_local=cells_local, cells_total=cells_total, n_global=w["n_global"],
+             np_grid=np_grid, state_bytes=state_bytes, checksum=cs, bad_cells=int(bad), state=state,
+             n_fields=G.H.n_fields, halo=G.halo_kind(), overlap=G.overlap, mhd=w["mhd"], weak=w["weak"])
     G.close()
     del G
     torch.cuda.empty_cache()
-    return dict(value=value, ms=ms, corr_ms_step=corr_ms_step, pred_ms_step=pred_ms_step, e2e=e2e, launches=launches,
-                clocks=clocks, cells_local=cells_local, n_global=n_global, np_grid=np_grid, state_bytes=state_bytes)
+    return r
+
+
+def golden_checksums():
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_checksums.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+def config_entries(ctx, args):
+    """BASELINE.json configs 2-5 (the ones that are not the headline), each measured like the headline with fixed step
+    counts.  N = 1 adds the reference-kernel number and the parity flag of every fp64 entry."""
+    import torch
+    world, rank = ctx["world"], ctx["rank"]
+    specs = [
+        ("C2 sound wave 256^3 PPMC+HLLC", dict(workload="sound", global_size=256, recon="ppmc", solver="hllc")),
+        ("C3 Kelvin-Helmholtz 512^3 PPMC+HLLC", dict(workload="kh", global_size=512, recon="ppmc", solver="hllc")),
+        ("C3 Kelvin-Helmholtz 512^3 PPMC+Roe", dict(workload="kh", global_size=512, recon="ppmc", solver="roe")),
+        ("C4 Orszag-Tang 256^3 PPMC+HLLD+CT", dict(workload="ot", global_size=256, recon="ppmc", solver="hlld")),
+        ("C5 blast %d^3 per GPU PPMC+HLLC fp32" % args.size, dict(workload="blast", size=args.size, recon="ppmc",
+                                                                  solver="hllc", precision=1)),
+    ]
+    peak, _ = measured_hbm_peak()
+    golden = golden_checksums()
+    out = []
+    for name, spec in specs:
+        fp32 = spec.get("precision", 2) == 1
+        try:
+            r = run_b200(spec, "fast" if fp32 else "strict", CONFIG_STEPS, CONFIG_WARMUP, ctx, keep_state=fp32)
+        except Exception as e:  # noqa: BLE001 -- one config must not take the headline down with it
+            out.append({"name": name, "error": repr(e)[:300]})
+            continue
+        b_alg = 40.0 * r["n_fields"] * (0.5 if fp32 else 1.0)
+        e = {"name": name, "value": r["value"], "unit": "cell-updates/s", "ms_per_step": r["ms_per_step"],
+             "global_cells": r["n_global"], "decomposition": r["np_grid"], "steps": CONFIG_STEPS, "warmup": CONFIG_WARMUP,
+             "arithmetic": "fp32 product" if fp32 else "strict fp64", "scaling": "weak" if r["weak"] else "strong",
+             "roofline_frac": r["value"] / world * b_alg / 1e9 / peak, "algorithmic_bytes_per_cell": b_alg,
+             "halo": r["halo"], "overlap": r["overlap"], "bad_cells": r["bad_cells"], "checksum": r["checksum"]}
+        if fp32:
+            # the reference has no fp32 build (error_handling.cpp:81): parity unpinned, measured against this library's
+            # strict fp64 state of the same workload after the same number of steps when the headline ran that many
+            e["parity"] = {"pinned": False, "note": "no fp32 reference build exists; see tests/test_gpu_parity.py::"
+                           "test_fp32_against_fp64_oracle (<= 1e-5 relative L1 against the fp64 oracle)"}
+            if world == 1:
+                try:
+                    r64 = run_b200(dict(spec, precision=2), "strict", CONFIG_STEPS, CONFIG_WARMUP, ctx, keep_state=True)
+                    a, b = r["state"].double(), r64["state"]
+                    e["parity"]["rel_l1_vs_strict_fp64_same_steps"] = float(((a - b).abs().sum() / b.abs().sum()).item())
+                    e["parity"]["tolerance"] = 1e-5
+                    del a, b, r64
+                except Exception as ex:  # noqa: BLE001
+                    e["parity"]["error"] = repr(ex)[:200]
+        elif rank == 0:
+            key = "%s|%s|%s|%d" % (spec["workload"], spec["solver"], spec.get("global_size"), CONFIG_STEPS + CONFIG_WARMUP)
+            if key in golden:
+                e["checksum_equals_1gpu_run"] = golden[key] == r["checksum"]
+            if world == 1 and not args.no_parity:
+                ref = reference_child(spec, CONFIG_STEPS, CONFIG_WARMUP)
+                if "value" in ref:
+                    e["reference"] = {"value": ref["value"], "ms_per_step": ref["ms_per_step"], "checksum": ref["checksum"]}
+                    e["speedup_vs_reference"] = r["value"] / ref["value"]
+                    e["parity"] = {"bit_equal_vs_reference": ref["checksum"] == r["checksum"], "cells": r["cells_total"],
+                                   "steps": CONFIG_STEPS + CONFIG_WARMUP}
+                else:
+                    e["reference"] = ref
+        r["state"] = None
+        out.append(e)
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -300,26 +493,31 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=512, help="cells per axis PER GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "dropin"])
+    ap.add_argument("--size", type=int, default=512, help="cells per axis PER GPU (weak scaling)")
+    ap.add_argument("--global-size", type=int, default=None, help="cells per axis of the whole problem (fixed box)")
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"],
                     help="strict = bit-reproduces the reference (headline); fast = product arithmetic (FMA, shared "
                          "reciprocals), reported beside it")
-    ap.add_argument("--workload", default="blast", choices=["blast", "kh", "noise"],
-                    help="blast = BASELINE config 5 (headline); kh = Kelvin-Helmholtz (config 3 initial conditions); "
-                         "noise = random cell-to-cell state (worst case for the limiters)")
+    ap.add_argument("--workload", default="blast", choices=["blast", "kh", "noise", "sound", "sod", "ot"],
+                    help="blast = BASELINE config 5 (headline); kh = Kelvin-Helmholtz (config 3); sound / sod = config 2; "
+                         "ot = Orszag-Tang, MHD (config 4); noise = random cell-to-cell state (worst case for the limiters)")
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
-    ap.add_argument("--recon", default="ppmc", choices=["pcm", "plmc", "ppmc", "plmp", "ppmp"], help="headline: ppmc")
-    ap.add_argument("--solver", default="hllc", choices=["hllc", "roe", "hll", "exact"], help="headline: hllc")
+    ap.add_argument("--recon", default="ppmc", choices=sorted(RECONS), help="headline: ppmc")
+    ap.add_argument("--solver", default="hllc", choices=sorted(SOLVERS), help="headline: hllc")
     ap.add_argument("--integrator", default="vl", choices=["vl", "simple"],
                     help="headline: vl; simple = the reference's -DSIMPLE integrator (PCM / PLMC only)")
     ap.add_argument("--ref-variant", default="shipped", choices=["shipped", "nosync"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference-kernel child runs (parity keys)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs array (BASELINE configs 2-5)")
     ap.add_argument("--single-mode", action="store_true", help="do not also time the other arithmetic mode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
-    if args.impl == "reference":
+    if args.workload == "ot":
+        args.solver = "hlld"
+    if args.impl != "b200":
         return run_reference(args)
 
     import torch
@@ -336,53 +534,108 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout: keep the one JSON line clean
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         group = dist.group.WORLD
-    S = args.size
+    ctx = dict(world=world, rank=rank, local=local, group=group)
     mode = args.mode if args.precision == 2 else "fast"
-    r = run_b200(args, mode, world, rank, local, group, not args.no_e2e)
+    spec = dict(workload=args.workload, size=args.size, global_size=args.global_size, recon=args.recon, solver=args.solver,
+                precision=args.precision, integrator=args.integrator, clocks=True)
+    headline = (args.workload == "blast" and args.recon == "ppmc" and args.solver == "hllc" and args.integrator == "vl"
+                and args.precision == 2 and mode == "strict" and args.global_size is None)
+    want_configs = headline and not args.no_configs
+    r = run_b200(spec, mode, args.steps, args.warmup, ctx, not args.no_e2e)
     other = None
-    if not args.single_mode and args.precision == 2:
-        o = run_b200(args, "fast" if mode == "strict" else "strict", world, rank, local, group, False)
+    if not args.single_mode and args.precision == 2 and not r["mhd"]:
+        o = run_b200(dict(spec, clocks=False), "fast" if mode == "strict" else "strict", args.steps, args.warmup, ctx)
         other = {"mode": "fast" if mode == "strict" else "strict", "value": o["value"], "unit": "cell-updates/s",
-                 "ms_per_step": o["ms"] / args.steps, "predictor_ms_per_step": o["pred_ms_step"],
+                 "ms_per_step": o["ms_per_step"], "predictor_ms_per_step": o["pred_ms_step"],
                  "corrector_ms_per_step": o["corr_ms_step"],
                  "note": "same workload and timing in the other arithmetic mode (strict = the reference's bits; fast = "
-                         "FMA + shared reciprocals, within 1e-12 relative L1 on smooth data)"}
+                         "FMA + shared reciprocals: within 1e-12 relative L1 of the reference on SMOOTH data only -- not "
+                         "parity-valid on shock problems, where limiter decisions amplify 1-ulp differences)"}
+    configs = config_entries(ctx, args) if want_configs else None
     if rank != 0:
         dist.destroy_process_group()
         return 0
     peak, which = measured_hbm_peak()
+    nf = r["n_fields"]
     sweeps_ms = r["pred_ms_step"] + r["corr_ms_step"]
-    b_alg = B_ALG_STEP if args.precision == 2 else B_ALG_STEP / 2
+    b_alg = 40.0 * nf * (1.0 if args.precision == 2 else 0.5)
     achieved = r["cells_local"] * b_alg / (sweeps_ms * 1e-3) / 1e9 if sweeps_ms > 0 else None
-    tr = (ncu_traffic() or {}).get(mode if args.precision == 2 else "f32")
+    tr = (ncu_traffic() or {}).get(mode if args.precision == 2 else "f32") if headline else None
+    n_launch = 6 if not r["mhd"] else None
     out = {
         "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak" if r["weak"] else "strong",
         "vs_baseline": None, "dtype": "f64" if args.precision == 2 else "f32", "data": "synthetic",
-        "config": {"workload": "%s %d^3 per GPU, %s+%s, periodic, %s integrator, %s arithmetic"
-                               % (args.workload, S, args.recon.upper(), args.solver.upper(), args.integrator.upper(), mode),
+        "config": {"workload": "%s %s, %s+%s, %s integrator, %s arithmetic"
+                               % (args.workload, ("%d^3 per GPU" % args.size) if r["weak"] else ("%d^3 global" % args.global_size),
+                                  args.recon.upper(), args.solver.upper(), args.integrator.upper(), mode),
                    "global_cells": r["n_global"], "decomposition": r["np_grid"],
                    "l2": "inputs larger than L2 (%.1f GB state per GPU)" % (r["state_bytes"] / 1e9),
-                   "step": "set_dt + %s step (fused T-floor/CFL) + ghost fill/halo exchange" % args.integrator.upper()},
+                   "step": "set_dt + %s step (fused T-floor/CFL) + ghost fill/halo exchange" % args.integrator.upper(),
+                   "halo": {"transport": r["halo"], "overlapped_with_interior_update": r["overlap"]}},
         "e2e": r["e2e"],
         "gpu_launches": r["launches"],
         "clocks": r["clocks"],
+        "checksum": r["checksum"],
+        "bad_cells": r["bad_cells"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if achieved else None,
                      "traffic": tr.get("dram_bytes_per_step") if tr else None,
-                     "kernel": "vl_dir_kernel<PPMC,HLLC>: the six direction sweeps of one step (predictor x,y,z + "
-                               "corrector x,y,z), timed together by CUDA events on the launching stream",
-                     "ms_per_launch": sweeps_ms, "launches_per_step": 6,
+                     "kernel": "the direction sweeps of one step (predictor x,y,z + corrector x,y,z), timed together by "
+                               "CUDA events on the launching stream",
+                     "ms_per_launch": sweeps_ms, "launches_per_step": n_launch,
                      "algorithmic_bytes_per_launch": r["cells_local"] * b_alg,
                      "predictor_ms_per_step": r["pred_ms_step"], "corrector_ms_per_step": r["corr_ms_step"],
                      "step_frac_of_hbm_roofline": r["value"] / world * b_alg / 1e9 / peak,
-                     "fp64_pipe_busy": tr.get("fp64_pipe_busy_pct") if tr else None,
-                     "note": "achieved = %d B per cell-update (SURVEY 8d) x cells per step / time of the six sweeps; "
-                             "traffic = DRAM bytes of the same six launches from ncu (profiles/); peak " % b_alg + which +
-                             "; the sweeps are fp64-issue bound, not HBM bound, see DESIGN.md 3.1"},
+                     "note": "achieved = %d B per cell-update (SURVEY 8d) x cells per step / time of the sweeps; traffic = "
+                             "DRAM bytes of the same launches from ncu (profiles/); peak " % b_alg + which},
     }
+    if tr:
+        # the ceilings that bind: fp64 instructions per cell-update (ncu, dynamic) against the fp64 pipe, and all warp
+        # instructions against the issue slots; `achieved` scales the ncu counts to the rate measured live above
+        clk = (r["clocks"] or {}).get("sm_mhz") or 1965.0
+        cells_s = r["cells_local"] / (sweeps_ms * 1e-3)
+        fp64_peak = 148 * 64 * clk * 1e6          # fp64 thread-instructions / s: 64 lanes per SM per clock
+        issue_peak = 148 * 4 * 32 * clk * 1e6     # thread-instructions / s: 4 warp instructions per SM per clock
+        sec = {}
+        if tr.get("fp64_inst_per_cell"):
+            sec["fp64_pipe"] = {"inst_per_cell_update": tr["fp64_inst_per_cell"],
+                                "achieved_inst_per_s": tr["fp64_inst_per_cell"] * cells_s, "peak_inst_per_s": fp64_peak,
+                                "frac": tr["fp64_inst_per_cell"] * cells_s / fp64_peak,
+                                "ceiling_cell_updates_per_s": fp64_peak / tr["fp64_inst_per_cell"]}
+        if tr.get("inst_per_cell"):
+            sec["issue_slots"] = {"inst_per_cell_update": tr["inst_per_cell"],
+                                  "achieved_inst_per_s": tr["inst_per_cell"] * cells_s, "peak_inst_per_s": issue_peak,
+                                  "frac": tr["inst_per_cell"] * cells_s / issue_peak,
+                                  "ceiling_cell_updates_per_s": issue_peak / tr["inst_per_cell"]}
+        sec["ncu"] = {"fp64_pipe_busy_pct": tr.get("fp64_pipe_busy_pct"), "issue_slots_busy_pct": tr.get("issue_busy_pct"),
+                      "commit": tr.get("commit"), "file": "profiles/roofline_traffic.json"}
+        sec["note"] = ("fp64 stencil arithmetic: the bit-exact path needs %s fp64 and %s total instructions per cell-update, "
+                       "so the fp64 pipe / issue slots cap it far below the 200 B/cell HBM line (DESIGN.md 3.1)"
+                       % (tr.get("fp64_inst_per_cell"), tr.get("inst_per_cell")))
+        out["roofline"]["secondary"] = sec
     if other:
         out["other_mode"] = other
+    if world == 1 and headline and not args.no_parity:
+        ref = reference_child(dict(workload=args.workload, size=args.size, recon=args.recon, solver=args.solver),
+                              args.steps, args.warmup)
+        if "checksum" in ref:
+            out["parity"] = {"bit_equal_vs_reference": ref["checksum"] == r["checksum"], "cells": r["cells_total"],
+                             "steps": args.steps + args.warmup, "checksum": r["checksum"],
+                             "reference_checksum": ref["checksum"], "reference_value": ref["value"],
+                             "reference_ms_per_step": ref["ms_per_step"],
+                             "how": "the reference's own kernels (oracle/_ref) on the same initial conditions for the same "
+                                    "number of steps in a child process; position-weighted wrapping sums of the bit "
+                                    "patterns of all real cells"}
+        else:
+            out["parity"] = ref
+    elif world > 1 and headline:
+        out["parity"] = {"note": "N > 1: the reference needs MPI (absent): rank-count independence is asserted bit for bit by "
+                                 "tests/test_gpu_multi.py, and the fixed-size configs below carry checksums comparable with "
+                                 "the N = 1 run"}
+    if configs is not None:
+        out["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))

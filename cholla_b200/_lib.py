@@ -82,7 +82,8 @@ def lib():
     L.chl_debug_exact_sqrt.argtypes = [p, p, p, l, p]
     L.chl_debug_exact_div_flagged.argtypes = [p, p, p, p, i, l, p]
     L.chl_bad_cells.argtypes = [p, C.POINTER(C.c_ulonglong), p]
-    L.chl_set_tuning.argtypes = [p, i]
+    L.chl_set_tuning.argtypes = [p, i, i]
+    L.chl_mhd_max_divergence.argtypes = [p, p, C.POINTER(d), p]
     L.chl_halo_blob_bytes.restype = C.c_size_t
     L.chl_halo_create.argtypes = [p, ip, i, C.POINTER(p)]
     L.chl_halo_destroy.argtypes = [p]

@@ -102,6 +102,35 @@ __global__ void __launch_bounds__(256) pack_kernel(T *__restrict__ buf, T *__res
   }
 }
 
+// mhd::calculateMagneticDivergence (src/mhd/magnetic_divergence.cu:33-76): max over cells with x, y, z > 1 (ghost cells
+// whose low faces exist included) of |(Bx - Bx[i-1]) / dx + (By - By[j-1]) / dy + (Bz - Bz[k-1]) / dz|; the reduction is a
+// warp shuffle + one atomicMax per CTA on the bit pattern (non-negative doubles order like their bits)
+template <typename T>
+__global__ void __launch_bounds__(256) divb_kernel(const T *__restrict__ c, int nx, int ny, int nz, long n_cells, T dx, T dy,
+                                                   T dz, unsigned long long *out)
+{
+  double m = 0.0;
+  for (long id = blockIdx.x * (long)blockDim.x + threadIdx.x; id < n_cells; id += (long)gridDim.x * blockDim.x) {
+    int const x = (int)(id % nx);
+    long const r = id / nx;
+    int const y = (int)(r % ny), z = (int)(r / ny);
+    if (x > 1 && y > 1 && z > 1) {
+      T const d = ((c[id + 5 * n_cells] - c[id - 1 + 5 * n_cells]) / dx) + ((c[id + 6 * n_cells] - c[id - nx + 6 * n_cells]) / dy) +
+                  ((c[id + 7 * n_cells] - c[id - (long)nx * ny + 7 * n_cells]) / dz);
+      m = fmax(m, fabs((double)d));
+    }
+  }
+  __shared__ double sred[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) m = fmax(m, sred[w]);
+    atomicMax(out, (unsigned long long)__double_as_longlong(m));  // NaN sorts above every number: it is reported
+  }
+}
+
 inline int grid_for(long n)
 {
   long b = (n + 255) / 256;
@@ -145,6 +174,16 @@ cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields
   if (total <= 0) return cudaSuccess;
   if (real_bytes == 8) ghost_kernel<double><<<grid_for(total), 256, 0, s>>>((double *)c, a);
   else ghost_kernel<float><<<grid_for(total), 256, 0, s>>>((float *)c, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_divb(const void *c, int nx, int ny, int nz, double dx, double dy, double dz, unsigned long long *out,
+                        size_t real_bytes, cudaStream_t s)
+{
+  long const n = (long)nx * ny * nz;
+  int const g = grid_for(n) > 148 * 8 ? 148 * 8 : grid_for(n);
+  if (real_bytes == 8) divb_kernel<double><<<g, 256, 0, s>>>((const double *)c, nx, ny, nz, n, dx, dy, dz, out);
+  else divb_kernel<float><<<g, 256, 0, s>>>((const float *)c, nx, ny, nz, n, (float)dx, (float)dy, (float)dz, out);
   return cudaGetLastError();
 }
 

@@ -52,8 +52,9 @@ struct chl_ctx {
   void *d_ctf;                // MHD: 9 * n_cells flux components kept for constrained transport
   void *d_E;                  // MHD: 3 * n_cells edge EMFs
   int dir_chunk;              // marching length override (0 = auto), chl_set_tuning
-  unsigned long long *d_key;  // [0] CFL accumulator (ordered key), [1] count of cells with density <= 0
-  unsigned long long *h_key;  // pinned, 2 words
+  int fused_predictor;        // chl_set_tuning: 1 = the single-launch predictor (vl_predictor.cuh) instead of three sweeps
+  unsigned long long *d_key;  // [0] CFL accumulator (ordered key), [1] count of cells with density <= 0, [2] max |div B|
+  unsigned long long *h_key;  // pinned, 3 words
   size_t n_cells;
   int ndim;
   int profiling;                       // record events around each stage
@@ -139,6 +140,7 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->mhd = mhd;
   c->d_prim = c->d_ctf = c->d_E = nullptr;
   c->dir_chunk = 0;
+  c->fused_predictor = 0;
   c->d_key = nullptr;
   c->h_key = nullptr;
   c->profiling = 0;
@@ -155,10 +157,10 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
     if (e == cudaSuccess) e = cudaMemset(c->d_ctf, 0, 9 * w);
     if (e == cudaSuccess) e = cudaMemset(c->d_E, 0, 6 * w);
   }
-  if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, 2 * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, 3 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, 3 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(c->d_half, 0, bytes);
-  if (e == cudaSuccess) e = cudaMemset(c->d_key, 0, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(c->d_key, 0, 3 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     chl_destroy(c);
     return fail(CHL_ERR_CUDA, "chl_create: allocation", e);
@@ -246,6 +248,7 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
   a.simple = 0;
   a.part = 0;
   a.shell = 0;
+  a.fused_predictor = c->fused_predictor;
   auto const sweep = c->ops->sweep_split;
   int const n[3] = {g.nx, g.ny, g.nz};
   // ---- predictor: every cell but the outermost ring (VL_3D_cuda.cu:408) ----
@@ -340,6 +343,7 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
   a.simple = 1;
   a.part = 0;
   a.shell = 0;
+  a.fused_predictor = 0;
   int const n[3] = {g.nx, g.ny, g.nz};
   for (int d = 0; d < 3; d++) {
     bool const on = d == 0 || (d == 1 && a.has_y) || (d == 2 && a.has_z);
@@ -441,10 +445,25 @@ int chl_bad_cells(chl_ctx *c, unsigned long long *h_count, void *stream)
   return CHL_OK;
 }
 
-int chl_set_tuning(chl_ctx *c, int dir_chunk)
+int chl_mhd_max_divergence(chl_ctx *c, const void *U, double *h_max, void *stream)
+{
+  if (!c || !U || !h_max) return fail(CHL_ERR_INVALID, "chl_mhd_max_divergence: null argument");
+  if (!c->mhd) return fail(CHL_ERR_INVALID, "chl_mhd_max_divergence: not an MHD context");
+  cudaStream_t s = (cudaStream_t)stream;
+  chl_config const &g = c->cfg;
+  CHL_CUDA(cudaMemsetAsync(c->d_key + 2, 0, sizeof(unsigned long long), s));
+  CHL_CUDA(chl::launch_divb(U, g.nx, g.ny, g.nz, g.dx, g.dy, g.dz, c->d_key + 2, c->ops->real_bytes, s));
+  CHL_CUDA(cudaMemcpyAsync(c->h_key + 2, c->d_key + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CHL_CUDA(cudaStreamSynchronize(s));
+  memcpy(h_max, c->h_key + 2, sizeof(double));
+  return CHL_OK;
+}
+
+int chl_set_tuning(chl_ctx *c, int dir_chunk, int fused_predictor)
 {
   if (!c || dir_chunk < 0) return fail(CHL_ERR_INVALID, "chl_set_tuning: bad argument");
   c->dir_chunk = dir_chunk;
+  c->fused_predictor = fused_predictor ? 1 : 0;
   return CHL_OK;
 }
 

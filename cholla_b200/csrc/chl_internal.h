@@ -16,6 +16,7 @@ struct SweepArgs {  // everything in double; each mode TU narrows to its Real
   int dir_chunk;  // cells per thread along the marching direction (0 = choose)
   int part;       // 0 = the whole stage; 1 = all but the interior box of the last pass; 2 = that interior box
   int shell;      // thickness of the boundary shell completed first when part != 0 (the ghost depth)
+  int fused_predictor;  // 1: the predictor of a 3-D grid as ONE launch (vl_predictor.cuh) instead of three direction sweeps
   int simple;     // 1: SIMPLE integrator -- stage 1 reconstructs with the -DSIMPLE forms (PLMC gains its tracing)
   double dtodx, dtody, dtodz, gamma, density_floor;
   int apply_tfloor;

@@ -21,16 +21,26 @@ constexpr Real kHlldSmall = RC(1.0e-8);  // hlld_cuda.h:35
 
 // A denominator several quotients share.  Strict: exact_div.cuh's Den / qdiv (the bits of a / b).  Product mode: one
 // straight-line reciprocal and a multiplication per quotient.
+// The policy of exact_div.cuh applies (K::kDiv): the sweeps evaluate their quotients branch-free with a sticky flag and redo a
+// flagged block with IEEE divisions; msq() is the square root with exact zeros (a vanishing slow speed) on the fast path.
 #if CHL_STRICT
 typedef Den RDen;
-__device__ __forceinline__ RDen rden(Real b) { return den(b); }
-__device__ __forceinline__ Real rdiv(Real a, RDen const &d) { return qdiv(a, d); }
+template <class K>
+__device__ __forceinline__ RDen rden(Real b, K const &k) { return den(b, k); }
+template <class K>
+__device__ __forceinline__ Real rdiv(Real a, RDen const &d, K const &k) { return qdiv(a, d, k); }
+template <class K>
+__device__ __forceinline__ Real msq(Real x, K const &k) { return sqrt_r<true>(x, k); }
 #else
 struct RDen {
   Real y;
 };
-__device__ __forceinline__ RDen rden(Real b) { return RDen{rcp_r(b)}; }
-__device__ __forceinline__ Real rdiv(Real a, RDen const &d) { return a * d.y; }
+template <class K>
+__device__ __forceinline__ RDen rden(Real b, K const &k) { (void)k; return RDen{rcp_r(b)}; }
+template <class K>
+__device__ __forceinline__ Real rdiv(Real a, RDen const &d, K const &k) { (void)k; return a * d.y; }
+template <class K>
+__device__ __forceinline__ Real msq(Real x, K const &k) { (void)k; return sqrt_r(x); }
 #endif
 
 __device__ __forceinline__ Real dot3(Real a1, Real a2, Real a3, Real b1, Real b2, Real b3)
@@ -42,36 +52,44 @@ __device__ __forceinline__ Real total_pressure(Real p, Real bx, Real by, Real bz
 {
   return max_s(p + mag_energy(bx, by, bz), kTiny);
 }
-__device__ __forceinline__ Real msonic_disc(Real p, Real bx, Real by, Real bz, Real gamma, Real &t1)
+template <class K>
+__device__ __forceinline__ Real msonic_disc(Real p, Real bx, Real by, Real bz, K const &k, Real &t1)
 {
+  Real const gamma = k.gamma;
   Real const bx2 = bx * bx;
   Real const b2  = bx2 + ((by * by) + (bz * bz));
   t1             = gamma * p + b2;
   Real t2        = (t1 * t1) - RC(4.) * gamma * p * bx2;
 #if CHL_STRICT
-  t2 = sqrt_r(t2);
+  t2 = msq(t2, k);
 #else
   t2 = t2 > RC(0.0) ? sqrt_r(t2) : RC(0.0);  // (gamma p - bx^2)^2 when the transverse field vanishes: can be an exact zero
 #endif
   return t2;
 }
 // _magnetosonicSpeed (mhd_utilities.h:48-73), wave = +1 fast / -1 slow
-__device__ __forceinline__ Real magnetosonic(Real d, Real p, Real bx, Real by, Real bz, Real gamma, Real wave)
+template <class K>
+__device__ __forceinline__ Real magnetosonic(Real d, Real p, Real bx, Real by, Real bz, K const &k, Real wave)
 {
   Real t1;
-  Real const t2 = msonic_disc(p, bx, by, bz, gamma, t1);
-  return sqrt_r(rdiv(t1 + wave * t2, rden(RC(2.0) * max_s(d, kTiny))));
+  Real const t2 = msonic_disc(p, bx, by, bz, k, t1);
+  return msq(rdiv(t1 + wave * t2, rden(RC(2.0) * max_s(d, kTiny), k), k), k);
 }
 // fast and slow speed of one state: the discriminant and the division by 2 rho are shared
-__device__ __forceinline__ void magnetosonic_pair(Real d, Real p, Real bx, Real by, Real bz, Real gamma, Real &cf, Real &cs)
+template <class K>
+__device__ __forceinline__ void magnetosonic_pair(Real d, Real p, Real bx, Real by, Real bz, K const &k, Real &cf, Real &cs)
 {
   Real t1;
-  Real const t2 = msonic_disc(p, bx, by, bz, gamma, t1);
-  RDen const dd = rden(RC(2.0) * max_s(d, kTiny));
-  cf = sqrt_r(rdiv(t1 + RC(1.0) * t2, dd));
-  cs = sqrt_r(rdiv(t1 + RC(-1.0) * t2, dd));
+  Real const t2 = msonic_disc(p, bx, by, bz, k, t1);
+  RDen const dd = rden(RC(2.0) * max_s(d, kTiny), k);
+  cf = msq(rdiv(t1 + RC(1.0) * t2, dd, k), k);
+  cs = msq(rdiv(t1 + RC(-1.0) * t2, dd, k), k);
 }
-__device__ __forceinline__ Real alfven_speed(Real bx, Real d) { return rdiv(fabs(bx), rden(sqrt_r(max_s(d, kTiny)))); }
+template <class K>
+__device__ __forceinline__ Real alfven_speed(Real bx, Real d, K const &k)
+{
+  return rdiv(fabs(bx), rden(msq(max_s(d, kTiny), k), k), k);
+}
 // hydro_utilities.h:34-45 / 106-118 (MHD)
 __device__ __forceinline__ Real mhd_pressure(Real E, Real d, Real vx, Real vy, Real vz, Real gamma, Real bx, Real by,
                                              Real bz)
@@ -80,11 +98,12 @@ __device__ __forceinline__ Real mhd_pressure(Real E, Real d, Real vx, Real vy, R
   p -= mag_energy(bx, by, bz);
   return max_s((gamma - RC(1.)) * p, kTiny);
 }
-__device__ __forceinline__ Real mhd_energy(Real P, Real d, Real vx, Real vy, Real vz, KC const &k, Real bx, Real by,
+template <class K>
+__device__ __forceinline__ Real mhd_energy(Real P, Real d, Real vx, Real vy, Real vz, K const &k, Real bx, Real by,
                                            Real bz)
 {
 #if CHL_STRICT
-  Real e = qdiv(max_s(P, kTiny), k.g1) + RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
+  Real e = qdiv<false>(max_s(P, kTiny), k.g1, k) + RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
 #else
   Real e = (max_s(P, kTiny) * k.ig1) + RC(0.5) * d * dot3(vx, vy, vz, vx, vy, vz);
 #endif
@@ -104,14 +123,16 @@ struct Eigen {
   Real cf, cs, cf2, cs2, alpha_f, alpha_s, beta_y, beta_z, n_fs, sign, q_f, q_s, a_f, a_s, qp_f, qp_s, ap_f, ap_s;
   Real d, a2, isd, sqd;
   RDen dd, da2;  // the two denominators of Primitive_To_Characteristic: rho and a^2
-  __device__ __forceinline__ void init(MPrim const &w, Real gamma)
+  template <class K>
+  __device__ __forceinline__ void init(MPrim const &w, K const &k)
   {
-    dd           = rden(w.d);
-    Real const a = sqrt_r(rdiv(gamma * w.p, dd));  // hydro_utilities::Calc_Sound_Speed
+    Real const gamma = k.gamma;
+    dd           = rden(w.d, k);
+    Real const a = msq(rdiv(gamma * w.p, dd, k), k);  // hydro_utilities::Calc_Sound_Speed
     a2           = a * a;
-    da2          = rden(a2);
+    da2          = rden(a2, k);
     d            = w.d;
-    magnetosonic_pair(w.d, w.p, w.bx, w.by, w.bz, gamma, cf, cs);
+    magnetosonic_pair(w.d, w.p, w.bx, w.by, w.bz, k, cf, cs);
     cf2 = cf * cf;
     cs2 = cs * cs;
     Real const denom = cf2 - cs2, num2 = cf2 - a2;
@@ -124,39 +145,40 @@ struct Eigen {
         alpha_f = RC(0.0);
         alpha_s = RC(1.0);
       } else {
-        RDen const dn = rden(denom);
-        alpha_f       = sqrt_r(rdiv(num1, dn));
-        alpha_s       = sqrt_r(rdiv(num2, dn));
+        RDen const dn = rden(denom, k);
+        alpha_f       = msq(rdiv(num1, dn, k), k);
+        alpha_s       = msq(rdiv(num2, dn, k), k);
       }
     }
     Real const bd = rhypot(w.by, w.bz);
     beta_y        = isfinite(bd) ? w.by * bd : RC(1.0);
     beta_z        = isfinite(bd) ? w.bz * bd : RC(0.0);
     sign          = copysign(RC(1.0), w.bx);
-    n_fs          = rdiv(RC(0.5), da2);
+    n_fs          = rdiv(RC(0.5), da2, k);
     qp_f          = sign * n_fs * alpha_f * cf;
     qp_s          = sign * n_fs * alpha_s * cs;
     q_f           = sign * alpha_f * cf;
     q_s           = sign * alpha_s * cs;
-    sqd           = sqrt_r(w.d);
+    sqd           = msq(w.d, k);
     a_f           = alpha_f * a * sqd;
     a_s           = alpha_s * a * sqd;
-    RDen const das = rden(a * sqd);
-    ap_f           = rdiv(RC(0.5) * alpha_f, das);
-    ap_s           = rdiv(RC(0.5) * alpha_s, das);
+    RDen const das = rden(a * sqd, k);
+    ap_f           = rdiv(RC(0.5) * alpha_f, das, k);
+    ap_s           = rdiv(RC(0.5) * alpha_s, das, k);
     isd           = rsqrt(w.d);
   }
   // s = (d, vx, vy, vz, p, by, bz) of a state or of a difference
+  template <class K>
   __device__ __forceinline__ void project(Real sd, Real svx, Real svy, Real svz, Real sp, Real sby, Real sbz,
-                                          Real (&o)[7]) const
+                                          Real (&o)[7], K const &k) const
   {
-    Real const spd = rdiv(sp, dd);
+    Real const spd = rdiv(sp, dd, k);
     o[0] = n_fs * alpha_f * (spd - cf * svx) + qp_s * (beta_y * svy + beta_z * svz) +
            ap_s * (beta_y * sby + beta_z * sbz);
     o[1] = RC(0.5) * (beta_y * (sbz * sign * isd + svz) - beta_z * (sby * sign * isd + svy));
     o[2] = n_fs * alpha_s * (spd - cs * svx) - qp_f * (beta_y * svy + beta_z * svz) -
            ap_f * (beta_y * sby + beta_z * sbz);
-    o[3] = sd - rdiv(sp, da2);
+    o[3] = sd - rdiv(sp, da2, k);
     o[4] = n_fs * alpha_s * (spd + cs * svx) + qp_f * (beta_y * svy + beta_z * svz) -
            ap_f * (beta_y * sby + beta_z * sbz);
     o[5] = RC(0.5) * (beta_y * (sbz * sign * isd - svz) - beta_z * (sby * sign * isd - svy));
@@ -214,11 +236,11 @@ __device__ __forceinline__ void mhd_floor(MPrim &l, MPrim &r)
 // family at a time -- the four magneto-sonic ones, the two Alfven ones, the entropy one -- each family reloading the few
 // primitives it needs (L1) and handing its 5-cell stencils straight to ppm_single, so the projection-only part of the
 // eigen-system dies after the first family.  Every expression keeps Eigen::project()'s association (same bits).
-__device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const &o, KC const &k, MPrim &L, MPrim &R)
+template <class K>
+__device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const &o, K const &k, MPrim &L, MPrim &R)
 {
-  Real const gamma = k.gamma;
   Eigen e;
-  e.init(load_mprim(c, o, 0), gamma);
+  e.init(load_mprim(c, o, 0), k);
   Real cl[7], cr[7];
   {  // fast / slow magneto-sonic pairs: characteristics 0, 6 (fast) and 2, 4 (slow)
     Real const nf = e.n_fs * e.alpha_f, ns = e.n_fs * e.alpha_s;
@@ -228,7 +250,7 @@ __device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const 
       const Real *q  = c + (long)(i - 2) * o.s;
       Real const svx = __ldg(q + o.v1), svy = __ldg(q + o.v2), svz = __ldg(q + o.v3);
       Real const sby = __ldg(q + o.b2), sbz = __ldg(q + o.b3);
-      Real const spd = rdiv(__ldg(q + o.p), e.dd);
+      Real const spd = rdiv(__ldg(q + o.p), e.dd, k);
       Real const A = e.beta_y * svy + e.beta_z * svz, B = e.beta_y * sby + e.beta_z * sbz;
       Real const qsA = e.qp_s * A, qfA = e.qp_f * A, asB = e.ap_s * B, afB = e.ap_f * B;
       Real const fx = e.cf * svx, sx = e.cs * svx;
@@ -260,7 +282,7 @@ __device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const 
 #pragma unroll
     for (int i = 0; i < 5; i++) {
       const Real *q = c + (long)(i - 2) * o.s;
-      t3[i]         = __ldg(q) - rdiv(__ldg(q + o.p), e.da2);
+      t3[i]         = __ldg(q) - rdiv(__ldg(q + o.p), e.da2, k);
     }
     ppm_single(t3[0], t3[1], t3[2], t3[3], t3[4], cl[3], cr[3], k);
   }
@@ -269,11 +291,12 @@ __device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const 
   mhd_floor(L, R);
 }
 
-__device__ __forceinline__ void mhd_plmc(const Real *__restrict__ c, MOff const &o, Real gamma, MPrim &L, MPrim &R)
+template <class K>
+__device__ __forceinline__ void mhd_plmc(const Real *__restrict__ c, MOff const &o, K const &k, MPrim &L, MPrim &R)
 {
   MPrim const wi = load_mprim(c, o, 0), wm = load_mprim(c, o, -1), wp = load_mprim(c, o, 1);
   Eigen e;
-  e.init(wi, gamma);
+  e.init(wi, k);
   Real const im[7] = {wm.d, wm.vx, wm.vy, wm.vz, wm.p, wm.by, wm.bz};
   Real const ii[7] = {wi.d, wi.vx, wi.vy, wi.vz, wi.p, wi.by, wi.bz};
   Real const ip[7] = {wp.d, wp.vx, wp.vy, wp.vz, wp.p, wp.by, wp.bz};
@@ -283,13 +306,13 @@ __device__ __forceinline__ void mhd_plmc(const Real *__restrict__ c, MOff const 
     dL[f] = RC(1.0) * (ii[f] - im[f]);
     dR[f] = RC(1.0) * (ip[f] - ii[f]);
     dC[f] = RC(0.5) * (ip[f] - im[f]);
-    dG[f] = vl_slope(dL[f], dR[f]);
+    dG[f] = vl_slope(dL[f], dR[f], k);
   }
   Real aL[7], aR[7], aC[7], aG[7], am[7];
-  e.project(dL[0], dL[1], dL[2], dL[3], dL[4], dL[5], dL[6], aL);
-  e.project(dR[0], dR[1], dR[2], dR[3], dR[4], dR[5], dR[6], aR);
-  e.project(dC[0], dC[1], dC[2], dC[3], dC[4], dC[5], dC[6], aC);
-  e.project(dG[0], dG[1], dG[2], dG[3], dG[4], dG[5], dG[6], aG);
+  e.project(dL[0], dL[1], dL[2], dL[3], dL[4], dL[5], dL[6], aL, k);
+  e.project(dR[0], dR[1], dR[2], dR[3], dR[4], dR[5], dR[6], aR, k);
+  e.project(dC[0], dC[1], dC[2], dC[3], dC[4], dC[5], dC[6], aC, k);
+  e.project(dG[0], dG[1], dG[2], dG[3], dG[4], dG[5], dG[6], aG, k);
 #pragma unroll
   for (int f = 0; f < 7; f++) am[f] = mono_slope(aL[f], aR[f], aC[f], aG[f]);
   MPrim const dm = e.unproject(am);
@@ -308,7 +331,8 @@ __device__ __forceinline__ void mhd_plmc(const Real *__restrict__ c, MOff const 
 
 // Write_Data (reconstruction.h:918-968): interface primitives -> (d, m1, m2, m3, E, By, Bz); the energy uses the
 // FACE-centred normal field of the face the state sits on
-__device__ __forceinline__ M7 mhd_interface(MPrim const &q, Real bface, KC const &k)
+template <class K>
+__device__ __forceinline__ M7 mhd_interface(MPrim const &q, Real bface, K const &k)
 {
   M7 s;
   s.v[0] = q.d;
@@ -328,14 +352,16 @@ struct HState {
 struct HStar {
   Real d, vy, vz, E, by, bz;
 };
-__device__ __forceinline__ HState hlld_load(M7 const &q, Real bx, Real gamma)
+template <class K>
+__device__ __forceinline__ HState hlld_load(M7 const &q, Real bx, K const &k)
 {
+  Real const gamma = k.gamma;
   HState s;
   s.d  = max_s(q.v[0], kTiny);
-  RDen const dd = rden(s.d);
-  s.vx = rdiv(q.v[1], dd);
-  s.vy = rdiv(q.v[2], dd);
-  s.vz = rdiv(q.v[3], dd);
+  RDen const dd = rden(s.d, k);
+  s.vx = rdiv(q.v[1], dd, k);
+  s.vy = rdiv(q.v[2], dd, k);
+  s.vz = rdiv(q.v[3], dd, k);
   s.E  = max_s(q.v[4], kTiny);
   s.by = q.v[5];
   s.bz = q.v[6];
@@ -355,30 +381,31 @@ __device__ __forceinline__ M7 hlld_nonstar(HState const &s, Real bx)
   f.v[4] = s.vx * (s.E + s.pt) - bx * (s.vx * bx + ((s.vy * s.by) + (s.vz * s.bz)));
   return f;
 }
-__device__ __forceinline__ HStar hlld_star(HState const &s, Real S, Real SM, Real bx, Real pts)
+template <class K>
+__device__ __forceinline__ HStar hlld_star(HState const &s, Real S, Real SM, Real bx, Real pts, K const &k)
 {
   HStar o;
-  RDen const dsm = rden(S - SM);
-  o.d = rdiv(s.d * (S - s.vx), dsm);
+  RDen const dsm = rden(S - SM, k);
+  o.d = rdiv(s.d * (S - s.vx), dsm, k);
   if (fabs(s.d * (S - s.vx) * (S - SM) - (bx * bx)) < pts * kHlldSmall) {
     o.vy = s.vy;
     o.vz = s.vz;
     o.by = s.by;
     o.bz = s.bz;
   } else {
-    RDen const dn = rden(s.d * (S - s.vx) * (S - SM) - (bx * bx));
-    Real coef     = rdiv(bx * (SM - s.vx), dn);
+    RDen const dn = rden(s.d * (S - s.vx) * (S - SM) - (bx * bx), k);
+    Real coef     = rdiv(bx * (SM - s.vx), dn, k);
     o.vy          = s.vy - s.by * coef;
     o.vz          = s.vz - s.bz * coef;
     Real t        = (S - s.vx);
     t             = t * t;
-    coef          = rdiv(s.d * t - (bx * bx), dn);
+    coef          = rdiv(s.d * t - (bx * bx), dn, k);
     o.by          = s.by * coef;
     o.bz          = s.bz * coef;
   }
   o.E = rdiv(s.E * (S - s.vx) - s.pt * s.vx + pts * SM +
                  bx * (dot3(s.vx, s.vy, s.vz, bx, s.by, s.bz) - dot3(SM, o.vy, o.vz, bx, o.by, o.bz)),
-             dsm);
+             dsm, k);
   return o;
 }
 __device__ __forceinline__ M7 hlld_star_flux(HStar const &st, HState const &s, M7 const &f, Real SM, Real S)
@@ -410,11 +437,12 @@ __device__ __forceinline__ M7 hlld_dstar_flux(Real vyd, Real vzd, Real byd, Real
 
 // Calculate_HLLD_Fluxes_CUDA for one interface.  Returns false when no branch of the reference fires (NaN input);
 // the reference kernel then leaves its flux array untouched -- here the flux is zero.
-__device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, Real gamma, M7 &f)
+template <class K>
+__device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, K const &k, M7 &f)
 {
-  HState const l = hlld_load(ql, bx, gamma), r = hlld_load(qr, bx, gamma);
-  Real const cfl  = magnetosonic(l.d, l.pg, bx, l.by, l.bz, gamma, RC(1.0));
-  Real const cfr  = magnetosonic(r.d, r.pg, bx, r.by, r.bz, gamma, RC(1.0));
+  HState const l = hlld_load(ql, bx, k), r = hlld_load(qr, bx, k);
+  Real const cfl  = magnetosonic(l.d, l.pg, bx, l.by, l.bz, k, RC(1.0));
+  Real const cfr  = magnetosonic(r.d, r.pg, bx, r.by, r.bz, k, RC(1.0));
   Real const cmax = fmax(cfl, cfr);
   Real const SL = fmin(l.vx, r.vx) - cmax, SR = fmax(l.vx, r.vx) + cmax;
   M7 const fl = hlld_nonstar(l, bx);
@@ -429,19 +457,19 @@ __device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, R
   }
   Real const rdiff = SR - r.vx, ldiff = SL - l.vx;
   // (rdiff * r.d - ldiff * l.d) and (r.d * (SR - r.vx) - l.d * (SL - l.vx)) are the same products: one denominator
-  RDen const dsm = rden(rdiff * r.d - ldiff * l.d);
-  Real const SM  = rdiv(rdiff * r.d * r.vx - ldiff * l.d * l.vx - r.pt + l.pt, dsm);
+  RDen const dsm = rden(rdiff * r.d - ldiff * l.d, k);
+  Real const SM  = rdiv(rdiff * r.d * r.vx - ldiff * l.d * l.vx - r.pt + l.pt, dsm, k);
   Real const pts = rdiv(r.d * l.pt * (SR - r.vx) - l.d * r.pt * (SL - l.vx) +
                             l.d * r.d * (SR - r.vx) * (SL - l.vx) * (r.vx - l.vx),
-                        dsm);
-  HStar const sl = hlld_star(l, SL, SM, bx, pts);
-  Real const SLs = SM + RC(-1.0) * alfven_speed(bx, sl.d);
+                        dsm, k);
+  HStar const sl = hlld_star(l, SL, SM, bx, pts, k);
+  Real const SLs = SM + RC(-1.0) * alfven_speed(bx, sl.d, k);
   if (SLs > RC(0.0) && SL <= RC(0.0)) {
     f = hlld_star_flux(sl, l, fl, SM, SL);
     return true;
   }
-  HStar const sr = hlld_star(r, SR, SM, bx, pts);
-  Real const SRs = SM + RC(1.0) * alfven_speed(bx, sr.d);
+  HStar const sr = hlld_star(r, SR, SM, bx, pts, k);
+  Real const SRs = SM + RC(1.0) * alfven_speed(bx, sr.d, k);
   if (SRs <= RC(0.0) && SR >= RC(0.0)) {
     f = hlld_star_flux(sr, r, fr, SM, SR);
     return true;
@@ -454,8 +482,8 @@ __device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, R
       vyd = sr.vy; vzd = sr.vz; byd = sr.by; bzd = sr.bz; EdR = sr.E;
     }
   } else {
-    Real const sdl = sqrt_r(sl.d), sdr = sqrt_r(sr.d);
-    Real const inv = rdiv(RC(1.0), rden(sdl + sdr));
+    Real const sdl = msq(sl.d, k), sdr = msq(sr.d, k);
+    Real const inv = rdiv(RC(1.0), rden(sdl + sdr, k), k);
     Real const sg  = copysign(RC(1.0), bx);
     vyd = inv * (sdl * sl.vy + sdr * sr.vy + sg * (sr.by - sl.by));
     vzd = inv * (sdl * sl.vz + sdr * sr.vz + sg * (sr.bz - sl.bz));
@@ -482,8 +510,9 @@ __device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, R
 __device__ __forceinline__ Real mhd_inverse_crossing_time(Real E, Real d, Real vx, Real vy, Real vz, Real bx, Real by,
                                                           Real bz, Real dx, Real dy, Real dz, Real gamma)
 {
+  KC const kb   = make_kc(gamma);  // once per cell and step: the per-quotient fallback branch is fine here
   Real const p  = mhd_pressure(E, d, vx, vy, vz, gamma, bx, by, bz);
-  Real const cf = magnetosonic(d, p, bx, by, bz, gamma, RC(1.0));
+  Real const cf = magnetosonic(d, p, bx, by, bz, kb, RC(1.0));
   Real m        = fmax((fabs(vx) + cf) / dx, (fabs(vy) + cf) / dy);
   m             = fmax(m, (fabs(vz) + cf) / dz);
   m             = fmax(m, RC(0.0));

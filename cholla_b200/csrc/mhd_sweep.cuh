@@ -78,10 +78,76 @@ __device__ __forceinline__ void cell_centred_b(const Real *__restrict__ U, size_
 __device__ __forceinline__ void cell_emf(Real *__restrict__ ecen, size_t N, size_t id, Real d, Real mx, Real my, Real mz,
                                          Real bx, Real by, Real bz)
 {
-  RDen const dd    = rden(d);
-  ecen[id]         = rdiv(mz * by - my * bz, dd);
-  ecen[N + id]     = rdiv(mx * bz - mz * bx, dd);
-  ecen[2 * N + id] = rdiv(my * bx - mx * by, dd);
+  KC kb;  // once per cell and stage: the per-quotient fallback branch (kDivBranchy) is fine here
+  kb.bad           = false;
+  RDen const dd    = rden(d, kb);
+  ecen[id]         = rdiv(mz * by - my * bz, dd, kb);
+  ecen[N + id]     = rdiv(mx * bz - mz * bx, dd, kb);
+  ecen[2 * N + id] = rdiv(my * bx - mx * by, dd, kb);
+}
+
+// ---- the two blocks of a sweep iteration: branch-free arithmetic, one flag test, out-of-line IEEE redo (as in
+// sweep_common.cuh) ------------------------------------------------------------------------------------------------
+struct M7x2 {
+  M7 L, R;
+};
+template <int RECON, class K>
+__device__ __forceinline__ void mhd_recon(const Real *__restrict__ c, MOff const &o, Real bhi, Real blo, K const &k, M7 &L,
+                                          M7 &R)
+{
+  if (RECON == kPCM) {
+    MPrim const w = load_mprim(c, o, 0);  // PCM corrector: interface = cell, energy from the cell state
+    L             = mhd_interface(w, w.bx, k);
+    // PCM copies the conserved energy; rebuilding it from primitives with the centred field is the same sum
+    R = L;
+    return;
+  }
+  MPrim l, r;
+  if (RECON == kPPMC) mhd_ppmc(c, o, k, l, r);
+  else mhd_plmc(c, o, k, l, r);
+  L = mhd_interface(l, bhi, k);
+  R = mhd_interface(r, blo, k);
+}
+#if CHL_STRICT
+template <int RECON>
+static __device__ __noinline__ M7x2 mhd_recon_ieee(const Real *c, MOff o, Real bhi, Real blo, Real gamma)
+{
+  KCS const k = make_kct<KCS>(gamma);
+  M7x2 out;
+  mhd_recon<RECON>(c, o, bhi, blo, k, out.L, out.R);
+  return out;
+}
+static __device__ __noinline__ M7 hlld_ieee(M7 L, M7 R, Real bface, Real gamma)
+{
+  KCS const k = make_kct<KCS>(gamma);
+  M7 f;
+  hlld_flux(L, R, bface, k, f);
+  return f;
+}
+#endif
+template <int RECON>
+__device__ __forceinline__ void mhd_recon_checked(const Real *__restrict__ c, MOff const &o, Real bhi, Real blo, KH const &k,
+                                                  M7 &L, M7 &R)
+{
+  mhd_recon<RECON>(c, o, bhi, blo, k, L, R);
+#if CHL_STRICT
+  if (k.bad) {
+    M7x2 const out = mhd_recon_ieee<RECON>(c, o, bhi, blo, k.gamma);
+    L     = out.L;
+    R     = out.R;
+    k.bad = false;
+  }
+#endif
+}
+__device__ __forceinline__ void hlld_checked(M7 const &L, M7 const &R, Real bface, KH const &k, M7 &F)
+{
+  hlld_flux(L, R, bface, k, F);
+#if CHL_STRICT
+  if (k.bad) {
+    F     = hlld_ieee(L, R, bface, k.gamma);
+    k.bad = false;
+  }
+#endif
 }
 
 template <int RECON, int STAGE, int DIR, bool FIRST, bool LAST>
@@ -130,7 +196,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
   int const pstride  = DIR == 0 ? kRowsPerCta : kDirThreads;
   Real *const staged = stage + threadIdx.x;
   constexpr int field_of_comp[5] = {0, 1 + DIR, 1 + (DIR + 1) % 3, 1 + (DIR + 2) % 3, 4};
-  KC const kc = make_kc(gamma);
+  KH const kc = make_kct<KH>(gamma);
 
   Real Lc[7], Fc[5];
 #pragma unroll
@@ -178,19 +244,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
       } else {
         Real const bhi = __ldg(P.Bsrc + (size_t)(5 + DIR) * N + id);            // +face of cell c
         Real const blo = c > 0 ? __ldg(P.Bsrc + (size_t)(5 + DIR) * N + id - o.s) : bhi;  // -face of cell c
-        if (RECON == kPCM) {
-          MPrim const w = load_mprim(P.in + id, o, 0);  // PCM corrector: interface = cell, energy from the cell state
-          MPrim q       = w;
-          L             = mhd_interface(q, w.bx, kc);
-          // PCM copies the conserved energy; rebuilding it from primitives with the centred field is the same sum
-          R = L;
-        } else {
-          MPrim l, r;
-          if (RECON == kPPMC) mhd_ppmc(P.in + id, o, kc, l, r);
-          else mhd_plmc(P.in + id, o, gamma, l, r);
-          L = mhd_interface(l, bhi, kc);
-          R = mhd_interface(r, blo, kc);
-        }
+        mhd_recon_checked<RECON>(P.in + id, o, bhi, blo, kc, L, R);
       }
     } else {
 #pragma unroll
@@ -201,7 +255,7 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
     M7 F;
     if (face) {
       Real const bface = __ldg(P.Bsrc + (size_t)(5 + DIR) * N + id - o.s);
-      hlld_flux(Lp, R, bface, gamma, F);
+      hlld_checked(Lp, R, bface, kc, F);
       size_t const idm = id - o.s;
       P.ctf[idm]         = F.v[0];
       P.ctf[N + idm]     = F.v[5];
@@ -381,8 +435,10 @@ __global__ void __launch_bounds__(128) mhd_prim_kernel(const Real *__restrict__ 
   if (x >= nx - lo) return;
   size_t const id = CIDX(x, y, z);
   Real const d  = H[id];
-  RDen const dd = rden(d);
-  Real const vx = rdiv(H[N + id], dd), vy = rdiv(H[2 * N + id], dd), vz = rdiv(H[3 * N + id], dd), E = H[4 * N + id];
+  KC kb;  // one pass per cell and step: the per-quotient fallback branch is fine here
+  kb.bad        = false;
+  RDen const dd = rden(d, kb);
+  Real const vx = rdiv(H[N + id], dd, kb), vy = rdiv(H[2 * N + id], dd, kb), vz = rdiv(H[3 * N + id], dd, kb), E = H[4 * N + id];
   Real bx, by, bz;
   cell_centred_b(H, N, id, x, y, z, nx, ny, bx, by, bz);
   cell_emf(ecen, N, id, d, H[N + id], H[2 * N + id], H[3 * N + id], bx, by, bz);

@@ -5,7 +5,9 @@
 // resident warps/SM (fp64 pipe 37 % busy; top stalls: fixed-latency wait, barrier, local-memory spills, instruction
 // cache misses; profiles/r1_*).  With most of the HBM bandwidth idle, the cheaper trade on B200 for the CORRECTOR is
 // the opposite one: spend a few more bytes per cell and make every launch a small, barrier-free loop that keeps the
-// fp64 pipe fed.  (The predictor -- PCM, one-cell stencil -- is a single fused launch again: vl_predictor.cuh.)
+// fp64 pipe fed.  (The same holds for the predictor: its single-launch form, vl_predictor.cuh, moves 14 GB instead of
+// 50 GB per step at 512^3 but takes 16.4 ms against 13.4 ms for the three sweeps here -- round-2 measurement,
+// profiles/r3_predictor_fused.md -- and is kept as a tested option, chl_set_tuning.)
 //
 // Each launch sweeps ONE direction.  A thread (y/z sweeps) or a warp (x sweep) MARCHES along that direction and
 // carries the low-side interface state and the lower-face flux from cell to cell, so every cell is reconstructed
@@ -61,6 +63,12 @@ struct DirParams {
   unsigned long long *dti_key;
   unsigned long long *bad_cells;  // last corrector pass: running count of cells whose density came out <= 0
   int xw_log2;                    // y / z sweeps: log2 of the CTA's extent along x (7 = 128 x 1 threads, 2 = 4 x 32)
+  // several boxes in ONE launch (the six thin boxes of the boundary shell: no drained-GPU tail between them): a 1-D grid,
+  // CTAs [cta0[b], cta0[b + 1]) belong to box b and are laid out gx x gy x (chunks) inside it.  nbox = 0: lo / hi above.
+  int nbox;
+  struct Box {
+    int lo[3], hi[3], chunk, xw_log2, cta0, gx, gy;
+  } box[6];
 };
 
 __device__ __forceinline__ void cp_async_real(Real *smem_dst, const Real *gsrc)
@@ -221,17 +229,35 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
     c_first = P.lo[0] - 1;
     c_last  = P.hi[0];
   } else {
+    int lo[3] = {P.lo[0], P.lo[1], P.lo[2]}, hi[3] = {P.hi[0], P.hi[1], P.hi[2]};
+    int chunk = P.chunk, xw_log2 = P.xw_log2, bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    if (P.nbox > 0) {  // which box does this CTA belong to (uniform over the CTA)
+      int b = 0;
+      while (b + 1 < P.nbox && (int)blockIdx.x >= P.box[b + 1].cta0) b++;
+      DirParams::Box const &B = P.box[b];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        lo[d] = B.lo[d];
+        hi[d] = B.hi[d];
+      }
+      chunk   = B.chunk;
+      xw_log2 = B.xw_log2;
+      int const l = blockIdx.x - B.cta0;
+      bx = l % B.gx;
+      by = (l / B.gx) % B.gy;
+      bz = l / (B.gx * B.gy);
+    }
     // a CTA covers 2^xw_log2 cells along x and 128 / 2^xw_log2 along the other fixed axis: 128 x 1 for ordinary boxes,
     // 4 x 32 for the four-cell-wide x shells of the boundary-first last pass (same sectors per warp either way)
-    int const tx = threadIdx.x & ((1 << P.xw_log2) - 1), to = threadIdx.x >> P.xw_log2;
-    int const x  = P.lo[0] + (blockIdx.x << P.xw_log2) + tx;
+    int const tx = threadIdx.x & ((1 << xw_log2) - 1), to = threadIdx.x >> xw_log2;
+    int const x  = lo[0] + (bx << xw_log2) + tx;
     int const od = DIR == 1 ? 2 : 1;  // the other fixed axis
-    int const o  = P.lo[od] + blockIdx.y * (kDirThreads >> P.xw_log2) + to;
-    live         = x < P.hi[0] && o < P.hi[od];
+    int const o  = lo[od] + by * (kDirThreads >> xw_log2) + to;
+    live         = x < hi[0] && o < hi[od];
     base         = DIR == 1 ? (size_t)x + (size_t)nx * ny * o : (size_t)x + (size_t)nx * o;
-    int const b  = P.lo[DIR] + blockIdx.z * P.chunk;
+    int const b  = lo[DIR] + bz * chunk;
     c_first      = b - 1;
-    c_last       = min(b + P.chunk, P.hi[DIR]);
+    c_last       = min(b + chunk, hi[DIR]);
   }
   double dti = -1.7976931348623157e308;
   int n_bad  = 0;

@@ -8,6 +8,7 @@
 
 #include "chl_internal.h"
 #include "vl_dirsweep.cuh"
+#include "vl_predictor.cuh"
 
 #ifndef CHL_MODE
 #error "CHL_MODE must be defined (f64_strict | f64_fast | f32_fast)"
@@ -25,6 +26,12 @@ namespace
 template <int RECON, int SOLVER, int STAGE, int DIR, bool FIRST, bool LAST>
 cudaError_t launch_dir(DirParams const &p, cudaStream_t s)
 {
+  if (p.nbox > 0 && DIR != 0) {  // several boxes, one launch: the table was filled by the caller
+    DirParams::Box const &last = p.box[p.nbox - 1];
+    int const total = last.cta0 + last.gx * last.gy * ((last.hi[DIR] - last.lo[DIR] + last.chunk - 1) / last.chunk);
+    vl_dir_kernel<RECON, SOLVER, STAGE, DIR, FIRST, LAST><<<total, kDirThreads, 0, s>>>(p);
+    return cudaGetLastError();
+  }
   int const ox = p.hi[0] - p.lo[0], oy = p.hi[1] - p.lo[1], oz = p.hi[2] - p.lo[2];
   if (ox <= 0 || oy <= 0 || oz <= 0) return cudaSuccess;
   dim3 grid;
@@ -76,25 +83,85 @@ cudaError_t run_dirs(DirParams p, SweepArgs const &a, cudaStream_t s)
     return launch_dir<RECON, SOLVER, STAGE, 2, false, true>(p, s);
   }
   int const lo[3] = {p.lo[0], p.lo[1], p.lo[2]}, hi[3] = {p.hi[0], p.hi[1], p.hi[2]}, sh = a.shell;
-  auto box = [&](int x0, int x1, int y0, int y1, int z0, int z1, int xw_log2) {
-    p.lo[0] = x0; p.hi[0] = x1; p.lo[1] = y0; p.hi[1] = y1; p.lo[2] = z0; p.hi[2] = z1;
-    p.xw_log2 = xw_log2;
-    p.chunk   = chunk_for(2);
+  if (a.part == 2) {
+    p.lo[0] = lo[0] + sh; p.hi[0] = hi[0] - sh; p.lo[1] = lo[1] + sh; p.hi[1] = hi[1] - sh;
+    p.lo[2] = lo[2] + sh; p.hi[2] = hi[2] - sh;
+    p.chunk = chunk_for(2);
     return launch_dir<RECON, SOLVER, STAGE, 2, false, true>(p, s);
+  }
+  // the six thin boxes of the shell in ONE launch (DirParams::box)
+  int cta = 0;
+  p.nbox  = 0;
+  auto box = [&](int x0, int x1, int y0, int y1, int z0, int z1, int xw_log2) {
+    DirParams::Box &B = p.box[p.nbox++];
+    B.lo[0] = x0; B.hi[0] = x1; B.lo[1] = y0; B.hi[1] = y1; B.lo[2] = z0; B.hi[2] = z1;
+    B.xw_log2 = xw_log2;
+    int const xw = 1 << xw_log2, ow = kDirThreads >> xw_log2;
+    B.gx = (x1 - x0 + xw - 1) / xw;
+    B.gy = (y1 - y0 + ow - 1) / ow;
+    // few columns: march short chunks so that the launch fills 148 SMs x 7-8 CTAs (a chunk of c cells reconstructs c + 2,
+    // so 8 is the floor; the z slabs are `sh` thick and take what they are)
+    B.chunk = z1 - z0 < 8 ? z1 - z0 : 8;
+    B.cta0  = cta;
+    cta += B.gx * B.gy * ((z1 - z0 + B.chunk - 1) / B.chunk);
   };
-  if (a.part == 2) return box(lo[0] + sh, hi[0] - sh, lo[1] + sh, hi[1] - sh, lo[2] + sh, hi[2] - sh, 7);
   int xs = 0;
   while ((1 << xs) < sh) xs++;  // the x shells are `sh` cells wide: 2^xs x (128 >> xs) threads per CTA
-  if ((e = box(lo[0], hi[0], lo[1], hi[1], lo[2], lo[2] + sh, 7)) != cudaSuccess) return e;                  // -z
-  if ((e = box(lo[0], hi[0], lo[1], hi[1], hi[2] - sh, hi[2], 7)) != cudaSuccess) return e;                  // +z
-  if ((e = box(lo[0], hi[0], lo[1], lo[1] + sh, lo[2] + sh, hi[2] - sh, 7)) != cudaSuccess) return e;        // -y
-  if ((e = box(lo[0], hi[0], hi[1] - sh, hi[1], lo[2] + sh, hi[2] - sh, 7)) != cudaSuccess) return e;        // +y
-  if ((e = box(lo[0], lo[0] + sh, lo[1] + sh, hi[1] - sh, lo[2] + sh, hi[2] - sh, xs)) != cudaSuccess) return e;  // -x
-  return box(hi[0] - sh, hi[0], lo[1] + sh, hi[1] - sh, lo[2] + sh, hi[2] - sh, xs);                         // +x
+  box(lo[0], hi[0], lo[1], hi[1], lo[2], lo[2] + sh, 7);                        // -z
+  box(lo[0], hi[0], lo[1], hi[1], hi[2] - sh, hi[2], 7);                        // +z
+  box(lo[0], hi[0], lo[1], lo[1] + sh, lo[2] + sh, hi[2] - sh, 7);              // -y
+  box(lo[0], hi[0], hi[1] - sh, hi[1], lo[2] + sh, hi[2] - sh, 7);              // +y
+  box(lo[0], lo[0] + sh, lo[1] + sh, hi[1] - sh, lo[2] + sh, hi[2] - sh, xs);   // -x
+  box(hi[0] - sh, hi[0], lo[1] + sh, hi[1] - sh, lo[2] + sh, hi[2] - sh, xs);   // +x
+  return launch_dir<RECON, SOLVER, STAGE, 2, false, true>(p, s);
+}
+
+// ---- fused predictor (vl_predictor.cuh): 3-D grids, one launch ----
+template <int SOLVER>
+cudaError_t launch_predictor(SweepArgs const &a, int plmp, cudaStream_t s)
+{
+  PredParams p;
+  p.U = (const Real *)a.in;
+  p.W = (Real *)a.out;
+  p.nx = a.nx; p.ny = a.ny; p.nz = a.nz;
+  for (int d = 0; d < 3; d++) { p.lo[d] = a.lo[d]; p.hi[d] = a.hi[d]; }
+  p.dto[0] = (Real)a.dtodx; p.dto[1] = (Real)a.dtody; p.dto[2] = (Real)a.dtodz;
+  p.gamma = (Real)a.gamma; p.density_floor = (Real)a.density_floor;
+  p.plmp = plmp;
+  int const ox = p.hi[0] - p.lo[0], oy = p.hi[1] - p.lo[1], oz = p.hi[2] - p.lo[2];
+  if (ox <= 0 || oy <= 0 || oz <= 0) return cudaSuccess;
+  int const bx = (ox + kPTX - 1) / kPTX, by = (oy + kPTY - 1) / kPTY;
+  // planes per CTA: long marches amortise the two extra planes a chunk converts, but the grid must still fill
+  // 148 SMs x 2 CTAs several times over
+  int zchunk = a.dir_chunk > 0 ? a.dir_chunk : 64;
+  while (zchunk > 8 && (long)bx * by * ((oz + zchunk - 1) / zchunk) < 148 * 2 * 6) zchunk /= 2;
+  if (zchunk > oz) zchunk = oz;
+  p.zchunk = zchunk;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(vl_predictor_kernel<SOLVER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kPSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 const grid(bx, by, (oz + zchunk - 1) / zchunk);
+  vl_predictor_kernel<SOLVER><<<grid, kPThreads, kPSmemBytes, s>>>(p);
+  return cudaGetLastError();
 }
 
 cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s)
 {
+  if (stage == 0 && a.has_y && a.has_z && a.fused_predictor) {
+    int const plmp = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
+#ifdef CHL_DEV_SUBSET
+    if (solver == kHLLC) return launch_predictor<kHLLC>(a, plmp, s);
+#else
+    if (solver == kROE) return launch_predictor<kROE>(a, plmp, s);
+    if (solver == kHLL) return launch_predictor<kHLL>(a, plmp, s);
+    if (solver == kEXACT) return launch_predictor<kEXACT>(a, plmp, s);
+    return launch_predictor<kHLLC>(a, plmp, s);
+#endif
+  }
   DirParams p;
   p.in  = (const Real *)a.in;
   p.U   = (const Real *)a.in;
@@ -112,6 +179,7 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   p.dti_key   = a.dti_key;
   p.bad_cells = a.bad_cells;
   p.xw_log2   = 7;
+  p.nbox      = 0;
   p.plmp      = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
 #ifdef CHL_DEV_SUBSET  // development builds (make VARIANT=... EXTRA=-DCHL_DEV_SUBSET): the headline combination only
   if (solver != kHLLC || recon != kPPMC) return cudaErrorNotSupported;

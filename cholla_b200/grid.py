@@ -202,6 +202,10 @@ class Grid3D:
     def _cflags(self):
         return (C.c_int * 6)(*self.flags)
 
+    def set_tuning(self, dir_chunk=0, fused_predictor=False):
+        """chl_set_tuning: marching length per thread (0 = automatic) and the single-launch predictor."""
+        check(_lib.lib().chl_set_tuning(self._ctx, int(dir_chunk), int(bool(fused_predictor))), "chl_set_tuning")
+
     def set_profiling(self, on):
         check(_lib.lib().chl_set_profiling(self._ctx, int(bool(on))), "chl_set_profiling")
 
@@ -324,7 +328,7 @@ class Grid3D:
                 check(L.chl_vl_step_exchange(self._ctx, self._halo_h, self._ptr(), self.H.dt, self._stream()),
                       "chl_vl_step_exchange")
                 self._exchanged = True
-                self.gpu_launches += self._exchange_launches() + (6 if self.ndim == 3 and not self.mhd else 0)
+                self.gpu_launches += self._exchange_launches() + (1 if self.ndim == 3 and not self.mhd else 0)
             else:
                 check(L.chl_vl_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_vl_step_fused")
             self.gpu_launches += self._sweep_launches()
@@ -354,6 +358,22 @@ class Grid3D:
         n = C.c_ulonglong()
         check(_lib.lib().chl_bad_cells(self._ctx, C.byref(n), self._stream()), "chl_bad_cells")
         return int(n.value)
+
+    def max_magnetic_divergence(self):
+        """mhd::checkMagneticDivergence (magnetic_divergence.cu:79-112): max |div B| reduced on the device and, across
+        ranks, with a MAX all-reduce (ReduceRealMax).  The caller applies the reference's 1e-9 limit."""
+        out = C.c_double()
+        check(_lib.lib().chl_mhd_max_divergence(self._ctx, self._ptr(), C.byref(out), self._stream()),
+              "chl_mhd_max_divergence")
+        self.gpu_launches += 1
+        v = out.value
+        if self.nproc > 1:
+            dist, torch = self.torch.distributed, self.torch
+            dev = self.device if dist.get_backend(self.dist_group) == "nccl" else "cpu"
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.dist_group)
+            v = float(t.item())
+        return v
 
     def Update_Time(self):
         self.H.t += self.H.dt

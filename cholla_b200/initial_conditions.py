@@ -267,9 +267,10 @@ def _mhd_pack(d, vx, vy, vz, P, B, gamma):
     return out
 
 
-def orszag_tang(n, g, gamma=1.666666666666667):
-    """Grid3D::Orszag_Tang_Vortex (initial_conditions.cpp:1926-1984, examples/3D/orszag_tang_vortex.txt)."""
-    X, Y, Z, d = _mhd_mesh(n, g, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0))
+def orszag_tang(n, g, gamma=1.666666666666667, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0)):
+    """Grid3D::Orszag_Tang_Vortex (initial_conditions.cpp:1926-1984, examples/3D/orszag_tang_vortex.txt).  The
+    reference's formulas take the cell positions of the deck's domain as they are (one period per unit length)."""
+    X, Y, Z, d = _mhd_mesh(n, g, lengths, lo)
     b0, d0, v0, p0 = 1.0 / np.sqrt(4.0 * np.pi), 25.0 / (36.0 * np.pi), 1.0, 5.0 / (12.0 * np.pi)
     Az = b0 / (4.0 * np.pi) * (np.cos(4.0 * np.pi * X) + 2.0 * np.cos(2.0 * np.pi * Y))
     B = _curl_faces(np.zeros_like(Az), np.zeros_like(Az), Az, d)
@@ -302,16 +303,23 @@ def mhd_smooth(n, g, seed=0, gamma=5.0 / 3.0, amp=0.3, b_amp=0.5):
     return _mhd_pack(rho, vx, vy, vz, P, B, gamma)
 
 
-def mhd_blast(n, g, gamma=5.0 / 3.0):
-    """MHD_Spherical_Blast-like (initial_conditions.cpp:1865-1924): uniform oblique field, over-pressured sphere."""
-    X, Y, Z, d = _mhd_mesh(n, g, (1.0, 1.0, 1.0), (-0.5, -0.5, -0.5))
+def mhd_blast(n, g, gamma=5.0 / 3.0, lengths=(1.0, 1.0, 1.0), lo=(-0.5, -0.5, -0.5), rho=1.0, v=(0.0, 0.0, 0.0), P=0.1,
+              P_blast=10.0, radius=0.1, B=(0.70710678118654746, 0.70710678118654746, 0.0)):
+    """Grid3D::MHD_Spherical_Blast (initial_conditions.cpp:1865-1924, examples/3D/mhd_blast.txt): uniform state and field
+    from the deck (rho, vx.., P, Bx..), pressure P_blast inside `radius` of the origin.  Like the reference it insists
+    on a domain centred on the origin and larger than the blast (its two asserts, :1869-1874)."""
+    if any(lo[a] + 0.5 * lengths[a] != 0.0 for a in range(3)):
+        raise ValueError("MHD_Spherical_Blast: the domain must be centred at zero (initial_conditions.cpp:1869)")
+    if not np.sqrt(sum((0.5 * v_) ** 2 for v_ in lengths)) > radius:
+        raise ValueError("MHD_Spherical_Blast: the domain must be larger than the blast radius (initial_conditions.cpp:1873)")
+    X, Y, Z, d = _mhd_mesh(n, g, lengths, lo)
     r = np.sqrt(X * X + Y * Y + Z * Z)
-    P = np.where(r < 0.1, 10.0, 0.1)
-    B = np.zeros((3,) + X.shape)
-    B[0] += 1.0 / np.sqrt(2.0)
-    B[1] += 1.0 / np.sqrt(2.0)
-    z = np.zeros_like(X)
-    return _mhd_pack(np.ones_like(X), z, z, z, P, B, gamma)
+    pres = np.where(r < radius, P_blast, P)
+    Bf = np.zeros((3,) + X.shape)
+    for a in range(3):
+        Bf[a] += B[a]
+    one = np.ones_like(X)
+    return _mhd_pack(rho * one, v[0] * one, v[1] * one, v[2] * one, pres, Bf, gamma)
 
 
 def mhd_riemann(n, g, lengths, lo, left, right, diaph, gamma):
@@ -330,25 +338,42 @@ def mhd_riemann(n, g, lengths, lo, left, right, diaph, gamma):
     return out
 
 
-def mhd_linear_wave(n, g, lengths, lo, rho, vx, P, B0, A, eigenvector, wave_length=1.0, gamma=5.0 / 3.0):
-    """Grid3D::Linear_Wave, -DMHD build, grid-aligned (pitch = yaw = 0; the reference's rotated set-up is commented out
-    as unstable, initial_conditions.cpp:312-358): examples/3D/alfven_wave.txt, fast_magnetosonic.txt,
-    slow_magnetosonic.txt, mhd_contact_wave.txt.  eigenvector = (rho, mx, my, mz, E, Bx, By, Bz).  The face fields are
-    evaluated at the cell-centre abscissa like the reference's; the box is periodic, so the ghost zones are generated
-    too."""
+def mhd_linear_wave(n, g, lengths, lo, rho, vx, P, B0, A, eigenvector, wave_length=1.0, gamma=5.0 / 3.0, pitch=0.0,
+                    yaw=0.0):
+    """Grid3D::Linear_Wave, -DMHD build (initial_conditions.cpp:302-432): examples/3D/alfven_wave.txt,
+    fast_magnetosonic.txt, slow_magnetosonic.txt, mhd_contact_wave.txt, and the reference's MHD linear-wave system
+    tests, which also run the waves along y and z (yaw or pitch = pi / 2).  eigenvector = (rho, mx, my, mz, E, Bx, By,
+    Bz).  Only the vector-potential variant of the rotated set-up is commented out in the reference (:312-358); the live
+    code (:360-392) rotates the wave coordinate, the momenta and the field exactly as below, with the face fields
+    evaluated at the cell-CENTRE coordinate.  The box is periodic, so the ghost zones are generated too."""
     X, Y, Z, d = _mhd_mesh(n, g, lengths, lo)
-    sine = np.sin(X * (2.0 * np.pi / wave_length)) + 0.0 * (Y + Z)
+    sy, cy, sp, cp = np.sin(yaw), np.cos(yaw), np.sin(pitch), np.cos(pitch)
+    xr = cp * (X * cy + Y * sy) + Z * sp
+    sine = np.sin(xr * (2.0 * np.pi / wave_length)) + 0.0 * (X + Y + Z)
     e_rho, e_mx, e_my, e_mz, e_E, e_bx, e_by, e_bz = eigenvector
     out = np.empty((8,) + sine.shape)
     out[0] = rho + A * e_rho * sine
-    out[1] = rho * vx + A * e_mx * sine
-    out[2] = A * e_my * sine
-    out[3] = A * e_mz * sine
+    mx, my, mz = rho * vx + A * e_mx * sine, A * e_my * sine, A * e_mz * sine
+    out[1] = mx * cp * cy - my * sy - mz * sp * cy
+    out[2] = mx * cp * sy + my * cy - mz * sp * sy
+    out[3] = mx * sp + mz * cp
     out[4] = P / (gamma - 1.0) + 0.5 * rho * vx * vx + A * sine * e_E + 0.5 * (B0[0] * B0[0] + B0[1] * B0[1] + B0[2] * B0[2])
-    out[5] = B0[0] + A * e_bx * sine
-    out[6] = B0[1] + A * e_by * sine
-    out[7] = B0[2] + A * e_bz * sine
+    bx, by, bz = B0[0] + A * e_bx * sine, B0[1] + A * e_by * sine, B0[2] + A * e_bz * sine
+    out[5] = bx * cp * cy - by * sy - bz * sp * cy
+    out[6] = bx * cp * sy + by * cy - bz * sp * sy
+    out[7] = bx * sp + bz * cp
     return out
+
+
+def mhd_constant(n, g, lengths, lo, rho=1.0, v=(0.0, 0.0, 0.0), P=1.0, B=(0.0, 0.0, 0.0), gamma=5.0 / 3.0):
+    """Grid3D::Constant in an -DMHD build (initial_conditions.cpp:180-242): uniform state with a uniform field from the
+    deck (Bx, By, Bz); used by the reference's MHD system tests (constant state must stay constant)."""
+    X, Y, Z, d = _mhd_mesh(n, g, lengths, lo)
+    one = np.ones_like(X + Y + Z)
+    Bf = np.zeros((3,) + one.shape)
+    for a in range(3):
+        Bf[a] += B[a]
+    return _mhd_pack(rho * one, v[0] * one, v[1] * one, v[2] * one, P * one, Bf, gamma)
 
 
 def _mhd_pack_momentum(rho, mx, my, mz, P, B, gamma):

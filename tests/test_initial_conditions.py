@@ -205,3 +205,89 @@ def test_mhd_generators_are_rank_count_independent(gen):
         # (the curl helper leaves index 0 at zero and the energy of index 1 averages with it; the exchange refills both)
         want = whole[:, off[2] + 2:off[2] + nl[2] + 2 * g, off[1] + 2:off[1] + nl[1] + 2 * g, off[0] + 2:off[0] + nl[0] + 2 * g]
         assert np.array_equal(part[:, 2:, 2:, 2:], want), rank
+
+
+MHD_BLAST_DECK = """
+nx=20
+ny=30
+nz=20
+tout=0.2
+outstep=0.2
+init=MHD_Spherical_Blast
+xmin=-0.5
+ymin=-0.75
+zmin=-0.5
+xlen=1.0
+ylen=1.5
+zlen=1.0
+xl_bcnd=1
+xu_bcnd=1
+yl_bcnd=1
+yu_bcnd=1
+zl_bcnd=1
+zu_bcnd=1
+outdir=./
+rho=2.0
+vx=0.0
+vy=0.25
+vz=0.0
+P=0.1
+P_blast=10.0
+radius=0.2
+Bx=0.70710678118654746
+By=0.70710678118654746
+Bz=0.0
+gamma=1.666666666666667
+"""
+
+
+def test_mhd_blast_takes_the_decks_domain_and_parameters():
+    """examples/3D/mhd_blast.txt is not cubic (ny = 300, ylen = 1.5): the blast must be a sphere of the deck's radius in
+    the deck's coordinates, with the deck's rho, v, P, P_blast and B (initial_conditions.cpp:1865-1924)."""
+    P = pm.parse_text(MHD_BLAST_DECK)
+    g = 5
+    f = run.initial_fields(P, True, g)
+    assert f.shape == (8, 20 + 2 * g, 30 + 2 * g, 20 + 2 * g)
+    real = f[:, g:-g, g:-g, g:-g]
+    assert np.all(real[0] == 2.0) and np.all(real[2] == 2.0 * 0.25) and np.all(real[5] == P.Bx)
+    d = 0.05  # the same cell size on every axis: dy = 1.5 / 30
+    x = -0.5 + (np.arange(20) + 0.5) * d
+    y = -0.75 + (np.arange(30) + 0.5) * d
+    Z, Y, X = np.meshgrid(x, y, x, indexing="ij")
+    inside = np.sqrt(X * X + Y * Y + Z * Z) < 0.2
+    e_mag, e_kin = 0.5 * (P.Bx ** 2 + P.By ** 2), 0.5 * 2.0 * 0.25 ** 2
+    pres = (real[4] - e_mag - e_kin) * (P.gamma - 1.0)
+    assert np.allclose(pres[inside], 10.0) and np.allclose(pres[~inside], 0.1)
+    assert inside.sum() > 0 and inside.sum() == (np.abs(pres - 10.0) < 1e-9).sum()
+    # the blast is round in index space too (equal cell sizes): as many cells across in y as in x
+    ii = np.argwhere(inside)
+    assert np.ptp(ii[:, 1]) == np.ptp(ii[:, 2]) == np.ptp(ii[:, 0])
+    # the reference's asserts: a domain that is not centred on the origin is refused
+    with pytest.raises(ValueError):
+        run.initial_fields(pm.parse_text(MHD_BLAST_DECK.replace("ymin=-0.75", "ymin=-0.5")), True, g)
+
+
+def test_mhd_linear_wave_rotations_and_mhd_constant():
+    """The reference's MHD linear-wave system tests run every wave along x, y and z (yaw or pitch = pi / 2,
+    mhd_system_tests.cpp:129-505): the rotated generator must be the x-aligned one with its axes permuted, and
+    `Constant` must build a uniform 8-field state with the deck's field."""
+    n, g = (8, 8, 8), 5
+    L, lo = (1.0, 1.0, 1.0), (0.0, 0.0, 0.0)
+    ev = (0.3, -0.2, 0.1, 0.05, 0.4, 0.0, 0.25, -0.15)
+    B0 = (1.0, 1.5, 0.5)
+    base = ic.mhd_linear_wave(n, g, L, lo, 1.0, 0.2, 0.6, B0, 1e-3, ev, 1.0, 5.0 / 3.0)
+    ywave = ic.mhd_linear_wave(n, g, L, lo, 1.0, 0.2, 0.6, B0, 1e-3, ev, 1.0, 5.0 / 3.0, yaw=0.5 * np.pi)
+    # yaw = pi/2: x' = y, and (vx', vy') -> (-vy', vx'): fields as functions of y equal the base as functions of x
+    a = base[:, 0, 0, :]     # vary along x
+    b = ywave[:, 0, :, 0]    # vary along y
+    assert np.allclose(b[0], a[0], atol=1e-15) and np.allclose(b[4], a[4], atol=1e-15)
+    assert np.allclose(b[2], a[1], atol=1e-15) and np.allclose(b[1], -a[2], atol=1e-15) and np.allclose(b[3], a[3], atol=1e-15)
+    assert np.allclose(b[6], a[5], atol=1e-15) and np.allclose(b[5], -a[6], atol=1e-15) and np.allclose(b[7], a[7], atol=1e-15)
+    zwave = ic.mhd_linear_wave(n, g, L, lo, 1.0, 0.2, 0.6, B0, 1e-3, ev, 1.0, 5.0 / 3.0, pitch=0.5 * np.pi)
+    c = zwave[:, :, 0, 0]    # vary along z
+    assert np.allclose(c[0], a[0], atol=1e-15) and np.allclose(c[3], a[1], atol=1e-15) and np.allclose(c[1], -a[3], atol=1e-15)
+    P = pm.parse_text(MHD_BLAST_DECK.replace("init=MHD_Spherical_Blast", "init=Constant"))
+    f = run.initial_fields(P, True, g)
+    assert f.shape[0] == 8 and np.all(f[5] == P.Bx) and np.all(f[0] == 2.0) and np.all(f[2] == 0.5)
+    with pytest.raises(NotImplementedError):
+        run.initial_fields(pm.parse_text(MHD_BLAST_DECK.replace("init=MHD_Spherical_Blast", "init=KH")), True, g)

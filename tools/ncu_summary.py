@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (ncu --set full) into the handful of numbers DESIGN.md quotes: per-kernel duration, DRAM
 bytes, pipe utilisation, occupancy, stall reasons and the dynamic SASS opcode mix.  Usage:
-    python scratch/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.md"""
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.md"""
 import collections
 import csv
 import re
