@@ -24,7 +24,8 @@ class Config(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("n_ghost", C.c_int), ("n_fields", C.c_int),
                 ("recon", C.c_int), ("solver", C.c_int), ("precision", C.c_int), ("strict", C.c_int), ("mhd", C.c_int),
                 ("gamma", C.c_double), ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
-                ("density_floor", C.c_double), ("temperature_floor_U", C.c_double)]
+                ("density_floor", C.c_double), ("temperature_floor_U", C.c_double),
+                ("n_scalars", C.c_int), ("dual_energy", C.c_int)]
 
 
 _lib = None
@@ -69,6 +70,7 @@ def lib():
     L.chl_set_profiling.argtypes = [p, i]
     L.chl_stage_times.argtypes = [p, C.POINTER(d), ip]
     L.chl_apply_temperature_floor.argtypes = [p, p, d, p]
+    L.chl_apply_scalar_floor.argtypes = [p, p, i, d, p]
     L.chl_set_ghost_cells.argtypes = [p, p, ip, i, p]
     L.chl_set_boundaries.argtypes = [p, p, ip, p]
     L.chl_set_ghost_cells_ext.argtypes = [p, i, i, i, i, i, i, ip, i, i, i, i, i, i, i, i, i, p]

@@ -159,6 +159,20 @@ __global__ void __launch_bounds__(256) snapshot_pack_kernel(const Tin *__restric
     if (i < n_i && k < n_k) out[k + (long)n_k * (j + (long)n_j * i)] = (Tout)tile[threadIdx.x][r];
   }
 }
+// Scalar_Floor_Kernel (hydro_cuda.cu:1284-1307): one field, real cells of a 3-D grid
+template <typename T>
+__global__ void __launch_bounds__(256) scalar_floor_kernel(T *field, int nx, int ny, int nz, int g, T floor_value)
+{
+  int const rx = nx - 2 * g, ry = ny - 2 * g, rz = nz - 2 * g;
+  long const n = (long)rx * ry * rz;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    int const x = (int)(t % rx) + g;
+    long const r = t / rx;
+    int const y = (int)(r % ry) + g, z = (int)(r / ry) + g;
+    long const id = x + (long)nx * (y + (long)ny * z);
+    if (field[id] < floor_value) field[id] = floor_value;
+  }
+}
 }  // namespace
 
 cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields, long n_cells, int n_ghost,
@@ -177,6 +191,17 @@ cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields
   return cudaGetLastError();
 }
 
+cudaError_t launch_scalar_floor(void *c, int nx, int ny, int nz, int n_ghost, int field_num, double floor_value,
+                                int real_bytes, cudaStream_t s)
+{
+  if (nx <= 2 * n_ghost || ny <= 2 * n_ghost || nz <= 2 * n_ghost) return cudaSuccess;  // the kernel's guard
+  long const n = (long)(nx - 2 * n_ghost) * (ny - 2 * n_ghost) * (nz - 2 * n_ghost);
+  long const N = (long)nx * ny * nz;
+  int const g = grid_for(n) > 148 * 8 ? 148 * 8 : grid_for(n);
+  if (real_bytes == 8) scalar_floor_kernel<double><<<g, 256, 0, s>>>((double *)c + field_num * N, nx, ny, nz, n_ghost, floor_value);
+  else scalar_floor_kernel<float><<<g, 256, 0, s>>>((float *)c + field_num * N, nx, ny, nz, n_ghost, (float)floor_value);
+  return cudaGetLastError();
+}
 cudaError_t launch_divb(const void *c, int nx, int ny, int nz, double dx, double dy, double dz, unsigned long long *out,
                         size_t real_bytes, cudaStream_t s)
 {

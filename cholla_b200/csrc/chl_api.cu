@@ -46,7 +46,8 @@ struct chl_ctx {
   chl_config cfg;
   chl::ModeOps const *ops;
   void *d_half;               // W at t + dt/2 (primitives), half_fields * n_cells reals
-  void *d_acc;                // direction-split sweeps: running sum of flux differences, 5 * n_cells reals
+  void *d_acc;                // direction-split sweeps: running sum of flux differences, (5 + passive) * n_cells reals
+  void *d_de;                 // -DDE contexts: n_cells reals, the p div v term / partially updated GasEnergy (de_term)
   chl::MhdOps const *mhd;     // non-null in an MHD context
   void *d_prim;               // MHD: half-step primitives + cell-centred fields
   void *d_ctf;                // MHD: 9 * n_cells flux components kept for constrained transport
@@ -99,8 +100,13 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
     if (cfg->n_fields != 8) return fail(CHL_ERR_UNSUPPORTED, "chl_create: an MHD grid has n_fields = 8");
     if (cfg->solver != CHL_SOLVER_HLLD) return fail(CHL_ERR_INVALID, "chl_create: MHD only supports the HLLD solver");
     if (cfg->ny == 1 || cfg->nz == 1) return fail(CHL_ERR_INVALID, "chl_create: MHD runs must be 3D");
+    if (cfg->n_scalars || cfg->dual_energy)
+      return fail(CHL_ERR_UNSUPPORTED, "chl_create: scalars / dual energy are built for hydro contexts only");
   } else {
-    if (cfg->n_fields != 5) return fail(CHL_ERR_UNSUPPORTED, "chl_create: a hydro grid has n_fields = 5");
+    if (cfg->n_scalars < 0 || (cfg->dual_energy != 0 && cfg->dual_energy != 1))
+      return fail(CHL_ERR_INVALID, "chl_create: n_scalars / dual_energy");
+    if (cfg->n_fields != 5 + cfg->n_scalars + cfg->dual_energy)
+      return fail(CHL_ERR_INVALID, "chl_create: a hydro grid has n_fields = 5 + n_scalars + dual_energy (grid_enum.h:21-78)");
     if (cfg->solver == CHL_SOLVER_HLLD) return fail(CHL_ERR_INVALID, "chl_create: HLLD needs mhd = 1");
   }
   int const need_ghost =
@@ -112,7 +118,16 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
       (cfg->nz > 1 && cfg->nz <= 2 * cfg->n_ghost))
     return fail(CHL_ERR_INVALID, "chl_create: grid smaller than its ghost layers");
   chl::ModeOps const *ops = nullptr;
-  if (cfg->precision == 2 || cfg->precision == 0) {
+  bool const passive = !cfg->mhd && (cfg->n_scalars > 0 || cfg->dual_energy);
+  if (passive) {  // the reference compiles NSCALARS / DE in; here each built combination is its own kernel TU
+    if (cfg->precision == 1) return fail(CHL_ERR_UNSUPPORTED, "chl_create: scalars / dual energy are built in fp64 only");
+    if (cfg->recon > CHL_RECON_PPMC || (cfg->solver != CHL_SOLVER_HLLC && cfg->solver != CHL_SOLVER_ROE && cfg->solver != CHL_SOLVER_HLL))
+      return fail(CHL_ERR_UNSUPPORTED, "chl_create: scalars / dual energy are built for PCM, PLMC, PPMC with HLLC, Roe, HLL");
+    if (cfg->n_scalars == 1 && !cfg->dual_energy) ops = cfg->strict ? chl::mode_ops_f64_strict_s1() : chl::mode_ops_f64_fast_s1();
+    else if (cfg->n_scalars == 0) ops = cfg->strict ? chl::mode_ops_f64_strict_de() : chl::mode_ops_f64_fast_de();
+    else if (cfg->n_scalars == 1) ops = cfg->strict ? chl::mode_ops_f64_strict_de_s1() : chl::mode_ops_f64_fast_de_s1();
+    if (!ops) return fail(CHL_ERR_UNSUPPORTED, "chl_create: built passive-field combinations: 1 scalar, dual energy, dual energy + 1 scalar");
+  } else if (cfg->precision == 2 || cfg->precision == 0) {
     ops = cfg->strict ? chl::mode_ops_f64_strict() : chl::mode_ops_f64_fast();
   } else if (cfg->precision == 1) {
     if (cfg->strict)
@@ -137,6 +152,7 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->ndim = 1 + (cfg->ny > 1) + (cfg->nz > 1);
   c->d_half = nullptr;
   c->d_acc = nullptr;
+  c->d_de = nullptr;
   c->mhd = mhd;
   c->d_prim = c->d_ctf = c->d_E = nullptr;
   c->dir_chunk = 0;
@@ -145,9 +161,13 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->h_key = nullptr;
   c->profiling = 0;
   c->ev_steps = 0;
-  size_t const bytes = c->n_cells * (mhd ? 8 : ops->half_fields) * ops->real_bytes;
+  size_t const bytes = c->n_cells * (mhd ? 8 : ops->half_fields + ops->n_passive) * ops->real_bytes;
   cudaError_t e = cudaMalloc(&c->d_half, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&c->d_acc, c->n_cells * 5 * ops->real_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_acc, c->n_cells * (5 + (mhd ? 0 : ops->n_passive)) * ops->real_bytes);
+  if (e == cudaSuccess && !mhd && ops->dual_energy) {
+    e = cudaMalloc(&c->d_de, c->n_cells * ops->real_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->d_de, 0, c->n_cells * ops->real_bytes);
+  }
   if (mhd) {
     size_t const w = c->n_cells * ops->real_bytes;
     if (e == cudaSuccess) e = cudaMalloc(&c->d_prim, mhd->prim_fields * w);
@@ -174,6 +194,7 @@ int chl_destroy(chl_ctx *c)
   if (!c) return CHL_OK;
   if (c->d_half) cudaFree(c->d_half);
   if (c->d_acc) cudaFree(c->d_acc);
+  if (c->d_de) cudaFree(c->d_de);
   if (c->d_prim) cudaFree(c->d_prim);
   if (c->d_ctf) cudaFree(c->d_ctf);
   if (c->d_E) cudaFree(c->d_E);
@@ -187,7 +208,8 @@ int chl_destroy(chl_ctx *c)
 size_t chl_scratch_bytes(const chl_ctx *c)
 {
   if (!c) return 0;
-  size_t fields = c->mhd ? 8 + 5 + c->mhd->prim_fields + 9 + 6 : c->ops->half_fields + 5;
+  size_t fields = c->mhd ? 8 + 5 + c->mhd->prim_fields + 9 + 6
+                         : c->ops->half_fields + 5 + 2 * c->ops->n_passive + c->ops->dual_energy;
   return c->n_cells * fields * c->ops->real_bytes + 2 * sizeof(unsigned long long);
 }
 
@@ -249,6 +271,8 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
   a.part = 0;
   a.shell = 0;
   a.fused_predictor = c->fused_predictor;
+  a.de_term = c->d_de;
+  bool const de = c->ops->dual_energy != 0;
   auto const sweep = c->ops->sweep_split;
   int const n[3] = {g.nx, g.ny, g.nz};
   // ---- predictor: every cell but the outermost ring (VL_3D_cuda.cu:408) ----
@@ -275,6 +299,7 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
     }
     CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps], s));
   }
+  if (de) CHL_CUDA(c->ops->de_term(U, c->d_de, g.nx, g.ny, g.nz, a.lo, a.hi, a.dtodx, a.dtody, a.dtodz, g.gamma, 0, s));
   CHL_CUDA(sweep(0, g.recon, g.solver, a, s));
   if (prof) CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 1], s));
   // ---- corrector: real cells (hydro_cuda.cu:225) ----
@@ -288,13 +313,26 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
   a.dtodx = dt / g.dx;
   a.dtody = dt / g.dy;
   a.dtodz = dt / g.dz;
+  int const want_tfloor = (fused && g.temperature_floor_U > 0.0 && c->ndim == 3) ? 1 : 0;
   if (fused) {
-    a.apply_tfloor = (g.temperature_floor_U > 0.0 && c->ndim == 3) ? 1 : 0;
+    // a -DDE context floors and reduces after Select_Internal_Energy / Sync_Energies (ModeOps::de_finish), not in the sweep
+    a.apply_tfloor = de ? 0 : want_tfloor;
     a.U_floor = g.temperature_floor_U;
-    a.do_dti = 1;
+    a.do_dti = de ? 0 : 1;
     CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
   }
-  if (halo && c->ndim == 3) {
+  if (de) {
+    // Partial_Update_Advected_Internal_Energy (from U^n, before anything is updated), the corrector, then
+    // Select_Internal_Energy + Sync_Energies over the completed cells; the exchange needs their result: no overlap
+    CHL_CUDA(c->ops->de_term(U, c->d_de, g.nx, g.ny, g.nz, a.lo, a.hi, a.dtodx, a.dtody, a.dtodz, g.gamma, 1, s));
+    CHL_CUDA(sweep(1, g.recon, g.solver, a, s));
+    CHL_CUDA(c->ops->de_finish(U, g.nx, g.ny, g.nz, g.n_ghost, g.gamma, want_tfloor, g.temperature_floor_U, fused ? 1 : 0,
+                               g.dx, g.dy, g.dz, c->d_key, s));
+    if (halo) {
+      int const r = halo_exchange_impl(halo, U, s);
+      if (r != CHL_OK) return r;
+    }
+  } else if (halo && c->ndim == 3) {
     a.part  = 1;
     a.shell = g.n_ghost;
     CHL_CUDA(sweep(1, g.recon, g.solver, a, s));  // x and y passes, then the boundary shell of the z pass
@@ -327,6 +365,8 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
   if (!c || !U) return fail(CHL_ERR_INVALID, "chl_simple_step: null argument");
   chl_config const &g = c->cfg;
   if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: MHD requires the Van Leer integrator (error_handling.cpp:89)");
+  if (c->ops->n_passive)
+    return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: scalars / dual energy are built for the Van Leer integrator");
   if (g.recon != CHL_RECON_PCM && g.recon != CHL_RECON_PLMC)
     return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: PCM and PLMC only (the CTU forms of PLMP / PPMP / PPMC are not built)");
   chl::SweepArgs a;
@@ -344,6 +384,7 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
   a.part = 0;
   a.shell = 0;
   a.fused_predictor = 0;
+  a.de_term = nullptr;
   int const n[3] = {g.nx, g.ny, g.nz};
   for (int d = 0; d < 3; d++) {
     bool const on = d == 0 || (d == 1 && a.has_y) || (d == 2 && a.has_z);
@@ -492,6 +533,16 @@ int chl_apply_temperature_floor(chl_ctx *c, void *U, double U_floor, void *strea
   if (!c || !U) return fail(CHL_ERR_INVALID, "chl_apply_temperature_floor: null argument");
   chl_config const &g = c->cfg;
   CHL_CUDA(c->ops->tfloor(U, g.nx, g.ny, g.nz, g.n_ghost, U_floor, (cudaStream_t)stream));
+  return CHL_OK;
+}
+
+int chl_apply_scalar_floor(chl_ctx *c, void *U, int field_num, double scalar_floor, void *stream)
+{
+  if (!c || !U) return fail(CHL_ERR_INVALID, "chl_apply_scalar_floor: null argument");
+  chl_config const &g = c->cfg;
+  if (field_num < 0 || field_num >= g.n_fields) return fail(CHL_ERR_INVALID, "chl_apply_scalar_floor: field_num");
+  CHL_CUDA(chl::launch_scalar_floor(U, g.nx, g.ny, g.nz, g.n_ghost, field_num, scalar_floor, (int)c->ops->real_bytes,
+                                    (cudaStream_t)stream));
   return CHL_OK;
 }
 

@@ -13,6 +13,8 @@ cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields
                                    int dir, int diode, size_t real_bytes, cudaStream_t s);
 cudaError_t launch_divb(const void *c, int nx, int ny, int nz, double dx, double dy, double dz, unsigned long long *out,
                         size_t real_bytes, cudaStream_t s);
+cudaError_t launch_scalar_floor(void *c, int nx, int ny, int nz, int n_ghost, int field_num, double floor_value,
+                                int real_bytes, cudaStream_t s);
 cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset,
                         int isize, int jsize, int ksize, int unpack, size_t real_bytes, cudaStream_t s);
 cudaError_t launch_snapshot_pack(void *out, const void *field, int nx, int ny, int nz, int n_ghost, int nx_out,

@@ -25,6 +25,7 @@ struct SweepArgs {  // everything in double; each mode TU narrows to its Real
   double dx, dy, dz;
   unsigned long long *dti_key;
   unsigned long long *bad_cells;  // corrector: count of cells whose density came out <= 0
+  const void *de_term;            // -DDE builds: n_cells reals from ModeOps::de_term (see DirParams::de_term)
 };
 
 struct ModeOps {
@@ -36,7 +37,14 @@ struct ModeOps {
   // SIMPLE integrator: primitives of U for every cell -> W, then sweep_split(1, ...) with simple = 1 in SweepArgs
   cudaError_t (*prim_from_cons)(const void *U, void *W, size_t n_cells, double gamma, int recon, cudaStream_t s);
   size_t real_bytes;
-  int half_fields;  // fields of the half-step scratch array (5, or 7 in strict mode)
+  int half_fields;  // hydro fields of the half-step scratch array (5, or 7 in strict mode); the passive ones follow
+  // -DSCALAR / -DDE builds (TUs compiled with CHL_NP / CHL_DE): passive fields riding with the five hydro fields
+  // (GasEnergy last when dual_energy), and the dual-energy passes around the sweeps (nullptr without DE)
+  int n_passive, dual_energy;
+  cudaError_t (*de_term)(const void *U, void *out, int nx, int ny, int nz, const int lo[3], const int hi[3], double dtodx,
+                         double dtody, double dtodz, double gamma, int mode, cudaStream_t s);
+  cudaError_t (*de_finish)(void *U, int nx, int ny, int nz, int n_ghost, double gamma, int apply_tfloor, double U_floor,
+                           int do_dti, double dx, double dy, double dz, unsigned long long *key, cudaStream_t s);
 };
 
 // ---- MHD (mhd_inst.cu) ----
@@ -63,5 +71,12 @@ MhdOps const *mhd_ops_f64_fast();
 ModeOps const *mode_ops_f64_strict();
 ModeOps const *mode_ops_f64_fast();
 ModeOps const *mode_ops_f32_fast();  // nullptr when the fp32 TU is not linked
+// fp64 TUs with passive fields: _s1 one scalar, _de dual energy, _de_s1 both (Makefile: PASSIVE_MODES)
+ModeOps const *mode_ops_f64_strict_s1();
+ModeOps const *mode_ops_f64_strict_de();
+ModeOps const *mode_ops_f64_strict_de_s1();
+ModeOps const *mode_ops_f64_fast_s1();
+ModeOps const *mode_ops_f64_fast_de();
+ModeOps const *mode_ops_f64_fast_de_s1();
 
 }  // namespace chl

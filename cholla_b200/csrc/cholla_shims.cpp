@@ -89,6 +89,10 @@ chl_ctx *context(int nx, int ny, int nz, int n_ghost, int n_fields, Real dx, Rea
   c.strict = (PRECISION == 2) && !(s && s[0] == '0');
   c.gamma = gama; c.dx = dx; c.dy = dy; c.dz = dz; c.density_floor = density_floor;
   c.temperature_floor_U = 0.0;
+#ifdef DE  // -DDE: GasEnergy is the last field; -DSCALAR: whatever lies between Energy and it (grid_enum.h:33-78)
+  c.dual_energy = 1;
+#endif
+  if (!kMhd) c.n_scalars = n_fields - 5 - c.dual_energy;
   if (g_ctx && memcmp(&c, &g_cfg, sizeof(c)) == 0) return g_ctx;
   if (g_ctx) chl_destroy(g_ctx);
   g_ctx = nullptr;

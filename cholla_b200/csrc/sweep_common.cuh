@@ -16,12 +16,25 @@ typedef KC KH;
 
 struct S5 {
   Real v[5];
+#if CHL_NP > 0
+  Real q[CHL_NP];  // passive fields: conserved (strict) / per unit mass (product mode)
+#endif
 };  // strict: sweep-frame conserved; product mode: sweep-frame primitives
 struct S5x2 {
   S5 L, R;
 };
 struct Half {
   Real w[kHalfFields];
+#if CHL_NP > 0
+  Real q[CHL_NP];  // passive fields per unit mass, stored after the kHalfFields hydro entries
+#endif
+};
+// the five hydro values of a cell plus its passive ones, as the update / half-state routines pass them around
+struct U5 {
+  Real u[5];
+#if CHL_NP > 0
+  Real q[CHL_NP];
+#endif
 };
 
 // ordered-bits encoding so that an unsigned atomicMax orders doubles
@@ -35,9 +48,18 @@ template <class K>
 __device__ __forceinline__ Face to_face(S5 const &s, K const &k)
 {
 #if CHL_STRICT
-  return face_from_cons(Cons{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]}, k);
+  Cons c{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]};
 #else
-  return face_from_prim(Prim{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]}, k);
+  Prim c{s.v[0], s.v[1], s.v[2], s.v[3], s.v[4]};
+#endif
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) c.q[i] = s.q[i];
+#endif
+#if CHL_STRICT
+  return face_from_cons(c, k);
+#else
+  return face_from_prim(c, k);
 #endif
 }
 template <class K>
@@ -45,11 +67,17 @@ __device__ __forceinline__ S5 iface_state(Prim const &q, K const &k)
 {
 #if CHL_STRICT
   Cons const c = cons_from_prim(q, k);  // Write_Data (reconstruction.h:918-968)
-  return S5{{c.d, c.mx, c.my, c.mz, c.E}};
+  S5 o{{c.d, c.mx, c.my, c.mz, c.E}};
 #else
   (void)k;
-  return S5{{q.d, q.vx, q.vy, q.vz, q.p}};
+  Prim const &c = q;
+  S5 o{{q.d, q.vx, q.vy, q.vz, q.p}};
 #endif
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) o.q[i] = c.q[i];
+#endif
+  return o;
 }
 
 // where the five sweep-frame components of direction `dir` live in a [field][N] array
@@ -57,6 +85,7 @@ struct DirMap {
   size_t o1, o2, o3, op;  // element offsets: normal / transverse-1 / transverse-2 vector component, fifth scalar
   long stride;            // cell stride along dir
   int f1, f2, f3;         // the vector components as field numbers (to un-rotate fluxes)
+  size_t N;               // field stride
 };
 __device__ __forceinline__ DirMap dir_map(int dir, size_t N, int nx, int ny, int fifth_field)
 {
@@ -68,6 +97,7 @@ __device__ __forceinline__ DirMap dir_map(int dir, size_t N, int nx, int ny, int
   m.o2 = (size_t)m.f2 * N;
   m.o3 = (size_t)m.f3 * N;
   m.op = (size_t)fifth_field * N;
+  m.N  = N;
   m.stride = dir == 0 ? 1 : (dir == 1 ? (long)nx : (long)nx * ny);
   return m;
 }
@@ -78,10 +108,15 @@ __device__ __forceinline__ void pcm_from_cons(Cons const &u, K const &k, S5 &L)
 {
 #if CHL_STRICT
   (void)k;
+  Cons const &w = u;
   L = S5{{u.d, u.mx, u.my, u.mz, u.E}};
 #else
   Prim const w = prim_from_cons(u, k);
   L = S5{{w.d, w.vx, w.vy, w.vz, w.p}};
+#endif
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) L.q[i] = w.q[i];
 #endif
 }
 
@@ -93,17 +128,30 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
 {
   const Real *__restrict__ c = in + id;
   if (STAGE == 0) {  // first order: both sides are the cell itself (pcm_cuda.cu); the input is conserved
-    pcm_from_cons(Cons{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)}, k, L);
+    Cons u{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)};
+#if CHL_NP > 0
+#pragma unroll
+    for (int i = 0; i < kNP; i++) u.q[i] = __ldg(c + (size_t)(5 + i) * m.N);  // conserved input: fields 5 ..
+#endif
+    pcm_from_cons(u, k, L);
     R = L;
     return;
   }
   if (RECON == kPCM) {
-    Prim const wi{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)};
+    Prim wi{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)};
+#if CHL_NP > 0
+#pragma unroll
+    for (int i = 0; i < kNP; i++) wi.q[i] = __ldg(c + (size_t)(kHalfFields + i) * m.N);
+#endif
     L = iface_state(wi, k);
     R = L;
     return;
   }
+#if CHL_NP > 0
+  GlobalStencil const ld{c, {0, m.o1, m.o2, m.o3, m.op}, m.stride, (size_t)kHalfFields * m.N, m.N};
+#else
   GlobalStencil const ld{c, {0, m.o1, m.o2, m.o3, m.op}, m.stride};
+#endif
   Prim l, r;
   if (RECON == kPLMP || RECON == kPPMP) {
     if (RECON == kPPMP) ppmp_stencil(ld, k, l, r);
@@ -127,11 +175,21 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
 // Half-step state of one cell, from its conserved half-step values: what Load_Data (reconstruction.h:139-212)
 // derives, stored once instead of being recomputed by every stencil that touches the cell.
 template <class K>
-__device__ __forceinline__ Half half_state(Real const (&u)[5], K const &k, int plmp)
+__device__ __forceinline__ Half half_state(U5 const &c, K const &k, int plmp)
 {
   Real const gamma = k.gamma;
-  Prim const w = prim_from_cons(Cons{u[0], u[1], u[2], u[3], u[4]}, k);  // P with the x-sweep association
+  Real const(&u)[5] = c.u;
+  Cons uc{u[0], u[1], u[2], u[3], u[4]};
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) uc.q[i] = c.q[i];
+#endif
+  Prim const w = prim_from_cons(uc, k);  // P with the x-sweep association
   Half h;
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) h.q[i] = w.q[i];
+#endif
   h.w[0] = w.d;
   h.w[1] = w.vx;
   h.w[2] = w.vy;
@@ -152,8 +210,13 @@ __device__ __forceinline__ Half half_state(Real const (&u)[5], K const &k, int p
   // y sweep sums vy^2 + (vz^2 + vx^2), z sweep vz^2 + (vx^2 + vy^2)
   Real const ey = u[4] - RC(0.5) * w.d * sq3(w.vy, w.vz, w.vx);
   Real const ez = u[4] - RC(0.5) * w.d * sq3(w.vz, w.vx, w.vy);
+#if CHL_DE
+  h.w[5] = de_pressure(u[4], ey, c.q[kNP - 1], k);
+  h.w[6] = de_pressure(u[4], ez, c.q[kNP - 1], k);
+#else
   h.w[5] = max_s((gamma - RC(1.)) * ey, kTiny);
   h.w[6] = max_s((gamma - RC(1.)) * ez, kTiny);
+#endif
 #else
   (void)plmp;
   (void)gamma;
@@ -209,11 +272,10 @@ static __device__ __noinline__ Cons riemann_ieee(S5 L, S5 R, Real gamma)
   KCS const k = make_kct<KCS>(gamma);
   return riemann_flux<SOLVER>(to_face(L, k), to_face(R, k), k);
 }
-static __device__ __noinline__ Half half_state_ieee(Real u0, Real u1, Real u2, Real u3, Real u4, Real gamma, int plmp)
+static __device__ __noinline__ Half half_state_ieee(U5 c, Real gamma, int plmp)
 {
-  KCS const k     = make_kct<KCS>(gamma);
-  Real const u[5] = {u0, u1, u2, u3, u4};
-  return half_state(u, k, plmp);
+  KCS const k = make_kct<KCS>(gamma);
+  return half_state(c, k, plmp);
 }
 struct Epi {
   Real E, dti;
@@ -258,12 +320,12 @@ __device__ __forceinline__ Cons riemann_checked(S5 const &L, S5 const &R, KH con
 #endif
   return f;
 }
-__device__ __forceinline__ Half half_state_checked(Real const (&u)[5], KH const &k, int plmp)
+__device__ __forceinline__ Half half_state_checked(U5 const &c, KH const &k, int plmp)
 {
-  Half h = half_state(u, k, plmp);
+  Half h = half_state(c, k, plmp);
 #if CHL_STRICT
   if (k.bad) {
-    h     = half_state_ieee(u[0], u[1], u[2], u[3], u[4], k.gamma, plmp);
+    h     = half_state_ieee(c, k.gamma, plmp);
     k.bad = false;
   }
 #endif
@@ -292,6 +354,10 @@ __device__ __forceinline__ void store_half(Real *__restrict__ out, size_t N, siz
 {
 #pragma unroll
   for (int f = 0; f < kHalfFields; f++) out[(size_t)f * N + id] = h.w[f];
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) out[(size_t)(kHalfFields + i) * N + id] = h.q[i];
+#endif
 }
 
 }  // namespace CHL_NS

@@ -62,6 +62,10 @@ struct DirParams {
   Real dx, dy, dz, idx, idy, idz;
   unsigned long long *dti_key;
   unsigned long long *bad_cells;  // last corrector pass: running count of cells whose density came out <= 0
+  // -DDE builds (CHL_DE), [N] reals filled by de_term_kernel before the stage: last predictor pass -- the p div v term
+  // of the half-step GasEnergy (VL_3D_cuda.cu:471-477); last corrector pass -- GasEnergy after
+  // Partial_Update_Advected_Internal_Energy (hydro_cuda.cu:754-833), taken instead of the old GasEnergy
+  const Real *de_term;
   int xw_log2;                    // y / z sweeps: log2 of the CTA's extent along x (7 = 128 x 1 threads, 2 = 4 x 32)
   // several boxes in ONE launch (the six thin boxes of the boundary shell: no drained-GPU tail between them): a 1-D grid,
   // CTAs [cta0[b], cta0[b + 1]) belong to box b and are laid out gx x gy x (chunks) inside it.  nbox = 0: lo / hi above.
@@ -155,55 +159,94 @@ __device__ __forceinline__ void from_low_side5(Real const (&v)[5], Real (&carry)
 }
 
 template <int STAGE, int DIR, bool FIRST, bool LAST, bool STAGED>
-__device__ __forceinline__ void finish_cell(DirParams const &P, KH const &k, size_t N, size_t id, Real const (&Flo)[5],
-                                            Real const (&Fhi)[5], double &dti, int &n_bad, const Real *staged)
+__device__ __forceinline__ void finish_cell(DirParams const &P, KH const &k, size_t N, size_t id, Cons const &Flo,
+                                            Cons const &Fhi, double &dti, int &n_bad, const Real *staged)
 {
   // staged (STAGED only): this thread's shared-memory column, component k at staged[k * kDirThreads]: the five
-  // running-sum / U operands in sweep-frame order, then (last corrector pass) the five old-U values in field order
+  // running-sum / U operands in sweep-frame order, then (last corrector pass) the five old-U values in field order.
+  // Passive fields (CHL_NP) are read straight from global memory.
   typedef StageGeom<STAGE, FIRST, LAST> SG;
   // sweep frame (normal, t1, t2) -> fields: (x,y,z), (y,z,x), (z,x,y)
   constexpr int field_of_comp[5] = {0, 1 + DIR, 1 + (DIR + 1) % 3, 1 + (DIR + 2) % 3, 4};
-  Real u[5];
+  Real const flo[5] = {Flo.d, Flo.mx, Flo.my, Flo.mz, Flo.E}, fhi[5] = {Fhi.d, Fhi.mx, Fhi.my, Fhi.mz, Fhi.E};
+  U5 c;
+  Real(&u)[5] = c.u;
 #pragma unroll
-  for (int c = 0; c < 5; c++) {
-    int const f  = field_of_comp[c];
-    Real const t = P.dto * (Flo[c] - Fhi[c]);
+  for (int cc = 0; cc < 5; cc++) {
+    int const f  = field_of_comp[cc];
+    Real const t = P.dto * (flo[cc] - fhi[cc]);
     Real v;
-    if (STAGED && SG::n_sum) v = staged[c * kDirThreads] + t;
+    if (STAGED && SG::n_sum) v = staged[cc * kDirThreads] + t;
     else if (STAGE == 0) v = (FIRST ? __ldg(P.U + f * N + id) : P.acc[f * N + id]) + t;
     else v = FIRST ? t : P.acc[f * N + id] + t;
     if (!LAST) P.acc[f * N + id] = v;
     u[f] = v;
   }
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) {
+    size_t const o = (size_t)(5 + i) * N + id;
+    Real const t   = P.dto * (Flo.q[i] - Fhi.q[i]);
+    Real v;
+    if (STAGE == 0) v = (FIRST ? __ldg(P.U + o) : P.acc[o]) + t;
+    else v = FIRST ? t : P.acc[o] + t;
+    if (!LAST) P.acc[o] = v;
+    c.q[i] = v;
+  }
+#endif
   if (!LAST) return;
   bool const floors = P.ndim == 3;  // the reference's 1-D / 2-D update kernels have no floors (hydro_cuda.cu:20-170)
   if (STAGE == 0) {
-    if (floors && u[0] < P.density_floor) {  // VL_3D_cuda.cu:479-493
+#if CHL_DE
+    c.q[kNP - 1] = c.q[kNP - 1] + __ldg(P.de_term + id);  // + 0.5 P (dt/dx dvx + ...), VL_3D_cuda.cu:471-477
+#endif
+    if (floors && u[0] < P.density_floor) {  // VL_3D_cuda.cu:479-493: momenta, Energy and GasEnergy; not the scalars
       Real const d0 = u[0];
       u[0]          = P.density_floor;
 #pragma unroll
       for (int f = 1; f < 5; f++) u[f] *= (P.density_floor / d0);
+#if CHL_DE
+      c.q[kNP - 1] *= (P.density_floor / d0);
+#endif
     }
-    store_half(P.out, N, id, half_state_checked(u, k, P.plmp));
+    store_half(P.out, N, id, half_state_checked(c, k, P.plmp));
     return;
   }
 #pragma unroll
   for (int f = 0; f < 5; f++) u[f] = (STAGED ? staged[(SG::n_sum + f) * kDirThreads] : P.out[f * N + id]) + u[f];
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) {
+    Real old = P.out[(size_t)(5 + i) * N + id];
+#if CHL_DE
+    if (i == kNP - 1) old = __ldg(P.de_term + id);
+#endif
+    c.q[i] = old + c.q[i];
+  }
+#endif
   if (floors) {
     if (u[0] < P.density_floor && u[0] > RC(0.)) {  // hydro_cuda.cu:279-291
       Real const d0 = u[0];
       u[0]          = P.density_floor;
 #pragma unroll
       for (int f = 1; f < 5; f++) u[f] *= (P.density_floor / d0);
+#if CHL_DE
+      c.q[kNP - 1] *= (P.density_floor / d0);
+#endif
     }
   }
   // a cell whose density came out non-positive is counted (chl_bad_cells): the reference averages its neighbours inside
   // the in-place update, a race with no bits to match (hydro_cuda.cu:292-297), and leaves the decision to the host
   if (!(u[0] > RC(0.))) n_bad++;
+  // (-DDE builds: the temperature floor and the CFL maximum follow Select_Internal_Energy / Sync_Energies, de_sync_kernel)
   Real const v = cell_epilogue_checked(u, k, floors && P.apply_tfloor, P.U_floor, P.do_dti, P.ndim, P.idx, P.idy, P.idz,
                                        P.dx, P.dy, P.dz);
 #pragma unroll
   for (int f = 0; f < 5; f++) P.out[f * N + id] = u[f];
+#if CHL_NP > 0
+#pragma unroll
+  for (int i = 0; i < kNP; i++) P.out[(size_t)(5 + i) * N + id] = c.q[i];
+#endif
   if (P.do_dti) dti = fmax(dti, (double)v);
 }
 
@@ -264,7 +307,8 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
 
   typedef StageGeom<STAGE, FIRST, LAST> SG;
   constexpr bool kStage = CHL_DIR_STAGE && SG::n > 0;
-  constexpr int kParkN  = CHL_DIR_PARK ? (DIR == 0 ? 10 * kRowsPerCta : 10 * kDirThreads) : 1;
+  constexpr int kParkV  = 10 + 2 * kNP;  // parked per thread / warp: low-side state and lower-face flux
+  constexpr int kParkN  = CHL_DIR_PARK ? (DIR == 0 ? kParkV * kRowsPerCta : kParkV * kDirThreads) : 1;
   __shared__ Real stage[kStage ? SG::n * kDirThreads : 1];
   __shared__ Real parked[kParkN];
 
@@ -272,6 +316,11 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
     Real Lc[5], Fc[5];  // carried: low-side state of the face below / flux through the face below the previous cell
 #pragma unroll
     for (int c = 0; c < 5; c++) Lc[c] = Fc[c] = RC(0.0);
+#if CHL_NP > 0
+    Real Lqc[kNP], Fqc[kNP];
+#pragma unroll
+    for (int c = 0; c < kNP; c++) Lqc[c] = Fqc[c] = RC(0.0);
+#endif
     int const step = DIR == 0 ? 32 : 1;
     constexpr int field_of_comp[5] = {0, 1 + DIR, 1 + (DIR + 1) % 3, 1 + (DIR + 2) % 3, 4};
     Real *const park   = parked + (DIR == 0 ? (threadIdx.x >> 5) : threadIdx.x);
@@ -302,21 +351,36 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
       } else {
 #pragma unroll
         for (int k = 0; k < 5; k++) L.v[k] = R.v[k] = RC(1.0);
+#if CHL_NP > 0
+#pragma unroll
+        for (int k = 0; k < kNP; k++) L.q[k] = R.q[k] = RC(1.0);
+#endif
       }
       S5 Lp;
       from_low_side5<DIR>(L.v, Lc, Lp.v, park, pstride, lane);
+#if CHL_NP > 0
+      from_low_side_n<DIR, kNP>(L.q, Lqc, Lp.q, park + 10 * pstride, pstride, lane);
+#endif
       Real F[5];
+      Cons Fhi;
       if (face) {
-        Cons const f = riemann_checked<SOLVER>(Lp, R, kc);
-        F[0] = f.d; F[1] = f.mx; F[2] = f.my; F[3] = f.mz; F[4] = f.E;
+        Fhi = riemann_checked<SOLVER>(Lp, R, kc);
       } else {
+        Fhi.d = Fhi.mx = Fhi.my = Fhi.mz = Fhi.E = RC(0.0);
+#if CHL_NP > 0
 #pragma unroll
-        for (int k = 0; k < 5; k++) F[k] = RC(0.0);
+        for (int k = 0; k < kNP; k++) Fhi.q[k] = RC(0.0);
+#endif
       }
+      F[0] = Fhi.d; F[1] = Fhi.mx; F[2] = Fhi.my; F[3] = Fhi.mz; F[4] = Fhi.E;
       Real Fp[5];
       from_low_side5<DIR>(F, Fc, Fp, park + 5 * pstride, pstride, lane);
+      Cons Flo{Fp[0], Fp[1], Fp[2], Fp[3], Fp[4]};
+#if CHL_NP > 0
+      from_low_side_n<DIR, kNP>(Fhi.q, Fqc, Flo.q, park + (10 + kNP) * pstride, pstride, lane);
+#endif
       if (kStage) cp_async_wait_all();
-      if (fin) finish_cell<STAGE, DIR, FIRST, LAST, kStage>(P, kc, N, id - (size_t)m.stride, Fp, F, dti, n_bad, staged);
+      if (fin) finish_cell<STAGE, DIR, FIRST, LAST, kStage>(P, kc, N, id - (size_t)m.stride, Flo, Fhi, dti, n_bad, staged);
     }
   }
 

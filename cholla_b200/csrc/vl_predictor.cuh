@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(kPThreads, CHL_PRED_MINB) vl_predictor_kernel(
     // ======================= phase C: complete cell (cx, cy, q) =======================
     if (active && do_xy) {
       size_t const id = col + plane * (size_t)q;
-      Real u[5];
+      U5 c;  // five-field builds only (CHL_NP = 0): the dispatcher never selects this kernel for passive fields
+      Real(&u)[5] = c.u;
 #pragma unroll
       for (int f = 0; f < 5; f++) {
         Real v = __ldg(P.U + (size_t)f * N + id) + P.dto[0] * (fxb[f * kPFx + fxs - 1] - fxb[f * kPFx + fxs]);
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kPThreads, CHL_PRED_MINB) vl_predictor_kernel(
 #pragma unroll
         for (int f = 1; f < 5; f++) u[f] *= (P.density_floor / d0);
       }
-      store_half(P.W, N, id, half_state_checked(u, kc, P.plmp));
+      store_half(P.W, N, id, half_state_checked(c, kc, P.plmp));
     }
     if (active && p >= kz0) {
 #pragma unroll

@@ -151,6 +151,7 @@ cudaError_t launch_predictor(SweepArgs const &a, int plmp, cudaStream_t s)
 
 cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cudaStream_t s)
 {
+#if CHL_NP == 0
   if (stage == 0 && a.has_y && a.has_z && a.fused_predictor) {
     int const plmp = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
 #ifdef CHL_DEV_SUBSET
@@ -162,6 +163,7 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
     return launch_predictor<kHLLC>(a, plmp, s);
 #endif
   }
+#endif
   DirParams p;
   p.in  = (const Real *)a.in;
   p.U   = (const Real *)a.in;
@@ -181,7 +183,29 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   p.xw_log2   = 7;
   p.nbox      = 0;
   p.plmp      = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
-#ifdef CHL_DEV_SUBSET  // development builds (make VARIANT=... EXTRA=-DCHL_DEV_SUBSET): the headline combination only
+  p.de_term   = (const Real *)a.de_term;
+#if CHL_NP > 0
+  // -DSCALAR / -DDE builds: the Van Leer integrator with PCM / PLMC / PPMC and HLLC / Roe / HLL
+  if (a.simple || (solver != kHLLC && solver != kROE && solver != kHLL)) return cudaErrorNotSupported;
+  if (CHL_DE && !p.de_term) return cudaErrorInvalidValue;
+  if (stage == 0) {
+    if (solver == kROE) return run_dirs<kPCM, kROE, 0>(p, a, s);
+    if (solver == kHLL) return run_dirs<kPCM, kHLL, 0>(p, a, s);
+    return run_dirs<kPCM, kHLLC, 0>(p, a, s);
+  }
+  switch (recon * 4 + solver) {
+    case kPCM * 4 + kHLLC: return run_dirs<kPCM, kHLLC, 1>(p, a, s);
+    case kPCM * 4 + kROE: return run_dirs<kPCM, kROE, 1>(p, a, s);
+    case kPCM * 4 + kHLL: return run_dirs<kPCM, kHLL, 1>(p, a, s);
+    case kPLMC * 4 + kHLLC: return run_dirs<kPLMC, kHLLC, 1>(p, a, s);
+    case kPLMC * 4 + kROE: return run_dirs<kPLMC, kROE, 1>(p, a, s);
+    case kPLMC * 4 + kHLL: return run_dirs<kPLMC, kHLL, 1>(p, a, s);
+    case kPPMC * 4 + kHLLC: return run_dirs<kPPMC, kHLLC, 1>(p, a, s);
+    case kPPMC * 4 + kROE: return run_dirs<kPPMC, kROE, 1>(p, a, s);
+    case kPPMC * 4 + kHLL: return run_dirs<kPPMC, kHLL, 1>(p, a, s);
+  }
+  return cudaErrorNotSupported;
+#elif defined(CHL_DEV_SUBSET)  // development builds (make VARIANT=... EXTRA=-DCHL_DEV_SUBSET): the headline combination only
   if (solver != kHLLC || recon != kPPMC) return cudaErrorNotSupported;
   if (stage == 0) return run_dirs<kPCM, kHLLC, 0>(p, a, s);
   return run_dirs<kPPMC, kHLLC, 1>(p, a, s);
@@ -301,6 +325,10 @@ __global__ void __launch_bounds__(256) tfloor_kernel(Real *U, int nx, int ny, in
     Real const E = U[4 * N + id];
     Real const Ekin = RC(0.5) * d * (vx * vx + vy * vy + vz * vz);
     if ((E - Ekin) / d < U_floor) U[4 * N + id] = Ekin + d * U_floor;
+#if CHL_DE  // hydro_cuda.cu:1146-1151
+    size_t const ge = (size_t)(5 + kNP - 1) * N + id;
+    if (U[ge] / d < U_floor) U[ge] = d * U_floor;
+#endif
   }
 }
 
@@ -322,8 +350,12 @@ __global__ void __launch_bounds__(256) prim_from_cons_kernel(const Real *__restr
 {
   KH const kc = make_kct<KH>(gamma);
   for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < N; id += (size_t)gridDim.x * blockDim.x) {
-    Real const u[5] = {__ldg(U + id), __ldg(U + N + id), __ldg(U + 2 * N + id), __ldg(U + 3 * N + id), __ldg(U + 4 * N + id)};
-    store_half(W, N, id, half_state_checked(u, kc, plmp));
+    U5 c{{__ldg(U + id), __ldg(U + N + id), __ldg(U + 2 * N + id), __ldg(U + 3 * N + id), __ldg(U + 4 * N + id)}};
+#if CHL_NP > 0
+#pragma unroll
+    for (int i = 0; i < kNP; i++) c.q[i] = __ldg(U + (size_t)(5 + i) * N + id);
+#endif
+    store_half(W, N, id, half_state_checked(c, kc, plmp));
   }
 }
 
@@ -336,7 +368,181 @@ cudaError_t prim_from_cons(const void *U, void *W, size_t n_cells, double gamma,
   return cudaGetLastError();
 }
 
-ModeOps const ops = {sweep_split, calc_dti, tfloor, prim_from_cons, sizeof(Real), kHalfFields};
+#if CHL_DE
+// ---- dual energy (-DDE): the three small passes around the sweeps.  Plain IEEE divisions (cold code; the strict TU is
+// built -fmad=false, so every operation rounds like the reference's). ----
+__device__ __forceinline__ Real de_pressure_ieee(Real E, Real U_total, Real U_advected, Real gamma)
+{  // Get_Pressure_From_DE, hydro_utilities.h:136-151
+  Real const U = (U_total / E > kDeEta1) ? U_total : U_advected;
+  return fmax(U * (gamma - RC(1.0)), kTiny);
+}
+// mode 0, before the predictor: out = 0.5 P (dt/2dx (vx_imo - vx_ipo) + ...), the last term of the half-step GasEnergy
+//   (VL_3D_cuda.cu:408-426, 471-477; the 1-D / 2-D kernels take the plain pressure: VL_2D_cuda.cu:213, VL_1D_cuda.cu:183);
+// mode 1, before the corrector: out = GasEnergy + 0.5 P (dt/dx (vx_imo - vx_ipo) + ...), i.e. GasEnergy after
+//   Partial_Update_Advected_Internal_Energy_{1,2,3}D (hydro_cuda.cu:662-833).  Both read U^n only.
+template <int NDIM>
+__global__ void __launch_bounds__(256) de_term_kernel(const Real *__restrict__ U, Real *__restrict__ out, int nx, int ny,
+                                                      int nz, int lo0, int lo1, int lo2, int hi0, int hi1, int hi2,
+                                                      Real dtodx, Real dtody, Real dtodz, Real gamma, int mode)
+{
+  size_t const N = (size_t)nx * ny * nz;
+  int const rx = hi0 - lo0, ry = hi1 - lo1, rz = hi2 - lo2;
+  size_t const n = (size_t)rx * ry * rz;
+  size_t const sy = nx, sz = (size_t)nx * ny, GE = (size_t)(5 + kNP - 1) * N;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    int const x = (int)(t % rx) + lo0;
+    size_t const r = t / rx;
+    int const y = (int)(r % ry) + lo1, z = (int)(r / ry) + lo2;
+    size_t const id = (size_t)x + sy * y + sz * z;
+    Real const d = U[id], d_inv = RC(1.0) / d;
+    Real const vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv;
+    Real const E = U[4 * N + id], ge = U[GE + id];
+    Real P;
+    if (mode == 0 && NDIM < 3) {
+      P = (E - RC(0.5) * d * (vx * vx + vy * vy + vz * vz)) * (gamma - RC(1.0));
+    } else {
+      Real const E_kin = NDIM == 3 ? RC(0.5) * d * sq3(vx, vy, vz) : RC(0.5) * d * (vx * vx + vy * vy + vz * vz);
+      P = fmax(de_pressure_ieee(E, E - E_kin, ge, gamma), kTiny);
+    }
+    Real div = dtodx * (U[N + id - 1] / U[id - 1] - U[N + id + 1] / U[id + 1]);
+    if (NDIM > 1) div = div + dtody * (U[2 * N + id - sy] / U[id - sy] - U[2 * N + id + sy] / U[id + sy]);
+    if (NDIM > 2) div = div + dtodz * (U[3 * N + id - sz] / U[id - sz] - U[3 * N + id + sz] / U[id + sz]);
+    Real const term = RC(0.5) * P * (div);
+    out[id] = mode == 0 ? term : ge + term;
+  }
+}
+
+cudaError_t de_term(const void *U, void *out, int nx, int ny, int nz, const int lo[3], const int hi[3], double dtodx,
+                    double dtody, double dtodz, double gamma, int mode, cudaStream_t s)
+{
+  int const ndim = 1 + (ny > 1) + (nz > 1);
+  size_t const n = (size_t)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+  if (n == 0) return cudaSuccess;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+#define CHL_DE_TERM(ND)                                                                                              \
+  de_term_kernel<ND><<<(unsigned)blocks, 256, 0, s>>>((const Real *)U, (Real *)out, nx, ny, nz, lo[0], lo[1], lo[2], \
+                                                      hi[0], hi[1], hi[2], (Real)dtodx, (Real)dtody, (Real)dtodz,    \
+                                                      (Real)gamma, mode)
+  if (ndim == 3) CHL_DE_TERM(3);
+  else if (ndim == 2) CHL_DE_TERM(2);
+  else CHL_DE_TERM(1);
+#undef CHL_DE_TERM
+  return cudaGetLastError();
+}
+
+// Select_Internal_Energy_{1,2,3}D (hydro_cuda.cu:835-1010): which internal energy the cell keeps -- decided from the
+// total energies of the cell and its neighbours (clamped to the real cells) BEFORE any of them is re-synchronised, so it
+// is a launch of its own; writes GasEnergy only.
+template <int NDIM>
+__global__ void __launch_bounds__(256) de_select_kernel(Real *__restrict__ U, int nx, int ny, int nz, int g)
+{
+  size_t const N = (size_t)nx * ny * nz;
+  int const rx = nx - 2 * g, ry = NDIM > 1 ? ny - 2 * g : 1, rz = NDIM > 2 ? nz - 2 * g : 1;
+  size_t const n = (size_t)rx * ry * rz;
+  size_t const sy = nx, sz = (size_t)nx * ny, GE = (size_t)(5 + kNP - 1) * N;
+  const Real *__restrict__ Et = U + 4 * N;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    int const x = (int)(t % rx) + g;
+    size_t const r = t / rx;
+    int const y = NDIM > 1 ? (int)(r % ry) + g : 0, z = NDIM > 2 ? (int)(r / ry) + g : 0;
+    size_t const id = (size_t)x + sy * y + sz * z;
+    Real const d = U[id], d_inv = RC(1.0) / d;
+    Real const vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv;
+    Real const E = Et[id], U_advected = U[GE + id];
+    Real const U_total = E - RC(0.5) * d * (vx * vx + vy * vy + vz * vz);
+    Real Emax = fmax(Et[id - (x - 1 >= g ? 1 : 0)], E);
+    Emax      = fmax(Emax, Et[id + (x + 1 <= nx - g - 1 ? 1 : 0)]);
+    if (NDIM > 1) {
+      Emax = fmax(Emax, Et[id - (y - 1 >= g ? sy : 0)]);
+      Emax = fmax(Emax, Et[id + (y + 1 <= ny - g - 1 ? sy : 0)]);
+    }
+    if (NDIM > 2) {
+      Emax = fmax(Emax, Et[id - (z - 1 >= g ? sz : 0)]);
+      Emax = fmax(Emax, Et[id + (z + 1 <= nz - g - 1 ? sz : 0)]);
+    }
+    Real const Us = ((U_total / E > kDeEta1) || (U_total / Emax > kDeEta2)) ? U_total : U_advected;
+    U[GE + id] = fmax(Us, kTiny);
+  }
+}
+
+// Sync_Energies_{1,2,3}D (hydro_cuda.cu:1012-1099) with what follows it in Grid3D::Update_Hydro_Grid folded in, like the
+// last corrector pass of a build without DE: the temperature floor of a -DDE build (hydro_cuda.cu:1117-1153; 3-D only) and
+// the cell's inverse crossing time for Calc_dt_GPU.
+template <int NDIM>
+__global__ void __launch_bounds__(256) de_sync_kernel(Real *__restrict__ U, int nx, int ny, int nz, int g, Real gamma,
+                                                      int apply_tfloor, Real U_floor, int do_dti, Real dx, Real dy,
+                                                      Real dz, unsigned long long *key)
+{
+  __shared__ double sred[8];
+  size_t const N = (size_t)nx * ny * nz;
+  int const rx = nx - 2 * g, ry = NDIM > 1 ? ny - 2 * g : 1, rz = NDIM > 2 ? nz - 2 * g : 1;
+  size_t const n = (size_t)rx * ry * rz;
+  size_t const sy = nx, sz = (size_t)nx * ny, GE = (size_t)(5 + kNP - 1) * N;
+  Real const idx = RC(1.0) / dx, idy = RC(1.0) / dy, idz = RC(1.0) / dz;
+  KCS const kc = make_kct<KCS>(gamma);
+  double m = -DBL_MAX;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    int const x = (int)(t % rx) + g;
+    size_t const r = t / rx;
+    int const y = NDIM > 1 ? (int)(r % ry) + g : 0, z = NDIM > 2 ? (int)(r / ry) + g : 0;
+    size_t const id = (size_t)x + sy * y + sz * z;
+    Real const d = U[id], d_inv = RC(1.0) / d;
+    Real const mx = U[N + id], my = U[2 * N + id], mz = U[3 * N + id];
+    Real const vx = mx * d_inv, vy = my * d_inv, vz = mz * d_inv;
+    Real ge = U[GE + id];
+    Real const Ekin = RC(0.5) * d * (vx * vx + vy * vy + vz * vz);
+    Real E = Ekin + ge;
+    if (apply_tfloor && NDIM == 3) {
+      if ((E - Ekin) / d < U_floor) E = Ekin + d * U_floor;
+      if (ge / d < U_floor) {
+        ge         = d * U_floor;
+        U[GE + id] = ge;
+      }
+    }
+    U[4 * N + id] = E;
+    if (do_dti) m = fmax(m, (double)inverse_crossing_time<NDIM>(d, mx, my, mz, E, idx, idy, idz, dx, dy, dz, kc));
+  }
+  if (!do_dti) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < 8 ? sred[threadIdx.x] : -DBL_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMax(key, dti_encode(m));
+  }
+}
+
+cudaError_t de_finish(void *U, int nx, int ny, int nz, int g, double gamma, int apply_tfloor, double U_floor, int do_dti,
+                      double dx, double dy, double dz, unsigned long long *key, cudaStream_t s)
+{
+  int const ndim = 1 + (ny > 1) + (nz > 1);
+  size_t const n = (size_t)(nx - 2 * g) * (ndim > 1 ? ny - 2 * g : 1) * (ndim > 2 ? nz - 2 * g : 1);
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  Real *u = (Real *)U;
+#define CHL_DE_FIN(ND)                                                                                                \
+  de_select_kernel<ND><<<(unsigned)blocks, 256, 0, s>>>(u, nx, ny, nz, g);                                             \
+  de_sync_kernel<ND><<<(unsigned)blocks, 256, 0, s>>>(u, nx, ny, nz, g, (Real)gamma, apply_tfloor, (Real)U_floor, do_dti, \
+                                                      (Real)dx, (Real)dy, (Real)dz, key)
+  if (ndim == 3) { CHL_DE_FIN(3); }
+  else if (ndim == 2) { CHL_DE_FIN(2); }
+  else { CHL_DE_FIN(1); }
+#undef CHL_DE_FIN
+  return cudaGetLastError();
+}
+#else
+cudaError_t (*const de_term)(const void *, void *, int, int, int, const int[3], const int[3], double, double, double, double,
+                             int, cudaStream_t) = nullptr;
+cudaError_t (*const de_finish)(void *, int, int, int, int, double, int, double, int, double, double, double,
+                               unsigned long long *, cudaStream_t) = nullptr;
+#endif
+
+ModeOps const ops = {sweep_split, calc_dti, tfloor, prim_from_cons, sizeof(Real), kHalfFields, kNP, CHL_DE, de_term, de_finish};
 }  // namespace
 ModeOps const *get_ops() { return &ops; }
 }  // namespace CHL_NS

@@ -120,7 +120,7 @@ class Grid3D:
     def __init__(self, n_global, domain_len, bounds_min=(0.0, 0.0, 0.0), recon=_lib.PPMC, solver=_lib.HLLC,
                  gamma=5.0 / 3.0, bc=(1, 1, 1, 1, 1, 1), precision=2, strict=True, density_floor=0.0,
                  temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True, mhd=False,
-                 integrator="vl", halo_transport="p2p", overlap=True):
+                 integrator="vl", halo_transport="p2p", overlap=True, n_scalars=0, dual_energy=False):
         import torch
         self.torch = torch
         if integrator not in ("vl", "simple"):  # -DVL / -DSIMPLE, builds/make.type.hydro:8-12
@@ -129,6 +129,8 @@ class Grid3D:
         self.recon, self.solver, self.gamma = recon, solver, float(gamma)
         self.precision, self.strict, self.fused = precision, bool(strict), bool(fused)
         self.mhd = bool(mhd) or solver == _lib.HLLD
+        # -DSCALAR / -DDE builds: fields 5 .. are the scalars, GasEnergy is the last field (grid_enum.h:33-78)
+        self.n_scalars, self.dual_energy = int(n_scalars), bool(dual_energy)
         if self.mhd:
             self.solver = solver = _lib.HLLD  # error_handling.cpp:93-96: MHD only supports HLLD
         self.dist_group, self.nproc, self.rank = dist_group, nproc, rank
@@ -139,7 +141,7 @@ class Grid3D:
         g = n_ghost_for(recon, self.mhd)
         H = Header()
         H.n_ghost = g
-        H.n_fields = 8 if self.mhd else N_FIELDS
+        H.n_fields = 8 if self.mhd else N_FIELDS + self.n_scalars + int(self.dual_energy)
         H.nx_real, H.ny_real, H.nz_real = self.decomp.n_local
         H.nx = H.nx_real + 2 * g
         H.ny = H.ny_real + 2 * g if n_global[1] > 1 else 1
@@ -159,7 +161,7 @@ class Grid3D:
         torch.cuda.set_device(self.device)
         self.C_device = torch.zeros(H.n_fields * H.n_cells, dtype=self.dtype, device=self.device)
         cfg = Config(H.nx, H.ny, H.nz, g, H.n_fields, recon, solver, precision, int(self.strict), int(self.mhd), self.gamma,
-                     H.dx, H.dy, H.dz, float(density_floor), self.U_floor)
+                     H.dx, H.dy, H.dz, float(density_floor), self.U_floor, self.n_scalars, int(self.dual_energy))
         self._cfg = cfg
         self._ctx = C.c_void_p()
         check(_lib.lib().chl_create(C.byref(cfg), C.byref(self._ctx)), "chl_create")
@@ -314,8 +316,15 @@ class Grid3D:
 
     def _sweep_launches(self):
         """Kernels one step launches: VL a predictor and a corrector sweep per direction (direction-split default);
-        SIMPLE the primitive pass and one sweep per direction."""
-        return 1 + self.ndim if self.integrator == "simple" else 2 * self.ndim
+        SIMPLE the primitive pass and one sweep per direction; a dual-energy context adds the two p div v passes and
+        Select_Internal_Energy / Sync_Energies."""
+        return 1 + self.ndim if self.integrator == "simple" else 2 * self.ndim + (4 if self.dual_energy else 0)
+
+    def Apply_Scalar_Floor(self, field_num, scalar_floor):
+        """Apply_Scalar_Floor (hydro_cuda.cu:1267-1307; grid3D.cpp:505-510 calls it for the dust density)."""
+        check(_lib.lib().chl_apply_scalar_floor(self._ctx, self._ptr(), int(field_num), float(scalar_floor), self._stream()),
+              "chl_apply_scalar_floor")
+        self.gpu_launches += 1
 
     def Update_Hydro_Grid(self):
         """Grid3D::Update_Hydro_Grid (grid3D.cpp:474-585): integrator, temperature floor, new inverse dt."""

@@ -221,6 +221,34 @@ def random_smooth(n, seed=0, gamma=5.0 / 3.0):
     return _pack(d, d * vx, d * vy, d * vz, E)
 
 
+def with_passive(fields, n_scalars=0, dual_energy=False, gamma=5.0 / 3.0, seed=1):
+    """Append the passive fields of a -DSCALAR / -DDE build to a 5-field state: n_scalars scalars (conserved: density
+    times a seeded mass fraction in (0.1, 0.9)), then GasEnergy = Energy - kinetic energy, which is what the reference's
+    generators store (initial_conditions.cpp: `C.GasEnergy[id] = P / (gama - 1.0)`)."""
+    f = np.asarray(fields)
+    rng = np.random.default_rng(seed)
+    extra = [f[0] * (0.1 + 0.8 * rng.random(f[0].shape)) for _ in range(int(n_scalars))]
+    if dual_energy:
+        extra.append(f[4] - 0.5 * (f[1] ** 2 + f[2] ** 2 + f[3] ** 2) / f[0])
+    return np.concatenate([f, np.stack(extra)]) if extra else f.copy()
+
+
+def cold_flow(n, seed=0, gamma=5.0 / 3.0, mach=40.0):
+    """A fast, cold, perturbed stream: thermal energy is about a thousandth of the total, so that cells fall on both sides
+    of the dual-energy switches (DE_ETA_1 = 0.001, DE_ETA_2 = 0.035; global.h:53-73)."""
+    rng = np.random.default_rng(seed)
+    shape = _shape(n)
+    d = 0.8 + 0.4 * rng.random(shape)
+    P = 0.6 * (0.5 + rng.random(shape))
+    cs = np.sqrt(gamma * 0.6 / 1.0)
+    v0 = mach * cs
+    vx = v0 * (0.7 + 0.6 * rng.random(shape)) / np.sqrt(3.0)
+    vy = v0 * (0.7 + 0.6 * rng.random(shape)) / np.sqrt(3.0) if len([m for m in n if m > 1]) > 1 else np.zeros(shape)
+    vz = v0 * (0.7 + 0.6 * rng.random(shape)) / np.sqrt(3.0) if len([m for m in n if m > 1]) > 2 else np.zeros(shape)
+    E = P / (gamma - 1.0) + 0.5 * d * (vx * vx + vy * vy + vz * vz)
+    return _pack(d, d * vx, d * vy, d * vz, E)
+
+
 # ---- MHD (8 fields, face-centred magnetic field) ---------------------------------------------------------------
 # These return the FULL local array, ghost cells included, as (8, nz + 2g, ny + 2g, nx + 2g): the face-centred field is
 # the discrete curl of a vector potential sampled over the ghost zones too, so div B = 0 to round-off everywhere and

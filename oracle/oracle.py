@@ -40,6 +40,10 @@ def lib():
         _lib.orc_calc_dti.argtypes = [p, i, i, i, i, d, d, d, d]
         _lib.orc_calc_dti.restype = d
         _lib.orc_temperature_floor.argtypes = [p, i, i, i, i, d]
+        _lib.orc_vl_step_x.argtypes = [p, i, i, i, i, d, d, d, d, d, i, i, d, i, i]
+        _lib.orc_vl_step_x.restype = i
+        _lib.orc_temperature_floor_x.argtypes = [p, i, i, i, i, d, i, i]
+        _lib.orc_scalar_floor.argtypes = [p, i, i, i, i, i, d]
         _lib.orc_boundary_extents.argtypes = [i, i, i, i, i, p, p]
         _lib.orc_set_ghost_cells.argtypes = [p, i, i, i, i, i, p, i]
         _lib.orc_set_boundaries.argtypes = [p, i, i, i, i, i, p]
@@ -83,6 +87,25 @@ def riemann_single(solver, left, right, gamma):
 def vl_step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor=0.0):
     """In-place VL_Algorithm_{1,2,3}D_CUDA on U (flat SoA incl. ghosts)."""
     lib().orc_vl_step(_ptr(U), nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor)
+    return U
+
+
+def vl_step_x(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor=0.0, n_scalars=0,
+              dual_energy=False):
+    """In-place VL step of a -DSCALAR / -DDE build: 5 + n_scalars + dual_energy fields (GasEnergy last)."""
+    if lib().orc_vl_step_x(_ptr(U), nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor, n_scalars,
+                           int(bool(dual_energy))) != 0:
+        raise NotImplementedError("passive fields are restated for PCM / PLMC / PPMC with HLLC / Roe / HLL")
+    return U
+
+
+def temperature_floor_x(U, nx, ny, nz, n_ghost, U_floor, n_fields, dual_energy):
+    lib().orc_temperature_floor_x(_ptr(U), nx, ny, nz, n_ghost, U_floor, n_fields, int(bool(dual_energy)))
+    return U
+
+
+def scalar_floor(U, nx, ny, nz, n_ghost, field_num, floor):
+    lib().orc_scalar_floor(_ptr(U), nx, ny, nz, n_ghost, field_num, floor)
     return U
 
 
@@ -144,11 +167,23 @@ def unpack(buf, U, nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize):
 
 
 def advance(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_steps, cfl=0.3,
-            density_floor=0.0, U_floor=0.0, integrator="vl"):
+            density_floor=0.0, U_floor=0.0, integrator="vl", n_scalars=0, dual_energy=False):
     """The reference's main loop body (main.cpp:247-379) without I/O: dt from the CFL reduction, VL (or SIMPLE) step,
     temperature floor, ghost fill.  Returns the list of dt used."""
     dts = []
     step = {"vl": vl_step, "simple": simple_step}[integrator]
+    n_fields = 5 + n_scalars + int(bool(dual_energy))
+    if n_fields > 5:
+        assert integrator == "vl"
+        dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
+        for _ in range(n_steps):
+            dt = cfl / dti
+            vl_step_x(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor, n_scalars, dual_energy)
+            temperature_floor_x(U, nx, ny, nz, n_ghost, U_floor, n_fields, dual_energy)
+            dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
+            set_boundaries(U, nx, ny, nz, n_fields, n_ghost, flags)
+            dts.append(dt)
+        return dts
     dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
     for _ in range(n_steps):
         dt = cfl / dti

@@ -32,11 +32,9 @@ int chprintf(const char *__restrict sdata, ...)
   va_end(ap);
   return n;
 }
-#ifdef MHD
-static const int kFields = 8;  // grid_enum::num_fields of an -DMHD build
-#else
-static const int kFields = 5;
-#endif
+#include "grid/grid_enum.h"
+// 5; 8 in an -DMHD build; + NSCALARS with -DSCALAR; + 1 (GasEnergy, last) with -DDE
+static const int kFields = grid_enum::num_fields;
 
 static void boundary_extents(int dir, int nx, int ny, int nz, int g, int *lo, int *hi)
 {  // Grid3D::Set_Boundary_Extents lives in a host TU (boundary_conditions.cpp:419-) that needs the whole Grid3D;

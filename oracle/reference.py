@@ -12,23 +12,24 @@ _SOLV = {0: "hllc", 1: "roe", 2: "hlld", 3: "hll", 4: "exact"}
 _libs = {}
 
 
-def lib_path(recon, solver, nosync=False, dropin=False, simple=False):
+def lib_path(recon, solver, nosync=False, dropin=False, simple=False, variant=""):
     """dropin=True: the same driver linked against cholla_b200/csrc/cholla_shims.cpp + libcholla_b200.so instead of
     the reference's kernel objects (oracle/ref_build/Makefile, target `dropin`)."""
     sfx = "_simple" if simple else ""  # a -DSIMPLE build (Simple_Algorithm_*_CUDA) instead of -DVL
+    sfx += variant  # "_de", "_s1", "_de_s1": -DDE / -DSCALAR -DBASIC_SCALAR builds (oracle/ref_build/Makefile: PASSIVE)
     if dropin:
         return os.path.join(REF_DIR, "libcholla_dropin_%s_%s%s.so" % (_NAMES[recon], _SOLV[solver], sfx))
     return os.path.join(REF_DIR, "libcholla_ref_%s_%s%s%s.so" % (_NAMES[recon], _SOLV[solver], sfx, "_nosync" if nosync else ""))
 
 
-def available(recon, solver, nosync=False, dropin=False, simple=False):
-    return os.path.exists(lib_path(recon, solver, nosync, dropin, simple))
+def available(recon, solver, nosync=False, dropin=False, simple=False, variant=""):
+    return os.path.exists(lib_path(recon, solver, nosync, dropin, simple, variant))
 
 
-def lib(recon, solver, nosync=False, dropin=False, simple=False):
-    key = (recon, solver, nosync, dropin, simple)
+def lib(recon, solver, nosync=False, dropin=False, simple=False, variant=""):
+    key = (recon, solver, nosync, dropin, simple, variant)
     if key not in _libs:
-        L = C.CDLL(lib_path(recon, solver, nosync, dropin, simple))  # RTLD_LOCAL: several builds of the same symbols coexist
+        L = C.CDLL(lib_path(recon, solver, nosync, dropin, simple, variant))  # RTLD_LOCAL: several builds of the same symbols coexist
         i, d, p = C.c_int, C.c_double, C.c_void_p
         L.ref_build_flags.restype = C.c_char_p
         L.ref_set_gamma.argtypes = [d]
@@ -39,16 +40,18 @@ def lib(recon, solver, nosync=False, dropin=False, simple=False):
         L.ref_set_boundaries.argtypes = [p, i, i, i, i, i, p]
         L.ref_advance.argtypes = [p, i, i, i, i, d, d, d, p, i, d, d, d, p, p]
         L.ref_advance.restype = d
+        L.ref_n_fields.restype = i
         _libs[key] = L
     return _libs[key]
 
 
 def advance(dev_tensor, dims, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_steps, cfl=0.3, density_floor=0.0,
-            U_floor=0.0, nosync=False, timed=False, dropin=False, simple=False):
+            U_floor=0.0, nosync=False, timed=False, dropin=False, simple=False, variant=""):
     """Run the reference's step loop on a torch CUDA float64 tensor (flat SoA, ghosts included), in place.
     Returns (dts, last_dti, ms or None).  One process may only use ONE grid shape per library: the reference
     keeps its scratch in globals sized at the first call (VL_3D_cuda.cu:58-133)."""
-    L = lib(recon, solver, nosync, dropin, simple)
+    L = lib(recon, solver, nosync, dropin, simple, variant)
+    assert dev_tensor.numel() == L.ref_n_fields() * dims[0] * dims[1] * dims[2], "field count of this reference build"
     L.ref_set_gamma(gamma)
     fl = (C.c_int * 6)(*flags)
     dts = (C.c_double * max(n_steps, 1))()

@@ -489,17 +489,42 @@ static void pcm_dir(const double *U, double *QL, double *QR, int nx, int ny, int
 /* ---- Riemann solvers: one interface ---- */
 typedef struct { double d, mx, my, mz, E; } cons_t;
 
+/* Passive fields of a -DSCALAR / -DDE build riding along one interface: np conserved values per side (the scalars,
+ * then GasEnergy last when de != 0: grid_enum.h:33-78) and their fluxes.  NULL = a plain hydro build. */
+typedef struct {
+  int np, de;
+  const double *ql, *qr;
+  double *fq;
+} pass_t;
+#define ORC_DE_ETA_1 0.001 /* global.h:65-68 (non-cosmology) */
+#define ORC_DE_ETA_2 0.035 /* global.h:71-73 */
+/* hydro_utilities.h:136-151 Get_Pressure_From_DE */
+static inline double de_pressure(double E, double U_total, double U_advected, double gamma)
+{
+  double U = (U_total / E > ORC_DE_ETA_1) ? U_total : U_advected;
+  return fmax(U * (gamma - 1.0), ORC_TINY);
+}
+/* the solvers' own load of one side's pressure (hllc_cuda.cu:107-113, roe_cuda.cu:109-115, hll_cuda.cu:106-112) */
+static inline double side_pressure(cons_t u, double vx, double vy, double vz, double gamma, const pass_t *ps, int right)
+{
+  if (ps && ps->de) {
+    double E_kin = 0.5 * u.d * (vx * vx + vy * vy + vz * vz);
+    double dge   = right ? ps->qr[ps->np - 1] : ps->ql[ps->np - 1];
+    return fmax(de_pressure(u.E, u.E - E_kin, dge, gamma), ORC_TINY);
+  }
+  return fmax((u.E - 0.5 * u.d * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0), ORC_TINY);
+}
+
 /* hllc_cuda.cu:103-305 */
-static cons_t hllc_flux(cons_t l, cons_t r, double gamma)
+static cons_t hllc_flux_x(cons_t l, cons_t r, double gamma, const pass_t *pv)
 {
   cons_t f;
   double g1 = gamma - 1.0;
+  int const np = pv ? pv->np : 0;
   double vxl = l.mx / l.d, vyl = l.my / l.d, vzl = l.mz / l.d;
-  double pl = (l.E - 0.5 * l.d * (vxl * vxl + vyl * vyl + vzl * vzl)) * (gamma - 1.0);
-  pl = fmax(pl, ORC_TINY);
+  double pl = side_pressure(l, vxl, vyl, vzl, gamma, pv, 0);
   double vxr = r.mx / r.d, vyr = r.my / r.d, vzr = r.mz / r.d;
-  double pr = (r.E - 0.5 * r.d * (vxr * vxr + vyr * vyr + vzr * vzr)) * (gamma - 1.0);
-  pr = fmax(pr, ORC_TINY);
+  double pr = side_pressure(r, vxr, vyr, vzr, gamma, pv, 1);
   double Hl = (l.E + pl) / l.d, Hr = (r.E + pr) / r.d;
   double sl = sqrt(l.d), sr = sqrt(r.d);
   double vx = (sl * vxl + sr * vxr) / (sl + sr);
@@ -517,8 +542,16 @@ static cons_t hllc_flux(cons_t l, cons_t r, double gamma)
   Sr = ((Sr < 0) ? -1 : 1) * fmax(fabs(Sr), 0.0);
   double fdl = l.mx, fmxl = l.mx * vxl + pl, fmyl = l.my * vxl, fmzl = l.mz * vxl, fEl = (l.E + pl) * vxl;
   double fdr = r.mx, fmxr = r.mx * vxr + pr, fmyr = r.my * vxr, fmzr = r.mz * vxr, fEr = (r.E + pr) * vxr;
-  if (Sl > 0.0) { f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl; return f; }
-  if (Sr < 0.0) { f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr; return f; }
+  if (Sl > 0.0) {
+    f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl;
+    for (int i = 0; i < np; i++) pv->fq[i] = pv->ql[i] * vxl; /* hllc_cuda.cu:183-190, 211-218 */
+    return f;
+  }
+  if (Sr < 0.0) {
+    f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr;
+    for (int i = 0; i < np; i++) pv->fq[i] = pv->qr[i] * vxr;
+    return f;
+  }
   double Sm = (r.d * vxr * (Sr - vxr) - l.d * vxl * (Sl - vxl) + pl - pr) / (r.d * (Sr - vxr) - l.d * (Sl - vxl));
   double ps = l.d * (vxl - Sl) * (vxl - Sm) + pl;
   double dls = l.d * (Sl - vxl) / (Sl - Sm);
@@ -534,25 +567,41 @@ static cons_t hllc_flux(cons_t l, cons_t r, double gamma)
   f.my = 0.5 * (fmyl + fmyr + (Sr - fabs(Sm)) * myrs + (Sl + fabs(Sm)) * myls - Sl * l.my - Sr * r.my);
   f.mz = 0.5 * (fmzl + fmzr + (Sr - fabs(Sm)) * mzrs + (Sl + fabs(Sm)) * mzls - Sl * l.mz - Sr * r.mz);
   f.E  = 0.5 * (fEl + fEr + (Sr - fabs(Sm)) * Ers + (Sl + fabs(Sm)) * Els - Sl * l.E - Sr * r.E);
+  for (int i = 0; i < np; i++) { /* hllc_cuda.cu:119-131, 249-283 */
+    double dql = pv->ql[i], dqr = pv->qr[i];
+    double sql = dql / l.d, sqr = dqr / r.d;
+    double qls = dls * sql, qrs = drs * sqr;
+    pv->fq[i] = 0.5 * (dql * vxl + dqr * vxr + (Sr - fabs(Sm)) * qrs + (Sl + fabs(Sm)) * qls - Sl * dql - Sr * dqr);
+  }
   return f;
 }
+static cons_t hllc_flux(cons_t l, cons_t r, double gamma) { return hllc_flux_x(l, r, gamma, NULL); }
 
 /* hll_cuda.cu:62-262: Davis wave-speed bounds from the two sound speeds, single-state HLL flux */
-static cons_t hll_flux(cons_t l, cons_t r, double gamma)
+static cons_t hll_flux_x(cons_t l, cons_t r, double gamma, const pass_t *ps)
 {
   cons_t f;
+  int const np = ps ? ps->np : 0;
   double vxl = l.mx / l.d, vyl = l.my / l.d, vzl = l.mz / l.d;
-  double pl = (l.E - 0.5 * l.d * (vxl * vxl + vyl * vyl + vzl * vzl)) * (gamma - 1.0);
-  pl = fmax(pl, ORC_TINY);
+  double pl = side_pressure(l, vxl, vyl, vzl, gamma, ps, 0);
   double vxr = r.mx / r.d, vyr = r.my / r.d, vzr = r.mz / r.d;
-  double pr = (r.E - 0.5 * r.d * (vxr * vxr + vyr * vyr + vzr * vzr)) * (gamma - 1.0);
-  pr = fmax(pr, ORC_TINY);
+  double pr = side_pressure(r, vxr, vyr, vzr, gamma, ps, 1);
   double cfl = sqrt(gamma * pl / l.d), cfr = sqrt(gamma * pr / r.d);
   double Sl = fmin(vxr - cfr, vxl - cfl), Sr = fmax(vxl + cfl, vxr + cfr);
   double fdl = l.mx, fmxl = l.mx * vxl + pl, fmyl = l.my * vxl, fmzl = l.mz * vxl, fEl = (l.E + pl) * vxl;
   double fdr = r.mx, fmxr = r.mx * vxr + pr, fmyr = r.my * vxr, fmzr = r.mz * vxr, fEr = (r.E + pr) * vxr;
-  if (Sl > 0.0) { f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl; return f; }
-  if (Sr < 0.0) { f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr; return f; }
+  if (Sl > 0.0) {
+    f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl;
+    for (int i = 0; i < np; i++) ps->fq[i] = ps->ql[i] * vxl; /* hll_cuda.cu:181-188 */
+    return f;
+  }
+  if (Sr < 0.0) {
+    f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr;
+    for (int i = 0; i < np; i++) ps->fq[i] = ps->qr[i] * vxr;
+    return f;
+  }
+  for (int i = 0; i < np; i++) /* hll_cuda.cu:243-250 */
+    ps->fq[i] = ((Sr * (ps->ql[i] * vxl)) - (Sl * (ps->qr[i] * vxr)) + Sl * Sr * (ps->qr[i] - ps->ql[i])) / (Sr - Sl);
   f.d  = ((Sr * fdl) - (Sl * fdr) + Sl * Sr * (r.d - l.d)) / (Sr - Sl);
   f.mx = ((Sr * fmxl) - (Sl * fmxr) + Sl * Sr * (r.mx - l.mx)) / (Sr - Sl);
   f.my = ((Sr * fmyl) - (Sl * fmyr) + Sl * Sr * (r.my - l.my)) / (Sr - Sl);
@@ -560,18 +609,18 @@ static cons_t hll_flux(cons_t l, cons_t r, double gamma)
   f.E  = ((Sr * fEl) - (Sl * fEr) + Sl * Sr * (r.E - l.E)) / (Sr - Sl);
   return f;
 }
+static cons_t hll_flux(cons_t l, cons_t r, double gamma) { return hll_flux_x(l, r, gamma, NULL); }
 
 /* roe_cuda.cu:105-398 (etah = 0) */
-static cons_t roe_flux(cons_t l, cons_t r, double gamma)
+static cons_t roe_flux_x(cons_t l, cons_t r, double gamma, const pass_t *ps)
 {
   cons_t f;
   double g1 = gamma - 1.0, etah = 0.0;
+  int const np = ps ? ps->np : 0;
   double vxl = l.mx / l.d, vyl = l.my / l.d, vzl = l.mz / l.d;
-  double pl = (l.E - 0.5 * l.d * (vxl * vxl + vyl * vyl + vzl * vzl)) * (gamma - 1.0);
-  pl = fmax(pl, ORC_TINY);
+  double pl = side_pressure(l, vxl, vyl, vzl, gamma, ps, 0);
   double vxr = r.mx / r.d, vyr = r.my / r.d, vzr = r.mz / r.d;
-  double pr = (r.E - 0.5 * r.d * (vxr * vxr + vyr * vyr + vzr * vzr)) * (gamma - 1.0);
-  pr = fmax(pr, ORC_TINY);
+  double pr = side_pressure(r, vxr, vyr, vzr, gamma, ps, 1);
   double Hl = (l.E + pl) / l.d, Hr = (r.E + pr) / r.d;
   double sl = sqrt(l.d), sr = sqrt(r.d);
   double vx = (sl * vxl + sr * vxr) / (sl + sr);
@@ -584,8 +633,16 @@ static cons_t roe_flux(cons_t l, cons_t r, double gamma)
   double lm = vx - a, l0 = vx, lp = vx + a;
   double fdl = l.mx, fmxl = l.mx * vxl + pl, fmyl = l.mx * vyl, fmzl = l.mx * vzl, fEl = (l.E + pl) * vxl;
   double fdr = r.mx, fmxr = r.mx * vxr + pr, fmyr = r.mx * vyr, fmzr = r.mx * vzr, fEr = (r.E + pr) * vxr;
-  if (lm >= 0.0) { f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl; return f; }
-  if (lp <= 0.0) { f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr; return f; }
+  if (lm >= 0.0) {
+    f.d = fdl; f.mx = fmxl; f.my = fmyl; f.mz = fmzl; f.E = fEl;
+    for (int i = 0; i < np; i++) ps->fq[i] = l.mx * (ps->ql[i] / l.d); /* roe_cuda.cu:116-123, 174-181 */
+    return f;
+  }
+  if (lp <= 0.0) {
+    f.d = fdr; f.mx = fmxr; f.my = fmyr; f.mz = fmzr; f.E = fEr;
+    for (int i = 0; i < np; i++) ps->fq[i] = r.mx * (ps->qr[i] / r.d);
+    return f;
+  }
   double dd = r.d - l.d, dmx = r.mx - l.mx, dmy = r.my - l.my, dmz = r.mz - l.mz, dE = r.E - l.E;
   double Na = 0.5 / asq, coeff;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
@@ -637,6 +694,10 @@ static cons_t roe_flux(cons_t l, cons_t r, double gamma)
     f.my = 0.5 * (fmyl + fmyr) + (fmyl - fmyr) * tmp;
     f.mz = 0.5 * (fmzl + fmzr) + (fmzl - fmzr) * tmp;
     f.E  = 0.5 * (fEl + fEr) + (fEl - fEr) * tmp;
+    for (int i = 0; i < np; i++) { /* roe_cuda.cu:343-371 */
+      double fl = ps->ql[i] * (vxl - bm), fr = ps->qr[i] * (vxr - bp);
+      ps->fq[i] = 0.5 * (fl + fr) + (fl - fr) * tmp;
+    }
     return f;
   }
   f.d  = 0.5 * (fdl + fdr - s0);
@@ -644,8 +705,11 @@ static cons_t roe_flux(cons_t l, cons_t r, double gamma)
   f.my = 0.5 * (fmyl + fmyr - s2);
   f.mz = 0.5 * (fmzl + fmzr - s3);
   f.E  = 0.5 * (fEl + fEr - s4);
+  for (int i = 0; i < np; i++) /* upwinded on the sign of the mass flux, roe_cuda.cu:381-396 */
+    ps->fq[i] = (f.d >= 0.0) ? f.d * (ps->ql[i] / l.d) : f.d * (ps->qr[i] / r.d);
   return f;
 }
+static cons_t roe_flux(cons_t l, cons_t r, double gamma) { return roe_flux_x(l, r, gamma, NULL); }
 
 /* one launch of Calculate_{HLLC,Roe}_Fluxes_CUDA: every cell, F[id] = flux(Q_L[id], Q_R[id]) */
 /* exact_cuda.cu:21-334 (Toro 1999, 4.9).  PARITY UNPINNED ON THE CPU: the reference evaluates its powers with the
@@ -848,6 +912,292 @@ void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, doub
   (void)dd;
   free(Uh);
   for (int d = 0; d < ndim; d++) { free(QL[d]); free(QR[d]); free(F[d]); }
+}
+
+/* ==== -DSCALAR / -DDE builds =================================================================================
+ * ns passive scalars ride in fields 5 .. 5+ns-1 and, with de, the advected internal energy (GasEnergy) in the last
+ * field nf-1 = 5+ns (grid_enum.h:33-78).  The scalars never feed back on the five hydro fields; DE replaces every
+ * pressure on the path by Get_Pressure_From_DE (hydro_utilities.h:136-151), adds the p div v term to the GasEnergy
+ * updates and ends the step with Select_Internal_Energy + Sync_Energies (hydro_cuda.cu:754-1099).
+ * Restated for the Van Leer integrator with PCM / PLMC / PPMC and HLLC / Roe / HLL. */
+#define ORC_MAXP 8
+static prim_t load_prim_x(const double *U, size_t id, size_t N, int o1, int o2, int o3, double gamma, int ns, int de,
+                          double *q)
+{ /* reconstruction.h:139-212 */
+  prim_t w;
+  w.d  = U[id];
+  w.vx = U[(size_t)o1 * N + id] / w.d;
+  w.vy = U[(size_t)o2 * N + id] / w.d;
+  w.vz = U[(size_t)o3 * N + id] / w.d;
+  if (de) {
+    double E = U[4 * N + id], ge = U[(size_t)(5 + ns) * N + id];
+    double E_non_thermal = 0.5 * w.d * square_mag(w.vx, w.vy, w.vz); /* Calc_Kinetic_Energy_From_Velocity */
+    w.p   = de_pressure(E, E - E_non_thermal, ge, gamma);
+    q[ns] = ge / w.d;
+  } else {
+    double pr = U[4 * N + id] - 0.5 * w.d * square_mag(w.vx, w.vy, w.vz);
+    w.p = fmax((gamma - 1.) * pr, ORC_TINY);
+  }
+  for (int i = 0; i < ns; i++) q[i] = U[(size_t)(5 + i) * N + id] / w.d;
+  return w;
+}
+static void store_interface_x(prim_t w, const double *q, double *Q, size_t id, size_t N, int o1, int o2, int o3,
+                              double gamma, int np)
+{ /* reconstruction.h:918-968 */
+  store_interface(w, Q, id, N, o1, o2, o3, gamma);
+  for (int i = 0; i < np; i++) Q[(size_t)(5 + i) * N + id] = w.d * q[i];
+}
+/* a field without characteristics under PLMC: slopes, Monotonize, Calc_Interface_Linear, Plm_Limit_Interfaces
+ * (reconstruction.h:224-296, 519-556, 645-723) */
+static void plm_passive(double qm, double qi, double qp, double *l, double *r)
+{
+  double dL = 1.0 * (qi - qm), dR = 1.0 * (qp - qi), dC = 0.5 * (qp - qm), dG = vl_slope(dL, dR);
+  double dm = mono(dL, dR, dC, dG);
+  *l = qi + 1.0 * 0.5 * dm;
+  *r = qi + -1.0 * 0.5 * dm;
+  clamp_pair(l, r, qm, qi, qp);
+}
+static void reconstruct_x(int recon, const double *U, double *QL, double *QR, int nx, int ny, int nz, double gamma,
+                          int dir, int ns, int de)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int o1, o2, o3, np = ns + de;
+  dir_perm(dir, &o1, &o2, &o3);
+  long stride = dir == 0 ? 1 : (dir == 1 ? nx : (long)nx * ny);
+  int order = recon == ORC_PPMC ? 3 : 2;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        if (outside_guard(order, nx, ny, nz, x, y, z)) continue;
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        double qi[ORC_MAXP], qm[ORC_MAXP], qp[ORC_MAXP], qm2[ORC_MAXP], qp2[ORC_MAXP], ql[ORC_MAXP], qr[ORC_MAXP];
+        prim_t wi = load_prim_x(U, id, N, o1, o2, o3, gamma, ns, de, qi);
+        prim_t wm = load_prim_x(U, id - stride, N, o1, o2, o3, gamma, ns, de, qm);
+        prim_t wp = load_prim_x(U, id + stride, N, o1, o2, o3, gamma, ns, de, qp);
+        prim_t L, R;
+        if (recon == ORC_PPMC) {
+          prim_t wm2 = load_prim_x(U, id - 2 * stride, N, o1, o2, o3, gamma, ns, de, qm2);
+          prim_t wp2 = load_prim_x(U, id + 2 * stride, N, o1, o2, o3, gamma, ns, de, qp2);
+          ppmc_cell(wm2, wm, wi, wp, wp2, gamma, &L, &R);
+          for (int i = 0; i < np; i++) /* ppmc_cuda.cu:660-671 */
+            orc_ppm_single_variable(qm2[i], qm[i], qi[i], qp[i], qp2[i], &ql[i], &qr[i]);
+        } else {
+          plmc_cell_t(wm, wi, wp, gamma, 0, 0.0, &L, &R);
+          for (int i = 0; i < np; i++) plm_passive(qm[i], qi[i], qp[i], &ql[i], &qr[i]);
+        }
+        store_interface_x(L, ql, QL, id, N, o1, o2, o3, gamma, np);
+        store_interface_x(R, qr, QR, id - stride, N, o1, o2, o3, gamma, np);
+      }
+}
+static void pcm_dir_x(const double *U, double *QL, double *QR, int nx, int ny, int nz, int dir, int nf)
+{
+  size_t N = (size_t)nx * ny * nz;
+  long stride = dir == 0 ? 1 : (dir == 1 ? nx : (long)nx * ny);
+  for (int f = 0; f < nf; f++) {
+#pragma omp parallel for schedule(static)
+    for (long id = 0; id < (long)N; id++) {
+      QL[f * N + id] = U[f * N + id];
+      int x = id % nx, y = (id / nx) % ny, z = id / ((long)nx * ny);
+      int c = dir == 0 ? x : (dir == 1 ? y : z);
+      if (c > 0) QR[f * N + id - stride] = U[f * N + id];
+    }
+  }
+}
+static void riemann_x(int solver, const double *QL, const double *QR, double *F, int nx, int ny, int nz, double gamma,
+                      int dir, int ns, int de)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int o1, o2, o3, np = ns + de;
+  dir_perm(dir, &o1, &o2, &o3);
+#pragma omp parallel for schedule(static)
+  for (long id = 0; id < (long)N; id++) {
+    cons_t l = {QL[id], QL[o1 * N + id], QL[o2 * N + id], QL[o3 * N + id], QL[4 * N + id]};
+    cons_t r = {QR[id], QR[o1 * N + id], QR[o2 * N + id], QR[o3 * N + id], QR[4 * N + id]};
+    double ql[ORC_MAXP], qr[ORC_MAXP], fq[ORC_MAXP];
+    for (int i = 0; i < np; i++) {
+      ql[i] = QL[(size_t)(5 + i) * N + id];
+      qr[i] = QR[(size_t)(5 + i) * N + id];
+    }
+    pass_t ps = {np, de, ql, qr, fq};
+    cons_t f = solver == ORC_ROE ? roe_flux_x(l, r, gamma, &ps)
+                                 : (solver == ORC_HLL ? hll_flux_x(l, r, gamma, &ps) : hllc_flux_x(l, r, gamma, &ps));
+    F[id] = f.d; F[o1 * N + id] = f.mx; F[o2 * N + id] = f.my; F[o3 * N + id] = f.mz; F[4 * N + id] = f.E;
+    for (int i = 0; i < np; i++) F[(size_t)(5 + i) * N + id] = fq[i];
+  }
+}
+
+/* one Van Leer step of a build with ns scalars and (de) dual energy: VL_{1,2,3}D_cuda.cu, hydro_cuda.cu:20-300,
+ * 662-1099.  Returns -1 for combinations that are not restated. */
+int orc_vl_step_x(double *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz, double dt,
+                  double gamma, int recon, int solver, double density_floor, int ns, int de)
+{
+  if (recon != ORC_PCM && recon != ORC_PLMC && recon != ORC_PPMC) return -1;
+  if (solver != ORC_HLLC && solver != ORC_ROE && solver != ORC_HLL) return -1;
+  if (ns + de > ORC_MAXP) return -1;
+  size_t N = (size_t)nx * ny * nz;
+  int ndim = 1 + (ny > 1) + (nz > 1), nf = 5 + ns + de, GE = nf - 1;
+  long st[3] = {1, nx, (long)nx * ny};
+  double *Uh = calloc(nf * N, sizeof(double));
+  double *QL[3], *QR[3], *F[3];
+  for (int d = 0; d < ndim; d++) {
+    QL[d] = calloc(nf * N, sizeof(double));
+    QR[d] = calloc(nf * N, sizeof(double));
+    F[d]  = calloc(nf * N, sizeof(double));
+  }
+  for (int d = 0; d < ndim; d++) {
+    pcm_dir_x(U, QL[d], QR[d], nx, ny, nz, d, nf);
+    riemann_x(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d, ns, de);
+  }
+  { /* half-step update (VL_3D_cuda.cu:379-495, VL_2D_cuda.cu:178-260, VL_1D_cuda.cu:160-215) */
+    double h = 0.5 * dt;
+    double dto[3] = {h / dx, h / dy, h / dz};
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+          if (!(x > 0 && x < nx - 1)) continue;
+          if (ndim > 1 && !(y > 0 && y < ny - 1)) continue;
+          if (ndim > 2 && !(z > 0 && z < nz - 1)) continue;
+          size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+          for (int f = 0; f < nf; f++) {
+            double v = U[f * N + id];
+            for (int d = 0; d < ndim; d++) v = v + dto[d] * (F[d][f * N + id - st[d]] - F[d][f * N + id]);
+            Uh[f * N + id] = v;
+          }
+          if (de) {
+            double d = U[id], d_inv = 1.0 / d;
+            double vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv, P;
+            if (ndim == 3) { /* PRESSURE_DE, VL_3D_cuda.cu:408-426 */
+              double E = U[4 * N + id], ge = U[(size_t)GE * N + id];
+              double E_kin = 0.5 * d * square_mag(vx, vy, vz);
+              P = fmax(de_pressure(E, E - E_kin, ge, gamma), ORC_TINY);
+            } else { /* the 1-D and 2-D half updates use the plain pressure (VL_2D_cuda.cu:213, VL_1D_cuda.cu:183) */
+              P = (U[4 * N + id] - 0.5 * d * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
+            }
+            double div = dto[0] * (U[1 * N + id - 1] / U[id - 1] - U[1 * N + id + 1] / U[id + 1]);
+            for (int dd = 1; dd < ndim; dd++)
+              div = div + dto[dd] * (U[(size_t)(1 + dd) * N + id - st[dd]] / U[id - st[dd]] -
+                                     U[(size_t)(1 + dd) * N + id + st[dd]] / U[id + st[dd]]);
+            Uh[(size_t)GE * N + id] = Uh[(size_t)GE * N + id] + 0.5 * P * (div);
+          }
+          if (ndim == 3 && Uh[id] < density_floor) { /* VL_3D_cuda.cu:479-493: momenta, Energy, GasEnergy; not the scalars */
+            double d0 = Uh[id];
+            Uh[id] = density_floor;
+            for (int f = 1; f < 5; f++) Uh[f * N + id] *= (density_floor / d0);
+            if (de) Uh[(size_t)GE * N + id] *= (density_floor / d0);
+          }
+        }
+  }
+  for (int d = 0; d < ndim; d++) {
+    if (recon == ORC_PCM) pcm_dir_x(Uh, QL[d], QR[d], nx, ny, nz, d, nf);
+    else reconstruct_x(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d, ns, de);
+    riemann_x(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d, ns, de);
+  }
+  double dto[3] = {dt / dx, dt / dy, dt / dz};
+  int g = n_ghost;
+#define ORC_REAL_CELL(x, y, z)                                                                      \
+  ((x) > g - 1 && (x) < nx - g && (ndim < 2 || ((y) > g - 1 && (y) < ny - g)) && (ndim < 3 || ((z) > g - 1 && (z) < nz - g)))
+  if (de) { /* Partial_Update_Advected_Internal_Energy_{1,2,3}D (hydro_cuda.cu:662-833): before the update, from U^n */
+    double *gep = malloc(N * sizeof(double));
+    memcpy(gep, U + (size_t)GE * N, N * sizeof(double));
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+          if (!ORC_REAL_CELL(x, y, z)) continue;
+          size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+          double d = U[id], d_inv = 1.0 / d;
+          double vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv;
+          double E = U[4 * N + id], ge = U[(size_t)GE * N + id];
+          double E_kin = ndim == 3 ? 0.5 * d * square_mag(vx, vy, vz) : 0.5 * d * (vx * vx + vy * vy + vz * vz);
+          double P = fmax(de_pressure(E, E - E_kin, ge, gamma), ORC_TINY);
+          double div = dto[0] * (U[1 * N + id - 1] / U[id - 1] - U[1 * N + id + 1] / U[id + 1]);
+          for (int dd = 1; dd < ndim; dd++)
+            div = div + dto[dd] * (U[(size_t)(1 + dd) * N + id - st[dd]] / U[id - st[dd]] -
+                                   U[(size_t)(1 + dd) * N + id + st[dd]] / U[id + st[dd]]);
+          gep[id] = ge + 0.5 * P * (div);
+        }
+    memcpy(U + (size_t)GE * N, gep, N * sizeof(double));
+    free(gep);
+  }
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        if (!ORC_REAL_CELL(x, y, z)) continue;
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        for (int f = 0; f < nf; f++) {
+          double s = dto[0] * (F[0][f * N + id - st[0]] - F[0][f * N + id]);
+          for (int d = 1; d < ndim; d++) s = s + dto[d] * (F[d][f * N + id - st[d]] - F[d][f * N + id]);
+          U[f * N + id] += s;
+        }
+        if (ndim == 3 && U[id] < density_floor && U[id] > 0) { /* hydro_cuda.cu:279-291 */
+          double d0 = U[id];
+          U[id] = density_floor;
+          for (int f = 1; f < 5; f++) U[f * N + id] *= (density_floor / d0);
+          if (de) U[(size_t)GE * N + id] *= (density_floor / d0);
+        }
+      }
+  if (de) { /* Select_Internal_Energy_{1,2,3}D then Sync_Energies_{1,2,3}D (hydro_cuda.cu:835-1099) */
+    double *sel = malloc(N * sizeof(double));
+    int hi[3] = {nx - g - 1, ny - g - 1, nz - g - 1};
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+          if (!ORC_REAL_CELL(x, y, z)) continue;
+          size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+          int c[3] = {x, y, z};
+          double d = U[id], d_inv = 1.0 / d;
+          double vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv;
+          double E = U[4 * N + id], U_advected = U[(size_t)GE * N + id];
+          double U_total = E - 0.5 * d * (vx * vx + vy * vy + vz * vz);
+          double Emax = E; /* neighbours clamped to the real cells; order imo, (E), ipo, jmo, jpo, kmo, kpo */
+          for (int dd = 0; dd < ndim; dd++) {
+            int lo = c[dd] - 1 > g ? c[dd] - 1 : g, up = c[dd] + 1 < hi[dd] ? c[dd] + 1 : hi[dd];
+            size_t il = id + (size_t)((long)(lo - c[dd]) * st[dd]), iu = id + (size_t)((long)(up - c[dd]) * st[dd]);
+            if (dd == 0) Emax = fmax(U[4 * N + il], E);
+            else Emax = fmax(Emax, U[4 * N + il]);
+            Emax = fmax(Emax, U[4 * N + iu]);
+          }
+          double Usel = ((U_total / E > ORC_DE_ETA_1) || (U_total / Emax > ORC_DE_ETA_2)) ? U_total : U_advected;
+          sel[id] = fmax(Usel, ORC_TINY);
+        }
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < nz; z++)
+      for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+          if (!ORC_REAL_CELL(x, y, z)) continue;
+          size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+          double d = U[id], d_inv = 1.0 / d;
+          double vx = U[N + id] * d_inv, vy = U[2 * N + id] * d_inv, vz = U[3 * N + id] * d_inv;
+          U[(size_t)GE * N + id] = sel[id];
+          U[4 * N + id] = 0.5 * d * (vx * vx + vy * vy + vz * vz) + sel[id];
+        }
+    free(sel);
+  }
+#undef ORC_REAL_CELL
+  free(Uh);
+  for (int d = 0; d < ndim; d++) { free(QL[d]); free(QR[d]); free(F[d]); }
+  return 0;
+}
+
+/* Temperature_Floor_Kernel of a -DDE build (hydro_cuda.cu:1117-1153): the advected internal energy is floored too */
+void orc_temperature_floor(double *U, int nx, int ny, int nz, int n_ghost, double U_floor);
+void orc_temperature_floor_x(double *U, int nx, int ny, int nz, int n_ghost, double U_floor, int nf, int de)
+{
+  orc_temperature_floor(U, nx, ny, nz, n_ghost, U_floor);
+  if (!de) return;
+  size_t N = (size_t)nx * ny * nz;
+  int g = n_ghost;
+  for (int z = g; z < nz - g; z++)
+    for (int y = g; y < ny - g; y++)
+      for (int x = g; x < nx - g; x++) {
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        double d = U[id];
+        if (U[(size_t)(nf - 1) * N + id] / d < U_floor) U[(size_t)(nf - 1) * N + id] = d * U_floor;
+      }
 }
 
 /* hydro_cuda.cu:404-418 */
@@ -1071,4 +1421,17 @@ void orc_unpack(const double *buf, double *U, int nx, int ny, int n_fields, long
     long idx = i + (j + k * ny) * nx + idxoffset;
     for (int f = 0; f < n_fields; f++) U[idx + f * n_cells] = buf[id + f * nb];
   }
+}
+
+/* Scalar_Floor_Kernel (hydro_cuda.cu:1284-1307): real cells of a 3-D grid, one field */
+void orc_scalar_floor(double *U, int nx, int ny, int nz, int n_ghost, int field_num, double scalar_floor)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int g = n_ghost;
+  for (int z = g; z < nz - g; z++)
+    for (int y = g; y < ny - g; y++)
+      for (int x = g; x < nx - g; x++) {
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        if (U[(size_t)field_num * N + id] < scalar_floor) U[(size_t)field_num * N + id] = scalar_floor;
+      }
 }

@@ -20,7 +20,7 @@ def ghosted(fields, g, flags):
 
 def real_view(flat, dims, g):
     NX, NY, NZ = dims
-    a = flat.reshape(5, NZ, NY, NX)
+    a = flat.reshape(-1, NZ, NY, NX)
     gz = g if NZ > 1 else 0
     gy = g if NY > 1 else 0
     return a[:, gz:NZ - gz, gy:NY - gy, g:NX - g]

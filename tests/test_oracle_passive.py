@@ -1,0 +1,76 @@
+"""CPU checks of the oracle's -DSCALAR / -DDE restatement (orc_vl_step_x): properties that hold whatever the reference
+build, so that the restatement is constrained here as well as by the side-by-side GPU runs of tests/test_gpu_passive.py."""
+import numpy as np
+import pytest
+
+import oracle
+from cholla_b200 import initial_conditions as ic
+from helpers import ghosted, real_view
+
+
+def _state(n, ns, de, gamma, recon, icname="random_smooth"):
+    g = {0: 2, 1: 3, 2: 4}[recon]
+    fields = ic.with_passive(getattr(ic, icname)(n, seed=3), ns, de, gamma)
+    flat, dims = ghosted(fields, g, [1, 1, 1, 1, 1, 1] if n[2] > 1 else ([1, 1, 1, 1, 0, 0] if n[1] > 1 else [1, 1, 0, 0, 0, 0]))
+    return flat, dims, g
+
+
+@pytest.mark.parametrize("recon", [0, 1, 2])
+@pytest.mark.parametrize("solver", [0, 1, 3])
+def test_scalars_do_not_feed_back_and_follow_the_mass(recon, solver):
+    n, gamma = (14, 12, 10), 1.4
+    flat, dims, g = _state(n, 1, False, gamma, recon)
+    N = dims[0] * dims[1] * dims[2]
+    plain = flat[:5 * N].copy()
+    flat[5 * N:] = 0.7 * flat[:N]  # a constant mass fraction
+    oracle.vl_step(plain, *dims, g, 0.1, 0.1, 0.1, 0.004, gamma, recon, solver)
+    oracle.vl_step_x(flat, *dims, g, 0.1, 0.1, 0.1, 0.004, gamma, recon, solver, 0.0, 1, False)
+    assert np.array_equal(flat[:5 * N], plain)                     # the five hydro fields are untouched by the scalar
+    r = real_view(flat, dims, g)
+    assert np.abs(r[5] - 0.7 * r[0]).max() < 1e-14                # and a constant mass fraction stays constant
+
+
+@pytest.mark.parametrize("n", [(14, 12, 10), (20, 14, 1), (40, 1, 1)])
+def test_dual_energy_warm_gas_keeps_total_energy_branch(n):
+    """Thermal energy far above DE_ETA_1 of E: every pressure comes from E - Ekin, so the five hydro fields equal the
+    plain build's up to the last Sync_Energies (E = Ekin + (E - Ekin), one rounding), and GasEnergy ends as E - Ekin."""
+    gamma = 5.0 / 3.0
+    flat, dims, g = _state(n, 0, True, gamma, 2)
+    N = dims[0] * dims[1] * dims[2]
+    plain = flat[:5 * N].copy()
+    d = [1.0 / m for m in n]
+    oracle.vl_step(plain, *dims, g, d[0], d[1], d[2], 0.002, gamma, 2, 0)
+    oracle.vl_step_x(flat, *dims, g, d[0], d[1], d[2], 0.002, gamma, 2, 0, 0.0, 0, True)
+    r, p = real_view(flat, dims, g), real_view(plain, dims, g)
+    assert np.array_equal(r[:4], p[:4])
+    assert np.abs(r[4] - p[4]).max() <= 4e-16 * np.abs(p[4]).max()
+    ekin = 0.5 * (r[1] ** 2 + r[2] ** 2 + r[3] ** 2) / r[0]
+    assert np.abs(r[5] - (p[4] - ekin)).max() <= 1e-14 * np.abs(p[4]).max()
+
+
+def test_dual_energy_cold_flow_uses_the_advected_energy():
+    n, gamma = (16, 12, 10), 5.0 / 3.0
+    flat, dims, g = _state(n, 0, True, gamma, 2, "cold_flow")
+    N = dims[0] * dims[1] * dims[2]
+    flat[5 * N:] *= 1.03  # the advected energy has drifted from E - Ekin
+    before = real_view(flat.copy(), dims, g)
+    oracle.advance(flat, *dims, g, 1 / 16, 1 / 12, 1 / 10, gamma, 2, 0, [1] * 6, 2, n_scalars=0, dual_energy=True)
+    r = real_view(flat, dims, g)
+    ut = r[4] - 0.5 * (r[1] ** 2 + r[2] ** 2 + r[3] ** 2) / r[0]
+    assert np.isfinite(flat).all() and (r[5] > 0).all()
+    frac = (before[4] - 0.5 * (before[1] ** 2 + before[2] ** 2 + before[3] ** 2) / before[0]) / before[4]
+    assert 0.02 < (frac > 0.001).mean() < 0.98          # the input straddles DE_ETA_1
+    assert np.abs(r[5] - ut).max() <= 1e-9 * r[4].max()  # Sync_Energies: E = Ekin + GasEnergy afterwards
+
+
+def test_floors():
+    n, gamma = (10, 9, 8), 1.4
+    flat, dims, g = _state(n, 1, True, gamma, 2)
+    N = dims[0] * dims[1] * dims[2]
+    a = flat.copy()
+    oracle.scalar_floor(a, *dims, g, 5, 0.9)
+    assert real_view(a, dims, g)[5].min() == 0.9 and np.array_equal(a[:5 * N], flat[:5 * N])
+    b = flat.copy()
+    oracle.temperature_floor_x(b, *dims, g, 3.0, 7, True)
+    r = real_view(b, dims, g)
+    assert (r[6] / r[0]).min() >= 3.0 * (1 - 1e-15)
