@@ -47,6 +47,8 @@ struct chl_ctx {
   chl::ModeOps const *ops;
   void *d_half;               // W at t + dt/2 (primitives), half_fields * n_cells reals
   void *d_acc;                // direction-split sweeps: running sum of flux differences, (5 + passive) * n_cells reals
+  void *d_grav;               // static gravity: [ndim][n_cells] accelerations (nullptr = off), chl_set_static_gravity
+  void *d_gold;               // static gravity: (rho, momentum)^n, 4 * n_cells reals, copied before the corrector
   void *d_de;                 // -DDE contexts: n_cells reals, the p div v term / partially updated GasEnergy (de_term)
   chl::MhdOps const *mhd;     // non-null in an MHD context
   void *d_prim;               // MHD: half-step primitives + cell-centred fields
@@ -153,6 +155,7 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->d_half = nullptr;
   c->d_acc = nullptr;
   c->d_de = nullptr;
+  c->d_grav = c->d_gold = nullptr;
   c->mhd = mhd;
   c->d_prim = c->d_ctf = c->d_E = nullptr;
   c->dir_chunk = 0;
@@ -195,6 +198,8 @@ int chl_destroy(chl_ctx *c)
   if (c->d_half) cudaFree(c->d_half);
   if (c->d_acc) cudaFree(c->d_acc);
   if (c->d_de) cudaFree(c->d_de);
+  if (c->d_grav) cudaFree(c->d_grav);
+  if (c->d_gold) cudaFree(c->d_gold);
   if (c->d_prim) cudaFree(c->d_prim);
   if (c->d_ctf) cudaFree(c->d_ctf);
   if (c->d_E) cudaFree(c->d_E);
@@ -245,7 +250,7 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
       c->ev_steps++;
     }
     if (fused) {  // the same epilogue as the hydro path, as separate launches: temperature floor, then the CFL max
-      if (g.temperature_floor_U > 0.0)
+      if (g.temperature_floor_U >= 0.0)
         CHL_CUDA(c->ops->tfloor(U, g.nx, g.ny, g.nz, g.n_ghost, g.temperature_floor_U, s));
       CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
       CHL_CUDA(c->mhd->calc_dti(U, g.nx, g.ny, g.nz, g.n_ghost, g.dx, g.dy, g.dz, g.gamma, c->d_key, s));
@@ -313,21 +318,35 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
   a.dtodx = dt / g.dx;
   a.dtody = dt / g.dy;
   a.dtodz = dt / g.dz;
-  int const want_tfloor = (fused && g.temperature_floor_U > 0.0 && c->ndim == 3) ? 1 : 0;
+  // -DTEMPERATURE_FLOOR builds floor unconditionally (grid3D.cpp:493-503): with the default threshold 0 the pass resets a
+  // negative internal energy to zero; a negative temperature_floor_U stands for a build without the macro
+  int const want_tfloor = (fused && g.temperature_floor_U >= 0.0 && c->ndim == 3) ? 1 : 0;
+  bool const grav = c->d_grav != nullptr;
   if (fused) {
-    // a -DDE context floors and reduces after Select_Internal_Energy / Sync_Energies (ModeOps::de_finish), not in the sweep
-    a.apply_tfloor = de ? 0 : want_tfloor;
+    // a -DDE context floors and reduces after Select_Internal_Energy / Sync_Energies (ModeOps::de_finish), a context with
+    // static gravity after the source terms -- not in the sweep
+    a.apply_tfloor = (de || grav) ? 0 : want_tfloor;
     a.U_floor = g.temperature_floor_U;
-    a.do_dti = de ? 0 : 1;
+    a.do_dti = (de || grav) ? 0 : 1;
     CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
   }
-  if (de) {
-    // Partial_Update_Advected_Internal_Energy (from U^n, before anything is updated), the corrector, then
-    // Select_Internal_Energy + Sync_Energies over the completed cells; the exchange needs their result: no overlap
-    CHL_CUDA(c->ops->de_term(U, c->d_de, g.nx, g.ny, g.nz, a.lo, a.hi, a.dtodx, a.dtody, a.dtodz, g.gamma, 1, s));
+  if (de || grav) {
+    // Partial_Update_Advected_Internal_Energy (from U^n, before anything is updated) and / or the copy of (rho, momentum)^n
+    // the gravity terms average with; the corrector; the gravity source terms (inside the reference's update kernel:
+    // before everything that follows it); Select_Internal_Energy + Sync_Energies over the completed cells.  The exchange
+    // needs their result: no overlap here.
+    size_t const rb = c->ops->real_bytes;
+    if (de) CHL_CUDA(c->ops->de_term(U, c->d_de, g.nx, g.ny, g.nz, a.lo, a.hi, a.dtodx, a.dtody, a.dtodz, g.gamma, 1, s));
+    if (grav) CHL_CUDA(cudaMemcpyAsync(c->d_gold, U, 4 * c->n_cells * rb, cudaMemcpyDeviceToDevice, s));
     CHL_CUDA(sweep(1, g.recon, g.solver, a, s));
-    CHL_CUDA(c->ops->de_finish(U, g.nx, g.ny, g.nz, g.n_ghost, g.gamma, want_tfloor, g.temperature_floor_U, fused ? 1 : 0,
-                               g.dx, g.dy, g.dz, c->d_key, s));
+    if (grav) CHL_CUDA(chl::launch_gravity_source(U, c->d_gold, c->d_grav, g.nx, g.ny, g.nz, g.n_ghost, dt, (int)rb, s));
+    if (de) {
+      CHL_CUDA(c->ops->de_finish(U, g.nx, g.ny, g.nz, g.n_ghost, g.gamma, want_tfloor, g.temperature_floor_U, fused ? 1 : 0,
+                                 g.dx, g.dy, g.dz, c->d_key, s));
+    } else if (fused) {
+      if (want_tfloor) CHL_CUDA(c->ops->tfloor(U, g.nx, g.ny, g.nz, g.n_ghost, g.temperature_floor_U, s));
+      CHL_CUDA(c->ops->calc_dti(U, g.nx, g.ny, g.nz, g.n_ghost, g.dx, g.dy, g.dz, g.gamma, c->d_key, s));
+    }
     if (halo) {
       int const r = halo_exchange_impl(halo, U, s);
       if (r != CHL_OK) return r;
@@ -365,6 +384,7 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
   if (!c || !U) return fail(CHL_ERR_INVALID, "chl_simple_step: null argument");
   chl_config const &g = c->cfg;
   if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: MHD requires the Van Leer integrator (error_handling.cpp:89)");
+  if (c->d_grav) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: static gravity is built for the Van Leer integrator");
   if (c->ops->n_passive)
     return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: scalars / dual energy are built for the Van Leer integrator");
   if (g.recon != CHL_RECON_PCM && g.recon != CHL_RECON_PLMC)
@@ -400,7 +420,7 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
   a.U_floor = 0.0;
   a.do_dti = 0;
   if (fused) {
-    a.apply_tfloor = (g.temperature_floor_U > 0.0 && c->ndim == 3) ? 1 : 0;
+    a.apply_tfloor = (g.temperature_floor_U >= 0.0 && c->ndim == 3) ? 1 : 0;
     a.U_floor = g.temperature_floor_U;
     a.do_dti = 1;
     CHL_CUDA(cudaMemsetAsync(c->d_key, 0, sizeof(unsigned long long), s));
@@ -533,6 +553,63 @@ int chl_apply_temperature_floor(chl_ctx *c, void *U, double U_floor, void *strea
   if (!c || !U) return fail(CHL_ERR_INVALID, "chl_apply_temperature_floor: null argument");
   chl_config const &g = c->cfg;
   CHL_CUDA(c->ops->tfloor(U, g.nx, g.ny, g.nz, g.n_ghost, U_floor, (cudaStream_t)stream));
+  return CHL_OK;
+}
+
+static int gravity_alloc(chl_ctx *c)
+{
+  size_t const w = c->n_cells * c->ops->real_bytes;
+  if (!c->d_grav) CHL_CUDA(cudaMalloc(&c->d_grav, (size_t)c->ndim * w));
+  if (!c->d_gold) CHL_CUDA(cudaMalloc(&c->d_gold, 4 * w));
+  return CHL_OK;
+}
+
+int chl_set_static_gravity(chl_ctx *c, int custom_grav, int x_off, int y_off, int z_off, double xbound, double ybound,
+                           double zbound, void *stream)
+{
+  if (!c) return fail(CHL_ERR_INVALID, "chl_set_static_gravity: null context");
+  if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_set_static_gravity: hydro contexts only");
+  if (custom_grav < 0) {
+    CHL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (c->d_grav) cudaFree(c->d_grav);
+    if (c->d_gold) cudaFree(c->d_gold);
+    c->d_grav = c->d_gold = nullptr;
+    return CHL_OK;
+  }
+  int const r = gravity_alloc(c);
+  if (r != CHL_OK) return r;
+  chl_config const &g = c->cfg;
+  int const off[3] = {x_off, y_off, z_off};
+  double const d[3] = {g.dx, g.dy, g.dz}, bound[3] = {xbound, ybound, zbound};
+  CHL_CUDA(chl::launch_static_gravity_field(c->d_grav, g.nx, g.ny, g.nz, g.n_ghost, custom_grav, off, d, bound,
+                                            (int)c->ops->real_bytes, (cudaStream_t)stream));
+  return CHL_OK;
+}
+
+int chl_set_gravity_field(chl_ctx *c, const void *d_g, void *stream)
+{
+  if (!c || !d_g) return fail(CHL_ERR_INVALID, "chl_set_gravity_field: null argument");
+  if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_set_gravity_field: hydro contexts only");
+  int const r = gravity_alloc(c);
+  if (r != CHL_OK) return r;
+  CHL_CUDA(cudaMemcpyAsync(c->d_grav, d_g, (size_t)c->ndim * c->n_cells * c->ops->real_bytes, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return CHL_OK;
+}
+
+int chl_gravity_field_ptr(chl_ctx *c, void **d_g)
+{
+  if (!c || !d_g) return fail(CHL_ERR_INVALID, "chl_gravity_field_ptr: null argument");
+  *d_g = c->d_grav;
+  return CHL_OK;
+}
+
+int chl_copy_gravity_field(chl_ctx *c, void *d_dst, void *stream)
+{
+  if (!c || !d_dst) return fail(CHL_ERR_INVALID, "chl_copy_gravity_field: null argument");
+  if (!c->d_grav) return fail(CHL_ERR_INVALID, "chl_copy_gravity_field: gravity is off");
+  CHL_CUDA(cudaMemcpyAsync(d_dst, c->d_grav, (size_t)c->ndim * c->n_cells * c->ops->real_bytes, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
   return CHL_OK;
 }
 

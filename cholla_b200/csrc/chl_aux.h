@@ -13,6 +13,11 @@ cudaError_t launch_set_ghost_cells(void *c, int nx, int ny, int nz, int n_fields
                                    int dir, int diode, size_t real_bytes, cudaStream_t s);
 cudaError_t launch_divb(const void *c, int nx, int ny, int nz, double dx, double dy, double dz, unsigned long long *out,
                         size_t real_bytes, cudaStream_t s);
+// grav_kernels.cu: static gravity (-DSTATIC_GRAV): the acceleration field, once; the corrector's source terms, per step
+cudaError_t launch_static_gravity_field(void *g_out, int nx, int ny, int nz, int n_ghost, int custom_grav, const int off[3],
+                                        const double d[3], const double bound[3], int real_bytes, cudaStream_t s);
+cudaError_t launch_gravity_source(void *U, const void *old, const void *g, int nx, int ny, int nz, int n_ghost, double dt,
+                                  int real_bytes, cudaStream_t s);
 cudaError_t launch_scalar_floor(void *c, int nx, int ny, int nz, int n_ghost, int field_num, double floor_value,
                                 int real_bytes, cudaStream_t s);
 cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset,

@@ -101,6 +101,24 @@ chl_ctx *context(int nx, int ny, int nz, int n_ghost, int n_fields, Real dx, Rea
   g_cfg = c;
   return g_ctx;
 }
+// -DSTATIC_GRAV: the integrators receive Parameters::custom_grav, the rank's offsets and the domain corner on every call
+// (grid3D.cpp:431-465); the library evaluates the field once per distinct set
+void gravity(chl_ctx *c, int custom_grav, int x_off, int y_off, int z_off, Real xbound, Real ybound, Real zbound)
+{
+#ifdef STATIC_GRAV
+  static chl_ctx *last_ctx = nullptr;
+  static double last[7];
+  double const now[7] = {(double)custom_grav, (double)x_off, (double)y_off, (double)z_off, (double)xbound, (double)ybound,
+                         (double)zbound};
+  if (c == last_ctx && memcmp(now, last, sizeof(now)) == 0) return;
+  int const rc = chl_set_static_gravity(c, custom_grav, x_off, y_off, z_off, xbound, ybound, zbound, nullptr);
+  if (rc != CHL_OK) die("chl_set_static_gravity", rc);
+  last_ctx = c;
+  memcpy(last, now, sizeof(now));
+#else
+  (void)c; (void)custom_grav; (void)x_off; (void)y_off; (void)z_off; (void)xbound; (void)ybound; (void)zbound;
+#endif
+}
 }  // namespace
 
 // src/integrators/VL_3D_cuda.h:9-11
@@ -108,9 +126,10 @@ void VL_Algorithm_3D_CUDA(Real *d_conserved, Real *d_grav_potential, int nx, int
                           int z_off, int n_ghost, Real dx, Real dy, Real dz, Real xbound, Real ybound, Real zbound,
                           Real dt, int n_fields, int custom_grav, Real density_floor, Real *host_grav_potential)
 {
-  (void)d_grav_potential; (void)x_off; (void)y_off; (void)z_off; (void)xbound; (void)ybound; (void)zbound;
-  (void)custom_grav; (void)host_grav_potential;  // gravity builds are out of scope
-  int const rc = chl_vl_step(context(nx, ny, nz, n_ghost, n_fields, dx, dy, dz, density_floor), d_conserved, dt, nullptr);
+  (void)d_grav_potential; (void)host_grav_potential;  // self-gravity (-DGRAVITY) builds are out of scope
+  chl_ctx *const c = context(nx, ny, nz, n_ghost, n_fields, dx, dy, dz, density_floor);
+  gravity(c, custom_grav, x_off, y_off, z_off, xbound, ybound, zbound);
+  int const rc = chl_vl_step(c, d_conserved, dt, nullptr);
   if (rc != CHL_OK) die("chl_vl_step", rc);
 }
 
@@ -118,8 +137,9 @@ void VL_Algorithm_3D_CUDA(Real *d_conserved, Real *d_grav_potential, int nx, int
 void VL_Algorithm_2D_CUDA(Real *d_conserved, int nx, int ny, int x_off, int y_off, int n_ghost, Real dx, Real dy,
                           Real xbound, Real ybound, Real dt, int n_fields, int custom_grav)
 {
-  (void)x_off; (void)y_off; (void)xbound; (void)ybound; (void)custom_grav;
-  int const rc = chl_vl_step(context(nx, ny, 1, n_ghost, n_fields, dx, dy, dy, 0.0), d_conserved, dt, nullptr);
+  chl_ctx *const c = context(nx, ny, 1, n_ghost, n_fields, dx, dy, dy, 0.0);
+  gravity(c, custom_grav, x_off, y_off, 0, xbound, ybound, 0.0);
+  int const rc = chl_vl_step(c, d_conserved, dt, nullptr);
   if (rc != CHL_OK) die("chl_vl_step", rc);
 }
 
@@ -127,8 +147,9 @@ void VL_Algorithm_2D_CUDA(Real *d_conserved, int nx, int ny, int x_off, int y_of
 void VL_Algorithm_1D_CUDA(Real *d_conserved, int nx, int x_off, int n_ghost, Real dx, Real xbound, Real dt,
                           int n_fields, int custom_grav)
 {
-  (void)x_off; (void)xbound; (void)custom_grav;
-  int const rc = chl_vl_step(context(nx, 1, 1, n_ghost, n_fields, dx, dx, dx, 0.0), d_conserved, dt, nullptr);
+  chl_ctx *const c = context(nx, 1, 1, n_ghost, n_fields, dx, dx, dx, 0.0);
+  gravity(c, custom_grav, x_off, 0, 0, xbound, 0.0, 0.0);
+  int const rc = chl_vl_step(c, d_conserved, dt, nullptr);
   if (rc != CHL_OK) die("chl_vl_step", rc);
 }
 

@@ -320,6 +320,28 @@ class Grid3D:
         Select_Internal_Energy / Sync_Energies."""
         return 1 + self.ndim if self.integrator == "simple" else 2 * self.ndim + (4 if self.dual_energy else 0)
 
+    def Set_Static_Gravity(self, custom_grav):
+        """A -DSTATIC_GRAV build with Parameters::custom_grav = custom_grav (static_grav.h; < 0 switches gravity off): the
+        analytic acceleration is evaluated once on the device from this rank's offsets and the domain corner, every later
+        step adds the time-centred source terms of Update_Conserved_Variables_{1,2,3}D."""
+        o, H = self.decomp.offset, self.H
+        check(_lib.lib().chl_set_static_gravity(self._ctx, int(custom_grav), o[0], o[1], o[2], H.xbound, H.ybound, H.zbound,
+                                                self._stream()), "chl_set_static_gravity")
+        self.static_gravity = custom_grav >= 0
+        self.gpu_launches += 1
+        if self.static_gravity:
+            self.overlap = False  # the source terms follow the whole corrector: the exchange cannot start before them
+
+    def gravity_field(self):
+        """The device's [ndim][n_cells] acceleration arrays as a host array (None when gravity is off)."""
+        p = C.c_void_p()
+        check(_lib.lib().chl_gravity_field_ptr(self._ctx, C.byref(p)), "chl_gravity_field_ptr")
+        if not p.value:
+            return None
+        out = self.torch.empty(self.ndim * self.H.n_cells, dtype=self.dtype, device=self.device)
+        check(_lib.lib().chl_copy_gravity_field(self._ctx, self._ptr(out), self._stream()), "chl_copy_gravity_field")
+        return out.cpu().numpy().astype(np.float64)
+
     def Apply_Scalar_Floor(self, field_num, scalar_floor):
         """Apply_Scalar_Floor (hydro_cuda.cu:1267-1307; grid3D.cpp:505-510 calls it for the dust density)."""
         check(_lib.lib().chl_apply_scalar_floor(self._ctx, self._ptr(), int(field_num), float(scalar_floor), self._stream()),

@@ -44,6 +44,8 @@ def lib():
         _lib.orc_vl_step_x.restype = i
         _lib.orc_temperature_floor_x.argtypes = [p, i, i, i, i, d, i, i]
         _lib.orc_scalar_floor.argtypes = [p, i, i, i, i, i, d]
+        _lib.orc_static_gravity_field.argtypes = [p, i, i, i, i, i, i, i, i, d, d, d, d, d, d]
+        _lib.orc_set_gravity.argtypes = [p]
         _lib.orc_boundary_extents.argtypes = [i, i, i, i, i, p, p]
         _lib.orc_set_ghost_cells.argtypes = [p, i, i, i, i, i, p, i]
         _lib.orc_set_boundaries.argtypes = [p, i, i, i, i, i, p]
@@ -107,6 +109,25 @@ def temperature_floor_x(U, nx, ny, nz, n_ghost, U_floor, n_fields, dual_energy):
 def scalar_floor(U, nx, ny, nz, n_ghost, field_num, floor):
     lib().orc_scalar_floor(_ptr(U), nx, ny, nz, n_ghost, field_num, floor)
     return U
+
+
+_gravity_keepalive = None
+
+
+def static_gravity_field(nx, ny, nz, n_ghost, custom_grav, offsets, dx, dy, dz, bounds):
+    """calc_g_{1,2,3}D (static_grav.h) for every cell of the local array: float64 [ndim * n_cells]."""
+    ndim = 1 + (ny > 1) + (nz > 1)
+    g = np.zeros(ndim * nx * ny * nz)
+    lib().orc_static_gravity_field(_ptr(g), nx, ny, nz, n_ghost, custom_grav, offsets[0], offsets[1], offsets[2], dx, dy, dz,
+                                   bounds[0], bounds[1], bounds[2])
+    return g
+
+
+def set_gravity(g):
+    """The acceleration field every later vl_step / vl_step_x adds the -DSTATIC_GRAV source terms of (None: off)."""
+    global _gravity_keepalive
+    _gravity_keepalive = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
+    lib().orc_set_gravity(None if g is None else _ptr(_gravity_keepalive))
 
 
 def simple_step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor=0.0):

@@ -49,9 +49,19 @@ static void boundary_extents(int dir, int nx, int ny, int nz, int g, int *lo, in
   if (dir % 2 == 0) { lo[ax] = 0; hi[ax] = g; } else { lo[ax] = n[ax] - g; hi[ax] = n[ax]; }
 }
 
+// Parameters::custom_grav and the domain's lower corner, as Grid3D hands them to the integrators (grid3D.cpp:431-465);
+// only a -DSTATIC_GRAV build reads them
+static int g_custom_grav = 0;
+static double g_bound[3] = {0.0, 0.0, 0.0};
+
 extern "C" {
 
 const char *ref_build_flags(void) { return REF_BUILD_FLAGS; }
+void ref_set_gravity(int custom_grav, double xbound, double ybound, double zbound)
+{
+  g_custom_grav = custom_grav;
+  g_bound[0] = xbound; g_bound[1] = ybound; g_bound[2] = zbound;
+}
 
 void ref_set_gamma(double g) { gama = g; }
 
@@ -67,15 +77,16 @@ void ref_vl_step(double *d_conserved, int nx, int ny, int nz, int n_ghost, doubl
     Simple_Algorithm_3D_CUDA(d_conserved, nullptr, nx, ny, nz, 0, 0, 0, n_ghost, dx, dy, dz, 0.0, 0.0, 0.0, dt, n_fields,
                              0, density_floor, nullptr);
 #else
-  if (ny == 1 && nz == 1) VL_Algorithm_1D_CUDA(d_conserved, nx, 0, n_ghost, dx, 0.0, dt, n_fields, 0);
-  else if (nz == 1) VL_Algorithm_2D_CUDA(d_conserved, nx, ny, 0, 0, n_ghost, dx, dy, 0.0, 0.0, dt, n_fields, 0);
+  if (ny == 1 && nz == 1) VL_Algorithm_1D_CUDA(d_conserved, nx, 0, n_ghost, dx, g_bound[0], dt, n_fields, g_custom_grav);
+  else if (nz == 1)
+    VL_Algorithm_2D_CUDA(d_conserved, nx, ny, 0, 0, n_ghost, dx, dy, g_bound[0], g_bound[1], dt, n_fields, g_custom_grav);
   else {
   #ifdef REF_NO_VL3D  // the reference's VL_3D_cuda.cu does not compile in this configuration (see the Makefile)
     fprintf(stderr, "ref_driver: this reference build has no 3-D Van Leer integrator\n");
     chexit(-1);
   #else
-    VL_Algorithm_3D_CUDA(d_conserved, nullptr, nx, ny, nz, 0, 0, 0, n_ghost, dx, dy, dz, 0.0, 0.0, 0.0, dt, n_fields, 0,
-                         density_floor, nullptr);
+    VL_Algorithm_3D_CUDA(d_conserved, nullptr, nx, ny, nz, 0, 0, 0, n_ghost, dx, dy, dz, g_bound[0], g_bound[1], g_bound[2],
+                         dt, n_fields, g_custom_grav, density_floor, nullptr);
   #endif
   }
 #endif

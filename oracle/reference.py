@@ -41,18 +41,21 @@ def lib(recon, solver, nosync=False, dropin=False, simple=False, variant=""):
         L.ref_advance.argtypes = [p, i, i, i, i, d, d, d, p, i, d, d, d, p, p]
         L.ref_advance.restype = d
         L.ref_n_fields.restype = i
+        L.ref_set_gravity.argtypes = [i, d, d, d]
         _libs[key] = L
     return _libs[key]
 
 
 def advance(dev_tensor, dims, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_steps, cfl=0.3, density_floor=0.0,
-            U_floor=0.0, nosync=False, timed=False, dropin=False, simple=False, variant=""):
+            U_floor=0.0, nosync=False, timed=False, dropin=False, simple=False, variant="", custom_grav=0,
+            bounds=(0.0, 0.0, 0.0)):
     """Run the reference's step loop on a torch CUDA float64 tensor (flat SoA, ghosts included), in place.
     Returns (dts, last_dti, ms or None).  One process may only use ONE grid shape per library: the reference
     keeps its scratch in globals sized at the first call (VL_3D_cuda.cu:58-133)."""
     L = lib(recon, solver, nosync, dropin, simple, variant)
     assert dev_tensor.numel() == L.ref_n_fields() * dims[0] * dims[1] * dims[2], "field count of this reference build"
     L.ref_set_gamma(gamma)
+    L.ref_set_gravity(custom_grav, bounds[0], bounds[1], bounds[2])  # read by -DSTATIC_GRAV builds (variant "..._sg") only
     fl = (C.c_int * 6)(*flags)
     dts = (C.c_double * max(n_steps, 1))()
     ms = C.c_float(0.0)

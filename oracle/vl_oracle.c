@@ -831,6 +831,103 @@ void orc_riemann_single(int solver, const double *l5, const double *r5, double g
   f5[0] = f.d; f5[1] = f.mx; f5[2] = f.my; f5[3] = f.mz; f5[4] = f.E;
 }
 
+/* ---- static gravity (-DSTATIC_GRAV) ------------------------------------------------------------------------------
+ * calc_g_{1,2,3}D (src/gravity/static_grav.h:16-210) evaluated for every cell of the local array, and the source terms
+ * of Update_Conserved_Variables_{1,2,3}D (hydro_cuda.cu:59-68, 141-153, 301-317).  PARITY UNPINNED ON THE CPU for the
+ * profiles that call log / pow / atan2 / cos / sin: the device library's results are not correctly rounded and no CPU
+ * libm reproduces their bits (the Rayleigh-Taylor field, custom_grav = 2 in 2-D, is exact).  The bit-level check of the
+ * CUDA path is the reference's own -DSTATIC_GRAV build (tests/test_gpu_gravity.py). */
+#define ORC_GN 4.49451e-18     /* global.h:29 */
+#define ORC_MSUN_CGS 1.98847e33 /* global.h:35 */
+static inline double pow2(double x) { return x * x; }
+static void disk_halo_3d(double x_pos, double y_pos, double z_pos, double M_vir, double M_d, double R_d, double z_d,
+                         double R_vir, double c_vir, double *gx, double *gy, double *gz)
+{ /* static_grav.h:142-199 */
+  double r_disk = sqrt(x_pos * x_pos + y_pos * y_pos);
+  double r_halo = sqrt(x_pos * x_pos + y_pos * y_pos + z_pos * z_pos);
+  double M_h = M_vir - M_d, R_h = R_vir / c_vir;
+  double phi_0_h = ORC_GN * M_h / (log(1.0 + c_vir) - c_vir / (1.0 + c_vir));
+  double x = r_halo / R_h;
+  double a_halo = -phi_0_h * (log(1 + x) - x / (1 + x)) / (r_halo * r_halo);
+  double a_halo_r = a_halo * (r_disk / r_halo), a_halo_z = a_halo * (z_pos / r_halo);
+  double a_disk_r = -ORC_GN * M_d * r_disk * pow(r_disk * r_disk + pow2(R_d + sqrt(z_pos * z_pos + z_d * z_d)), -1.5);
+  double a_disk_z = -ORC_GN * M_d * z_pos * (R_d + sqrt(z_pos * z_pos + z_d * z_d)) /
+                    (pow(r_disk * r_disk + pow2(R_d + sqrt(z_pos * z_pos + z_d * z_d)), 1.5) * sqrt(z_pos * z_pos + z_d * z_d));
+  *gx = (x_pos / r_disk) * (a_disk_r + a_halo_r);
+  *gy = (y_pos / r_disk) * (a_disk_r + a_halo_r);
+  *gz = a_disk_z + a_halo_z;
+}
+void orc_static_gravity_field(double *g, int nx, int ny, int nz, int n_ghost, int custom_grav, int x_off, int y_off,
+                              int z_off, double dx, double dy, double dz, double xbound, double ybound, double zbound)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int ndim = 1 + (ny > 1) + (nz > 1);
+  for (int zid = 0; zid < nz; zid++)
+    for (int yid = 0; yid < ny; yid++)
+      for (int xid = 0; xid < nx; xid++) {
+        size_t id = (size_t)xid + (size_t)nx * ((size_t)yid + (size_t)ny * zid);
+        double gx = 0, gy = 0, gz = 0;
+        double x_pos = (x_off + xid - n_ghost + 0.5) * dx + xbound;
+        if (ndim == 1) {
+          if (custom_grav == 1) { /* static_grav.h:22-55 */
+            double r_disk = 13.9211647546, r_halo = sqrt(x_pos * x_pos + r_disk * r_disk);
+            double M_vir = 1.0e12, M_d = 6.5e10, M_h = M_vir - M_d, R_vir = 261, c_vir = 20.0, R_h = R_vir / c_vir;
+            double R_d = 3.5, z_d = 3.5 / 5.0;
+            double phi_0_h = ORC_GN * M_h / (log(1.0 + c_vir) - c_vir / (1.0 + c_vir));
+            double x = r_halo / R_h;
+            double a_halo = -phi_0_h * (log(1 + x) - x / (1 + x)) / (r_halo * r_halo);
+            double a_disk_z = -ORC_GN * M_d * x_pos * (R_d + sqrt(x_pos * x_pos + z_d * z_d)) /
+                              (pow(r_disk * r_disk + pow2(R_d + sqrt(x_pos * x_pos + z_d * z_d)), 1.5) *
+                               sqrt(x_pos * x_pos + z_d * z_d));
+            gx = (x_pos / r_halo) * a_halo + a_disk_z;
+          }
+        } else if (ndim == 2) { /* static_grav.h:60-124 */
+          double y_pos = (y_off + yid - n_ghost + 0.5) * dy + ybound;
+          double r = sqrt(x_pos * x_pos + y_pos * y_pos), phi = atan2(y_pos, x_pos);
+          if (custom_grav == 1) {
+            if (r < 0.2) { gx = -cos(phi) * 25.0 * r; gy = -sin(phi) * 25.0 * r; }
+            else if (r >= 0.2 && r < 0.4) {
+              gx = -cos(phi) * (4.0 - 20.0 * r + 25.0 * r * r) / r;
+              gy = -sin(phi) * (4.0 - 20.0 * r + 25.0 * r * r) / r;
+            }
+          } else if (custom_grav == 2) { gx = 0; gy = -1; }
+          else if (custom_grav == 3) {
+            double M = 1 * ORC_MSUN_CGS;
+            gx = -cos(phi) * ORC_GN * M / (r * r);
+            gy = -sin(phi) * ORC_GN * M / (r * r);
+          } else if (custom_grav == 4) {
+            double M_vir = 1.0e12, M_d = 6.5e10, M_h = M_vir - M_d, R_vir = 261, c_vir = 20, R_s = R_vir / c_vir, R_d = 3.5;
+            double x = r / R_s;
+            double a_d = ORC_GN * M_d * r * pow(r * r + R_d * R_d, -1.5);
+            double a_h = ORC_GN * M_h * (log(1 + x) - x / (1 + x)) / ((log(1 + c_vir) - c_vir / (1 + c_vir)) * r * r);
+            double a = a_d + a_h;
+            gx = -cos(phi) * a; gy = -sin(phi) * a;
+          }
+        } else {
+          double y_pos = (y_off + yid - n_ghost + 0.5) * dy + ybound, z_pos = (z_off + zid - n_ghost + 0.5) * dz + zbound;
+          if (custom_grav == 1) disk_halo_3d(x_pos, y_pos, z_pos, 1.0e12, 6.5e10, 3.5, 3.5 / 5.0, 261., 20.0, &gx, &gy, &gz);
+          else if (custom_grav == 2) disk_halo_3d(x_pos, y_pos, z_pos, 5.0e10, 1.0e10, 0.8, 0.15, 0.8 / 0.015, 10.0, &gx, &gy, &gz);
+        }
+        g[id] = gx;
+        if (ndim > 1) g[N + id] = gy;
+        if (ndim > 2) g[2 * N + id] = gz;
+      }
+}
+/* the field the next orc_vl_step / orc_vl_step_x calls add the source terms of ([ndim][N]; NULL = a build without gravity) */
+static const double *g_grav = NULL;
+void orc_set_gravity(const double *g) { g_grav = g; }
+/* one cell: old = (rho, momenta)^n read before the flux update, U already updated (and density-floored) */
+static void gravity_source_cell(double *U, size_t N, size_t id, int ndim, double dt, double d, const double *m_old)
+{
+  double d_inv = 1.0 / d, d_n = U[id], d_inv_n = 1.0 / d_n;
+  double v[3], v_n[3];
+  for (int c = 0; c < ndim; c++) { v[c] = m_old[c] * d_inv; v_n[c] = U[(size_t)(1 + c) * N + id] * d_inv_n; }
+  double dE = 0.25 * dt * g_grav[id] * (d + d_n) * (v[0] + v_n[0]);
+  for (int c = 1; c < ndim; c++) dE = dE + 0.25 * dt * g_grav[(size_t)c * N + id] * (d + d_n) * (v[c] + v_n[c]);
+  for (int c = 0; c < ndim; c++) U[(size_t)(1 + c) * N + id] += 0.5 * dt * g_grav[(size_t)c * N + id] * (d + d_n);
+  U[4 * N + id] += dE;
+}
+
 /* ---- one full VL step (VL_3D_cuda.cu:38-360; VL_2D_cuda.cu; VL_1D_cuda.cu) ---- */
 void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz, double dt,
                  double gamma, int recon, int solver, double density_floor)
@@ -895,6 +992,7 @@ void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, doub
           if (ndim > 1 && !(y > g - 1 && y < ny - g)) continue;
           if (ndim > 2 && !(z > g - 1 && z < nz - g)) continue;
           size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+          double d_old = U[id], m_old[3] = {U[N + id], U[2 * N + id], U[3 * N + id]};
           for (int f = 0; f < 5; f++) {
             double s = dto[0] * (F[0][f * N + id - st[0]] - F[0][f * N + id]);
             for (int d = 1; d < ndim; d++) s = s + dto[d] * (F[d][f * N + id - st[d]] - F[d][f * N + id]);
@@ -905,6 +1003,7 @@ void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, doub
             U[id] = density_floor;
             for (int f = 1; f < 5; f++) U[f * N + id] *= (density_floor / d0);
           }
+          if (g_grav) gravity_source_cell(U, N, id, ndim, dt, d_old, m_old);
           /* the rho<=0 neighbour-averaging branch (hydro_cuda.cu:292-297) races in the
            * reference and is not restated */
         }
@@ -1127,6 +1226,7 @@ int orc_vl_step_x(double *U, int nx, int ny, int nz, int n_ghost, double dx, dou
       for (int x = 0; x < nx; x++) {
         if (!ORC_REAL_CELL(x, y, z)) continue;
         size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        double d_old = U[id], m_old[3] = {U[N + id], U[2 * N + id], U[3 * N + id]};
         for (int f = 0; f < nf; f++) {
           double s = dto[0] * (F[0][f * N + id - st[0]] - F[0][f * N + id]);
           for (int d = 1; d < ndim; d++) s = s + dto[d] * (F[d][f * N + id - st[d]] - F[d][f * N + id]);
@@ -1138,6 +1238,7 @@ int orc_vl_step_x(double *U, int nx, int ny, int nz, int n_ghost, double dx, dou
           for (int f = 1; f < 5; f++) U[f * N + id] *= (density_floor / d0);
           if (de) U[(size_t)GE * N + id] *= (density_floor / d0);
         }
+        if (g_grav) gravity_source_cell(U, N, id, ndim, dt, d_old, m_old);
       }
   if (de) { /* Select_Internal_Energy_{1,2,3}D then Sync_Energies_{1,2,3}D (hydro_cuda.cu:835-1099) */
     double *sel = malloc(N * sizeof(double));

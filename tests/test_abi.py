@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), "libcholla_b200.so does not export %s" % n
-    assert L.chl_abi_version() == 1
+    assert L.chl_abi_version() == 2
     assert L.chl_has_precision(2) == 1
 
 

@@ -74,3 +74,36 @@ def test_floors():
     oracle.temperature_floor_x(b, *dims, g, 3.0, 7, True)
     r = real_view(b, dims, g)
     assert (r[6] / r[0]).min() >= 3.0 * (1 - 1e-15)
+
+
+def test_static_gravity_oracle_uniform_field_accelerates_a_uniform_gas():
+    """Rayleigh-Taylor field (custom_grav = 2, g = (0, -1)) on a uniform gas at rest, periodic: after a step every real cell
+    has momentum_y = -rho dt; the work term averages the velocities BEFORE the momentum source is added (hydro_cuda.cu:
+    146-152 reads v^{n+1} first), so the energy only moves from the second step on: 0.25 dt g (2 rho) (v_y + v_y) = 2 dt^2."""
+    nx, ny, g, gamma, dt = 16, 12, 3, 1.4, 0.01
+    fields = ic.constant((nx, ny, 1), rho=2.0, P=1.0, gamma=gamma)
+    flat, dims = ghosted(fields, g, [1, 1, 1, 1, 0, 0])
+    field = oracle.static_gravity_field(*dims, g, 2, (0, 0, 0), 0.1, 0.1, 1.0, (0.0, 0.0, 0.0))
+    assert set(np.unique(field)) == {-1.0, 0.0}
+    oracle.set_gravity(field)
+    try:
+        oracle.vl_step(flat, *dims, g, 0.1, 0.1, 1.0, dt, gamma, 1, 0)
+        r = real_view(flat, dims, g).copy()
+        assert np.all(r[0] == 2.0) and np.all(r[1] == 0.0)
+        assert np.allclose(r[2], -2.0 * dt, rtol=1e-14) and np.all(r[4] == fields[4].flat[0])
+        oracle.set_boundaries(flat, *dims, 5, g, [1, 1, 1, 1, 0, 0])
+        oracle.vl_step(flat, *dims, g, 0.1, 0.1, 1.0, dt, gamma, 1, 0)
+    finally:
+        oracle.set_gravity(None)
+    r = real_view(flat, dims, g)
+    assert np.allclose(r[2], -4.0 * dt, rtol=1e-13)
+    assert np.allclose(r[4] - fields[4].flat[0], 2.0 * dt * dt, rtol=1e-9)
+
+
+def test_static_gravity_fields_are_odd_and_point_inwards():
+    n, g = (12, 12, 12), 3
+    dims = tuple(m + 2 * g for m in n)
+    f = oracle.static_gravity_field(*dims, g, 1, (0, 0, 0), 1.0, 1.0, 1.0, (-6.0, -6.0, -6.0)).reshape(3, *dims[::-1])
+    assert np.isfinite(f).all()
+    assert np.allclose(f[0], -f[0][:, :, ::-1], rtol=1e-12) and np.allclose(f[2], -f[2][::-1], rtol=1e-12)
+    assert (f[0][:, :, dims[0] // 2 + 1:] < 0).all() and (f[2][dims[2] // 2 + 1:] < 0).all()
