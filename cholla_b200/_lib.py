@@ -71,6 +71,7 @@ def lib():
     L.chl_stage_times.argtypes = [p, C.POINTER(d), ip]
     L.chl_apply_temperature_floor.argtypes = [p, p, d, p]
     L.chl_apply_scalar_floor.argtypes = [p, p, i, d, p]
+    L.chl_cooling_update.argtypes = [p, p, d, p]
     L.chl_set_static_gravity.argtypes = [p, i, i, i, i, d, d, d, p]
     L.chl_set_gravity_field.argtypes = [p, p, p]
     L.chl_gravity_field_ptr.argtypes = [p, C.POINTER(p)]

@@ -613,6 +613,16 @@ int chl_copy_gravity_field(chl_ctx *c, void *d_dst, void *stream)
   return CHL_OK;
 }
 
+int chl_cooling_update(chl_ctx *c, void *U, double dt, void *stream)
+{
+  if (!c || !U) return fail(CHL_ERR_INVALID, "chl_cooling_update: null argument");
+  if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_cooling_update: hydro contexts only");
+  chl_config const &g = c->cfg;
+  CHL_CUDA(chl::launch_cooling_update(U, g.nx, g.ny, g.nz, g.n_ghost, g.n_fields, c->ops->dual_energy, dt, g.gamma,
+                                      (int)c->ops->real_bytes, (cudaStream_t)stream));
+  return CHL_OK;
+}
+
 int chl_apply_scalar_floor(chl_ctx *c, void *U, int field_num, double scalar_floor, void *stream)
 {
   if (!c || !U) return fail(CHL_ERR_INVALID, "chl_apply_scalar_floor: null argument");

@@ -18,6 +18,9 @@ cudaError_t launch_static_gravity_field(void *g_out, int nx, int ny, int nz, int
                                         const double d[3], const double bound[3], int real_bytes, cudaStream_t s);
 cudaError_t launch_gravity_source(void *U, const void *old, const void *g, int nx, int ny, int nz, int n_ghost, double dt,
                                   int real_bytes, cudaStream_t s);
+// cooling_kernels.cu: Cooling_Update with the analytic CIE curve (-DCOOLING_GPU without -DCLOUDY_COOL)
+cudaError_t launch_cooling_update(void *U, int nx, int ny, int nz, int n_ghost, int n_fields, int dual_energy, double dt,
+                                  double gamma, int real_bytes, cudaStream_t s);
 cudaError_t launch_scalar_floor(void *c, int nx, int ny, int nz, int n_ghost, int field_num, double floor_value,
                                 int real_bytes, cudaStream_t s);
 cudaError_t launch_pack(void *buf, const void *c, int nx, int ny, int n_fields, long n_cells, long idxoffset,

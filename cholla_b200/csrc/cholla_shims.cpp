@@ -121,6 +121,16 @@ void gravity(chl_ctx *c, int custom_grav, int x_off, int y_off, int z_off, Real 
 }
 }  // namespace
 
+// src/cooling/cooling_cuda.h: Cooling_Update (a -DCOOLING_GPU build calls it after the integrator, grid3D.cpp:512-522)
+void Cooling_Update(Real *dev_conserved, int nx, int ny, int nz, int n_ghost, int n_fields, Real dt, Real gamma)
+{
+  (void)gamma;  // the context carries the global `gama` the reference passes here
+  if (!g_ctx || g_cfg.nx != nx || g_cfg.ny != ny || g_cfg.nz != nz || g_cfg.n_ghost != n_ghost || g_cfg.n_fields != n_fields)
+    die("Cooling_Update before the first integrator call on this grid", CHL_ERR_INVALID);
+  int const rc = chl_cooling_update(g_ctx, dev_conserved, dt, nullptr);
+  if (rc != CHL_OK) die("chl_cooling_update", rc);
+}
+
 // src/integrators/VL_3D_cuda.h:9-11
 void VL_Algorithm_3D_CUDA(Real *d_conserved, Real *d_grav_potential, int nx, int ny, int nz, int x_off, int y_off,
                           int z_off, int n_ghost, Real dx, Real dy, Real dz, Real xbound, Real ybound, Real zbound,

@@ -21,11 +21,15 @@ cudaError_t launch_mhd_dir(MhdDirParams const &p, cudaStream_t s)
   if (ox <= 0 || oy <= 0 || oz <= 0) return cudaSuccess;
   dim3 grid;
   if (DIR == 0) grid = dim3((oy + kRowsPerCta - 1) / kRowsPerCta, oz, 1);
-  else {
-    int const om = DIR == 1 ? oy : oz;
-    grid = dim3((ox + kDirThreads - 1) / kDirThreads, DIR == 1 ? oz : oy, (om + p.chunk - 1) / p.chunk);
+  MhdDirParams q = p;
+  q.xw_log2 = 7;
+  if (DIR != 0) {
+    int const om = DIR == 1 ? oy : oz, oo = DIR == 1 ? oz : oy;
+    q.xw_log2 = pick_xw_log2(ox, oo);
+    int const xw = 1 << q.xw_log2, ow = kDirThreads >> q.xw_log2;
+    grid = dim3((ox + xw - 1) / xw, (oo + ow - 1) / ow, (om + p.chunk - 1) / p.chunk);
   }
-  mhd_dir_kernel<RECON, STAGE, DIR, FIRST, LAST><<<grid, kDirThreads, 0, s>>>(p);
+  mhd_dir_kernel<RECON, STAGE, DIR, FIRST, LAST><<<grid, kDirThreads, 0, s>>>(q);
   return cudaGetLastError();
 }
 

@@ -26,6 +26,9 @@ namespace CHL_NS
 #ifndef CHL_MHD_MINB
 #define CHL_MHD_MINB 4
 #endif
+#ifndef CHL_MHD_MINB0  // the predictor passes (PCM + HLLD) may want a different register budget
+#define CHL_MHD_MINB0 CHL_MHD_MINB
+#endif
 #if CHL_STRICT
 constexpr int kMhdPrimFields = 10;  // rho, vx, vy, vz, P_x, Bx, By, Bz, P_y, P_z
 #else
@@ -43,6 +46,7 @@ struct MhdDirParams {
   int flo[3], fhi[3];  // cells whose +face flux is produced: [flo, fhi) along the sweep; transverse cells [flo, fhi)
   int ulo[3], uhi[3];  // cells whose hydro fields are updated
   int chunk;
+  int xw_log2;  // y / z sweeps: log2 of the CTA's extent along x (pick_xw_log2, vl_dirsweep.cuh)
   Real dto, gamma, density_floor;
 };
 
@@ -151,7 +155,7 @@ __device__ __forceinline__ void hlld_checked(M7 const &L, M7 const &R, Real bfac
 }
 
 template <int RECON, int STAGE, int DIR, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdDirParams const P)
+__global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_MHD_MINB0 : CHL_MHD_MINB) mhd_dir_kernel(MhdDirParams const P)
 {
   int const nx = P.nx, ny = P.ny;
   size_t const N = (size_t)nx * ny * P.nz;
@@ -171,10 +175,11 @@ __global__ void __launch_bounds__(kDirThreads, CHL_MHD_MINB) mhd_dir_kernel(MhdD
     c_first = P.flo[0];
     c_last  = P.fhi[0];
   } else {
-    xyz[0]      = P.flo[0] + blockIdx.x * kDirThreads + threadIdx.x;
+    int const xw = 1 << P.xw_log2;
+    xyz[0]      = P.flo[0] + blockIdx.x * xw + (threadIdx.x & (xw - 1));
     int const q = DIR == 1 ? 2 : 1;
-    xyz[q]      = P.flo[q] + blockIdx.y;
-    live        = xyz[0] < P.fhi[0];
+    xyz[q]      = P.flo[q] + blockIdx.y * (kDirThreads >> P.xw_log2) + (threadIdx.x >> P.xw_log2);
+    live        = xyz[0] < P.fhi[0] && xyz[q] < P.fhi[q];
     int const b = P.flo[DIR] + blockIdx.z * P.chunk;  // this chunk completes cells [b, b + chunk)
     c_first     = max(b - 1, P.flo[DIR]);
     c_last      = min(b + P.chunk, P.fhi[DIR]);

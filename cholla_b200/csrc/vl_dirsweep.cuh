@@ -75,6 +75,25 @@ struct DirParams {
   } box[6];
 };
 
+// y / z sweeps: the CTA's extent along x (128, 64 or 32 threads; the rest of its 128 threads stack along the other fixed
+// axis) that leaves the fewest idle thread slots.  A CTA keeps its registers and shared memory until its last warp is
+// done, so a column of CTAs with a handful of live lanes (518 = 4 x 128 + 6 cells in the 512^3 predictor, 258 = 2 x 128 + 2
+// in the 256^3 MHD corrector) costs a fifth to a third of the resident warps of these latency-bound kernels.
+inline int pick_xw_log2(int ox, int oo)
+{
+  int best = 7;
+  long best_slots = -1;
+  for (int l = 7; l >= 5; l--) {
+    int const xw = 1 << l, ow = kDirThreads >> l;
+    long const slots = (long)((ox + xw - 1) / xw) * xw * ((oo + ow - 1) / ow) * ow;
+    if (best_slots < 0 || slots < best_slots) {
+      best_slots = slots;
+      best       = l;
+    }
+  }
+  return best;
+}
+
 __device__ __forceinline__ void cp_async_real(Real *smem_dst, const Real *gsrc)
 {
   unsigned const sa = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -35,13 +35,15 @@ cudaError_t launch_dir(DirParams const &p, cudaStream_t s)
   int const ox = p.hi[0] - p.lo[0], oy = p.hi[1] - p.lo[1], oz = p.hi[2] - p.lo[2];
   if (ox <= 0 || oy <= 0 || oz <= 0) return cudaSuccess;
   dim3 grid;
+  DirParams q = p;
   if (DIR == 0) grid = dim3((oy + kRowsPerCta - 1) / kRowsPerCta, oz, 1);
   else {
     int const om = DIR == 1 ? oy : oz, oo = DIR == 1 ? oz : oy;
-    int const xw = 1 << p.xw_log2, ow = kDirThreads >> p.xw_log2;
+    q.xw_log2 = pick_xw_log2(ox, oo);
+    int const xw = 1 << q.xw_log2, ow = kDirThreads >> q.xw_log2;
     grid = dim3((ox + xw - 1) / xw, (oo + ow - 1) / ow, (om + p.chunk - 1) / p.chunk);
   }
-  vl_dir_kernel<RECON, SOLVER, STAGE, DIR, FIRST, LAST><<<grid, kDirThreads, 0, s>>>(p);
+  vl_dir_kernel<RECON, SOLVER, STAGE, DIR, FIRST, LAST><<<grid, kDirThreads, 0, s>>>(q);
   return cudaGetLastError();
 }
 

@@ -120,7 +120,7 @@ class Grid3D:
     def __init__(self, n_global, domain_len, bounds_min=(0.0, 0.0, 0.0), recon=_lib.PPMC, solver=_lib.HLLC,
                  gamma=5.0 / 3.0, bc=(1, 1, 1, 1, 1, 1), precision=2, strict=True, density_floor=0.0,
                  temperature_floor_U=0.0, device=None, dist_group=None, rank=0, nproc=1, fused=True, mhd=False,
-                 integrator="vl", halo_transport="p2p", overlap=True, n_scalars=0, dual_energy=False):
+                 integrator="vl", halo_transport="p2p", overlap=True, n_scalars=0, dual_energy=False, cooling=None):
         import torch
         self.torch = torch
         if integrator not in ("vl", "simple"):  # -DVL / -DSIMPLE, builds/make.type.hydro:8-12
@@ -131,6 +131,9 @@ class Grid3D:
         self.mhd = bool(mhd) or solver == _lib.HLLD
         # -DSCALAR / -DDE builds: fields 5 .. are the scalars, GasEnergy is the last field (grid_enum.h:33-78)
         self.n_scalars, self.dual_energy = int(n_scalars), bool(dual_energy)
+        if cooling not in (None, "cie"):  # -DCOOLING_GPU (CIE curve); the Cloudy tables of -DCLOUDY_COOL are not built
+            raise ValueError("cooling must be None or 'cie'")
+        self.cooling = cooling
         if self.mhd:
             self.solver = solver = _lib.HLLD  # error_handling.cpp:93-96: MHD only supports HLLD
         self.dist_group, self.nproc, self.rank = dist_group, nproc, rank
@@ -172,7 +175,8 @@ class Grid3D:
         if halo_transport not in ("p2p", "nccl"):
             raise ValueError("halo_transport must be 'p2p' or 'nccl'")
         self.halo_transport = halo_transport if nproc > 1 else "none"
-        self.overlap = bool(overlap) and self.halo_transport == "p2p" and self.integrator == "vl" and self.fused
+        self.overlap = (bool(overlap) and self.halo_transport == "p2p" and self.integrator == "vl" and self.fused
+                        and not self.cooling)
         self._halo_h = None          # chl_halo*
         self._exchanged = False      # the step just taken already exchanged the ghost cells
         self._dti_is_global = False  # the dti just returned is already the maximum over ranks
@@ -351,7 +355,7 @@ class Grid3D:
     def Update_Hydro_Grid(self):
         """Grid3D::Update_Hydro_Grid (grid3D.cpp:474-585): integrator, temperature floor, new inverse dt."""
         L = _lib.lib()
-        if self.fused:
+        if self.fused and not self.cooling:
             if self.integrator == "simple":
                 check(L.chl_simple_step_fused(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_simple_step_fused")
             elif self.overlap:
@@ -376,10 +380,14 @@ class Grid3D:
             out = C.c_double()
             check(L.chl_dti_result(self._ctx, C.byref(out), self._stream()), "chl_dti_result")
             return out.value
+        # the reference's own order (grid3D.cpp:491-575): integrator, temperature floor, cooling, Calc_dt
         self.Execute_Hydro_Integrator()
-        if self.U_floor > 0.0:
+        if self.U_floor >= 0.0:
             check(L.chl_apply_temperature_floor(self._ctx, self._ptr(), self.U_floor, self._stream()),
                   "chl_apply_temperature_floor")
+            self.gpu_launches += 1
+        if self.cooling:
+            check(L.chl_cooling_update(self._ctx, self._ptr(), self.H.dt, self._stream()), "chl_cooling_update")
             self.gpu_launches += 1
         return self.Calc_Inverse_Timestep()
 

@@ -221,6 +221,38 @@ def random_smooth(n, seed=0, gamma=5.0 / 3.0):
     return _pack(d, d * vx, d * vy, d * vz, E)
 
 
+def rayleigh_taylor(n, lengths=(0.33333333, 1.0, 1.0), lo=(0.0, 0.0, 0.0), gamma=1.4):
+    """Grid3D::Rayleigh_Taylor (initial_conditions.cpp:881-931): a heavy slab (rho = 2) over a light one in hydrostatic
+    balance with g = -0.1, a tapered cosine perturbation of v_y; 2-D, run with custom_grav = 2."""
+    X, Y, _ = _mesh(n, lengths, lo)
+    dl, du, g = 1.0, 2.0, -0.1
+    vy = 0.01 * np.cos(6 * np.pi * X + np.pi) * np.exp(-(Y - 0.5 * lengths[1]) * (Y - 0.5 * lengths[1]) / 0.1)
+    lower = Y <= 0.5 * lengths[1]
+    d = np.where(lower, dl, du) + 0.0 * X
+    P = np.where(lower, (1.0 / gamma - dl * g * 0.5) + dl * g * Y, (1.0 / gamma - du * g * 0.5) + du * g * Y) + 0.0 * X
+    my = d * vy
+    E = P / (gamma - 1.0) + 0.5 * (my * my) / d
+    zero = np.zeros(np.broadcast(d, my).shape)
+    return _pack(d + zero, zero, my + zero, zero, E + zero)
+
+
+def basic_scalar_for(init, fields, P=None, lengths=None, lo=None, n=None):
+    """The -DBASIC_SCALAR field the reference's generators set (initial_conditions.cpp:481-497 Square_Wave, 565-582
+    Riemann, 719-732 KH): the density inside the marked region, zero elsewhere; generators that do not set it leave the
+    calloc'ed zero."""
+    d = fields[0]
+    if init == "Riemann":
+        X, _, _ = _mesh(n, lengths, lo)
+        return np.where(X < P.diaph, 1.0 * P.rho_l, 0.0 * P.rho_r) + 0.0 * d
+    if init == "Square_Wave":
+        X, _, _ = _mesh(n, lengths, lo)
+        return np.where((X > 0.25 * lengths[0]) & (X < 0.75 * lengths[0]), d * 1.0, d * 0.0)
+    if init == "KH":
+        _, Y, _ = _mesh(n, lengths, lo)
+        return np.where((Y > 0.25 * lengths[1]) & (Y < 0.75 * lengths[1]), 1.0 * d, 0.0) + 0.0 * d
+    return np.zeros_like(d)
+
+
 def with_passive(fields, n_scalars=0, dual_energy=False, gamma=5.0 / 3.0, seed=1):
     """Append the passive fields of a -DSCALAR / -DDE build to a 5-field state: n_scalars scalars (conserved: density
     times a seeded mass fraction in (0.1, 0.9)), then GasEnergy = Energy - kinetic energy, which is what the reference's

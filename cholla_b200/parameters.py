@@ -118,6 +118,7 @@ class Parameters:
     temperature_floor: float = 0.0
     density_floor: float = 0.0
     scalar_floor: float = 0.0
+    custom_grav: int = 0  # global.h:210: selects the analytic field of a -DSTATIC_GRAV build (static_grav.h)
     n_proc_x: int = 0
     n_proc_y: int = 0
     n_proc_z: int = 0
@@ -136,7 +137,7 @@ class Parameters:
 
 # names the reference accepts that have no meaning for this path (other physics, output selection): parsed, not stored
 _IGNORED = {"n_particle", "n_rotated_projection", "out_float32_GasEnergy",
-            "custom_grav", "snr_filename", "scale_outputs_file", "Omega_b", "bc_potential_type", "UVB_rates_file"}
+            "snr_filename", "scale_outputs_file", "Omega_b", "bc_potential_type", "UVB_rates_file"}
 # optionalParams, global.cpp:104-108
 _OPTIONAL = {"flag_delta", "ddelta_dt", "n_delta", "Lz", "Lx", "phi", "theta", "delta", "nzr", "nxr", "H0", "Omega_M",
              "Omega_L", "Init_redshift", "End_redshift", "tile_length", "n_proc_x", "n_proc_y", "n_proc_z"}

@@ -85,6 +85,8 @@ def initial_fields(P: Parameters, mhd=False, n_ghost=0):
         return ic.gresho(n, ln, lo, P.gamma)
     if name == "Implosion_2D":
         return ic.implosion_2d(n, ln, lo, P.gamma)
+    if name == "Rayleigh_Taylor":
+        return ic.rayleigh_taylor(n, ln, lo, P.gamma)
     if name == "Linear_Wave" and not mhd:
         return ic.linear_wave(n, ln, lo, P.rho, P.vx, P.P, P.A, (P.rEigenVec_rho, P.rEigenVec_MomentumX,
                               P.rEigenVec_MomentumY, P.rEigenVec_MomentumZ, P.rEigenVec_E), P.wave_length, P.pitch, P.yaw,
@@ -95,7 +97,7 @@ def initial_fields(P: Parameters, mhd=False, n_ghost=0):
         return ic.mhd_blast(n, n_ghost, P.gamma, ln, lo, P.rho, (P.vx, P.vy, P.vz), P.P, P.P_blast, P.radius,
                             (P.Bx, P.By, P.Bz))
     raise NotImplementedError("init=%s is not one of the generators of the hot-path scope (SURVEY 8d): Constant, Sound_Wave, "
-                              "Riemann, Square_Wave, Shu_Osher, Blast_1D, KH, KH_res_ind, Gresho, Implosion_2D, Linear_Wave, "
+                              "Riemann, Square_Wave, Shu_Osher, Blast_1D, KH, KH_res_ind, Gresho, Implosion_2D, Rayleigh_Taylor, Linear_Wave, "
                               "Spherical_Overpressure_3D, Orszag_Tang_Vortex, MHD_Spherical_Blast, Circularly_Polarized_Alfven_Wave, "
                               "Advecting_Field_Loop" % name)
 
@@ -118,7 +120,7 @@ def read_grid(G, P: Parameters):
     n_step come from the file."""
     from . import snapshot as snap
     path = "%s%d.h5.%d" % (P.indir, P.nfile, G.rank)
-    host, gamma, t, n_step = snap.read_grid(path, G.H, G.mhd)
+    host, gamma, t, n_step = snap.read_grid(path, G.H, G.mhd, G.n_scalars, G.dual_energy)
     if gamma != G.gamma:
         raise ValueError("%s was written with gamma = %r, the deck says %r" % (path, gamma, G.gamma))
     G.upload(host)
@@ -126,8 +128,11 @@ def read_grid(G, P: Parameters):
 
 
 def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mhd=False, outdir=None, device=None,
-        dist_group=None, rank=0, nproc=1, max_steps=None, log=print, integrator="vl"):
-    """main.cpp:63-379.  Returns (Grid3D, list of snapshot paths)."""
+        dist_group=None, rank=0, nproc=1, max_steps=None, log=print, integrator="vl", dual_energy=False, scalar=False,
+        static_gravity=False, cooling=False):
+    """main.cpp:63-379.  Returns (Grid3D, list of snapshot paths).  dual_energy / scalar / static_gravity / cooling stand
+    for the build macros -DDE, -DSCALAR -DBASIC_SCALAR, -DSTATIC_GRAV (the field is the deck's custom_grav) and
+    -DCOOLING_GPU (CIE curve) of the reference's make.type files."""
     from .grid import Grid3D, n_ghost_for
     mhd = mhd or solver == "hlld"
     lo, ln = P.domain()
@@ -135,7 +140,10 @@ def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mh
     G = Grid3D(P.n_global(), ln, bounds_min=lo, recon=RECON[recon], solver=SOLVER[solver], gamma=P.gamma,
                bc=P.boundary_flags(), precision=precision, strict=strict, density_floor=P.density_floor,
                temperature_floor_U=u_floor(P.temperature_floor, P.gamma), device=device, dist_group=dist_group,
-               rank=rank, nproc=nproc, mhd=mhd, integrator=integrator)
+               rank=rank, nproc=nproc, mhd=mhd, integrator=integrator, n_scalars=1 if scalar else 0,
+               dual_energy=dual_energy, cooling="cie" if cooling else None)
+    if static_gravity:
+        G.Set_Static_Gravity(P.custom_grav)
     is_restart = P.init == "Read_Grid"  # main.cpp:89-95
     if is_restart:
         read_grid(G, P)
@@ -144,7 +152,13 @@ def run(P: Parameters, recon="ppmc", solver="hllc", strict=True, precision=2, mh
             G.upload(initial_fields(P, True, n_ghost_for(RECON[recon], True)))
     else:
         with ic.block(G.decomp.offset, G.decomp.n_local):
-            G.Set_Initial_Conditions_Local(initial_fields(P))
+            f = initial_fields(P)
+            extra = []
+            if scalar:
+                extra.append(ic.basic_scalar_for(P.init, f, P, ln, lo, P.n_global()))
+            if dual_energy:  # the generators store P / (gamma - 1): E minus the kinetic energy, to round-off
+                extra.append(f[4] - 0.5 * (f[1] ** 2 + f[2] ** 2 + f[3] ** 2) / f[0])
+            G.Set_Initial_Conditions_Local(np.concatenate([f, np.stack(extra)]) if extra else f)
     G.Set_Boundary_Conditions_Grid()
     outdir = outdir if outdir is not None else (P.outdir or "./")
     files, nfile, outtime = [], P.nfile, 0.0
@@ -196,6 +210,10 @@ def main(argv=None):
     ap.add_argument("--mhd", action="store_true")
     ap.add_argument("--integrator", default="vl", choices=["vl", "simple"], help="-DVL / -DSIMPLE (make.type.hydro:8-12)")
     ap.add_argument("--fast", action="store_true", help="product arithmetic instead of the reference's bits")
+    ap.add_argument("--dual-energy", action="store_true", help="-DDE")
+    ap.add_argument("--scalar", action="store_true", help="-DSCALAR -DBASIC_SCALAR")
+    ap.add_argument("--static-gravity", action="store_true", help="-DSTATIC_GRAV with the deck's custom_grav")
+    ap.add_argument("--cooling", action="store_true", help="-DCOOLING_GPU (CIE curve)")
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2])
     ap.add_argument("--outdir", default=None, help="overrides the deck's outdir; 'none' writes nothing")
     ap.add_argument("--max-steps", type=int, default=None)
@@ -212,7 +230,8 @@ def main(argv=None):
         group = dist.group.WORLD
     G, files = run(P, a.recon, a.solver, strict=not a.fast and a.precision == 2, precision=a.precision, mhd=a.mhd,
                    outdir=a.outdir, device="cuda:%d" % local, dist_group=group, rank=rank, nproc=world,
-                   max_steps=a.max_steps, log=print if rank == 0 else (lambda *_: None), integrator=a.integrator)
+                   max_steps=a.max_steps, log=print if rank == 0 else (lambda *_: None), integrator=a.integrator,
+                   dual_energy=a.dual_energy, scalar=a.scalar, static_gravity=a.static_gravity, cooling=a.cooling)
     G.close()
     if world > 1:
         import torch.distributed as dist

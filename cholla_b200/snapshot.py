@@ -99,12 +99,23 @@ def header_attributes(H, gamma, n_global, n_local, offset, nprocs, bounds, domai
     return a
 
 
+def passive_datasets(H, mhd, n_scalars=0, dual_energy=False):
+    """(dataset name, field index) of the -DDE / -DSCALAR fields in the order Write_Grid_HDF5 emits them (io.cpp:1413-1424):
+    GasEnergy (the last field) right after Energy, then scalar0 (BASIC_SCALAR, field 5)."""
+    out = []
+    if not mhd and dual_energy:
+        out.append(("GasEnergy", H.n_fields - 1))
+    if not mhd and n_scalars:
+        out.append(("scalar0", 5))
+    return out
+
+
 def _ghosts(H):
     g = H.n_ghost
     return g, (g if H.ny > 1 else 0), (g if H.nz > 1 else 0)
 
 
-def grid_datasets(H, C_host, mhd=False, precision=2):
+def grid_datasets(H, C_host, mhd=False, precision=2, n_scalars=0, dual_energy=False):
     """Grid3D::Write_Grid_HDF5 with Output_Complete_Data, io.cpp:1350-1497.  C_host: (n_fields, nz, ny, nx) host array,
     ghost cells included.  1-D grids give (nx_real,), 2-D (nx_real, ny_real), 3-D (nx_real, ny_real, nz_real)."""
     C_host = np.asarray(C_host).reshape(H.n_fields, H.nz, H.ny, H.nx)
@@ -115,6 +126,9 @@ def grid_datasets(H, C_host, mhd=False, precision=2):
     for f, nm in enumerate(HYDRO_FIELDS):
         real = C_host[f, gz:gz + H.nz_real, gy:gy + H.ny_real, gx:gx + H.nx_real]
         t = real.transpose(2, 1, 0)  # [i][j][k]: dest = k + j*nz_real + i*nz_real*ny_real
+        out[nm] = np.ascontiguousarray(t.reshape(t.shape[:ndim])).astype(dt)
+    for nm, f in passive_datasets(H, mhd, n_scalars, dual_energy):
+        t = C_host[f, gz:gz + H.nz_real, gy:gy + H.ny_real, gx:gx + H.nx_real].transpose(2, 1, 0)
         out[nm] = np.ascontiguousarray(t.reshape(t.shape[:ndim])).astype(dt)
     if mhd and ndim == 3:  # io.cpp:1478-1487; the face on the low side of the first real cell is part of the output
         for d, nm in enumerate(MAGNETIC_FIELDS):
@@ -144,6 +158,8 @@ def write_data(G, P, nfile, outdir):
     dt = ">f8" if G.precision == 2 else ">f4"
     data = OrderedDict()
     for f, nm in enumerate(HYDRO_FIELDS):  # device-side transposition, one field at a time like the reference
+        data[nm] = G.snapshot_field(f).astype(dt)
+    for nm, f in passive_datasets(H, G.mhd, getattr(G, "n_scalars", 0), getattr(G, "dual_energy", False)):
         data[nm] = G.snapshot_field(f).astype(dt)
     if G.mhd and H.nz > 1:
         for d, nm in enumerate(MAGNETIC_FIELDS):
@@ -307,7 +323,7 @@ def write_projection(G, P, nfile, outdir):
     return path
 
 
-def read_grid(path, H, mhd=False):
+def read_grid(path, H, mhd=False, n_scalars=0, dual_energy=False):
     """Grid3D::Read_Grid_HDF5, io.cpp:2508-2720: returns (C_host (n_fields, nz, ny, nx) with the real cells -- and, for
     MHD, the real faces -- filled and the ghost cells zero, gamma, t, n_step).  The caller sets the boundaries next, as
     main.cpp does."""
@@ -319,7 +335,7 @@ def read_grid(path, H, mhd=False):
         t = float(f.attrs["t"][0])
         n_step = int(f.attrs["n_step"][0])
         want = (H.nx_real, H.ny_real, H.nz_real)[:ndim]
-        for i, nm in enumerate(HYDRO_FIELDS):
+        for nm, i in [(nm, i) for i, nm in enumerate(HYDRO_FIELDS)] + passive_datasets(H, mhd, n_scalars, dual_energy):
             a = f[nm].read()
             if a.shape != want:
                 raise ValueError("%s: dataset %s has shape %s, the grid expects %s" % (path, nm, a.shape, want))

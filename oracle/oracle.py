@@ -44,6 +44,9 @@ def lib():
         _lib.orc_vl_step_x.restype = i
         _lib.orc_temperature_floor_x.argtypes = [p, i, i, i, i, d, i, i]
         _lib.orc_scalar_floor.argtypes = [p, i, i, i, i, i, d]
+        _lib.orc_cooling_update.argtypes = [p, i, i, i, i, i, i, d, d]
+        _lib.orc_cie_cool.argtypes = [d, d]
+        _lib.orc_cie_cool.restype = d
         _lib.orc_static_gravity_field.argtypes = [p, i, i, i, i, i, i, i, i, d, d, d, d, d, d]
         _lib.orc_set_gravity.argtypes = [p]
         _lib.orc_boundary_extents.argtypes = [i, i, i, i, i, p, p]
@@ -109,6 +112,16 @@ def temperature_floor_x(U, nx, ny, nz, n_ghost, U_floor, n_fields, dual_energy):
 def scalar_floor(U, nx, ny, nz, n_ghost, field_num, floor):
     lib().orc_scalar_floor(_ptr(U), nx, ny, nz, n_ghost, field_num, floor)
     return U
+
+
+def cooling_update(U, nx, ny, nz, n_ghost, n_fields, dual_energy, dt, gamma):
+    """Cooling_Update with the CIE curve (cooling_cuda.cu:20-196, 293-317), in place."""
+    lib().orc_cooling_update(_ptr(U), nx, ny, nz, n_ghost, n_fields, int(bool(dual_energy)), dt, gamma)
+    return U
+
+
+def cie_cool(n, T):
+    return lib().orc_cie_cool(n, T)
 
 
 _gravity_keepalive = None
@@ -188,7 +201,7 @@ def unpack(buf, U, nx, ny, n_fields, n_cells, idxoffset, isize, jsize, ksize):
 
 
 def advance(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_steps, cfl=0.3,
-            density_floor=0.0, U_floor=0.0, integrator="vl", n_scalars=0, dual_energy=False):
+            density_floor=0.0, U_floor=0.0, integrator="vl", n_scalars=0, dual_energy=False, cooling=False):
     """The reference's main loop body (main.cpp:247-379) without I/O: dt from the CFL reduction, VL (or SIMPLE) step,
     temperature floor, ghost fill.  Returns the list of dt used."""
     dts = []
@@ -201,6 +214,8 @@ def advance(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_s
             dt = cfl / dti
             vl_step_x(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor, n_scalars, dual_energy)
             temperature_floor_x(U, nx, ny, nz, n_ghost, U_floor, n_fields, dual_energy)
+            if cooling:
+                cooling_update(U, nx, ny, nz, n_ghost, n_fields, dual_energy, dt, gamma)
             dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
             set_boundaries(U, nx, ny, nz, n_fields, n_ghost, flags)
             dts.append(dt)
@@ -210,6 +225,8 @@ def advance(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_s
         dt = cfl / dti
         step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor)
         temperature_floor(U, nx, ny, nz, n_ghost, U_floor)
+        if cooling:
+            cooling_update(U, nx, ny, nz, n_ghost, 5, False, dt, gamma)
         dti = calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma)
         set_boundaries(U, nx, ny, nz, 5, n_ghost, flags)
         dts.append(dt)

@@ -19,6 +19,9 @@
 #include "integrators/simple_1D_cuda.h"
 #include "integrators/simple_2D_cuda.h"
 #include "integrators/simple_3D_cuda.h"
+#ifdef COOLING_GPU
+  #include "cooling/cooling_cuda.h"
+#endif
 
 Real gama;
 [[noreturn]] void chexit(int code) { exit(code); }
@@ -132,6 +135,9 @@ double ref_advance(double *d_conserved, int nx, int ny, int nz, int n_ghost, dou
     double dt = cfl / dti;
     ref_vl_step(d_conserved, nx, ny, nz, n_ghost, dx, dy, dz, dt, kFields, density_floor);
     Apply_Temperature_Floor(d_conserved, nx, ny, nz, n_ghost, kFields, U_floor);
+#ifdef COOLING_GPU  // grid3D.cpp:512-522
+    Cooling_Update(d_conserved, nx, ny, nz, n_ghost, kFields, dt, gama);
+#endif
     dti = Calc_dt_GPU(d_conserved, nx, ny, nz, n_ghost, kFields, dx, dy, dz, gama);
     ref_set_boundaries(d_conserved, nx, ny, nz, kFields, n_ghost, flags);
     if (dts) dts[s] = dt;

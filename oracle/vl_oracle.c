@@ -1536,3 +1536,64 @@ void orc_scalar_floor(double *U, int nx, int ny, int nz, int n_ghost, int field_
         if (U[(size_t)field_num * N + id] < scalar_floor) U[(size_t)field_num * N + id] = scalar_floor;
       }
 }
+
+/* Cooling_Update / cooling_kernel with CIE_cool (src/cooling/cooling_cuda.cu:20-196, 293-317): the -DCOOLING_GPU source
+ * step.  PARITY UNPINNED ON THE CPU where log10 / pow are involved (device library bits); the bit-level check of the CUDA
+ * path is the reference's own -DCOOLING_GPU build (tests/test_gpu_cooling.py). */
+#define ORC_MP 1.672622e-24
+#define ORC_KB 1.380658e-16
+#define ORC_TIME_UNIT 3.15569e10
+#define ORC_LENGTH_UNIT 3.08567758e21
+#define ORC_MASS_UNIT 1.98847e33
+#define ORC_DENSITY_UNIT (ORC_MASS_UNIT / (ORC_LENGTH_UNIT * ORC_LENGTH_UNIT * ORC_LENGTH_UNIT))
+#define ORC_VELOCITY_UNIT (ORC_LENGTH_UNIT / ORC_TIME_UNIT)
+#define ORC_ENERGY_UNIT (ORC_DENSITY_UNIT * ORC_VELOCITY_UNIT * ORC_VELOCITY_UNIT)
+#define ORC_PRESSURE_UNIT (ORC_DENSITY_UNIT * ORC_VELOCITY_UNIT * ORC_VELOCITY_UNIT)
+#define ORC_SP_ENERGY_UNIT (ORC_VELOCITY_UNIT * ORC_VELOCITY_UNIT)
+double orc_cie_cool(double n, double T)
+{
+  double lambda = 0.0;
+  if (log10(T) < 4.0) lambda = 0.0;
+  else if (log10(T) >= 4.0 && log10(T) < 5.9) lambda = pow(10.0, (-1.3 * (log10(T) - 5.25) * (log10(T) - 5.25) - 21.25));
+  else if (log10(T) >= 5.9 && log10(T) < 7.4) lambda = pow(10.0, (0.7 * (log10(T) - 7.1) * (log10(T) - 7.1) - 22.8));
+  else lambda = pow(10.0, (0.45 * log10(T) - 26.065));
+  return n * n * lambda;
+}
+void orc_cooling_update(double *U, int nx, int ny, int nz, int n_ghost, int n_fields, int de, double dt_in, double gamma)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int g = n_ghost;
+  int js = ny == 1 ? 0 : g, je = ny == 1 ? 1 : ny - g, ks = nz == 1 ? 0 : g, ke = nz == 1 ? 1 : nz - g;
+  double mu = 0.6;
+  for (int z = ks; z < ke; z++)
+    for (int y = js; y < je; y++)
+      for (int x = g; x < nx - g; x++) {
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        double dt = dt_in, d = U[id], E = U[4 * N + id], ge = 0.0;
+        if (E < 0.0 || E != E) continue;
+        double vx = U[N + id] / d, vy = U[2 * N + id] / d, vz = U[3 * N + id] / d;
+        double p = (E - 0.5 * d * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
+        p = fmax(p, ORC_TINY);
+        if (de) { ge = U[(size_t)(n_fields - 1) * N + id] / d; ge = fmax(ge, ORC_TINY); }
+        double n = d * ORC_DENSITY_UNIT / (mu * ORC_MP);
+        double T_init = p * ORC_PRESSURE_UNIT / (n * ORC_KB);
+        if (de) T_init = d * ge * (gamma - 1.0) * ORC_PRESSURE_UNIT / (n * ORC_KB);
+        double T = T_init, cool = orc_cie_cool(n, T);
+        double del_T = cool * dt * ORC_TIME_UNIT * (gamma - 1.0) / (n * ORC_KB);
+        while (del_T / T > 0.01) {
+          double dt_sub = 0.01 * T * n * ORC_KB / (cool * ORC_TIME_UNIT * (gamma - 1.0));
+          T -= cool * dt_sub * ORC_TIME_UNIT * (gamma - 1.0) / (n * ORC_KB);
+          dt -= dt_sub;
+          cool = orc_cie_cool(n, T);
+          del_T = cool * dt * ORC_TIME_UNIT * (gamma - 1.0) / (n * ORC_KB);
+        }
+        T -= del_T;
+        del_T = T_init - T;
+        E -= n * ORC_KB * del_T / ((gamma - 1.0) * ORC_ENERGY_UNIT);
+        U[4 * N + id] = E;
+        if (de) {
+          ge -= ORC_KB * del_T / (mu * ORC_MP * (gamma - 1.0) * ORC_SP_ENERGY_UNIT);
+          U[(size_t)(n_fields - 1) * N + id] = d * ge;
+        }
+      }
+}

@@ -185,3 +185,60 @@ def test_reference_sound_wave_3d_system_test(tmp_path):
     phase = kx * 0.5 - 1.0 * 0.05 * 2 * np.pi
     assert system_test.analytic_sine(str(tmp_path), "density", 1.0, 1e-5, kx, 0.0, 0.0, phase, 1e-7)
     assert system_test.analytic_sine(str(tmp_path), "momentum_x", 0.0, 1e-5, kx, 0.0, 0.0, phase, 1e-7)
+
+
+def test_rayleigh_taylor_deck_with_static_gravity_matches_the_oracle_loop(tmp_path):
+    """examples/2D/Rayleigh_Taylor.txt at a smaller size: init=Rayleigh_Taylor, custom_grav=2 under -DSTATIC_GRAV (PLMC + HLLC
+    as builds/make.type.static_grav selects).  The field is exact (g = (0, -1)), so the oracle loop must give the bytes."""
+    import oracle
+    n, gamma, bc = (40, 80, 1), 1.4, [1, 1, 2, 2, 0, 0]
+    P = deck(tmp_path, "Rayleigh_Taylor", n, bc, gamma, (0.0, 0.0, 0.0), (0.33333333, 1.0, 1.0), custom_grav=2)
+    steps = 10
+    G, files = run.run(P, recon="plmc", solver="hllc", strict=True, max_steps=steps, log=lambda *_: None, static_gravity=True)
+    got, H = G.real_cells(), G.H
+    G.close()
+    g = n_ghost_for(cb.PLMC)
+    flat, dims = ghosted(run.initial_fields(P), g, bc)
+    start = flat.copy()
+    oracle.set_gravity(oracle.static_gravity_field(*dims, g, 2, (0, 0, 0), H.dx, H.dy, H.dz, (0.0, 0.0, 0.0)))
+    try:
+        oracle.advance(flat, *dims, g, H.dx, H.dy, H.dz, gamma, cb.PLMC, cb.HLLC, bc, steps)
+    finally:
+        oracle.set_gravity(None)
+    assert np.array_equal(got, real_view(flat, dims, g))
+    assert np.abs(real_view(flat, dims, g)[2] - real_view(start, dims, g)[2]).max() > 1e-3  # the slab is falling
+
+
+def test_sod_deck_with_dual_energy_and_scalar_snapshot_and_restart(tmp_path):
+    """A -DDE -DSCALAR -DBASIC_SCALAR run of the Riemann generator: oracle bytes, the GasEnergy and scalar0 datasets of
+    Write_Grid_HDF5 (io.cpp:1413-1424), and a restart from them (Read_Grid_HDF5, io.cpp:2538-2544)."""
+    import oracle
+    n, gamma, bc = (64, 1, 1), 1.4, [3, 3, 0, 0, 0, 0]
+    extra = dict(rho_l=1.0, vx_l=0.0, vy_l=0.0, vz_l=0.0, P_l=1.0, rho_r=0.1, vx_r=0.0, vy_r=0.0, vz_r=0.0, P_r=0.1, diaph=0.5)
+    P = deck(tmp_path, "Riemann", n, bc, gamma, **extra)
+    P.outstep = 0.02
+    G, files = run.run(P, recon="ppmc", solver="hllc", strict=True, max_steps=12, log=lambda *_: None, dual_energy=True,
+                       scalar=True)
+    got, H, t_end = G.real_cells(), G.H, G.H.t
+    G.close()
+    assert H.n_fields == 7 and len(files) >= 2
+    with h5lite.File(files[0]) as f:
+        assert f["GasEnergy"].shape == (64,) and f["scalar0"].shape == (64,)
+        assert np.allclose(f["scalar0"].read()[:32], 1.0) and np.all(f["scalar0"].read()[32:] == 0.0)
+        assert np.allclose(f["GasEnergy"].read()[:32], 1.0 / (gamma - 1.0))
+    # the scalar marks the left state: it stays within [0, rho] and follows the contact
+    assert got[5].min() >= 0.0 and np.all(got[5] <= got[0] * (1 + 1e-12))
+    # restart from the last full snapshot and continue to the same time: same bytes as the uninterrupted run
+    with h5lite.File(files[-1]) as f:
+        n_last = int(f.attrs["n_step"][0])
+    assert 0 < n_last < 12
+    import os
+    P2 = deck(tmp_path, "Read_Grid", n, bc, gamma, **extra)
+    P2.outstep, P2.nfile = 0.02, len(files) - 1
+    P2.indir = os.path.dirname(files[-1]) + "/"
+    G2, _ = run.run(P2, recon="ppmc", solver="hllc", strict=True, max_steps=12, log=lambda *_: None, dual_energy=True,
+                    scalar=True, outdir="none")
+    again = G2.real_cells()
+    assert G2.H.n_step == 12
+    G2.close()
+    assert np.array_equal(again, got)

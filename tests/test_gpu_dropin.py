@@ -79,10 +79,12 @@ def test_simple_integrator_driver_runs_unchanged_on_the_b200_library():
     assert r["equal"] and r["dt_equal"] and r["dti_equal"], r
 
 
-@pytest.mark.parametrize("recon,variant,custom_grav,lo", [(1, "_de_sg", 1, (-0.5, -0.5, -0.5)), (2, "_de_s1", 0, (0.0, 0.0, 0.0))])
+@pytest.mark.parametrize("recon,variant,custom_grav,lo", [(1, "_de_sg", 1, (-0.5, -0.5, -0.5)), (2, "_de_s1", 0, (0.0, 0.0, 0.0)),
+                                                          (1, "_de_cool", 0, (0.0, 0.0, 0.0))])
 def test_dual_energy_scalar_and_static_gravity_builds_run_unchanged_on_the_b200_library(recon, variant, custom_grav, lo):
-    """-DDE (-DSCALAR, -DSTATIC_GRAV) builds of the driver: the shims turn the macros into chl_config.dual_energy /
-    n_scalars and chl_set_static_gravity (custom_grav, offsets and bounds arrive with every VL_Algorithm_3D_CUDA call)."""
+    """-DDE (-DSCALAR, -DSTATIC_GRAV, -DCOOLING_GPU) builds of the driver: the shims turn the macros into
+    chl_config.dual_energy / n_scalars and chl_set_static_gravity (custom_grav, offsets and bounds arrive with every
+    VL_Algorithm_3D_CUDA call); the driver's Cooling_Update call lands in chl_cooling_update."""
     from oracle import reference
     if not (reference.available(recon, 0, variant=variant) and reference.available(recon, 0, dropin=True, variant=variant)):
         pytest.skip("oracle/_ref libraries for this combination were not built")

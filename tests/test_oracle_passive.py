@@ -107,3 +107,26 @@ def test_static_gravity_fields_are_odd_and_point_inwards():
     assert np.isfinite(f).all()
     assert np.allclose(f[0], -f[0][:, :, ::-1], rtol=1e-12) and np.allclose(f[2], -f[2][::-1], rtol=1e-12)
     assert (f[0][:, :, dims[0] // 2 + 1:] < 0).all() and (f[2][dims[2] // 2 + 1:] < 0).all()
+
+
+def test_cie_cooling_oracle_curve_and_energy_loss():
+    """CIE_cool (cooling_cuda.cu:293-317): no cooling below 10^4 K, continuous at the 10^5.9 K and 10^7.4 K joints of the fit
+    to a few per cent, n^2 scaling; and Cooling_Update lowers E by exactly n k dT / ((gamma - 1) ENERGY_UNIT)."""
+    assert oracle.cie_cool(1.0, 9.0e3) == 0.0
+    assert oracle.cie_cool(2.0, 1e6) == pytest.approx(4.0 * oracle.cie_cool(1.0, 1e6), rel=1e-15)
+    for Tj in (10 ** 5.9, 10 ** 7.4):
+        assert oracle.cie_cool(1.0, Tj * 0.999999) == pytest.approx(oracle.cie_cool(1.0, Tj * 1.000001), rel=0.15)
+    n, g, gamma = (6, 5, 4), 3, 5.0 / 3.0
+    MP, KB = 1.672622e-24, 1.380658e-16
+    DU = 1.98847e33 / 3.08567758e21 ** 3
+    PU = DU * (3.08567758e21 / 3.15569e10) ** 2
+    d = 1.0 * 0.6 * MP / DU
+    P = 1.0 * KB * 3.0e5 / PU
+    flat, dims = ghosted(ic.constant(n, rho=d, P=P, gamma=gamma), g, [1] * 6)
+    before = flat.copy()
+    oracle.cooling_update(flat, *dims, g, 5, False, 0.05, gamma)
+    r0, r1 = real_view(before, dims, g), real_view(flat, dims, g)
+    assert np.array_equal(r0[:4], r1[:4]) and (r1[4] < r0[4]).all()
+    T1 = r1[4] * (gamma - 1.0) * PU / (1.0 * KB)
+    assert np.all(T1 < 3.0e5) and np.all(T1 > 1.0e4)
+    assert np.array_equal(flat.reshape(5, -1)[:, 0], before.reshape(5, -1)[:, 0])  # ghost cells untouched
