@@ -123,8 +123,11 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   bool const passive = !cfg->mhd && (cfg->n_scalars > 0 || cfg->dual_energy);
   if (passive) {  // the reference compiles NSCALARS / DE in; here each built combination is its own kernel TU
     if (cfg->precision == 1) return fail(CHL_ERR_UNSUPPORTED, "chl_create: scalars / dual energy are built in fp64 only");
-    if (cfg->recon > CHL_RECON_PPMC || (cfg->solver != CHL_SOLVER_HLLC && cfg->solver != CHL_SOLVER_ROE && cfg->solver != CHL_SOLVER_HLL))
-      return fail(CHL_ERR_UNSUPPORTED, "chl_create: scalars / dual energy are built for PCM, PLMC, PPMC with HLLC, Roe, HLL");
+    bool const pxmp = cfg->recon == CHL_RECON_PLMP || cfg->recon == CHL_RECON_PPMP;
+    if ((cfg->solver != CHL_SOLVER_HLLC && cfg->solver != CHL_SOLVER_ROE && cfg->solver != CHL_SOLVER_HLL) ||
+        (pxmp && cfg->solver != CHL_SOLVER_HLLC))
+      return fail(CHL_ERR_UNSUPPORTED,
+                  "chl_create: scalars / dual energy are built for PCM, PLMC, PPMC with HLLC, Roe, HLL and PLMP, PPMP with HLLC");
     if (cfg->n_scalars == 1 && !cfg->dual_energy) ops = cfg->strict ? chl::mode_ops_f64_strict_s1() : chl::mode_ops_f64_fast_s1();
     else if (cfg->n_scalars == 0) ops = cfg->strict ? chl::mode_ops_f64_strict_de() : chl::mode_ops_f64_fast_de();
     else if (cfg->n_scalars == 1) ops = cfg->strict ? chl::mode_ops_f64_strict_de_s1() : chl::mode_ops_f64_fast_de_s1();

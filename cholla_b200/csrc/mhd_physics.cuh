@@ -259,6 +259,8 @@ __device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const 
       t4[i] = ns * (spd + sx) + qfA - afB;
       t6[i] = nf * (spd + fx) - qsA + asB;
     }
+    // (inlined on purpose: the out-of-line form that pays off in the hydro sweeps -- CHL_PPM_CALL, hydro_physics.cuh -- costs
+    // 17.2 -> 17.7 ms per Orszag-Tang 256^3 step here, gpurun_out/r16_run16.txt: at 128 registers the calls spill)
     ppm_single(t0[0], t0[1], t0[2], t0[3], t0[4], cl[0], cr[0], k);
     ppm_single(t6[0], t6[1], t6[2], t6[3], t6[4], cl[6], cr[6], k);
     ppm_single(t2[0], t2[1], t2[2], t2[3], t2[4], cl[2], cr[2], k);

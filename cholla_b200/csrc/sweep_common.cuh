@@ -160,6 +160,13 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
     Cons const cl = cons_from_prim_plmp(l, k), cr = cons_from_prim_plmp(r, k);
     L = S5{{cl.d, cl.mx, cl.my, cl.mz, cl.E}};
     R = S5{{cr.d, cr.mx, cr.my, cr.mz, cr.E}};
+#if CHL_NP > 0
+#pragma unroll
+    for (int i = 0; i < kNP; i++) {
+      L.q[i] = cl.q[i];
+      R.q[i] = cr.q[i];
+    }
+#endif
 #else
     L = iface_state(l, k);
     R = iface_state(r, k);
@@ -202,9 +209,15 @@ __device__ __forceinline__ Half half_state(U5 const &c, K const &k, int plmp)
     Real const ex = u[4] - RC(0.5) * w.d * (w.vx * w.vx + w.vy * w.vy + w.vz * w.vz);
     Real const ey = u[4] - RC(0.5) * w.d * (w.vy * w.vy + w.vz * w.vz + w.vx * w.vx);
     Real const ez = u[4] - RC(0.5) * w.d * (w.vz * w.vz + w.vx * w.vx + w.vy * w.vy);
+#if CHL_DE  // plmp_cuda.cu:116-124, ppmp_cuda.cu:163-170: Get_Pressure_From_DE on the same remainder
+    h.w[4] = de_pressure(u[4], ex, c.q[kNP - 1], k);
+    h.w[5] = de_pressure(u[4], ey, c.q[kNP - 1], k);
+    h.w[6] = de_pressure(u[4], ez, c.q[kNP - 1], k);
+#else
     h.w[4] = max_s(ex * (gamma - RC(1.)), kTiny);
     h.w[5] = max_s(ey * (gamma - RC(1.)), kTiny);
     h.w[6] = max_s(ez * (gamma - RC(1.)), kTiny);
+#endif
     return h;
   }
   // y sweep sums vy^2 + (vz^2 + vx^2), z sweep vz^2 + (vx^2 + vy^2)

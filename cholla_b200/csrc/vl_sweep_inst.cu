@@ -187,7 +187,7 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   p.plmp      = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
   p.de_term   = (const Real *)a.de_term;
 #if CHL_NP > 0
-  // -DSCALAR / -DDE builds: the Van Leer integrator with PCM / PLMC / PPMC and HLLC / Roe / HLL
+  // -DSCALAR / -DDE builds: the Van Leer integrator with PCM / PLMC / PPMC and HLLC / Roe / HLL, PLMP / PPMP with HLLC
   if (a.simple || (solver != kHLLC && solver != kROE && solver != kHLL)) return cudaErrorNotSupported;
   if (CHL_DE && !p.de_term) return cudaErrorInvalidValue;
   if (stage == 0) {
@@ -196,6 +196,8 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
     return run_dirs<kPCM, kHLLC, 0>(p, a, s);
   }
   switch (recon * 4 + solver) {
+    case kPLMP * 4 + kHLLC: return run_dirs<kPLMP, kHLLC, 1>(p, a, s);  // builds/make.type.cooling: PPMP + HLLC + DE
+    case kPPMP * 4 + kHLLC: return run_dirs<kPPMP, kHLLC, 1>(p, a, s);
     case kPCM * 4 + kHLLC: return run_dirs<kPCM, kHLLC, 1>(p, a, s);
     case kPCM * 4 + kROE: return run_dirs<kPCM, kROE, 1>(p, a, s);
     case kPCM * 4 + kHLL: return run_dirs<kPCM, kHLL, 1>(p, a, s);

@@ -1089,6 +1089,74 @@ static void reconstruct_x(int recon, const double *U, double *QL, double *QR, in
         store_interface_x(R, qr, QR, id - stride, N, o1, o2, o3, gamma, np);
       }
 }
+/* PLMP_cuda / PPMP_cuda of a -DDE / -DSCALAR build under -DVL (plmp_cuda.cu:108-262, ppmp_cuda.cu:155-283, 353-374):
+ * their own load (plain kinetic-energy sum of the rotated velocities, Get_Pressure_From_DE) and the limiter of the
+ * primitive variables applied to every passive field per unit mass */
+static prim_t plmp_load_x(const double *U, size_t id, size_t N, int o1, int o2, int o3, double gamma, int ns, int de, double *q)
+{
+  prim_t w;
+  w.d  = U[id];
+  w.vx = U[(size_t)o1 * N + id] / w.d;
+  w.vy = U[(size_t)o2 * N + id] / w.d;
+  w.vz = U[(size_t)o3 * N + id] / w.d;
+  if (de) {
+    double E = U[4 * N + id], E_kin = 0.5 * w.d * (w.vx * w.vx + w.vy * w.vy + w.vz * w.vz);
+    double dge = U[(size_t)(5 + ns) * N + id];
+    w.p   = de_pressure(E, E - E_kin, dge, gamma);
+    q[ns] = dge / w.d;
+  } else {
+    w.p = (U[4 * N + id] - 0.5 * w.d * (w.vx * w.vx + w.vy * w.vy + w.vz * w.vz)) * (gamma - 1.0);
+  }
+  w.p = fmax(w.p, ORC_TINY);
+  for (int i = 0; i < ns; i++) q[i] = U[(size_t)(5 + i) * N + id] / w.d;
+  return w;
+}
+static void pxmp_dir_x(int recon, const double *U, double *QL, double *QR, int nx, int ny, int nz, double gamma, int dir,
+                       int ns, int de)
+{
+  size_t N = (size_t)nx * ny * nz;
+  int o1, o2, o3, np = ns + de;
+  dir_perm(dir, &o1, &o2, &o3);
+  long stride = dir == 0 ? 1 : (dir == 1 ? nx : (long)nx * ny);
+  int n[3] = {nx, ny, nz};
+  int const ppm = recon == ORC_PPMP;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int z = 0; z < nz; z++)
+    for (int y = 0; y < ny; y++)
+      for (int x = 0; x < nx; x++) {
+        int c = dir == 0 ? x : (dir == 1 ? y : z);
+        if (ppm ? (c < 2 || c >= n[dir] - 3) : (c < 1 || c >= n[dir] - 2)) continue;
+        size_t id = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * z);
+        prim_t w[5];
+        double q[5][ORC_MAXP], qlo[ORC_MAXP], qhi[ORC_MAXP];
+        for (int k = ppm ? 0 : 1; k < (ppm ? 5 : 4); k++)
+          w[k] = plmp_load_x(U, id + (k - 2) * stride, N, o1, o2, o3, gamma, ns, de, q[k]);
+        prim_t lo, hi;
+        if (ppm) {
+          ppmp_var(w[0].d, w[1].d, w[2].d, w[3].d, w[4].d, &lo.d, &hi.d);
+          ppmp_var(w[0].vx, w[1].vx, w[2].vx, w[3].vx, w[4].vx, &lo.vx, &hi.vx);
+          ppmp_var(w[0].vy, w[1].vy, w[2].vy, w[3].vy, w[4].vy, &lo.vy, &hi.vy);
+          ppmp_var(w[0].vz, w[1].vz, w[2].vz, w[3].vz, w[4].vz, &lo.vz, &hi.vz);
+          ppmp_var(w[0].p, w[1].p, w[2].p, w[3].p, w[4].p, &lo.p, &hi.p);
+          for (int i = 0; i < np; i++) ppmp_var(q[0][i], q[1][i], q[2][i], q[3][i], q[4][i], &qlo[i], &qhi[i]);
+        } else {
+          plmp_interface(w[1].d, w[2].d, w[3].d, &lo.d, &hi.d);
+          plmp_interface(w[1].vx, w[2].vx, w[3].vx, &lo.vx, &hi.vx);
+          plmp_interface(w[1].vy, w[2].vy, w[3].vy, &lo.vy, &hi.vy);
+          plmp_interface(w[1].vz, w[2].vz, w[3].vz, &lo.vz, &hi.vz);
+          plmp_interface(w[1].p, w[2].p, w[3].p, &lo.p, &hi.p);
+          for (int i = 0; i < np; i++) plmp_interface(q[1][i], q[2][i], q[3][i], &qlo[i], &qhi[i]);
+        }
+        lo.d = fmax(lo.d, ORC_TINY); hi.d = fmax(hi.d, ORC_TINY);
+        lo.p = fmax(lo.p, ORC_TINY); hi.p = fmax(hi.p, ORC_TINY);
+        plmp_store(lo, QR, id - stride, N, o1, o2, o3, gamma);
+        plmp_store(hi, QL, id, N, o1, o2, o3, gamma);
+        for (int i = 0; i < np; i++) {
+          QR[(size_t)(5 + i) * N + id - stride] = lo.d * qlo[i];
+          QL[(size_t)(5 + i) * N + id]          = hi.d * qhi[i];
+        }
+      }
+}
 static void pcm_dir_x(const double *U, double *QL, double *QR, int nx, int ny, int nz, int dir, int nf)
 {
   size_t N = (size_t)nx * ny * nz;
@@ -1131,7 +1199,7 @@ static void riemann_x(int solver, const double *QL, const double *QR, double *F,
 int orc_vl_step_x(double *U, int nx, int ny, int nz, int n_ghost, double dx, double dy, double dz, double dt,
                   double gamma, int recon, int solver, double density_floor, int ns, int de)
 {
-  if (recon != ORC_PCM && recon != ORC_PLMC && recon != ORC_PPMC) return -1;
+  if (recon < ORC_PCM || recon > ORC_PPMP) return -1;
   if (solver != ORC_HLLC && solver != ORC_ROE && solver != ORC_HLL) return -1;
   if (ns + de > ORC_MAXP) return -1;
   size_t N = (size_t)nx * ny * nz;
@@ -1190,6 +1258,7 @@ int orc_vl_step_x(double *U, int nx, int ny, int nz, int n_ghost, double dx, dou
   }
   for (int d = 0; d < ndim; d++) {
     if (recon == ORC_PCM) pcm_dir_x(Uh, QL[d], QR[d], nx, ny, nz, d, nf);
+    else if (recon == ORC_PLMP || recon == ORC_PPMP) pxmp_dir_x(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d, ns, de);
     else reconstruct_x(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d, ns, de);
     riemann_x(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d, ns, de);
   }

@@ -77,7 +77,9 @@ def run_child(**kw):
 
 
 @pytest.mark.parametrize("recon,de,n,flags", [(2, 0, (29, 21, 19), [1, 1, 1, 1, 1, 1]), (1, 1, (29, 21, 19), [1, 1, 1, 1, 1, 1]),
-                                              (1, 1, (45, 23, 1), [3, 3, 3, 3, 0, 0]), (2, 0, (64, 1, 1), [3, 3, 0, 0, 0, 0])])
+                                              (1, 1, (45, 23, 1), [3, 3, 3, 3, 0, 0]), (2, 0, (64, 1, 1), [3, 3, 0, 0, 0, 0]),
+                                              # builds/make.type.cooling as shipped: PPMP + HLLC + VL + DE + COOLING_GPU
+                                              (4, 1, (29, 21, 19), [1, 1, 1, 1, 1, 1]), (4, 1, (45, 23, 1), [3, 3, 3, 3, 0, 0])])
 def test_cie_cooling_matches_the_reference_build(recon, de, n, flags):
     from oracle import reference
     variant = ("_de" if de else "") + "_cool"

@@ -226,8 +226,8 @@ def test_sod_deck_with_dual_energy_and_scalar_snapshot_and_restart(tmp_path):
         assert f["GasEnergy"].shape == (64,) and f["scalar0"].shape == (64,)
         assert np.allclose(f["scalar0"].read()[:32], 1.0) and np.all(f["scalar0"].read()[32:] == 0.0)
         assert np.allclose(f["GasEnergy"].read()[:32], 1.0 / (gamma - 1.0))
-    # the scalar marks the left state: it stays within [0, rho] and follows the contact
-    assert got[5].min() >= 0.0 and np.all(got[5] <= got[0] * (1 + 1e-12))
+    # the scalar marks the left state: it stays within [0, rho] (PPM undershoots by denormal amounts ahead of the contact)
+    assert got[5].min() >= -1e-100 and np.all(got[5] <= got[0] * (1 + 1e-12))
     # restart from the last full snapshot and continue to the same time: same bytes as the uninterrupted run
     with h5lite.File(files[-1]) as f:
         n_last = int(f.attrs["n_step"][0])

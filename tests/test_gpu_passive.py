@@ -88,7 +88,7 @@ def _have(recon, solver, ns, de):
 
 
 # (recon, solver, n_scalars, dual_energy): the -DDE / -DSCALAR reference builds of oracle/ref_build/Makefile
-REF_BUILDS = [(2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1), (1, 1, 1, 1), (1, 0, 0, 1), (2, 3, 1, 1)]
+REF_BUILDS = [(2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1), (1, 1, 1, 1), (1, 0, 0, 1), (2, 3, 1, 1), (3, 0, 1, 1)]  # 3 = PLMP
 
 
 @pytest.mark.parametrize("recon,solver,ns,de", REF_BUILDS)
@@ -132,7 +132,8 @@ def test_passive_density_floor_scales_gas_energy_not_scalars():
     assert r["oracle_vs_ref"]["ulp"] == 0 and r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], json.dumps(r)
 
 
-@pytest.mark.parametrize("recon,solver,ns,de", [(0, 0, 1, 1), (1, 3, 1, 0), (2, 1, 0, 1), (0, 1, 1, 0), (1, 0, 1, 1)])
+@pytest.mark.parametrize("recon,solver,ns,de", [(0, 0, 1, 1), (1, 3, 1, 0), (2, 1, 0, 1), (0, 1, 1, 0), (1, 0, 1, 1),
+                                                (4, 0, 1, 1), (3, 0, 1, 0), (4, 0, 0, 1)])  # 3 / 4 = PLMP / PPMP
 def test_passive_combinations_without_a_reference_build_match_the_oracle(recon, solver, ns, de):
     """The rest of the built matrix against the CPU oracle alone (itself bit-equal to the reference on the builds above).
     PCM's corrector reconstructs from primitives here, so it carries prim -> cons round-off like the five-field path."""

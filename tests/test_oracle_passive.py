@@ -9,14 +9,13 @@ from helpers import ghosted, real_view
 
 
 def _state(n, ns, de, gamma, recon, icname="random_smooth"):
-    g = {0: 2, 1: 3, 2: 4}[recon]
+    g = {0: 2, 1: 3, 2: 4, 3: 3, 4: 4}[recon]
     fields = ic.with_passive(getattr(ic, icname)(n, seed=3), ns, de, gamma)
     flat, dims = ghosted(fields, g, [1, 1, 1, 1, 1, 1] if n[2] > 1 else ([1, 1, 1, 1, 0, 0] if n[1] > 1 else [1, 1, 0, 0, 0, 0]))
     return flat, dims, g
 
 
-@pytest.mark.parametrize("recon", [0, 1, 2])
-@pytest.mark.parametrize("solver", [0, 1, 3])
+@pytest.mark.parametrize("recon,solver", [(r, s) for r in (0, 1, 2) for s in (0, 1, 3)] + [(3, 0), (4, 0)])
 def test_scalars_do_not_feed_back_and_follow_the_mass(recon, solver):
     n, gamma = (14, 12, 10), 1.4
     flat, dims, g = _state(n, 1, False, gamma, recon)
