@@ -76,6 +76,7 @@ def lib():
     L.chl_set_gravity_field.argtypes = [p, p, p]
     L.chl_gravity_field_ptr.argtypes = [p, C.POINTER(p)]
     L.chl_copy_gravity_field.argtypes = [p, p, p]
+    L.chl_set_gravity_potential.argtypes = [p, p, i]
     L.chl_set_ghost_cells.argtypes = [p, p, ip, i, p]
     L.chl_set_boundaries.argtypes = [p, p, ip, p]
     L.chl_set_ghost_cells_ext.argtypes = [p, i, i, i, i, i, i, ip, i, i, i, i, i, i, i, i, i, p]

@@ -48,7 +48,9 @@ struct chl_ctx {
   void *d_half;               // W at t + dt/2 (primitives), half_fields * n_cells reals
   void *d_acc;                // direction-split sweeps: running sum of flux differences, (5 + passive) * n_cells reals
   void *d_grav;               // static gravity: [ndim][n_cells] accelerations (nullptr = off), chl_set_static_gravity
-  void *d_gold;               // static gravity: (rho, momentum)^n, 4 * n_cells reals, copied before the corrector
+  const void *d_pot;          // -DGRAVITY: the caller's potential (nullptr = off), chl_set_gravity_potential
+  int pot_five_point;
+  void *d_gold;               // gravity: (rho, momentum)^n, 4 * n_cells reals, copied before the corrector
   void *d_de;                 // -DDE contexts: n_cells reals, the p div v term / partially updated GasEnergy (de_term)
   chl::MhdOps const *mhd;     // non-null in an MHD context
   void *d_prim;               // MHD: half-step primitives + cell-centred fields
@@ -159,6 +161,8 @@ int chl_create(const chl_config *cfg, chl_ctx **out)
   c->d_acc = nullptr;
   c->d_de = nullptr;
   c->d_grav = c->d_gold = nullptr;
+  c->d_pot = nullptr;
+  c->pot_five_point = 0;
   c->mhd = mhd;
   c->d_prim = c->d_ctf = c->d_E = nullptr;
   c->dir_chunk = 0;
@@ -324,7 +328,7 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
   // -DTEMPERATURE_FLOOR builds floor unconditionally (grid3D.cpp:493-503): with the default threshold 0 the pass resets a
   // negative internal energy to zero; a negative temperature_floor_U stands for a build without the macro
   int const want_tfloor = (fused && g.temperature_floor_U >= 0.0 && c->ndim == 3) ? 1 : 0;
-  bool const grav = c->d_grav != nullptr;
+  bool const grav = c->d_grav != nullptr || (c->d_pot != nullptr && c->ndim == 3);
   if (fused) {
     // a -DDE context floors and reduces after Select_Internal_Energy / Sync_Energies (ModeOps::de_finish), a context with
     // static gravity after the source terms -- not in the sweep
@@ -342,7 +346,10 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
     if (de) CHL_CUDA(c->ops->de_term(U, c->d_de, g.nx, g.ny, g.nz, a.lo, a.hi, a.dtodx, a.dtody, a.dtodz, g.gamma, 1, s));
     if (grav) CHL_CUDA(cudaMemcpyAsync(c->d_gold, U, 4 * c->n_cells * rb, cudaMemcpyDeviceToDevice, s));
     CHL_CUDA(sweep(1, g.recon, g.solver, a, s));
-    if (grav) CHL_CUDA(chl::launch_gravity_source(U, c->d_gold, c->d_grav, g.nx, g.ny, g.nz, g.n_ghost, dt, (int)rb, s));
+    if (c->d_grav) CHL_CUDA(chl::launch_gravity_source(U, c->d_gold, c->d_grav, g.nx, g.ny, g.nz, g.n_ghost, dt, (int)rb, s));
+    if (c->d_pot && c->ndim == 3)
+      CHL_CUDA(chl::launch_gravity_potential_source(U, c->d_gold, c->d_pot, g.nx, g.ny, g.nz, g.n_ghost, dt, g.dx, g.dy, g.dz,
+                                                    c->pot_five_point, (int)rb, s));
     if (de) {
       CHL_CUDA(c->ops->de_finish(U, g.nx, g.ny, g.nz, g.n_ghost, g.gamma, want_tfloor, g.temperature_floor_U, fused ? 1 : 0,
                                  g.dx, g.dy, g.dz, c->d_key, s));
@@ -387,7 +394,8 @@ static int simple_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s
   if (!c || !U) return fail(CHL_ERR_INVALID, "chl_simple_step: null argument");
   chl_config const &g = c->cfg;
   if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: MHD requires the Van Leer integrator (error_handling.cpp:89)");
-  if (c->d_grav) return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: static gravity is built for the Van Leer integrator");
+  if (c->d_grav || c->d_pot)
+    return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: the gravity source terms are built for the Van Leer integrator");
   if (c->ops->n_passive)
     return fail(CHL_ERR_UNSUPPORTED, "chl_simple_step: scalars / dual energy are built for the Van Leer integrator");
   if (g.recon != CHL_RECON_PCM && g.recon != CHL_RECON_PLMC)
@@ -559,11 +567,28 @@ int chl_apply_temperature_floor(chl_ctx *c, void *U, double U_floor, void *strea
   return CHL_OK;
 }
 
-static int gravity_alloc(chl_ctx *c)
+static int gravity_alloc(chl_ctx *c, bool field)
 {
   size_t const w = c->n_cells * c->ops->real_bytes;
-  if (!c->d_grav) CHL_CUDA(cudaMalloc(&c->d_grav, (size_t)c->ndim * w));
+  if (field && !c->d_grav) CHL_CUDA(cudaMalloc(&c->d_grav, (size_t)c->ndim * w));
   if (!c->d_gold) CHL_CUDA(cudaMalloc(&c->d_gold, 4 * w));
+  return CHL_OK;
+}
+
+int chl_set_gravity_potential(chl_ctx *c, const void *d_potential, int five_point)
+{
+  if (!c) return fail(CHL_ERR_INVALID, "chl_set_gravity_potential: null context");
+  if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_set_gravity_potential: hydro contexts only");
+  if (d_potential && c->ndim != 3)
+    return fail(CHL_ERR_INVALID, "chl_set_gravity_potential: the reference's -DGRAVITY source terms exist in 3-D only");
+  if (d_potential && five_point && c->cfg.n_ghost < 2)
+    return fail(CHL_ERR_INVALID, "chl_set_gravity_potential: the five-point gradient needs two ghost layers");
+  if (d_potential) {
+    int const r = gravity_alloc(c, false);
+    if (r != CHL_OK) return r;
+  }
+  c->d_pot = d_potential;
+  c->pot_five_point = five_point ? 1 : 0;
   return CHL_OK;
 }
 
@@ -575,11 +600,14 @@ int chl_set_static_gravity(chl_ctx *c, int custom_grav, int x_off, int y_off, in
   if (custom_grav < 0) {
     CHL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     if (c->d_grav) cudaFree(c->d_grav);
-    if (c->d_gold) cudaFree(c->d_gold);
-    c->d_grav = c->d_gold = nullptr;
+    c->d_grav = nullptr;
+    if (c->d_gold && !c->d_pot) {
+      cudaFree(c->d_gold);
+      c->d_gold = nullptr;
+    }
     return CHL_OK;
   }
-  int const r = gravity_alloc(c);
+  int const r = gravity_alloc(c, true);
   if (r != CHL_OK) return r;
   chl_config const &g = c->cfg;
   int const off[3] = {x_off, y_off, z_off};
@@ -593,7 +621,7 @@ int chl_set_gravity_field(chl_ctx *c, const void *d_g, void *stream)
 {
   if (!c || !d_g) return fail(CHL_ERR_INVALID, "chl_set_gravity_field: null argument");
   if (c->mhd) return fail(CHL_ERR_UNSUPPORTED, "chl_set_gravity_field: hydro contexts only");
-  int const r = gravity_alloc(c);
+  int const r = gravity_alloc(c, true);
   if (r != CHL_OK) return r;
   CHL_CUDA(cudaMemcpyAsync(c->d_grav, d_g, (size_t)c->ndim * c->n_cells * c->ops->real_bytes, cudaMemcpyDeviceToDevice,
                            (cudaStream_t)stream));

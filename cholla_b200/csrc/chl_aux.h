@@ -16,6 +16,9 @@ cudaError_t launch_divb(const void *c, int nx, int ny, int nz, double dx, double
 // grav_kernels.cu: static gravity (-DSTATIC_GRAV): the acceleration field, once; the corrector's source terms, per step
 cudaError_t launch_static_gravity_field(void *g_out, int nx, int ny, int nz, int n_ghost, int custom_grav, const int off[3],
                                         const double d[3], const double bound[3], int real_bytes, cudaStream_t s);
+cudaError_t launch_gravity_potential_source(void *U, const void *old, const void *pot, int nx, int ny, int nz, int n_ghost,
+                                            double dt, double dx, double dy, double dz, int five_point, int real_bytes,
+                                            cudaStream_t s);
 cudaError_t launch_gravity_source(void *U, const void *old, const void *g, int nx, int ny, int nz, int n_ghost, double dt,
                                   int real_bytes, cudaStream_t s);
 // cooling_kernels.cu: Cooling_Update with the analytic CIE curve (-DCOOLING_GPU without -DCLOUDY_COOL)

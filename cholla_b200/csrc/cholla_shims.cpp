@@ -136,9 +136,22 @@ void VL_Algorithm_3D_CUDA(Real *d_conserved, Real *d_grav_potential, int nx, int
                           int z_off, int n_ghost, Real dx, Real dy, Real dz, Real xbound, Real ybound, Real zbound,
                           Real dt, int n_fields, int custom_grav, Real density_floor, Real *host_grav_potential)
 {
-  (void)d_grav_potential; (void)host_grav_potential;  // self-gravity (-DGRAVITY) builds are out of scope
+  (void)host_grav_potential;
   chl_ctx *const c = context(nx, ny, nz, n_ghost, n_fields, dx, dy, dz, density_floor);
   gravity(c, custom_grav, x_off, y_off, z_off, xbound, ybound, zbound);
+#ifdef GRAVITY  // the potential-gradient source terms of the update kernel; the Poisson solve stays the reference's
+  #ifndef GRAVITY_GPU
+    #error "cholla_shims.cpp: -DGRAVITY needs -DGRAVITY_GPU (the potential must already be in device memory)"
+  #endif
+  #ifdef GRAVITY_5_POINTS_GRADIENT
+  int const rcp = chl_set_gravity_potential(c, d_grav_potential, 1);
+  #else
+  int const rcp = chl_set_gravity_potential(c, d_grav_potential, 0);
+  #endif
+  if (rcp != CHL_OK) die("chl_set_gravity_potential", rcp);
+#else
+  (void)d_grav_potential;
+#endif
   int const rc = chl_vl_step(c, d_conserved, dt, nullptr);
   if (rc != CHL_OK) die("chl_vl_step", rc);
 }

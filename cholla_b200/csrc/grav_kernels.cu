@@ -160,6 +160,44 @@ __global__ void __launch_bounds__(256) gravity_source_kernel(T *__restrict__ U, 
   }
 }
 
+// The -DGRAVITY branch of Update_Conserved_Variables_3D (hydro_cuda.cu:317-379): acceleration from the centred gradient of
+// the potential the caller's Poisson solver left in device memory (3-point, or -DGRAVITY_5_POINTS_GRADIENT -- whose y and
+// z components divide by 12 dx like the x one, reproduced here), momentum sources 0.5 dt g (rho^n + rho^{n+1}) and the work
+// 0.5 dt g . (rho v^n + rho v^{n+1}).  3-D only, like the reference.
+template <typename T>
+__global__ void __launch_bounds__(256) gravity_potential_source_kernel(T *__restrict__ U, const T *__restrict__ old,
+                                                                       const T *__restrict__ pot, int nx, int ny, int nz,
+                                                                       int ng, T dt, T dx, T dy, T dz, int five_point)
+{
+  long const N = (long)nx * ny * nz;
+  int const rx = nx - 2 * ng, ry = ny - 2 * ng, rz = nz - 2 * ng;
+  long const n = (long)rx * ry * rz, sy = nx, sz = (long)nx * ny;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    int const x = (int)(t % rx) + ng;
+    long const r = t / rx;
+    int const y = (int)(r % ry) + ng, z = (int)(r / ry) + ng;
+    long const id = x + (long)nx * (y + (long)ny * z);
+    T const d = old[id], d_inv = (T)1.0 / d;
+    T const vx = old[N + id] * d_inv, vy = old[2 * N + id] * d_inv, vz = old[3 * N + id] * d_inv;
+    T const d_n = U[id], d_inv_n = (T)1.0 / d_n;
+    T const vx_n = U[N + id] * d_inv_n, vy_n = U[2 * N + id] * d_inv_n, vz_n = U[3 * N + id] * d_inv_n;
+    T gx, gy, gz;
+    if (five_point) {
+      gx = -1 * (-pot[id + 2] + 8 * pot[id + 1] - 8 * pot[id - 1] + pot[id - 2]) / (12 * dx);
+      gy = -1 * (-pot[id + 2 * sy] + 8 * pot[id + sy] - 8 * pot[id - sy] + pot[id - 2 * sy]) / (12 * dx);
+      gz = -1 * (-pot[id + 2 * sz] + 8 * pot[id + sz] - 8 * pot[id - sz] + pot[id - 2 * sz]) / (12 * dx);
+    } else {
+      gx = (T)-0.5 * (pot[id + 1] - pot[id - 1]) / dx;
+      gy = (T)-0.5 * (pot[id + sy] - pot[id - sy]) / dy;
+      gz = (T)-0.5 * (pot[id + sz] - pot[id - sz]) / dz;
+    }
+    U[N + id] += (T)0.5 * dt * gx * (d + d_n);
+    U[2 * N + id] += (T)0.5 * dt * gy * (d + d_n);
+    U[3 * N + id] += (T)0.5 * dt * gz * (d + d_n);
+    U[4 * N + id] += (T)0.5 * dt * (gx * (d * vx + d_n * vx_n) + gy * (d * vy + d_n * vy_n) + gz * (d * vz + d_n * vz_n));
+  }
+}
+
 int grid_for(long n)
 {
   long b = (n + 255) / 256;
@@ -200,6 +238,20 @@ cudaError_t launch_gravity_source(void *U, const void *old, const void *g, int n
     if (ndim == 3) CHL_S(float, 3); else if (ndim == 2) CHL_S(float, 2); else CHL_S(float, 1);
   }
 #undef CHL_S
+  return cudaGetLastError();
+}
+cudaError_t launch_gravity_potential_source(void *U, const void *old, const void *pot, int nx, int ny, int nz, int n_ghost,
+                                            double dt, double dx, double dy, double dz, int five_point, int real_bytes,
+                                            cudaStream_t s)
+{
+  long const n = (long)(nx - 2 * n_ghost) * (ny - 2 * n_ghost) * (nz - 2 * n_ghost);
+  int const b = grid_for(n);
+  if (real_bytes == 8)
+    gravity_potential_source_kernel<double><<<b, 256, 0, s>>>((double *)U, (const double *)old, (const double *)pot, nx, ny,
+                                                             nz, n_ghost, dt, dx, dy, dz, five_point);
+  else
+    gravity_potential_source_kernel<float><<<b, 256, 0, s>>>((float *)U, (const float *)old, (const float *)pot, nx, ny, nz,
+                                                            n_ghost, (float)dt, (float)dx, (float)dy, (float)dz, five_point);
   return cudaGetLastError();
 }
 }  // namespace chl

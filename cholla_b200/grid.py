@@ -336,6 +336,23 @@ class Grid3D:
         if self.static_gravity:
             self.overlap = False  # the source terms follow the whole corrector: the exchange cannot start before them
 
+    def Set_Gravity_Potential(self, potential, five_point=True):
+        """A -DGRAVITY build: `potential` is this rank's potential with ghost cells (numpy (nz, ny, nx) or a device tensor),
+        as the reference's Poisson solver leaves it in d_grav_potential; None switches the source terms off.  The array is
+        kept on the device and read by every later step (chl_set_gravity_potential)."""
+        if potential is None:
+            self._potential = None
+            check(_lib.lib().chl_set_gravity_potential(self._ctx, None, 0), "chl_set_gravity_potential")
+            return
+        torch = self.torch
+        if not isinstance(potential, torch.Tensor):
+            potential = torch.from_numpy(np.ascontiguousarray(potential, dtype=np.float64).reshape(-1))
+        self._potential = potential.to(self.device, self.dtype).contiguous()
+        assert self._potential.numel() == self.H.n_cells
+        check(_lib.lib().chl_set_gravity_potential(self._ctx, self._ptr(self._potential), int(bool(five_point))),
+              "chl_set_gravity_potential")
+        self.overlap = False
+
     def gravity_field(self):
         """The device's [ndim][n_cells] acceleration arrays as a host array (None when gravity is off)."""
         p = C.c_void_p()

@@ -49,6 +49,7 @@ def lib():
         _lib.orc_cie_cool.restype = d
         _lib.orc_static_gravity_field.argtypes = [p, i, i, i, i, i, i, i, i, d, d, d, d, d, d]
         _lib.orc_set_gravity.argtypes = [p]
+        _lib.orc_set_gravity_potential.argtypes = [p, i]
         _lib.orc_boundary_extents.argtypes = [i, i, i, i, i, p, p]
         _lib.orc_set_ghost_cells.argtypes = [p, i, i, i, i, i, p, i]
         _lib.orc_set_boundaries.argtypes = [p, i, i, i, i, i, p]
@@ -141,6 +142,17 @@ def set_gravity(g):
     global _gravity_keepalive
     _gravity_keepalive = None if g is None else np.ascontiguousarray(g, dtype=np.float64)
     lib().orc_set_gravity(None if g is None else _ptr(_gravity_keepalive))
+
+
+_potential_keepalive = None
+
+
+def set_gravity_potential(pot, five_point=True):
+    """The potential (ghost cells included) whose gradient every later 3-D vl_step / vl_step_x adds the -DGRAVITY source
+    terms of (None: off)."""
+    global _potential_keepalive
+    _potential_keepalive = None if pot is None else np.ascontiguousarray(pot, dtype=np.float64).reshape(-1)
+    lib().orc_set_gravity_potential(None if pot is None else _ptr(_potential_keepalive), int(bool(five_point)))
 
 
 def simple_step(U, nx, ny, nz, n_ghost, dx, dy, dz, dt, gamma, recon, solver, density_floor=0.0):

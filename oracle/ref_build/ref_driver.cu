@@ -56,10 +56,13 @@ static void boundary_extents(int dir, int nx, int ny, int nz, int g, int *lo, in
 // only a -DSTATIC_GRAV build reads them
 static int g_custom_grav = 0;
 static double g_bound[3] = {0.0, 0.0, 0.0};
+// the device potential a -DGRAVITY -DGRAVITY_GPU build's Poisson solver would have left for the integrator
+static double *g_potential = nullptr;
 
 extern "C" {
 
 const char *ref_build_flags(void) { return REF_BUILD_FLAGS; }
+void ref_set_potential(double *d_potential) { g_potential = d_potential; }
 void ref_set_gravity(int custom_grav, double xbound, double ybound, double zbound)
 {
   g_custom_grav = custom_grav;
@@ -88,8 +91,8 @@ void ref_vl_step(double *d_conserved, int nx, int ny, int nz, int n_ghost, doubl
     fprintf(stderr, "ref_driver: this reference build has no 3-D Van Leer integrator\n");
     chexit(-1);
   #else
-    VL_Algorithm_3D_CUDA(d_conserved, nullptr, nx, ny, nz, 0, 0, 0, n_ghost, dx, dy, dz, g_bound[0], g_bound[1], g_bound[2],
-                         dt, n_fields, g_custom_grav, density_floor, nullptr);
+    VL_Algorithm_3D_CUDA(d_conserved, g_potential, nx, ny, nz, 0, 0, 0, n_ghost, dx, dy, dz, g_bound[0], g_bound[1],
+                         g_bound[2], dt, n_fields, g_custom_grav, density_floor, nullptr);
   #endif
   }
 #endif

@@ -42,13 +42,14 @@ def lib(recon, solver, nosync=False, dropin=False, simple=False, variant=""):
         L.ref_advance.restype = d
         L.ref_n_fields.restype = i
         L.ref_set_gravity.argtypes = [i, d, d, d]
+        L.ref_set_potential.argtypes = [p]
         _libs[key] = L
     return _libs[key]
 
 
 def advance(dev_tensor, dims, n_ghost, dx, dy, dz, gamma, recon, solver, flags, n_steps, cfl=0.3, density_floor=0.0,
             U_floor=0.0, nosync=False, timed=False, dropin=False, simple=False, variant="", custom_grav=0,
-            bounds=(0.0, 0.0, 0.0)):
+            bounds=(0.0, 0.0, 0.0), potential=None):
     """Run the reference's step loop on a torch CUDA float64 tensor (flat SoA, ghosts included), in place.
     Returns (dts, last_dti, ms or None).  One process may only use ONE grid shape per library: the reference
     keeps its scratch in globals sized at the first call (VL_3D_cuda.cu:58-133)."""
@@ -56,6 +57,8 @@ def advance(dev_tensor, dims, n_ghost, dx, dy, dz, gamma, recon, solver, flags, 
     assert dev_tensor.numel() == L.ref_n_fields() * dims[0] * dims[1] * dims[2], "field count of this reference build"
     L.ref_set_gamma(gamma)
     L.ref_set_gravity(custom_grav, bounds[0], bounds[1], bounds[2])  # read by -DSTATIC_GRAV builds (variant "..._sg") only
+    # -DGRAVITY builds ("..._grav5", "..._grav3"): a CUDA float64 tensor of n_cells, handed over as d_grav_potential
+    L.ref_set_potential(C.c_void_p(potential.data_ptr()) if potential is not None else None)
     fl = (C.c_int * 6)(*flags)
     dts = (C.c_double * max(n_steps, 1))()
     ms = C.c_float(0.0)

@@ -916,6 +916,32 @@ void orc_static_gravity_field(double *g, int nx, int ny, int nz, int n_ghost, in
 /* the field the next orc_vl_step / orc_vl_step_x calls add the source terms of ([ndim][N]; NULL = a build without gravity) */
 static const double *g_grav = NULL;
 void orc_set_gravity(const double *g) { g_grav = g; }
+/* -DGRAVITY (hydro_cuda.cu:317-379): potential with ghost cells, [N]; five_point = -DGRAVITY_5_POINTS_GRADIENT.  3-D only. */
+static const double *g_pot = NULL;
+static int g_pot5 = 0;
+void orc_set_gravity_potential(const double *pot, int five_point) { g_pot = pot; g_pot5 = five_point; }
+static void gravity_potential_cell(double *U, size_t N, size_t id, long sy, long sz, double dt, double dx, double dy,
+                                   double dz, double d, const double *m_old)
+{
+  double d_inv = 1.0 / d, vx = m_old[0] * d_inv, vy = m_old[1] * d_inv, vz = m_old[2] * d_inv;
+  double d_n = U[id], d_inv_n = 1.0 / d_n;
+  double vx_n = U[N + id] * d_inv_n, vy_n = U[2 * N + id] * d_inv_n, vz_n = U[3 * N + id] * d_inv_n;
+  const double *p = g_pot;
+  double gx, gy, gz;
+  if (g_pot5) { /* y and z divide by 12 dx as well, as the reference does */
+    gx = -1 * (-p[id + 2] + 8 * p[id + 1] - 8 * p[id - 1] + p[id - 2]) / (12 * dx);
+    gy = -1 * (-p[id + 2 * sy] + 8 * p[id + sy] - 8 * p[id - sy] + p[id - 2 * sy]) / (12 * dx);
+    gz = -1 * (-p[id + 2 * sz] + 8 * p[id + sz] - 8 * p[id - sz] + p[id - 2 * sz]) / (12 * dx);
+  } else {
+    gx = -0.5 * (p[id + 1] - p[id - 1]) / dx;
+    gy = -0.5 * (p[id + sy] - p[id - sy]) / dy;
+    gz = -0.5 * (p[id + sz] - p[id - sz]) / dz;
+  }
+  U[N + id] += 0.5 * dt * gx * (d + d_n);
+  U[2 * N + id] += 0.5 * dt * gy * (d + d_n);
+  U[3 * N + id] += 0.5 * dt * gz * (d + d_n);
+  U[4 * N + id] += 0.5 * dt * (gx * (d * vx + d_n * vx_n) + gy * (d * vy + d_n * vy_n) + gz * (d * vz + d_n * vz_n));
+}
 /* one cell: old = (rho, momenta)^n read before the flux update, U already updated (and density-floored) */
 static void gravity_source_cell(double *U, size_t N, size_t id, int ndim, double dt, double d, const double *m_old)
 {
@@ -1004,6 +1030,7 @@ void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, doub
             for (int f = 1; f < 5; f++) U[f * N + id] *= (density_floor / d0);
           }
           if (g_grav) gravity_source_cell(U, N, id, ndim, dt, d_old, m_old);
+          if (g_pot && ndim == 3) gravity_potential_cell(U, N, id, st[1], st[2], dt, dx, dy, dz, d_old, m_old);
           /* the rho<=0 neighbour-averaging branch (hydro_cuda.cu:292-297) races in the
            * reference and is not restated */
         }
@@ -1308,6 +1335,7 @@ int orc_vl_step_x(double *U, int nx, int ny, int nz, int n_ghost, double dx, dou
           if (de) U[(size_t)GE * N + id] *= (density_floor / d0);
         }
         if (g_grav) gravity_source_cell(U, N, id, ndim, dt, d_old, m_old);
+          if (g_pot && ndim == 3) gravity_potential_cell(U, N, id, st[1], st[2], dt, dx, dy, dz, d_old, m_old);
       }
   if (de) { /* Select_Internal_Energy_{1,2,3}D then Sync_Energies_{1,2,3}D (hydro_cuda.cu:835-1099) */
     double *sel = malloc(N * sizeof(double));

@@ -124,3 +124,76 @@ def test_gravity_with_dual_energy():
     assert "-DDE" in r["flags"].split() and "-DSTATIC_GRAV" in r["flags"].split(), json.dumps(r)
     assert r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], json.dumps(r)
     assert r["oracle"]["l1"] <= 1e-12, json.dumps(r)
+
+
+POT_CHILD = r"""
+import json, sys
+import numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import oracle
+from oracle import reference
+from cholla_b200 import initial_conditions as ic
+from cholla_b200.grid import Grid3D, n_ghost_for
+from helpers import ghosted, real_view, rel_l1, max_ulp
+
+recon, n, flags, gamma, steps, five, dropin = %(recon)d, %(n)r, %(flags)r, %(gamma)r, %(steps)d, %(five)d, %(dropin)d
+variant = "_grav5" if five else "_grav3"
+fields = ic.random_smooth(n, seed=8)
+g = n_ghost_for(recon)
+flat, dims = ghosted(fields, g, flags)
+d = [1.0 / n[i] for i in range(3)]
+# a smooth potential on the whole local array, ghost cells included (what the Poisson solver + its boundary fill leave)
+c = [((np.arange(dims[i]) - g) + 0.5) * d[i] for i in range(3)]
+Z, Y, X = np.meshgrid(c[2], c[1], c[0], indexing="ij")
+pot = -3.0 / np.sqrt((X - 0.45) ** 2 + (Y - 0.55) ** 2 + (Z - 0.5) ** 2 + 0.05) + 0.7 * np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y)
+pot = np.ascontiguousarray(pot.reshape(-1))
+out = {}
+pt = torch.from_numpy(pot).cuda()
+t = torch.from_numpy(flat.copy()).cuda()
+dts_ref, _, _ = reference.advance(t, dims, g, d[0], d[1], d[2], gamma, recon, 0, flags, steps, variant=variant, potential=pt)
+ref = t.cpu().numpy()
+out["flags"] = reference.lib(recon, 0, variant=variant).ref_build_flags().decode()
+if dropin:
+    t2 = torch.from_numpy(flat.copy()).cuda()
+    dts_d, _, _ = reference.advance(t2, dims, g, d[0], d[1], d[2], gamma, recon, 0, flags, steps, variant=variant, potential=pt,
+                                    dropin=True)
+    out["dropin"] = dict(equal=bool(np.array_equal(t2.cpu().numpy(), ref)), dt_equal=bool(dts_d == dts_ref))
+oracle.set_gravity_potential(pot, bool(five))
+orc = flat.copy()
+dts_orc = oracle.advance(orc, *dims, g, d[0], d[1], d[2], gamma, recon, 0, flags, steps)
+oracle.set_gravity_potential(None)
+plain = flat.copy()
+oracle.advance(plain, *dims, g, d[0], d[1], d[2], gamma, recon, 0, flags, steps)
+out["gravity_effect_l1"] = float(rel_l1(real_view(orc, dims, g), real_view(plain, dims, g)).max())
+out["oracle"] = dict(ulp=max_ulp(real_view(orc, dims, g), real_view(ref, dims, g)), dt_equal=bool(dts_orc == dts_ref))
+for strict in (True, False):
+    G = Grid3D(n, (1.0, 1.0, 1.0), recon=recon, solver=0, gamma=gamma, bc=flags, strict=strict)
+    G.Set_Gravity_Potential(pot.reshape(dims[2], dims[1], dims[0]), five_point=bool(five))
+    G.upload(flat)
+    dts = G.advance(steps)
+    got = G.download(); G.close()
+    out["strict" if strict else "fast"] = dict(ulp=max_ulp(real_view(got, dims, g), real_view(ref, dims, g)),
+                                               l1=float(rel_l1(real_view(got, dims, g), real_view(ref, dims, g)).max()),
+                                               dt_equal=bool(dts == dts_ref))
+print("RESULT " + json.dumps(out))
+"""
+
+
+@pytest.mark.parametrize("recon,five,dropin", [(2, 1, 1), (1, 0, 0)])
+def test_potential_gradient_source_terms_match_the_gravity_build(recon, five, dropin):
+    """-DGRAVITY -DGRAVITY_GPU (-DGRAVITY_5_POINTS_GRADIENT): the potential-gradient branch of Update_Conserved_Variables_3D
+    (hydro_cuda.cu:317-379) fed with a caller-supplied potential: reference kernels == oracle == strict kernels, and the
+    reference-signature driver linked against the shims gives the same bytes."""
+    variant = "_grav5" if five else "_grav3"
+    _need(recon, 0, variant)
+    kw = dict(root=ROOT, recon=recon, n=(29, 21, 19), flags=[1, 1, 1, 1, 1, 1], gamma=5.0 / 3.0, steps=3, five=five, dropin=dropin)
+    p = subprocess.run([sys.executable, "-c", POT_CHILD % kw], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    r = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert "-DGRAVITY" in r["flags"].split() and ("-DGRAVITY_5_POINTS_GRADIENT" in r["flags"].split()) == bool(five), json.dumps(r)
+    assert r["gravity_effect_l1"] > 1e-4, json.dumps(r)
+    assert r["oracle"]["ulp"] == 0 and r["oracle"]["dt_equal"], json.dumps(r)
+    assert r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], json.dumps(r)
+    assert r["fast"]["l1"] <= 1e-11, json.dumps(r)
+    if dropin:
+        assert r["dropin"]["equal"] and r["dropin"]["dt_equal"], json.dumps(r)

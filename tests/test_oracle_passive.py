@@ -129,3 +129,24 @@ def test_cie_cooling_oracle_curve_and_energy_loss():
     T1 = r1[4] * (gamma - 1.0) * PU / (1.0 * KB)
     assert np.all(T1 < 3.0e5) and np.all(T1 > 1.0e4)
     assert np.array_equal(flat.reshape(5, -1)[:, 0], before.reshape(5, -1)[:, 0])  # ghost cells untouched
+
+
+def test_gravity_potential_oracle_linear_potential_is_a_uniform_field():
+    """phi = a x + b y + c z: both gradient forms give g = -(a, b, c) -- except that the five-point y and z components divide
+    by 12 dx like the reference's (hydro_cuda.cu:345-365), so with dy = 2 dx the y acceleration doubles."""
+    n, g, gamma, dt = (12, 10, 8), 4, 1.4, 0.003
+    dx, dy, dz = 0.1, 0.2, 0.1
+    flat, dims = ghosted(ic.constant(n, rho=1.5, P=1.0, gamma=gamma), g, [1] * 6)
+    c = [np.arange(dims[i]) * s for i, s in enumerate((dx, dy, dz))]
+    Z, Y, X = np.meshgrid(c[2], c[1], c[0], indexing="ij")
+    pot = 0.3 * X + 0.5 * Y - 0.2 * Z
+    for five, gy in ((False, -0.5), (True, -0.5 * dy / dx)):
+        U = flat.copy()
+        oracle.set_gravity_potential(pot, five)
+        try:
+            oracle.vl_step(U, *dims, g, dx, dy, dz, dt, gamma, 2, 0)
+        finally:
+            oracle.set_gravity_potential(None)
+        r = real_view(U, dims, g)
+        assert np.allclose(r[1], 1.5 * dt * -0.3, rtol=1e-11) and np.allclose(r[3], 1.5 * dt * 0.2, rtol=1e-11)
+        assert np.allclose(r[2], 1.5 * dt * gy, rtol=1e-11)
