@@ -26,19 +26,28 @@ def main():
     mhd = os.environ.get("MGPU_MHD", "0") == "1"      # Orszag-Tang, PPMC + HLLD + CT (BASELINE config 4, reduced size)
     overlap = os.environ.get("MGPU_OVERLAP", "1") == "1"
     transport = os.environ.get("MGPU_TRANSPORT", "p2p")
-    nf = 8 if mhd else 5
+    # a -DDE -DSCALAR -DSTATIC_GRAV build: 7 fields through the exchange, Select_Internal_Energy reading neighbours across
+    # rank boundaries, and an analytic field evaluated from each rank's global offsets (Milky-Way model, custom_grav = 1)
+    passive = os.environ.get("MGPU_PASSIVE", "0") == "1"
+    nf = 8 if mhd else (7 if passive else 5)
     solver = cb.HLLD if mhd else cb.HLLC
     if mhd:
         n, steps, gamma = (64, 64, 64), 5, 1.666666666666667
     kw = dict(recon=cb.PPMC, solver=solver, gamma=gamma, bc=flags, strict=strict, mhd=mhd)
+    if passive:
+        kw.update(n_scalars=1, dual_energy=True, bounds_min=(-0.53, -0.49, -0.51))
     G = Grid3D(n, (1.0, 1.0, 1.0), device="cuda:%d" % local, dist_group=dist.group.WORLD, rank=rank, nproc=world,
                halo_transport=transport, overlap=overlap, **kw)
+    if passive:
+        G.Set_Static_Gravity(1)
     if mhd:
         from cholla_b200.grid import n_ghost_for
         with ic.block(G.decomp.offset, G.decomp.n_local):
             G.upload(ic.orszag_tang(n, n_ghost_for(cb.PPMC, True), gamma=gamma).reshape(-1))
     else:
         fields = ic.spherical_overpressure(n, gamma=gamma)
+        if passive:
+            fields = ic.with_passive(fields, 1, True, gamma)
         G.Set_Initial_Conditions(fields)
     G.Set_Boundary_Conditions_Grid()
     dts = G.advance(steps)
@@ -63,6 +72,8 @@ def main():
     G.close()
     if rank == 0:
         S = Grid3D(n, (1.0, 1.0, 1.0), device="cuda:0", **kw)
+        if passive:
+            S.Set_Static_Gravity(1)
         if mhd:
             S.upload(ic.orszag_tang(n, S.H.n_ghost, gamma=gamma).reshape(-1))
         else:

@@ -37,6 +37,15 @@ def test_config_validation():
     bad = cb.Config(40, 40, 40, 2, 5, cb.PPMC, cb.HLLC, 2, 0, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)  # too few ghosts
     assert L.chl_create(C.byref(bad), C.byref(ctx)) == -1
     bad = cb.Config(40, 40, 40, 4, 8, cb.PPMC, cb.HLLC, 2, 0, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)  # 8 fields = MHD
+    assert L.chl_create(C.byref(bad), C.byref(ctx)) == -1  # a hydro grid has 5 + n_scalars + dual_energy fields
+    # -DSCALAR / -DDE contexts: the field count must match, only the built combinations exist, MHD carries none
+    bad = cb.Config(40, 40, 40, 4, 6, cb.PPMC, cb.HLLC, 2, 1, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0, 1, 1)
+    assert L.chl_create(C.byref(bad), C.byref(ctx)) == -1
+    bad = cb.Config(40, 40, 40, 4, 7, cb.PPMC, cb.HLLC, 2, 1, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0, 2, 0)  # two scalars
+    assert L.chl_create(C.byref(bad), C.byref(ctx)) == -4
+    bad = cb.Config(40, 40, 40, 4, 6, cb.PPMP, cb.ROE, 2, 1, 0, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0, 0, 1)  # PPMP: HLLC only
+    assert L.chl_create(C.byref(bad), C.byref(ctx)) == -4
+    bad = cb.Config(40, 40, 40, 5, 8, cb.PPMC, cb.HLLD, 2, 1, 1, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0, 0, 1)  # MHD + DE
     assert L.chl_create(C.byref(bad), C.byref(ctx)) == -4
     # the reference's own MHD constraints (src/utils/error_handling.cpp:83-118): HLLD only, 3-D only, one more ghost
     bad = cb.Config(40, 40, 40, 5, 8, cb.PPMC, cb.HLLC, 2, 0, 1, 5.0 / 3.0, 0.1, 0.1, 0.1, 0.0, 0.0)

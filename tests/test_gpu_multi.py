@@ -57,3 +57,12 @@ def test_rank_count_independence_mhd(world):
     MHD system tests reuse one fiducial for 1, 2 and 4 ranks: src/system_tests/mhd_system_tests.cpp:555-690,703-787)."""
     r = _run(world, MGPU_MHD="1")
     assert r["mhd"], r
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_rank_count_independence_dual_energy_scalar_static_gravity(world):
+    """A -DDE -DSCALAR -DSTATIC_GRAV context across ranks: seven fields through the native exchange, the dual-energy passes
+    between the corrector and the exchange, the analytic field from each rank's global offsets.  (Select_Internal_Energy
+    clamps its neighbour reads to the rank's own real cells, in the reference as here -- hydro_cuda.cu:955-966 -- so its
+    second criterion is rank-local by construction; this warm blast decides on the first one everywhere.)"""
+    _run(world, MGPU_PASSIVE="1")
