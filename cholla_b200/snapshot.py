@@ -52,12 +52,22 @@ def format_fname(outdir, nfile, proc_id, pre_extension_suffix="", legacy_flat_ou
     return prefix + str(nfile) + pre_extension_suffix + ".h5" + "." + str(proc_id)
 
 
-def macro_flags(recon, solver, precision=2, mhd=False, integrator="vl"):
-    """The MACRO_FLAGS string of the equivalent reference build (Makefile:173-175, builds/make.type.hydro / .mhd)."""
+def macro_flags(recon, solver, precision=2, mhd=False, integrator="vl", G=None):
+    """The MACRO_FLAGS string of the equivalent reference build (Makefile:173-175, builds/make.type.*).  G: the live grid,
+    for the macros of a dual-energy / scalar / static-gravity / cooling context."""
     flags = ["-DCUDA", "-DMPI_CHOLLA", "-DPRECISION=%d" % precision, _RECON_FLAG[recon], _SOLVER_FLAG[solver], "-DSIMPLE" if integrator == "simple" else "-DVL",
              "-DDENSITY_FLOOR", "-DTEMPERATURE_FLOOR", "-DHDF5", "-DOUTPUT"]
     if mhd:
         flags.append("-DMHD")
+    if G is not None:
+        if getattr(G, "dual_energy", False):
+            flags.append("-DDE")
+        if getattr(G, "n_scalars", 0):
+            flags += ["-DSCALAR", "-DBASIC_SCALAR"]
+        if getattr(G, "static_gravity", False):
+            flags.append("-DSTATIC_GRAV")
+        if getattr(G, "cooling", None):
+            flags.append("-DCOOLING_GPU")
     return " ".join(flags)
 
 
@@ -154,7 +164,7 @@ def write_data(G, P, nfile, outdir):
     path = format_fname(outdir, nfile, G.rank, "", getattr(P, "legacy_flat_outdir", False))
     attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
                               (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
-                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl")))
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl"), G))
     dt = ">f8" if G.precision == 2 else ">f4"
     data = OrderedDict()
     for f, nm in enumerate(HYDRO_FIELDS):  # device-side transposition, one field at a time like the reference
@@ -204,7 +214,7 @@ def write_float32(G, P, nfile, outdir):
     path = format_fname(outdir, nfile, G.rank, ".float32", flat)
     attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
                               (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
-                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl")))
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl"), G))
     data = OrderedDict()
     for nm, f, key in FLOAT32_SELECT:
         if getattr(P, key, 0) > 0:
@@ -265,7 +275,7 @@ def write_slices(G, P, nfile, outdir):
     get = lambda f, ks, js, is_: C4[f, ks, js, is_].to("cpu", G.torch.float64).numpy()
     attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
                               (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
-                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl")))
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl"), G))
     h5lite.write(path, attrs, slice_datasets(H, get, G.n_global, G.decomp.offset, G.mhd, G.precision))
     return path
 
@@ -317,7 +327,7 @@ def write_projection(G, P, nfile, outdir):
     path = format_fname(outdir, nfile, G.rank, "_proj", flat)
     attrs = header_attributes(H, P.gamma, G.n_global, G.decomp.n_local, G.decomp.offset, G.decomp.np,
                               (P.xmin, P.ymin, P.zmin), (P.xlen, P.ylen, P.zlen), G.mhd,
-                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl")))
+                              macro=macro_flags(G.recon, G.solver, G.precision, G.mhd, getattr(G, "integrator", "vl"), G))
     C4 = G.C_device.view(H.n_fields, H.nz, H.ny, H.nx).to(G.torch.float64)
     h5lite.write(path, attrs, projection_datasets(H, C4, P.gamma, G.mhd, G.precision))
     return path
