@@ -270,9 +270,10 @@ def run_reference(args):
                                                   else " (as shipped: device sync after every stage)"))
     out.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "checksum": cs,
                 "total_steps": max(args.warmup, 1) + args.steps,
-                "config": {"workload": "%s %s^3 %s+%s fp64, %s integrator, %s" %
-                           (args.workload, n[0], args.recon.upper(), args.solver.upper(), args.integrator.upper(), kind),
-                           "l2": "inputs larger than L2", "build": L.ref_build_flags().decode()},
+                # the same `config` the b200 arm prints for this workload on one GPU (the arithmetic of the reference IS the
+                # strict one: IEEE divisions, no FMA contraction); what differs between the arms is under `implementation`
+                "config": bench_config(args, "strict", n, [1, 1, 1], U.numel() * 8, "none", False, None, weak=w["weak"]),
+                "implementation": {"kind": kind, "build": L.ref_build_flags().decode()},
                 "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "reference",
                                  "sample": "the reference has no CPU hydro path: this is its own unmodified CUDA "
                                            "build (oracle/_ref) on one B200, full workload, 1 host thread"},
@@ -488,6 +489,19 @@ def config_entries(ctx, args):
     return out
 
 
+def bench_config(args, mode, n_global, np_grid, state_bytes, halo, overlap, numa, weak=True):
+    """The `config` object of the JSON line -- one definition for the b200, reference and drop-in arms, so that the same
+    command line on one GPU names the same workload in all of them."""
+    return {"workload": "%s %s, %s+%s, %s integrator, %s arithmetic"
+                        % (args.workload, ("%d^3 per GPU" % args.size) if weak else ("%d^3 global" % args.global_size),
+                           args.recon.upper(), args.solver.upper(), args.integrator.upper(), mode),
+            "global_cells": list(n_global), "decomposition": list(np_grid),
+            "l2": "inputs larger than L2 (%.1f GB state per GPU)" % (state_bytes / 1e9),
+            "step": "set_dt + %s step (T-floor, CFL) + ghost fill/halo exchange" % args.integrator.upper(),
+            "halo": {"transport": halo, "overlapped_with_interior_update": bool(overlap)},
+            "host_numa_cpus_rank0": numa}
+
+
 def bind_to_gpu_numa_node(torch, local):
     """Pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated: cudaHostAlloc places the pages
     on the calling thread's NUMA node, and eight ranks copying 5.6 GB each way through the wrong socket's memory is what
@@ -593,14 +607,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak" if r["weak"] else "strong",
         "vs_baseline": None, "dtype": "f64" if args.precision == 2 else "f32", "data": "synthetic",
-        "config": {"workload": "%s %s, %s+%s, %s integrator, %s arithmetic"
-                               % (args.workload, ("%d^3 per GPU" % args.size) if r["weak"] else ("%d^3 global" % args.global_size),
-                                  args.recon.upper(), args.solver.upper(), args.integrator.upper(), mode),
-                   "global_cells": r["n_global"], "decomposition": r["np_grid"],
-                   "l2": "inputs larger than L2 (%.1f GB state per GPU)" % (r["state_bytes"] / 1e9),
-                   "step": "set_dt + %s step (fused T-floor/CFL) + ghost fill/halo exchange" % args.integrator.upper(),
-                   "halo": {"transport": r["halo"], "overlapped_with_interior_update": r["overlap"]},
-                   "host_numa_cpus_rank0": numa},
+        "config": bench_config(args, mode, r["n_global"], r["np_grid"], r["state_bytes"], r["halo"], r["overlap"], numa,
+                               weak=r["weak"]),
         "e2e": r["e2e"],
         "gpu_launches": r["launches"],
         "clocks": r["clocks"],
