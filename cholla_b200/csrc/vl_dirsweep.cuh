@@ -118,6 +118,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #endif
 // (Fetching the predictor's NEXT cell the same way, one iteration ahead into a two-slot buffer, was measured and
 // dropped: the extra 10 KB of shared memory per CTA shrinks L1 and the three predictor passes went 9.9 -> 13.3 ms.)
+// First-order predictor, strict HLLC: a cell's state is the high side of face c-1/2 AND the low side of face c+1/2, and
+// the solver's conversion of a Q_L / Q_R entry (three exact quotients by the density, the pressure) plus its per-side
+// terms (sqrt(d), the enthalpy, the sound speed) are a quarter of the pass's instructions.  With CHL_SIDE_CACHE the
+// converted state is what travels to the next cell (14 values + a "left the fast path" mark instead of 5), so each cell
+// is converted once.  Same expressions, same bits.
+#ifndef CHL_SIDE_CACHE
+#define CHL_SIDE_CACHE 1
+#endif
+constexpr int kSideVals = 14;  // d, mx, my, mz, E, vx, vy, vz, p, 1/d, sqrt(d), H, cf, mark
+
 template <int STAGE, bool FIRST, bool LAST>
 struct StageGeom {
   static constexpr int n_sum = (STAGE == 1 && FIRST) ? 0 : 5;  // U (predictor, first pass) or the running sum
@@ -326,7 +336,9 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
 
   typedef StageGeom<STAGE, FIRST, LAST> SG;
   constexpr bool kStage = CHL_DIR_STAGE && SG::n > 0;
-  constexpr int kParkV  = 10 + 2 * kNP;  // parked per thread / warp: low-side state and lower-face flux
+  constexpr bool kSide  = CHL_SIDE_CACHE && CHL_STRICT && kNP == 0 && STAGE == 0 && SOLVER == kHLLC;
+  constexpr int kStateV = kSide ? kSideVals : 5;
+  constexpr int kParkV  = kStateV + 5 + 2 * kNP;  // parked per thread / warp: low-side state and lower-face flux
   constexpr int kParkN  = CHL_DIR_PARK ? (DIR == 0 ? kParkV * kRowsPerCta : kParkV * kDirThreads) : 1;
   __shared__ Real stage[kStage ? SG::n * kDirThreads : 1];
   __shared__ Real parked[kParkN];
@@ -376,14 +388,48 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
 #endif
       }
       S5 Lp;
-      from_low_side5<DIR>(L.v, Lc, Lp.v, park, pstride, lane);
+#if CHL_STRICT
+      Face fL, fR;
+      bool side_bad = false;
+      if (kSide) {
+        fR = to_face(R, kc);
+        face_side_cache(fR, kc);
+        Real const mark = kc.bad ? RC(1.0) : RC(0.0);  // this state's conversion left the fast-path window
+        kc.bad          = false;
+        Real const cur[kSideVals] = {fR.d, fR.mx, fR.my, fR.mz, fR.E, fR.vx, fR.vy, fR.vz, fR.p, fR.dd.y, fR.sd, fR.H, fR.cf, mark};
+        Real low[kSideVals], unused[kSideVals];
+        from_low_side_n<DIR, kSideVals>(cur, unused, low, park, pstride, lane);
+        fL.d = low[0]; fL.mx = low[1]; fL.my = low[2]; fL.mz = low[3]; fL.E = low[4];
+        fL.vx = low[5]; fL.vy = low[6]; fL.vz = low[7]; fL.p = low[8];
+        fL.dd = Den{low[0], low[9]};
+        fL.sd = low[10]; fL.H = low[11]; fL.cf = low[12];
+#pragma unroll
+        for (int k = 0; k < 5; k++) Lp.v[k] = low[k];
+        side_bad = (mark != RC(0.0)) | (low[13] != RC(0.0));
+      } else
+#endif
+      {
+        from_low_side5<DIR>(L.v, Lc, Lp.v, park, pstride, lane);
+      }
 #if CHL_NP > 0
       from_low_side_n<DIR, kNP>(L.q, Lqc, Lp.q, park + 10 * pstride, pstride, lane);
 #endif
       Real F[5];
       Cons Fhi;
       if (face) {
-        Fhi = riemann_checked<SOLVER>(Lp, R, kc);
+#if CHL_STRICT
+        if (kSide) {
+          kc.bad = side_bad;
+          Fhi    = riemann_flux<SOLVER, true>(fL, fR, kc);
+          if (kc.bad) {
+            Fhi    = riemann_ieee<SOLVER>(Lp, R, kc.gamma);
+            kc.bad = false;
+          }
+        } else
+#endif
+        {
+          Fhi = riemann_checked<SOLVER>(Lp, R, kc);
+        }
       } else {
         Fhi.d = Fhi.mx = Fhi.my = Fhi.mz = Fhi.E = RC(0.0);
 #if CHL_NP > 0
@@ -393,7 +439,7 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
       }
       F[0] = Fhi.d; F[1] = Fhi.mx; F[2] = Fhi.my; F[3] = Fhi.mz; F[4] = Fhi.E;
       Real Fp[5];
-      from_low_side5<DIR>(F, Fc, Fp, park + 5 * pstride, pstride, lane);
+      from_low_side5<DIR>(F, Fc, Fp, park + kStateV * pstride, pstride, lane);
       Cons Flo{Fp[0], Fp[1], Fp[2], Fp[3], Fp[4]};
 #if CHL_NP > 0
       from_low_side_n<DIR, kNP>(Fhi.q, Fqc, Flo.q, park + (10 + kNP) * pstride, pstride, lane);
