@@ -118,7 +118,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #endif
 // (Fetching the predictor's NEXT cell the same way, one iteration ahead into a two-slot buffer, was measured and
 // dropped: the extra 10 KB of shared memory per CTA shrinks L1 and the three predictor passes went 9.9 -> 13.3 ms.)
-// First-order predictor, strict HLLC: a cell's state is the high side of face c-1/2 AND the low side of face c+1/2, and
+// First-order predictor, strict HLLC / Roe / HLL: a cell's state is the high side of face c-1/2 AND the low side of face c+1/2, and
 // the solver's conversion of a Q_L / Q_R entry (three exact quotients by the density, the pressure) plus its per-side
 // terms (sqrt(d), the enthalpy, the sound speed) are a quarter of the pass's instructions.  With CHL_SIDE_CACHE the
 // converted state is what travels to the next cell (14 values + a "left the fast path" mark instead of 5), so each cell
@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
 
   typedef StageGeom<STAGE, FIRST, LAST> SG;
   constexpr bool kStage = CHL_DIR_STAGE && SG::n > 0;
-  constexpr bool kSide  = CHL_SIDE_CACHE && CHL_STRICT && kNP == 0 && STAGE == 0 && SOLVER == kHLLC;
+  constexpr bool kSide  = CHL_SIDE_CACHE && CHL_STRICT && kNP == 0 && STAGE == 0 &&
+                          (SOLVER == kHLLC || SOLVER == kROE || SOLVER == kHLL);
   constexpr int kStateV = kSide ? kSideVals : 5;
   constexpr int kParkV  = kStateV + 5 + 2 * kNP;  // parked per thread / warp: low-side state and lower-face flux
   constexpr int kParkN  = CHL_DIR_PARK ? (DIR == 0 ? kParkV * kRowsPerCta : kParkV * kDirThreads) : 1;
