@@ -239,14 +239,27 @@ __device__ __forceinline__ Half half_state(U5 const &c, K const &k, int plmp)
 
 // The corrector's per-cell epilogue after the flux differences are in: temperature floor
 // (Temperature_Floor_Kernel, hydro_cuda.cu:1117-1153) and the cell's inverse crossing time.  u is updated in place.
-template <class K>
+// SHARED (strict sweeps, last corrector pass): 1 / d is formed once for the temperature floor and the CFL term (the same
+// expression on the same d: hydro_cuda.cu:1133, 534) and the cell sizes' shared reciprocals come from cell_dens.
+template <bool SHARED = false, class K>
 __device__ __forceinline__ Real cell_epilogue(Real (&u)[5], K const &k, int apply_tfloor, Real U_floor, int do_dti,
-                                              int ndim, Real idx, Real idy, Real idz, Real dx, Real dy, Real dz)
+                                              int ndim, Real idx, Real idy, Real idz, Real dx, Real dy, Real dz,
+                                              const Real *cell_dens = nullptr)
 {
+#if CHL_STRICT
+  Den dd     = Den{RC(0.), RC(0.)};
+  Real d_inv = RC(0.);
+  if (SHARED) {
+    dd    = den(u[0], k);
+    d_inv = qdiv<false>(RC(1.0), dd, k);
+  }
+#endif
   if (apply_tfloor) {
 #if CHL_STRICT
-    Den const dd     = den(u[0], k);
-    Real const d_inv = qdiv<false>(RC(1.0), dd, k);
+    if (!SHARED) {
+      dd    = den(u[0], k);
+      d_inv = qdiv<false>(RC(1.0), dd, k);
+    }
 #else
     Real const d_inv = RC(1.0) / u[0];
 #endif
@@ -260,9 +273,14 @@ __device__ __forceinline__ Real cell_epilogue(Real (&u)[5], K const &k, int appl
   }
   Real v = RC(0.0);
   if (do_dti) {
-    if (ndim == 3) v = inverse_crossing_time<3>(u[0], u[1], u[2], u[3], u[4], idx, idy, idz, dx, dy, dz, k);
-    else if (ndim == 2) v = inverse_crossing_time<2>(u[0], u[1], u[2], u[3], u[4], idx, idy, idz, dx, dy, dz, k);
-    else v = inverse_crossing_time<1>(u[0], u[1], u[2], u[3], u[4], idx, idy, idz, dx, dy, dz, k);
+#if CHL_STRICT
+    const Real *const di = &d_inv;
+#else
+    const Real *const di = nullptr;
+#endif
+    if (ndim == 3) v = inverse_crossing_time<3, SHARED>(u[0], u[1], u[2], u[3], u[4], idx, idy, idz, dx, dy, dz, k, di, cell_dens);
+    else if (ndim == 2) v = inverse_crossing_time<2, SHARED>(u[0], u[1], u[2], u[3], u[4], idx, idy, idz, dx, dy, dz, k, di, cell_dens);
+    else v = inverse_crossing_time<1, SHARED>(u[0], u[1], u[2], u[3], u[4], idx, idy, idz, dx, dy, dz, k, di, cell_dens);
   }
   return v;
 }
@@ -344,14 +362,15 @@ __device__ __forceinline__ Half half_state_checked(U5 const &c, KH const &k, int
 #endif
   return h;
 }
+template <bool SHARED = false>
 __device__ __forceinline__ Real cell_epilogue_checked(Real (&u)[5], KH const &k, int apply_tfloor, Real U_floor,
                                                       int do_dti, int ndim, Real idx, Real idy, Real idz, Real dx,
-                                                      Real dy, Real dz)
+                                                      Real dy, Real dz, const Real *cell_dens = nullptr)
 {
 #if CHL_STRICT
   Real const E0 = u[4];
 #endif
-  Real v = cell_epilogue(u, k, apply_tfloor, U_floor, do_dti, ndim, idx, idy, idz, dx, dy, dz);
+  Real v = cell_epilogue<SHARED>(u, k, apply_tfloor, U_floor, do_dti, ndim, idx, idy, idz, dx, dy, dz, cell_dens);
 #if CHL_STRICT
   if (k.bad) {
     Epi const e = cell_epilogue_ieee(u[0], u[1], u[2], u[3], E0, k.gamma, apply_tfloor, U_floor, do_dti, ndim, dx, dy, dz);

@@ -189,7 +189,8 @@ __device__ __forceinline__ void from_low_side5(Real const (&v)[5], Real (&carry)
 
 template <int STAGE, int DIR, bool FIRST, bool LAST, bool STAGED>
 __device__ __forceinline__ void finish_cell(DirParams const &P, KH const &k, size_t N, size_t id, Cons const &Flo,
-                                            Cons const &Fhi, double &dti, int &n_bad, const Real *staged)
+                                            Cons const &Fhi, double &dti, int &n_bad, const Real *staged,
+                                            const Real *cell_dens = nullptr)
 {
   // staged (STAGED only): this thread's shared-memory column, component k at staged[k * kDirThreads]: the five
   // running-sum / U operands in sweep-frame order, then (last corrector pass) the five old-U values in field order.
@@ -268,8 +269,8 @@ __device__ __forceinline__ void finish_cell(DirParams const &P, KH const &k, siz
   // the in-place update, a race with no bits to match (hydro_cuda.cu:292-297), and leaves the decision to the host
   if (!(u[0] > RC(0.))) n_bad++;
   // (-DDE builds: the temperature floor and the CFL maximum follow Select_Internal_Energy / Sync_Energies, de_sync_kernel)
-  Real const v = cell_epilogue_checked(u, k, floors && P.apply_tfloor, P.U_floor, P.do_dti, P.ndim, P.idx, P.idy, P.idz,
-                                       P.dx, P.dy, P.dz);
+  Real const v = cell_epilogue_checked<CHL_STRICT != 0>(u, k, floors && P.apply_tfloor, P.U_floor, P.do_dti, P.ndim, P.idx,
+                                                        P.idy, P.idz, P.dx, P.dy, P.dz, cell_dens);
 #pragma unroll
   for (int f = 0; f < 5; f++) P.out[f * N + id] = u[f];
 #if CHL_NP > 0
@@ -343,6 +344,24 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
   constexpr int kParkN  = CHL_DIR_PARK ? (DIR == 0 ? kParkV * kRowsPerCta : kParkV * kDirThreads) : 1;
   __shared__ Real stage[kStage ? SG::n * kDirThreads : 1];
   __shared__ Real parked[kParkN];
+  // last corrector pass, strict mode: the shared reciprocals of dx, dy, dz for the CFL term, one set per warp
+  constexpr bool kCellDens = CHL_STRICT && STAGE == 1 && LAST;
+  __shared__ Real s_cell_dens[kCellDens ? (kDirThreads / 32) * 7 : 1];
+  const Real *cell_dens = nullptr;
+#if CHL_STRICT
+  if (kCellDens && P.do_dti) {
+    Real *const w = s_cell_dens + (threadIdx.x >> 5) * 7;
+    if (lane == 0) {
+      Den const a = den(P.dx, kc), b = den(P.dy, kc), c = den(P.dz, kc);
+      w[0] = a.b; w[1] = a.y; w[2] = b.b; w[3] = b.y; w[4] = c.b; w[5] = c.y;
+      // a cell size outside the fast-path window (never, in practice): the mark sends every epilogue to its IEEE redo
+      w[6] = kc.bad ? RC(1.0) : RC(0.0);
+    }
+    kc.bad = false;
+    __syncwarp();
+    cell_dens = w;
+  }
+#endif
 
   if (live) {
     Real Lc[5], Fc[5];  // carried: low-side state of the face below / flux through the face below the previous cell
@@ -446,7 +465,8 @@ __global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_
       from_low_side_n<DIR, kNP>(Fhi.q, Fqc, Flo.q, park + (10 + kNP) * pstride, pstride, lane);
 #endif
       if (kStage) cp_async_wait_all();
-      if (fin) finish_cell<STAGE, DIR, FIRST, LAST, kStage>(P, kc, N, id - (size_t)m.stride, Flo, Fhi, dti, n_bad, staged);
+      if (fin)
+        finish_cell<STAGE, DIR, FIRST, LAST, kStage>(P, kc, N, id - (size_t)m.stride, Flo, Fhi, dti, n_bad, staged, cell_dens);
     }
   }
 
