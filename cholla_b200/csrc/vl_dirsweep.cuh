@@ -38,6 +38,12 @@ namespace CHL_NS
 #ifndef CHL_DIR_MINB0  // the predictor passes (PCM + Riemann) may want a different register budget
 #define CHL_DIR_MINB0 CHL_DIR_MINB
 #endif
+// the last corrector pass (old U staged too, floors + CFL epilogue): strict builds give it 80 registers / 6 CTAs -- 512^3
+// corrector 29.21 -> 28.99 / 29.02 ms (gpurun_out/r27_run27.txt, r28_run28.txt); 96 registers: 30.3 ms; 80 registers for the
+// x or y pass as well: 29.3 / 29.5 ms, 64 for the x pass: 29.2 ms
+#ifndef CHL_DIR_MINB_LAST
+#define CHL_DIR_MINB_LAST CHL_DIR_MINB
+#endif
 #ifndef CHL_DIR_THREADS
 #define CHL_DIR_THREADS 128
 #endif
@@ -117,7 +123,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #define CHL_DIR_PARK 1
 #endif
 // (Fetching the predictor's NEXT cell the same way, one iteration ahead into a two-slot buffer, was measured and
-// dropped: the extra 10 KB of shared memory per CTA shrinks L1 and the three predictor passes went 9.9 -> 13.3 ms.)
+// dropped: the extra 10 KB of shared memory per CTA shrinks L1 and the three predictor passes went 9.9 -> 13.3 ms.
+// The register form -- the next cell's five values loaded one iteration ahead -- was measured in the strict build after
+// the side cache: predictor 12.04 -> 13.06 ms at 72 registers, 12.83 ms at 80; gpurun_out/r27_run27.txt.  Dropped too.)
 // First-order predictor, strict HLLC / Roe / HLL: a cell's state is the high side of face c-1/2 AND the low side of face c+1/2, and
 // the solver's conversion of a Q_L / Q_R entry (three exact quotients by the density, the pressure) plus its per-side
 // terms (sqrt(d), the enthalpy, the sound speed) are a quarter of the pass's instructions.  With CHL_SIDE_CACHE the
@@ -281,7 +289,7 @@ __device__ __forceinline__ void finish_cell(DirParams const &P, KH const &k, siz
 }
 
 template <int RECON, int SOLVER, int STAGE, int DIR, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : CHL_DIR_MINB) vl_dir_kernel(DirParams const P)
+__global__ void __launch_bounds__(kDirThreads, STAGE == 0 ? CHL_DIR_MINB0 : (LAST ? CHL_DIR_MINB_LAST : CHL_DIR_MINB)) vl_dir_kernel(DirParams const P)
 {
   int const nx = P.nx, ny = P.ny;
   size_t const N = (size_t)nx * ny * P.nz;
