@@ -311,8 +311,15 @@ static int step_impl(chl_ctx *c, void *U, double dt, int fused, cudaStream_t s, 
     }
     CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps], s));
   }
-  if (de) CHL_CUDA(c->ops->de_term(U, c->d_de, g.nx, g.ny, g.nz, a.lo, a.hi, a.dtodx, a.dtody, a.dtodz, g.gamma, 0, s));
-  CHL_CUDA(sweep(0, g.recon, g.solver, a, s));
+  if (g.recon == CHL_RECON_PCM && c->ndim == 2) {
+    // VL_Algorithm_2D_CUDA has no -DPCM branch in its second reconstruction (VL_2D_cuda.cu:95-120; the 1-D and 3-D files
+    // do: VL_1D_cuda.cu:90, VL_3D_cuda.cu:226), so a -DPCM 2-D build solves the corrector's Riemann problems on the
+    // interface arrays of step 1 -- copies of U^n.  Reproduced: the corrector reads U^n instead of the half-step state.
+    CHL_CUDA(c->ops->prim_from_cons(U, c->d_half, c->n_cells, g.gamma, g.recon, s));
+  } else {
+    if (de) CHL_CUDA(c->ops->de_term(U, c->d_de, g.nx, g.ny, g.nz, a.lo, a.hi, a.dtodx, a.dtody, a.dtodz, g.gamma, 0, s));
+    CHL_CUDA(sweep(0, g.recon, g.solver, a, s));
+  }
   if (prof) CHL_CUDA(cudaEventRecord(c->ev[3 * c->ev_steps + 1], s));
   // ---- corrector: real cells (hydro_cuda.cu:225) ----
   for (int d = 0; d < 3; d++) {

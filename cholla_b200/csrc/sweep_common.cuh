@@ -138,12 +138,23 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
     return;
   }
   if (RECON == kPCM) {
+#if CHL_STRICT
+    // PCM_Reconstruction_{1,2,3}D copies the conserved values (pcm_cuda.cu:13-411): for a PCM corrector the predictor
+    // (or the SIMPLE integrator's elementwise pass) stored the half-step state CONSERVED (half_state, kHalfConserved),
+    // the energy in all three fifth-field slots, the passive fields as they are -- nothing is converted, same bits
+    L = S5{{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)}};
+#if CHL_NP > 0
+#pragma unroll
+    for (int i = 0; i < kNP; i++) L.q[i] = __ldg(c + (size_t)(kHalfFields + i) * m.N);
+#endif
+#else
     Prim wi{__ldg(c), __ldg(c + m.o1), __ldg(c + m.o2), __ldg(c + m.o3), __ldg(c + m.op)};
 #if CHL_NP > 0
 #pragma unroll
     for (int i = 0; i < kNP; i++) wi.q[i] = __ldg(c + (size_t)(kHalfFields + i) * m.N);
 #endif
     L = iface_state(wi, k);
+#endif
     R = L;
     return;
   }
@@ -179,6 +190,9 @@ __device__ __forceinline__ void recon_cell(const Real *__restrict__ in, size_t i
   R = iface_state(r, k);
 }
 
+// `plmp` argument of half_state: 0 = PLMC / PPMC, 1 = PLMP / PPMP (their summation order of the pressures), 2 = PCM
+constexpr int kHalfConserved = 2;
+__host__ __device__ inline int half_kind(int recon) { return recon == kPCM ? kHalfConserved : (recon == kPLMP || recon == kPPMP) ? 1 : 0; }
 // Half-step state of one cell, from its conserved half-step values: what Load_Data (reconstruction.h:139-212)
 // derives, stored once instead of being recomputed by every stencil that touches the cell.
 template <class K>
@@ -191,8 +205,19 @@ __device__ __forceinline__ Half half_state(U5 const &c, K const &k, int plmp)
 #pragma unroll
   for (int i = 0; i < kNP; i++) uc.q[i] = c.q[i];
 #endif
-  Prim const w = prim_from_cons(uc, k);  // P with the x-sweep association
   Half h;
+#if CHL_STRICT
+  if (plmp == kHalfConserved) {  // a PCM corrector reads the conserved values themselves (recon_cell)
+#pragma unroll
+    for (int f = 0; f < kHalfFields; f++) h.w[f] = u[f < 4 ? f : 4];
+#if CHL_NP > 0
+#pragma unroll
+    for (int i = 0; i < kNP; i++) h.q[i] = c.q[i];
+#endif
+    return h;
+  }
+#endif
+  Prim const w = prim_from_cons(uc, k);  // P with the x-sweep association
 #if CHL_NP > 0
 #pragma unroll
   for (int i = 0; i < kNP; i++) h.q[i] = w.q[i];

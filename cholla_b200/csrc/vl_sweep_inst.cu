@@ -155,7 +155,7 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
 {
 #if CHL_NP == 0
   if (stage == 0 && a.has_y && a.has_z && a.fused_predictor) {
-    int const plmp = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
+    int const plmp = half_kind(recon);
 #ifdef CHL_DEV_SUBSET
     if (solver == kHLLC) return launch_predictor<kHLLC>(a, plmp, s);
 #else
@@ -184,7 +184,7 @@ cudaError_t sweep_split(int stage, int recon, int solver, SweepArgs const &a, cu
   p.bad_cells = a.bad_cells;
   p.xw_log2   = 7;
   p.nbox      = 0;
-  p.plmp      = (recon == kPLMP || recon == kPPMP) ? 1 : 0;
+  p.plmp      = half_kind(recon);
   p.de_term   = (const Real *)a.de_term;
 #if CHL_NP > 0
   // -DSCALAR / -DDE builds: the Van Leer integrator with PCM / PLMC / PPMC and HLLC / Roe / HLL, PLMP / PPMP with HLLC
@@ -368,7 +368,7 @@ cudaError_t prim_from_cons(const void *U, void *W, size_t n_cells, double gamma,
   size_t blocks = (n_cells + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   prim_from_cons_kernel<<<(unsigned)blocks, 256, 0, s>>>((const Real *)U, (Real *)W, n_cells, (Real)gamma,
-                                                        (recon == kPLMP || recon == kPPMP) ? 1 : 0);
+                                                        half_kind(recon));
   return cudaGetLastError();
 }
 

@@ -1000,7 +1000,8 @@ void orc_vl_step(double *U, int nx, int ny, int nz, int n_ghost, double dx, doub
   }
   /* stage 4-5: second-order interfaces from the half-step state, then fluxes */
   for (int d = 0; d < ndim; d++) {
-    if (recon == ORC_PCM) pcm_dir(Uh, QL[d], QR[d], nx, ny, nz, d);
+    /* VL_2D_cuda.cu:95-120 has no -DPCM branch: the 2-D corrector re-solves the step-1 interface arrays (copies of U^n) */
+    if (recon == ORC_PCM) pcm_dir(ndim == 2 ? U : Uh, QL[d], QR[d], nx, ny, nz, d);
     else if (recon == ORC_PLMP) plmp_dir(Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
     else if (recon == ORC_PPMP) ppmp_dir(Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
     else orc_reconstruct(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d);
@@ -1284,7 +1285,7 @@ int orc_vl_step_x(double *U, int nx, int ny, int nz, int n_ghost, double dx, dou
         }
   }
   for (int d = 0; d < ndim; d++) {
-    if (recon == ORC_PCM) pcm_dir_x(Uh, QL[d], QR[d], nx, ny, nz, d, nf);
+    if (recon == ORC_PCM) pcm_dir_x(ndim == 2 ? U : Uh, QL[d], QR[d], nx, ny, nz, d, nf); /* VL_2D_cuda.cu:95-120 */
     else if (recon == ORC_PLMP || recon == ORC_PPMP) pxmp_dir_x(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d, ns, de);
     else reconstruct_x(recon, Uh, QL[d], QR[d], nx, ny, nz, gamma, d, ns, de);
     riemann_x(solver, QL[d], QR[d], F[d], nx, ny, nz, gamma, d, ns, de);

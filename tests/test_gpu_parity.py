@@ -57,13 +57,10 @@ def test_strict_mode_is_bit_exact_3d(recon, solver):
     got, ref, dims, g, dts_gpu, dts_cpu = run_both(fields, recon, solver, PERIODIC, 5.0 / 3.0, 3, strict=True)
     assert dts_gpu == dts_cpu  # CFL reduction is bit-exact too
     a, b = real_view(got, dims, g), real_view(ref, dims, g)
-    if recon == cb.PCM:
-        # the half-step state is kept as primitives, so a PCM *corrector* sees prim->cons round-off the
-        # reference does not; every other combination reproduces the reference's bits
-        assert rel_l1(a, b).max() <= TOL_F64
-    else:
-        assert max_ulp(a, b) == 0
-        assert np.array_equal(got, ref)  # ghosts too: same boundary routine semantics
+    # every combination reproduces the reference's bits -- a PCM corrector too: strict contexts keep its half-step state
+    # conserved, the values PCM_Reconstruction_3D copies (pcm_cuda.cu:256-411)
+    assert max_ulp(a, b) == 0
+    assert np.array_equal(got, ref)  # ghosts too: same boundary routine semantics
 
 
 @pytest.mark.parametrize("recon,solver", CASES_3D)

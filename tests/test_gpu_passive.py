@@ -88,7 +88,8 @@ def _have(recon, solver, ns, de):
 
 
 # (recon, solver, n_scalars, dual_energy): the -DDE / -DSCALAR reference builds of oracle/ref_build/Makefile
-REF_BUILDS = [(2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1), (1, 1, 1, 1), (1, 0, 0, 1), (2, 3, 1, 1), (3, 0, 1, 1)]  # 3 = PLMP
+REF_BUILDS = [(2, 0, 0, 1), (2, 0, 1, 0), (2, 0, 1, 1), (1, 1, 1, 1), (1, 0, 0, 1), (2, 3, 1, 1), (3, 0, 1, 1),
+              (0, 0, 1, 1)]  # recon 3 = PLMP, 0 = PCM
 
 
 @pytest.mark.parametrize("recon,solver,ns,de", REF_BUILDS)
@@ -135,15 +136,11 @@ def test_passive_density_floor_scales_gas_energy_not_scalars():
 @pytest.mark.parametrize("recon,solver,ns,de", [(0, 0, 1, 1), (1, 3, 1, 0), (2, 1, 0, 1), (0, 1, 1, 0), (1, 0, 1, 1),
                                                 (4, 0, 1, 1), (3, 0, 1, 0), (4, 0, 0, 1)])  # 3 / 4 = PLMP / PPMP
 def test_passive_combinations_without_a_reference_build_match_the_oracle(recon, solver, ns, de):
-    """The rest of the built matrix against the CPU oracle alone (itself bit-equal to the reference on the builds above).
-    PCM's corrector reconstructs from primitives here, so it carries prim -> cons round-off like the five-field path."""
+    """The rest of the built matrix against the CPU oracle alone (itself bit-equal to the reference on the builds above)."""
     r = run_child(recon=recon, solver=solver, n=(29, 17, 19), flags=[1, 1, 1, 1, 1, 1], gamma=1.4, steps=3,
                   ic="random_smooth", ns=ns, de=de, use_ref=0)
-    if recon == 0:
-        assert r["strict"]["l1"] <= 1e-12 and r["fast"]["l1"] <= 1e-12, json.dumps(r)
-    else:
-        assert r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], json.dumps(r)
-        assert r["fast"]["l1"] <= 1e-12, json.dumps(r)
+    assert r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], json.dumps(r)
+    assert r["fast"]["l1"] <= 1e-12, json.dumps(r)
 
 
 def test_scalar_floor_and_temperature_floor_with_dual_energy():

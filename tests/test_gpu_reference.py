@@ -127,13 +127,30 @@ def test_simple_integrator_plmc_reference_vs_oracle_vs_b200(n, flags, icname, st
 
 
 def test_simple_integrator_pcm_roe_reference():
-    """-DSIMPLE -DPCM -DROE: first-order update.  The oracle copies the conserved state like PCM_Reconstruction_3D and is
-    bit-exact; the kernels reconstruct from primitives, so they carry prim -> cons round-off (like the VL PCM corrector)."""
+    """-DSIMPLE -DPCM -DROE: first-order update.  The oracle and the strict kernels copy the conserved state like
+    PCM_Reconstruction_3D and are bit-exact; the product arithmetic reconstructs from primitives (prim -> cons round-off)."""
     _need(0, 1, simple=True)
     r = run_child(recon=0, solver=1, n=(37, 19, 21), flags=[1, 1, 1, 1, 1, 1], gamma=5.0 / 3.0, steps=3,
                   ic="random_smooth", integ="simple")
     assert r["oracle"]["ulp"] == 0 and r["oracle"]["dt_equal"], r
-    assert r["strict"]["l1"] <= 1e-12 and r["fast"]["l1"] <= 1e-12, r
+    assert r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], r
+    assert r["fast"]["l1"] <= 1e-12, r
+
+
+@pytest.mark.parametrize("n,flags,icname,steps", [((37, 19, 21), [1, 1, 1, 1, 1, 1], "random_smooth", 3),
+                                                  ((45, 23, 1), [1, 1, 1, 1, 0, 0], "random_smooth", 4),
+                                                  ((100, 1, 1), [3, 3, 0, 0, 0, 0], "riemann", 30)])
+def test_pcm_corrector_under_van_leer_reference_vs_oracle_vs_b200(n, flags, icname, steps):
+    """-DVL -DPCM -DHLLC: the corrector's interface states are copies of the conserved half-step state
+    (VL_3D_cuda.cu:226-229, pcm_cuda.cu); reference kernels == oracle == strict kernels, bit for bit, in 1-, 2- and 3-D."""
+    _need(0, 0)
+    r = run_child(recon=0, solver=0, n=n, flags=flags, gamma=5.0 / 3.0 if icname != "riemann" else 1.4, steps=steps,
+                  ic=icname)
+    assert "-DPCM" in r["flags"] and "-DVL" in r["flags"]
+    assert r["oracle"]["ulp"] == 0 and r["oracle"]["dt_equal"], r
+    assert r["strict"]["ulp"] == 0 and r["strict"]["dt_equal"], r
+    if icname == "random_smooth":
+        assert r["fast"]["l1"] <= 1e-12, r
 
 
 @pytest.mark.parametrize("recon,n,flags,icname,steps,integ", [
