@@ -133,7 +133,7 @@ def test_branch_free_policy_flag_clear_means_exact():
         with np.errstate(all="ignore"):
             want = a / b
         clear = (fl & 1) == 0
-        assert clear.sum() > 0.2 * a.size  # random bit patterns: a sizeable share stays in the fast-path window
+        assert clear.sum() > 0.15 * a.size  # random bit patterns: a sizeable share stays in the fast-path window
         assert _same_bits(q[clear], want[clear])
         assert not np.any(fl & 4)          # clear sqrt flag => the bits of sqrt(a)
     # the physical range, exact zeros of both signs included: no flag at all
@@ -153,3 +153,38 @@ def test_branch_free_policy_flag_clear_means_exact():
     pos = np.abs(a) + 1e-250               # inside the square root's fast-path window (2^-969 ... 2^1016)
     _, fl = _run_flagged(pos, b, True)
     assert not np.any(fl & 2)              # positive normal arguments never flag the square root
+
+
+def test_one_test_window_of_the_branch_free_policy():
+    """kDivFlag tests the denominator once (2^-400 <= |b| <= 2^400, on its reciprocal) and then only the quotient
+    (2^-560 < |q| < 2^1017): the numerator |a| = |q b| is then inside the stock fast-path window (>= 2^-969, finite) without
+    a test of its own.  Operands straddling every edge of that window: flag clear => the bits of a / b, and the window is
+    not wider than claimed (denominators outside it, quotients below it and non-finite operands always raise the flag)."""
+    rng = np.random.default_rng(29)
+    eb = np.array([-1022, -1000, -402, -401, -400, -399, -1, 0, 1, 399, 400, 401, 402, 1000, 1016, 1023], dtype=np.float64)
+    eq = np.array([-1074, -1023, -1022, -970, -969, -562, -561, -560, -559, -558, 0, 559, 560, 600, 1015, 1017], dtype=np.float64)
+    mb = 1.0 + rng.random((64, 1, 1))
+    mq = 1.0 + rng.random((64, 1, 1))
+    with np.errstate(all="ignore"):
+        b = (mb * 2.0 ** eb[None, :, None]) * np.ones((1, 1, eq.size))
+        a = (mq * 2.0 ** eq[None, None, :]) * b          # a = q b (rounded): q lands next to the edge exponent
+    a, b = a.ravel().copy(), b.ravel().copy()
+    sign = rng.integers(0, 2, a.size) * 2.0 - 1.0
+    a *= sign
+    for zero_ok in (True, False):
+        q, fl = _run_flagged(a, b, zero_ok)
+        with np.errstate(all="ignore"):
+            want = a / b
+        clear = (fl & 1) == 0
+        assert _same_bits(q[clear], want[clear])
+        assert clear.sum() > 0.15 * a.size
+        outside = (np.abs(b) < 2.0 ** -401) | (np.abs(b) > 2.0 ** 401) | ~np.isfinite(a) | ~np.isfinite(want) | \
+                  ((np.abs(want) < 2.0 ** -561) & (a != 0.0))
+        assert np.all(fl[outside] & 1)
+    # division by the constant 6 (PPM_Single_Variable) over the whole range of numerators
+    a = rng.integers(0, 1 << 64, 1 << 21, dtype=np.uint64).view(np.float64).copy()
+    q, fl = _run_flagged(a, np.full_like(a, 6.0), True)
+    with np.errstate(all="ignore"):
+        want = a / 6.0
+    clear = (fl & 1) == 0
+    assert _same_bits(q[clear], want[clear]) and np.all(fl[~np.isfinite(a)] & 1)
