@@ -27,8 +27,9 @@ constexpr Real kHlldSmall = RC(1.0e-8);  // hlld_cuda.h:35
 typedef Den RDen;
 template <class K>
 __device__ __forceinline__ RDen rden(Real b, K const &k) { return den(b, k); }
-template <class K>
-__device__ __forceinline__ Real rdiv(Real a, RDen const &d, K const &k) { return qdiv(a, d, k); }
+// NZ: the numerator cannot be an exact zero (a pressure, a density, a constant): exact_div.cuh's ZERO_OK = false hint
+template <bool NZ = false, class K>
+__device__ __forceinline__ Real rdiv(Real a, RDen const &d, K const &k) { return qdiv<!NZ>(a, d, k); }
 template <class K>
 __device__ __forceinline__ Real msq(Real x, K const &k) { return sqrt_r<true>(x, k); }
 #else
@@ -37,7 +38,7 @@ struct RDen {
 };
 template <class K>
 __device__ __forceinline__ RDen rden(Real b, K const &k) { (void)k; return RDen{rcp_r(b)}; }
-template <class K>
+template <bool NZ = false, class K>
 __device__ __forceinline__ Real rdiv(Real a, RDen const &d, K const &k) { (void)k; return a * d.y; }
 template <class K>
 __device__ __forceinline__ Real msq(Real x, K const &k) { (void)k; return sqrt_r(x); }
@@ -82,7 +83,7 @@ __device__ __forceinline__ void magnetosonic_pair(Real d, Real p, Real bx, Real 
   Real t1;
   Real const t2 = msonic_disc(p, bx, by, bz, k, t1);
   RDen const dd = rden(RC(2.0) * max_s(d, kTiny), k);
-  cf = msq(rdiv(t1 + RC(1.0) * t2, dd, k), k);
+  cf = msq(rdiv<true>(t1 + RC(1.0) * t2, dd, k), k);
   cs = msq(rdiv(t1 + RC(-1.0) * t2, dd, k), k);
 }
 template <class K>
@@ -128,7 +129,7 @@ struct Eigen {
   {
     Real const gamma = k.gamma;
     dd           = rden(w.d, k);
-    Real const a = msq(rdiv(gamma * w.p, dd, k), k);  // hydro_utilities::Calc_Sound_Speed
+    Real const a = msq(rdiv<true>(gamma * w.p, dd, k), k);  // hydro_utilities::Calc_Sound_Speed
     a2           = a * a;
     da2          = rden(a2, k);
     d            = w.d;
@@ -154,7 +155,7 @@ struct Eigen {
     beta_y        = isfinite(bd) ? w.by * bd : RC(1.0);
     beta_z        = isfinite(bd) ? w.bz * bd : RC(0.0);
     sign          = copysign(RC(1.0), w.bx);
-    n_fs          = rdiv(RC(0.5), da2, k);
+    n_fs          = rdiv<true>(RC(0.5), da2, k);
     qp_f          = sign * n_fs * alpha_f * cf;
     qp_s          = sign * n_fs * alpha_s * cs;
     q_f           = sign * alpha_f * cf;
@@ -250,7 +251,7 @@ __device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const 
       const Real *q  = c + (long)(i - 2) * o.s;
       Real const svx = __ldg(q + o.v1), svy = __ldg(q + o.v2), svz = __ldg(q + o.v3);
       Real const sby = __ldg(q + o.b2), sbz = __ldg(q + o.b3);
-      Real const spd = rdiv(__ldg(q + o.p), e.dd, k);
+      Real const spd = rdiv<true>(__ldg(q + o.p), e.dd, k);
       Real const A = e.beta_y * svy + e.beta_z * svz, B = e.beta_y * sby + e.beta_z * sbz;
       Real const qsA = e.qp_s * A, qfA = e.qp_f * A, asB = e.ap_s * B, afB = e.ap_f * B;
       Real const fx = e.cf * svx, sx = e.cs * svx;
@@ -284,7 +285,7 @@ __device__ __forceinline__ void mhd_ppmc(const Real *__restrict__ c, MOff const 
 #pragma unroll
     for (int i = 0; i < 5; i++) {
       const Real *q = c + (long)(i - 2) * o.s;
-      t3[i]         = __ldg(q) - rdiv(__ldg(q + o.p), e.da2, k);
+      t3[i]         = __ldg(q) - rdiv<true>(__ldg(q + o.p), e.da2, k);
     }
     ppm_single(t3[0], t3[1], t3[2], t3[3], t3[4], cl[3], cr[3], k);
   }
@@ -388,7 +389,7 @@ __device__ __forceinline__ HStar hlld_star(HState const &s, Real S, Real SM, Rea
 {
   HStar o;
   RDen const dsm = rden(S - SM, k);
-  o.d = rdiv(s.d * (S - s.vx), dsm, k);
+  o.d = rdiv<true>(s.d * (S - s.vx), dsm, k);
   if (fabs(s.d * (S - s.vx) * (S - SM) - (bx * bx)) < pts * kHlldSmall) {
     o.vy = s.vy;
     o.vz = s.vz;
@@ -405,7 +406,7 @@ __device__ __forceinline__ HStar hlld_star(HState const &s, Real S, Real SM, Rea
     o.by          = s.by * coef;
     o.bz          = s.bz * coef;
   }
-  o.E = rdiv(s.E * (S - s.vx) - s.pt * s.vx + pts * SM +
+  o.E = rdiv<true>(s.E * (S - s.vx) - s.pt * s.vx + pts * SM +
                  bx * (dot3(s.vx, s.vy, s.vz, bx, s.by, s.bz) - dot3(SM, o.vy, o.vz, bx, o.by, o.bz)),
              dsm, k);
   return o;
@@ -461,7 +462,7 @@ __device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, K
   // (rdiff * r.d - ldiff * l.d) and (r.d * (SR - r.vx) - l.d * (SL - l.vx)) are the same products: one denominator
   RDen const dsm = rden(rdiff * r.d - ldiff * l.d, k);
   Real const SM  = rdiv(rdiff * r.d * r.vx - ldiff * l.d * l.vx - r.pt + l.pt, dsm, k);
-  Real const pts = rdiv(r.d * l.pt * (SR - r.vx) - l.d * r.pt * (SL - l.vx) +
+  Real const pts = rdiv<true>(r.d * l.pt * (SR - r.vx) - l.d * r.pt * (SL - l.vx) +
                             l.d * r.d * (SR - r.vx) * (SL - l.vx) * (r.vx - l.vx),
                         dsm, k);
   HStar const sl = hlld_star(l, SL, SM, bx, pts, k);
@@ -485,7 +486,7 @@ __device__ __forceinline__ bool hlld_flux(M7 const &ql, M7 const &qr, Real bx, K
     }
   } else {
     Real const sdl = msq(sl.d, k), sdr = msq(sr.d, k);
-    Real const inv = rdiv(RC(1.0), rden(sdl + sdr, k), k);
+    Real const inv = rdiv<true>(RC(1.0), rden(sdl + sdr, k), k);
     Real const sg  = copysign(RC(1.0), bx);
     vyd = inv * (sdl * sl.vy + sdr * sr.vy + sg * (sr.by - sl.by));
     vzd = inv * (sdl * sl.vz + sdr * sr.vz + sg * (sr.bz - sl.bz));

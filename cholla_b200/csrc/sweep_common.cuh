@@ -291,7 +291,7 @@ __device__ __forceinline__ Real cell_epilogue(Real (&u)[5], K const &k, int appl
     Real const vx = u[1] * d_inv, vy = u[2] * d_inv, vz = u[3] * d_inv;
     Real const Ekin = RC(0.5) * u[0] * (vx * vx + vy * vy + vz * vz);
 #if CHL_STRICT
-    if (qdiv(u[4] - Ekin, dd, k) < U_floor) u[4] = Ekin + u[0] * U_floor;
+    if (qdiv<false>(u[4] - Ekin, dd, k) < U_floor) u[4] = Ekin + u[0] * U_floor;
 #else
     if ((u[4] - Ekin) / u[0] < U_floor) u[4] = Ekin + u[0] * U_floor;
 #endif
