@@ -70,3 +70,23 @@ def test_simple_step_is_restated_for_pcm_and_plmc_only():
     flat, dims = ghosted(ic.random_smooth((16, 1, 1), seed=1), 4, [1, 1, 0, 0, 0, 0])
     with pytest.raises(NotImplementedError):
         oracle.simple_step(flat, *dims, 4, 1.0 / 16, 1.0, 1.0, 1e-3, 1.4, oracle.PPMC, oracle.HLLC)
+
+
+@pytest.mark.parametrize("solver", [oracle.HLLC, oracle.ROE])
+def test_pcm_two_d_van_leer_step_is_the_first_order_step(solver):
+    """VL_Algorithm_2D_CUDA has no -DPCM branch in its second reconstruction (VL_2D_cuda.cu:95-120; the 1-D and 3-D files
+    have one), so a -DPCM 2-D build solves the corrector's Riemann problems on the interface arrays of step 1 -- copies of
+    U^n -- and its step is the SIMPLE integrator's first-order step, bit for bit.  (The GPU pin against the reference's own
+    -DPCM build is tests/test_gpu_reference.py::test_pcm_corrector_under_van_leer_reference_vs_oracle_vs_b200.)  In 3-D the
+    corrector really uses the half-step state and the two integrators differ."""
+    gamma, dt = 5.0 / 3.0, 2.0e-3
+    for n, flags, same in (((33, 21, 1), [1, 1, 1, 1, 0, 0], True), ((17, 13, 11), [1, 1, 1, 1, 1, 1], False)):
+        g = 2
+        flat, dims = ghosted(ic.random_smooth(n, seed=11), g, flags)
+        dx, dy, dz = 1.0 / n[0], 1.0 / n[1], 1.0 / n[2]
+        a, b = flat.copy(), flat.copy()
+        oracle.vl_step(a, *dims, g, dx, dy, dz, dt, gamma, oracle.PCM, solver)
+        oracle.simple_step(b, *dims, g, dx, dy, dz, dt, gamma, oracle.PCM, solver)
+        ra, rb = real_view(a, dims, g), real_view(b, dims, g)
+        assert np.array_equal(ra, rb) == same
+        assert not np.array_equal(ra, real_view(flat, dims, g))
