@@ -39,6 +39,8 @@ def lib():
         L.morc_calc_dti.restype = d
         L.morc_max_divergence.argtypes = [p, i, i, i, i, d, d, d]
         L.morc_max_divergence.restype = d
+        L.morc_check_magnetic_divergence.argtypes = [p, i, i, i, d, d, d]
+        L.morc_check_magnetic_divergence.restype = d
         L.morc_eigenvectors.argtypes = [p, d, p]
         L.morc_prim_to_char.argtypes = [p, p, p, d, p]
         L.morc_char_to_prim.argtypes = [p, p, p, d, p]
@@ -114,6 +116,11 @@ def calc_dti(U, nx, ny, nz, n_ghost, dx, dy, dz, gamma):
 
 def max_divergence(U, nx, ny, nz, n_ghost, dx, dy, dz):
     return lib().morc_max_divergence(_ptr(U), nx, ny, nz, n_ghost, dx, dy, dz)
+
+
+def check_magnetic_divergence(U, nx, ny, nz, dx, dy, dz):
+    """mhd::checkMagneticDivergence's range: every cell with x, y, z > 1, ghost cells included."""
+    return lib().morc_check_magnetic_divergence(_ptr(U), nx, ny, nz, dx, dy, dz)
 
 
 def eigenvectors(prim, gamma):

@@ -837,6 +837,25 @@ double morc_max_divergence(const double *U, int nx, int ny, int nz, int g, doubl
   return m;
 }
 
+/* mhd::calculateMagneticDivergence as the reference runs it (magnetic_divergence.cu:33-76): every cell whose three low
+ * faces exist -- x, y, z > 1, ghost cells included -- not only the real cells; what chl_mhd_max_divergence returns and what
+ * the reference's unit test pins (magnetic_divergence_tests.cu:27-70) */
+double morc_check_magnetic_divergence(const double *U, int nx, int ny, int nz, double dx, double dy, double dz)
+{
+  size_t const N = (size_t)nx * ny * nz;
+  double m       = 0.0;
+  for (int z = 2; z < nz; z++)
+    for (int y = 2; y < ny; y++)
+      for (int x = 2; x < nx; x++) {
+        size_t const id = IDX(x, y, z);
+        double const div = ((U[F_BX * N + id] - U[F_BX * N + id - 1]) / dx) +
+                           ((U[F_BY * N + id] - U[F_BY * N + id - nx]) / dy) +
+                           ((U[F_BZ * N + id] - U[F_BZ * N + id - (size_t)nx * ny]) / dz);
+        m = fmax(m, fabs(div));
+      }
+  return m;
+}
+
 /* ---- entry points for the reference's small-unit fiducials (reconstruction_tests.cu:51-175) ---- */
 static mprim_t prim_from8(const double p[8])
 {

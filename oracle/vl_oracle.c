@@ -141,6 +141,32 @@ static prim_t prim_diff(prim_t l, prim_t r, double coef)
   return s;
 }
 
+/* ---- test hooks: the building blocks above as the reference's helper-level unit tests call them
+ * (reconstruction_tests.cu:177-680, hydro_utilities_tests.cpp:225-236, math_utilities_tests.cpp:45-76); read by
+ * tests/test_oracle_helpers_golden.py only ---- */
+static prim_t prim_of(const double *v) { prim_t w = {v[0], v[1], v[2], v[3], v[4]}; return w; }
+static void prim_out(prim_t w, double *o) { o[0] = w.d; o[1] = w.vx; o[2] = w.vy; o[3] = w.vz; o[4] = w.p; }
+void orc_test_load_data(const double *U, long id, long N, int o1, int o2, int o3, double gamma, double *out5)
+{ prim_out(load_prim(U, (size_t)id, (size_t)N, o1, o2, o3, gamma), out5); }
+void orc_test_write_data(const double *prim5, double *Q, long id, long N, int o1, int o2, int o3, double gamma)
+{ store_interface(prim_of(prim5), Q, (size_t)id, (size_t)N, o1, o2, o3, gamma); }
+int orc_test_thread_guard(int order, int nx, int ny, int nz, int x, int y, int z)
+{ return outside_guard(order, nx, ny, nz, x, y, z); }
+void orc_test_compute_slope(const double *l5, const double *r5, double coef, double *out5)
+{ prim_out(prim_diff(prim_of(l5), prim_of(r5), coef), out5); }
+void orc_test_van_leer_slope(const double *l5, const double *r5, double *out5)
+{ for (int i = 0; i < 5; i++) out5[i] = vl_slope(l5[i], r5[i]); }
+void orc_test_monotonize_characteristic(const double *prim5, const double *aL, const double *aR, const double *aC,
+                                        const double *aG, double a, double a2, double *out5)
+{
+  char_t am = {mono(aL[0], aR[0], aC[0], aG[0]), mono(aL[1], aR[1], aC[1], aG[1]), mono(aL[2], aR[2], aC[2], aG[2]),
+               mono(aL[3], aR[3], aC[3], aG[3]), mono(aL[4], aR[4], aC[4], aG[4])};
+  prim_out(from_char(prim_of(prim5), am, a, a2), out5);
+}
+void orc_test_plm_limit_interfaces(double *l_iph5, double *r_imh5, const double *vm5, const double *vi5, const double *vp5)
+{ for (int i = 0; i < 5; i++) clamp_pair(&l_iph5[i], &r_imh5[i], vm5[i], vi5[i], vp5[i]); }
+double orc_test_square_magnitude(double a, double b, double c) { return square_mag(a, b, c); }
+
 /* one cell of PLMC_cuda (plmc_cuda.cu:60-128, 287-299).  trace = 0: a -DVL build, where the #ifndef VL block is dead;
  * trace = 1: a -DSIMPLE build, which evolves the interface values over dt/2 along the characteristics
  * (plmc_cuda.cu:130-285) with dtodx = dt / dx of the sweep direction. */
@@ -504,6 +530,8 @@ static inline double de_pressure(double E, double U_total, double U_advected, do
   double U = (U_total / E > ORC_DE_ETA_1) ? U_total : U_advected;
   return fmax(U * (gamma - 1.0), ORC_TINY);
 }
+double orc_test_de_pressure(double E, double U_total, double U_advected, double gamma)
+{ return de_pressure(E, U_total, U_advected, gamma); }
 /* the solvers' own load of one side's pressure (hllc_cuda.cu:107-113, roe_cuda.cu:109-115, hll_cuda.cu:106-112) */
 static inline double side_pressure(cons_t u, double vx, double vy, double vz, double gamma, const pass_t *ps, int right)
 {

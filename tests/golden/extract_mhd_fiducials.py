@@ -185,6 +185,17 @@ def scalars():
         "cell_centred": {"nx": 3, "ny": 3, "n_cells": 125, "xid": 1, "yid": 1, "zid": 1, "fiducial": [637.5, 761.5, 883.5],
                          "setup": "8-field grid of 125 cells per field filled with iota; indices use nx = ny = 3"},
     }
+    t = read("src/mhd/magnetic_divergence_tests.cu")
+    m = re.search(r"fiducialDivergence\s*=\s*(" + NUM + r")\s*/\s*(" + NUM + r")", t)
+    out["magnetic_divergence"] = {
+        "source": "src/mhd/magnetic_divergence_tests.cu:27-70",
+        "grid_size": int(re.search(r"gridSize\s*=\s*(\d+)", t).group(1)),
+        "n_ghost": int(re.search(r"n_ghost\s*=\s*(\d+)", t).group(1)),
+        "dx": float(re.search(r"G\.H\.dx\s*=\s*(" + NUM + r")", t).group(1)), "n_fields": 8,
+        "prng": "std::mt19937(1); std::uniform_real_distribution<double>(1, 5); every value of the 8-field grid, in "
+                "memory order, divided by 1E15",
+        "fiducial_numerator": float(m.group(1)), "fiducial_denominator": float(m.group(2)),
+    }
     return out
 
 

@@ -46,3 +46,16 @@ class UniformReal:
         if canon >= 1.0:
             canon = 1.0 - 2.0 ** -53
         return canon * (self.b - self.a) + self.a
+
+
+def mt19937_uniform_real(seed, a, b, count):
+    """`count` draws of std::uniform_real_distribution<double>(a, b) on a 32-bit std::mt19937(seed), as libstdc++ evaluates
+    them: generate_canonical<double, 53> takes two engine outputs, (x1 + x2 * 2^32) / 2^64 in double arithmetic, clamped
+    below 1.  numpy's MT19937 with its legacy seeding is init_genrand(seed), the engine's seeding."""
+    import numpy as np
+    bg = np.random.MT19937()
+    bg._legacy_seeding(seed)
+    raw = bg.random_raw(2 * count).astype(np.uint64)
+    canon = (raw[0::2].astype(np.float64) + raw[1::2].astype(np.float64) * 4294967296.0) / 18446744073709551616.0
+    canon[canon >= 1.0] = np.nextafter(1.0, 0.0)
+    return canon * (b - a) + a

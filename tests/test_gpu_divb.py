@@ -28,3 +28,28 @@ def test_divergence_matches_oracle_and_detects_a_monopole():
     d = G.max_magnetic_divergence()
     assert d == pytest.approx(1.0e-3 / H.dx, rel=1e-9) and d > 1e-9
     G.close()
+
+
+def test_reference_unit_test_fiducial(golden_dir):
+    """tMHDGrid3DcheckMagneticDivergence (magnetic_divergence_tests.cu:27-70): a (96 + 2 * 4)^3 grid of std::mt19937(1)
+    values, dx = dy = dz = 3; the reference's known answer, the CPU oracle's value and the device reduction agree.  The
+    maximum runs over every cell whose low faces exist, ghost cells included, like the reference's kernel."""
+    import json
+    import os
+
+    from test_oracle_golden import nearly_equal
+    from test_oracle_mhd_golden import divergence_test_grid
+
+    with open(os.path.join(golden_dir, "mhd_scalars.json")) as fh:
+        t = json.load(fh)["magnetic_divergence"]
+    U, n = divergence_test_grid(t)
+    nr, dx = t["grid_size"], t["dx"]
+    assert n_ghost_for(cb.PLMC, mhd=True) == t["n_ghost"]
+    G = Grid3D((nr, nr, nr), (dx * nr, dx * nr, dx * nr), recon=cb.PLMC, solver=cb.HLLD, gamma=5.0 / 3.0, bc=[1] * 6,
+               strict=True, mhd=True)
+    assert (G.H.nx, G.H.ny, G.H.nz) == (n, n, n) and G.H.dx == dx
+    G.upload(U)
+    got = G.max_magnetic_divergence()
+    G.close()
+    assert nearly_equal(got, t["fiducial_numerator"] / t["fiducial_denominator"]), got
+    assert got == pytest.approx(mhd.check_magnetic_divergence(U, n, n, n, dx, dx, dx), rel=1e-14)

@@ -164,3 +164,21 @@ def test_mhd_inverse_crossing_time_and_speeds(golden_dir):
     i5 = 2 + 5 * (2 + 5 * 2)
     assert b[0] == 0.5 * (grid[5 * 125 + i5] + grid[5 * 125 + i5 - 1])
     assert b[2] == 0.5 * (grid[7 * 125 + i5] + grid[7 * 125 + i5 - 25])
+
+
+def divergence_test_grid(t):
+    """The grid of tMHDGrid3DcheckMagneticDivergence (magnetic_divergence_tests.cu:29-49): (96 + 2 * 4)^3 cells, 8 fields,
+    every value uniform in [1, 5) / 1e15 from std::mt19937(1), in memory order."""
+    from stdrandom import mt19937_uniform_real
+    n = t["grid_size"] + 2 * t["n_ghost"]
+    return mt19937_uniform_real(1, 1.0, 5.0, n ** 3 * t["n_fields"]) / 1.0e15, n
+
+
+def test_check_magnetic_divergence_fiducial(golden_dir):
+    t = load(golden_dir, "mhd_scalars.json")["magnetic_divergence"]
+    U, n = divergence_test_grid(t)
+    assert U[0] * 1.0e15 == pytest.approx(1.0 + 4.0 * (1791095845 + 4282876139 * 2.0 ** 32) / 2.0 ** 64, rel=1e-15)
+    got = mhd.check_magnetic_divergence(U, n, n, n, t["dx"], t["dx"], t["dx"])
+    assert nearly_equal(got, t["fiducial_numerator"] / t["fiducial_denominator"]), got
+    # the reference's range includes ghost cells (x, y, z > 1): on this random grid the real-cell maximum is smaller
+    assert mhd.max_divergence(U, n, n, n, t["n_ghost"], t["dx"], t["dx"], t["dx"]) <= got
