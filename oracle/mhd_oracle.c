@@ -863,6 +863,32 @@ static mprim_t prim_from8(const double p[8])
   w.d = p[0]; w.vx = p[1]; w.vy = p[2]; w.vz = p[3]; w.p = p[4]; w.bx = p[5]; w.by = p[6]; w.bz = p[7];
   return w;
 }
+/* helper-level hooks (reconstruction_tests.cu:205-249, 336-392, 574-611, MHD branches); tests/test_oracle_helpers_golden.py */
+static void prim_to8(mprim_t o, double out[8])
+{
+  out[0] = o.d; out[1] = o.vx; out[2] = o.vy; out[3] = o.vz; out[4] = o.p; out[5] = o.bx; out[6] = o.by; out[7] = o.bz;
+}
+void morc_test_load_data(const double *U, int x, int y, int z, int nx, int ny, long N, int o1, int o2, int o3, double gamma,
+                         double out[8])
+{
+  prim_to8(load_prim(U, x, y, z, nx, ny, (size_t)N, o1, o2, o3, gamma), out);
+}
+void morc_test_write_data(const double prim[8], double *Q, const double *U, long id, long N, int o1, int o2, int o3,
+                          double gamma)
+{
+  write_interface(prim_from8(prim), Q, U, (size_t)id, (size_t)N, o1, o2, o3, gamma);
+}
+void morc_test_monotonize_characteristic(const double prim[8], const double aL[7], const double aR[7], const double aC[7],
+                                         const double aG[7], const double eig[18], double a2, double out[8])
+{
+  eigen_t e;
+  memcpy(&e, eig, 18 * sizeof(double));
+  mchar_t am;
+  for (int i = 0; i < 7; i++) am.a[i] = mono(aL[i], aR[i], aC[i], aG[i]);
+  mprim_t o = from_char(prim_from8(prim), am, e, a2);
+  o.bx = 0.0;
+  prim_to8(o, out);
+}
 void morc_eigenvectors(const double prim[8], double gamma, double out[18])
 {
   mprim_t const w = prim_from8(prim);

@@ -53,10 +53,10 @@ def preprocess(text, defined=()):
     return "\n".join(out)
 
 
-def test_body(text, name):
+def test_body(text, name, defined=()):
     a = text.index(name)
     b = re.search(r"\nTEST|\n__global__|\Z", text[a + 10:])
-    return preprocess(text[a:a + 10 + b.start()])
+    return preprocess(text[a:a + 10 + b.start()], defined)
 
 
 def braces(body, var):
@@ -120,6 +120,22 @@ def main():
     out["plm_limit_interfaces"] = {k: members(b, k) for k in
                                    ("interface_l_iph", "interface_r_imh", "cell_im1", "cell_i", "cell_ip1",
                                     "interface_l_iph_fiducial", "interface_r_imh_fiducial")}
+
+    # the -DMHD branches of the same tests (8-field states; the eigenvector struct of the monotonisation test is 17 .. 34)
+    M = ("MHD",)
+    b = test_body(rec, "TEST(tALLReconstructionLoadData", M)
+    out["mhd_load_data"] = {"n": 3, "energy_scale": 5.0e2, "gamma": 5.0 / 3.0, "xid": 1, "yid": 1, "zid": 1,
+                            "fiducial": braces(b, "fiducial_data")}
+    b = test_body(rec, "TEST(tALLReconstructionMonotonizeCharacteristicReturnPrimitive", M)
+    out["mhd_monotonize_characteristic"] = {
+        "primitive": braces(b, "primitive"), "del_a_L": braces(b, "del_a_L"), "del_a_R": braces(b, "del_a_R"),
+        "del_a_C": braces(b, "del_a_C"), "del_a_G": braces(b, "del_a_G"), "sound_speed": scalar(b, "sound_speed"),
+        "eigenvectors": braces(b, "eigenvectors"), "fiducial": braces(b, "fiducial_data")}
+    b = test_body(rec, "TEST(tALLReconstructionWriteData", M)
+    pairs = re.search(r"fiducial_interface\s*=\s*\{(.*?)\};", b, re.S).group(1)
+    out["mhd_write_data"] = {"interface": braces(b, "interface"), "n": 3, "gamma": 5.0 / 3.0, "xid": 1, "yid": 1, "zid": 1,
+                             "fiducial": {m.group(1): float(m.group(2))
+                                          for m in re.finditer(r"\{(\d+)\s*,\s*(" + NUM + r")\}", pairs)}}
 
     hu = preprocess(read("src/utils/hydro_utilities_tests.cpp"))
     b = test_body(hu, "TEST(tHYDROHydroUtilsGetPressureFromDE")

@@ -147,3 +147,47 @@ def test_scalar_floor_kernel(gd):
         U[t["field_num"]] = v
         oracle.scalar_floor(U, 1, 1, 1, 0, t["field_num"], t["scalar_floor"])
         assert U[t["field_num"]] == max(v, t["scalar_floor"]) and not U[:5].any()
+
+
+# ---- the -DMHD branches of the same reference tests, against oracle/mhd_oracle.c ------------------------------------
+@pytest.fixture(scope="module")
+def M():
+    from oracle import mhd
+    lib = mhd.lib()
+    d, i, p, l = C.c_double, C.c_int, C.c_void_p, C.c_long
+    lib.morc_test_load_data.argtypes = [p, i, i, i, i, i, l, i, i, i, d, p]
+    lib.morc_test_write_data.argtypes = [p, p, p, l, l, i, i, i, d]
+    lib.morc_test_monotonize_characteristic.argtypes = [p, p, p, p, p, p, d, p]
+    return lib
+
+
+def test_mhd_load_data(gd, M):
+    t = gd["mhd_load_data"]
+    n = t["n"]
+    N = n ** 3
+    U = np.arange(8 * N, dtype=np.float64)
+    U[4 * N:5 * N] *= t["energy_scale"]
+    out = np.zeros(8)
+    M.morc_test_load_data(_p(U), t["xid"], t["yid"], t["zid"], n, n, N, 1, 2, 3, t["gamma"], _p(out))
+    _close(out, t["fiducial"], "Load_Data (MHD)")
+
+
+def test_mhd_monotonize_characteristic_return_primitive(gd, M):
+    t = gd["mhd_monotonize_characteristic"]
+    out = np.zeros(8)
+    M.morc_test_monotonize_characteristic(_p(_a(t["primitive"])), _p(_a(t["del_a_L"])), _p(_a(t["del_a_R"])),
+                                          _p(_a(t["del_a_C"])), _p(_a(t["del_a_G"])), _p(_a(t["eigenvectors"])),
+                                          t["sound_speed"] ** 2, _p(out))
+    _close(out, t["fiducial"], "Monotonize_Characteristic_Return_Primitive (MHD)")
+
+
+def test_mhd_write_data(gd, M):
+    t = gd["mhd_write_data"]
+    n = t["n"]
+    N = n ** 3
+    cell = t["xid"] + n * (t["yid"] + n * t["zid"])
+    Q, U = np.zeros(8 * N), np.zeros(8 * N)  # the test's conserved array is all zeros: the face-normal field is 0
+    M.morc_test_write_data(_p(_a(t["interface"])), _p(Q), _p(U), cell, N, 1, 2, 3, t["gamma"])
+    want = {int(k): v for k, v in t["fiducial"].items()}
+    for k, v in enumerate(Q[:7 * N]):  # the reference's interface array has 7 fields per side (no normal field)
+        assert nearly_equal(float(v), want.get(k, 0.0)), ("Write_Data (MHD)", k, float(v))
