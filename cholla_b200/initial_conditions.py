@@ -95,6 +95,16 @@ def spherical_overpressure(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0), gamma
     return _pack(d, zero, zero, zero, P / (gamma - 1.0))
 
 
+def spherical_overdensity(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, 0.0, 0.0), gamma=1.66666667):
+    """Grid3D::Spherical_Overdensity_3D (initial_conditions.cpp:1253-1309): rho = 0.0005, P = 0.0005 background at rest;
+    rho = 1 (same pressure) inside r < 0.2 of (0.5, 0.5, 0.5) -- the centre is a literal in the reference."""
+    X, Y, Z = _mesh(n, lengths, lo)
+    r = np.sqrt((X - 0.5) * (X - 0.5) + (Y - 0.5) * (Y - 0.5) + (Z - 0.5) * (Z - 0.5))
+    d = np.where(r < 0.2, 1.0, 0.0005)
+    zero = np.zeros_like(d)
+    return _pack(d, zero, zero, zero, np.full_like(d, 0.0005) / (gamma - 1.0))
+
+
 def kh_res_ind(n, lengths=(1.0, 1.0, 1.0), lo=(0.0, -0.5, -0.5), gamma=5.0 / 3.0):
     """KH_res_ind, 3-D branch (examples/3D/KH_res_ind_3D.txt): dense cylinder along x sheared against the
     ambient gas, resolution-independent ramp."""

@@ -71,6 +71,8 @@ def initial_fields(P: Parameters, mhd=False, n_ghost=0):
                           P.diaph, P.gamma)
     if name == "Spherical_Overpressure_3D":
         return ic.spherical_overpressure(n, ln, lo, P.gamma)
+    if name == "Spherical_Overdensity_3D":
+        return ic.spherical_overdensity(n, ln, lo, P.gamma)
     if name == "KH_res_ind":
         return ic.kh_res_ind(n, ln, lo, P.gamma)
     if name == "Square_Wave":
@@ -98,7 +100,7 @@ def initial_fields(P: Parameters, mhd=False, n_ghost=0):
                             (P.Bx, P.By, P.Bz))
     raise NotImplementedError("init=%s is not one of the generators of the hot-path scope (SURVEY 8d): Constant, Sound_Wave, "
                               "Riemann, Square_Wave, Shu_Osher, Blast_1D, KH, KH_res_ind, Gresho, Implosion_2D, Rayleigh_Taylor, Linear_Wave, "
-                              "Spherical_Overpressure_3D, Orszag_Tang_Vortex, MHD_Spherical_Blast, Circularly_Polarized_Alfven_Wave, "
+                              "Spherical_Overpressure_3D, Spherical_Overdensity_3D, Orszag_Tang_Vortex, MHD_Spherical_Blast, Circularly_Polarized_Alfven_Wave, "
                               "Advecting_Field_Loop" % name)
 
 

@@ -135,7 +135,7 @@ def test_shipped_decks_build_their_initial_state():
     if not os.path.isdir(root):
         pytest.skip("reference tree not present")
     hydro = {"Constant", "Sound_Wave", "Riemann", "Square_Wave", "Shu_Osher", "Blast_1D", "KH", "KH_res_ind", "Gresho",
-             "Implosion_2D", "Spherical_Overpressure_3D"}
+             "Implosion_2D", "Spherical_Overpressure_3D", "Spherical_Overdensity_3D"}
     mhd_only = {"Orszag_Tang_Vortex", "MHD_Spherical_Blast", "Linear_Wave", "Circularly_Polarized_Alfven_Wave",
                 "Advecting_Field_Loop"}
     built = 0
@@ -291,3 +291,19 @@ def test_mhd_linear_wave_rotations_and_mhd_constant():
     assert f.shape[0] == 8 and np.all(f[5] == P.Bx) and np.all(f[0] == 2.0) and np.all(f[2] == 0.5)
     with pytest.raises(NotImplementedError):
         run.initial_fields(pm.parse_text(MHD_BLAST_DECK.replace("init=MHD_Spherical_Blast", "init=KH")), True, g)
+
+
+def test_spherical_overdensity():
+    """Grid3D::Spherical_Overdensity_3D (initial_conditions.cpp:1253-1309; examples/3D/Spherical_Collapse.txt): a unit-density
+    sphere of radius 0.2 about (0.5, 0.5, 0.5) in a rho = 0.0005 background, uniform pressure 0.0005, at rest."""
+    n, gamma = (20, 20, 20), 5.0 / 3.0
+    f = ic.spherical_overdensity(n, gamma=gamma)
+    assert f.shape == (5, 20, 20, 20) and not f[1:4].any()
+    assert np.array_equal(f[4], np.full((20, 20, 20), 0.0005 / (gamma - 1.0)))
+    x = (np.arange(20) + 0.5) / 20
+    Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+    inside = np.sqrt((X - 0.5) ** 2 + (Y - 0.5) ** 2 + (Z - 0.5) ** 2) < 0.2
+    assert np.array_equal(f[0] == 1.0, inside) and set(np.unique(f[0])) == {0.0005, 1.0}
+    assert abs(inside.mean() - 4.0 / 3.0 * np.pi * 0.2 ** 3) < 3e-3
+    P = pm.parse_text(DECK % ((16, 16, 16) + ("Spherical_Overdensity_3D",)))
+    assert run.initial_fields(P).shape == (5, 16, 16, 16)
