@@ -51,5 +51,6 @@ def test_reference_unit_test_fiducial(golden_dir):
     G.upload(U)
     got = G.max_magnetic_divergence()
     G.close()
-    assert nearly_equal(got, t["fiducial_numerator"] / t["fiducial_denominator"]), got
+    fid = t["fiducial_numerator"] / t["fiducial_denominator"]
+    assert nearly_equal(got, fid) and got == pytest.approx(fid, rel=1e-13), got
     assert got == pytest.approx(mhd.check_magnetic_divergence(U, n, n, n, dx, dx, dx), rel=1e-14)

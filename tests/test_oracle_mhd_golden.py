@@ -179,6 +179,8 @@ def test_check_magnetic_divergence_fiducial(golden_dir):
     U, n = divergence_test_grid(t)
     assert U[0] * 1.0e15 == pytest.approx(1.0 + 4.0 * (1791095845 + 4282876139 * 2.0 ** 32) / 2.0 ** 64, rel=1e-15)
     got = mhd.check_magnetic_divergence(U, n, n, n, t["dx"], t["dx"], t["dx"])
-    assert nearly_equal(got, t["fiducial_numerator"] / t["fiducial_denominator"]), got
+    fid = t["fiducial_numerator"] / t["fiducial_denominator"]
+    assert nearly_equal(got, fid), got
+    assert got == pytest.approx(fid, rel=1e-14)  # the reference's 1e-14 ABSOLUTE tolerance says little at 1e-15: also relative
     # the reference's range includes ghost cells (x, y, z > 1): on this random grid the real-cell maximum is smaller
     assert mhd.max_divergence(U, n, n, n, t["n_ghost"], t["dx"], t["dx"], t["dx"]) <= got
