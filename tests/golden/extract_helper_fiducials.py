@@ -143,6 +143,17 @@ def main():
                                    "U_advected": braces(hu, "U_advected"), "gamma": 5.0 / 3.0,
                                    "fiducial": braces(b, "fiducial_Ps")}
 
+    hu_raw = read("src/utils/hydro_utilities_tests.cpp")
+    params = {k: braces(hu, k) for k in ("d", "vx", "vy", "vz", "E", "P", "magnetic_x", "magnetic_y", "magnetic_z")}
+    out["pressure_energy_primitive"] = {"gamma": 5.0 / 3.0, "params": params}
+    for build, defined in (("hydro", ()), ("mhd", ("MHD",))):
+        tp = test_body(hu_raw, "TEST(tHYDROtMHDHydroUtilsCalcPressurePrimitive, CorrectInputExpectCorrectOutput", defined)
+        te = test_body(hu_raw, "TEST(tHYDROtMHDHydroUtilsCalcEnergyPrimitive, CorrectInputExpectCorrectOutput", defined)
+        tn = test_body(hu_raw, "TEST(tHYDROtMHDHydroUtilsCalcEnergyPrimitive, NegativePressureExpectAutomaticFix", defined)
+        out["pressure_energy_primitive"][build] = {"pressure": braces(tp, "fiducial_pressure"),
+                                                   "energy": braces(te, "fiducial_energy"),
+                                                   "energy_negative_pressure": braces(tn, "fiducial_energy")}
+
     mu = read("src/utils/math_utilities_tests.cpp")
     b = test_body(mu, "TEST(tALLDotProduct")
     ab = re.search(r"a\{([^{}]*)\},\s*b\{([^{}]*)\}", b)

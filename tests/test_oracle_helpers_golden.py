@@ -191,3 +191,23 @@ def test_mhd_write_data(gd, M):
     want = {int(k): v for k, v in t["fiducial"].items()}
     for k, v in enumerate(Q[:7 * N]):  # the reference's interface array has 7 fields per side (no normal field)
         assert nearly_equal(float(v), want.get(k, 0.0)), ("Write_Data (MHD)", k, float(v))
+
+
+@pytest.mark.parametrize("build", ["hydro", "mhd"])
+def test_pressure_and_energy_from_primitives(gd, M, build):
+    """hydro_utilities::Calc_Pressure_Primitive / Calc_Energy_Primitive (hydro_utilities.h:34-45, 106-118; known answers
+    hydro_utilities_tests.cpp:61-77, 155-171, 191-206): the routines Load_Data and Write_Data call.  The MHD oracle's
+    functions with a zero field are the hydro build's."""
+    d_, p_ = C.c_double, C.c_void_p
+    for fn in (M.morc_test_pressure_primitive, M.morc_test_energy_primitive):
+        fn.argtypes, fn.restype = [d_] * 9, d_
+    t = gd["pressure_energy_primitive"]
+    q, g, fid = t["params"], t["gamma"], t[build]
+    for i in range(3):
+        b = (q["magnetic_x"][i], q["magnetic_y"][i], q["magnetic_z"][i]) if build == "mhd" else (0.0, 0.0, 0.0)
+        v = (q["d"][i], q["vx"][i], q["vy"][i], q["vz"][i])
+        assert nearly_equal(M.morc_test_pressure_primitive(q["E"][i], *v, g, *b), fid["pressure"][i]), ("pressure", i)
+        assert nearly_equal(M.morc_test_energy_primitive(q["P"][i], *v, g, *b), fid["energy"][i]), ("energy", i)
+        assert nearly_equal(M.morc_test_energy_primitive(-q["P"][i], *v, g, *b), fid["energy_negative_pressure"][i]), ("E(-P)", i)
+        # a velocity 1e4 times larger makes the pressure negative: exactly TINY_NUMBER (hydro_utilities_tests.cpp:97-110)
+        assert M.morc_test_pressure_primitive(q["E"][i], q["d"][i], 1e4 * q["vx"][i], q["vy"][i], q["vz"][i], g, *b) == 1e-20
