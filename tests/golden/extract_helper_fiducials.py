@@ -154,6 +154,9 @@ def main():
                                                    "energy": braces(te, "fiducial_energy"),
                                                    "energy_negative_pressure": braces(tn, "fiducial_energy")}
 
+    b = test_body(hu_raw, "TEST(tHYDROtMHDCalcKineticEnergyFromVelocity")
+    out["kinetic_energy_from_velocity"] = {"coef": scalar(b, "coef"), "fiducial": braces(b, "fiducialEnergies")}
+
     mu = read("src/utils/math_utilities_tests.cpp")
     b = test_body(mu, "TEST(tALLDotProduct")
     ab = re.search(r"a\{([^{}]*)\},\s*b\{([^{}]*)\}", b)

@@ -211,3 +211,13 @@ def test_pressure_and_energy_from_primitives(gd, M, build):
         assert nearly_equal(M.morc_test_energy_primitive(-q["P"][i], *v, g, *b), fid["energy_negative_pressure"][i]), ("E(-P)", i)
         # a velocity 1e4 times larger makes the pressure negative: exactly TINY_NUMBER (hydro_utilities_tests.cpp:97-110)
         assert M.morc_test_pressure_primitive(q["E"][i], q["d"][i], 1e4 * q["vx"][i], q["vy"][i], q["vz"][i], g, *b) == 1e-20
+
+
+def test_kinetic_energy_from_velocity(gd, L):
+    """hydro_utilities::Calc_Kinetic_Energy_From_Velocity = 0.5 d SquareMagnitude(v) (hydro_utilities.h; the dual-energy
+    passes call it, VL_3D_cuda.cu:418, hydro_cuda.cu:789): the oracle's 0.5 * d * square_mag(...) on the reference's inputs."""
+    t, q = gd["kinetic_energy_from_velocity"], gd["pressure_energy_primitive"]["params"]
+    c = t["coef"]
+    for i in range(3):
+        got = 0.5 * (c * q["d"][i]) * L.orc_test_square_magnitude(c * q["vx"][i], c * q["vy"][i], c * q["vz"][i])
+        assert nearly_equal(got, t["fiducial"][i]), (i, got)
